@@ -1,0 +1,156 @@
+/* ofdm_b200.h — C ABI of libofdm_b200.so, the B200 (sm_100a) drop-in for the OFDM
+ * baseband hot path of rubiruchi/ofdm_uhd.
+ *
+ * Every entry point replaces a GNU Radio 3.6 block (or chain of blocks) that the
+ * reference reaches through SWIG; the reference call site is cited next to it
+ * (paths relative to /root/reference).  All data pointers are DEVICE pointers
+ * unless the name starts with `host_`; every call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*), returns 0 or a negative OFDM_E_* code and
+ * never throws; ofdm_last_error() gives the text.  The library allocates only
+ * its own constant tables (in ofdm_create / ofdm_sense_create); all stream,
+ * packet and scratch buffers are owned by the caller.
+ */
+#ifndef OFDM_B200_H
+#define OFDM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFDM_OK             0
+#define OFDM_E_INVAL       -1   /* bad argument / unsupported layout            */
+#define OFDM_E_CUDA        -2   /* a CUDA runtime call failed                   */
+#define OFDM_E_NOMEM       -3   /* workspace / capacity too small               */
+
+/* bits of ofdm_rx_io.status[0] (device side, sticky) */
+#define OFDM_ST_TRIG_OVERFLOW   1u   /* more triggers than max_frames              */
+#define OFDM_ST_SEG_OVERFLOW    2u   /* a detector segment overflowed its slot list */
+
+typedef struct ofdm_handle ofdm_handle;
+typedef struct ofdm_sense_handle ofdm_sense_handle;
+
+typedef struct ofdm_cfg {
+    int32_t fft_length;        /* options.fft_length      (ofdm.py:64)  */
+    int32_t occupied_tones;    /* options.occupied_tones  (ofdm.py:65)  */
+    int32_t cp_length;         /* options.cp_length       (ofdm.py:66)  */
+    int32_t constellation_size;/* arity, ofdm.py:88-89                   */
+    const float* host_constellation; /* 2*M floats (re,im): rotated_const of ofdm.py:94-101 */
+    float   tx_amplitude;      /* transmit_path.py:44,56-62 (clamped to [0,1]) */
+    int32_t device;            /* CUDA device ordinal                    */
+    uint64_t pad_seed;         /* seed of the pad-symbol generator (upstream: libc rand()) */
+    int32_t max_pkt_bytes;     /* bytes kept per received packet slot (<= 4096) */
+} ofdm_cfg;
+
+const char* ofdm_last_error(void);
+int ofdm_version(void);
+
+ofdm_handle* ofdm_create(const ofdm_cfg* cfg);
+void ofdm_destroy(ofdm_handle* h);
+/* transmit_path.set_tx_amplitude (transmit_path.py:56-62) */
+int ofdm_set_tx_amplitude(ofdm_handle* h, float ampl);
+/* derived layout: out[0]=zeros_on_left, [1]=data carriers, [2]=bits/carrier, [3]=symbol length,
+ * [4]=channel filter taps, [5]=overlap-save FFT size, [6]=packet slot stride, [7]=reserved */
+int ofdm_get_layout(const ofdm_handle* h, int32_t* out8);
+/* copy of the channel-filter taps (gr.firdes.low_pass, ofdm_receiver.py~:69-76) to host memory */
+int ofdm_get_chan_taps(const ofdm_handle* h, float* host_taps, int32_t max_taps);
+
+/* ---- framing: ofdm_packet_utils.make_packet / unmake_packet (ofdm_packet_utils.py:99-143,169-191)
+ *      + upstream crc.gen_and_append_crc32 / check_crc32 ------------------------------------- */
+/* pkt f = header(4) || whiten(payload_f || crc32 || 0x55 [|| 0x55 pad]).  pkt_off[f+1]-pkt_off[f]
+ * must equal the packet length computed by ofdm_packet_len(). */
+int32_t ofdm_packet_len(int32_t payload_len, int pad_for_usrp);
+int ofdm_make_packets(ofdm_handle* h, const uint8_t* payload, const int64_t* payload_off, int32_t n_pkts,
+                      int whitening, uint8_t* pkts, const int64_t* pkt_off, void* stream);
+
+/* ---- transmit: ofdm_mapper_bcv -> ofdm_insert_preamble -> fft_vcc(inverse) -> ofdm_cyclic_prefixer
+ *      -> multiply_const(1/sqrt(N)) -> multiply_const(amp)   (ofdm.py:106-117, transmit_path.py:48) ----
+ * sym_off[f] = number of OFDM symbols (preamble included) before frame f; frame f is written at
+ * out[sym_off[f]*(N+cp)]; total_syms = sym_off[n_frames].  If every frame has the same number of
+ * symbols pass it as uniform_syms (sym_off may then be NULL), else 0.  Pad carriers use
+ * pad_index(seed, first_frame+f, symbol, carrier). */
+int32_t ofdm_frame_symbols(const ofdm_handle* h, int32_t pkt_len);
+int ofdm_tx_modulate_batch(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames,
+                           int64_t first_frame, const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms,
+                           float* out_iq, void* stream);
+
+/* ---- receive -------------------------------------------------------------------------------- */
+typedef struct ofdm_rx_io {
+    /* capacity */
+    int32_t max_frames;        /* capacity of every per-trigger / per-frame array below */
+    int32_t pkt_stride;        /* bytes per packet slot in pkt_bytes                    */
+    /* scratch (sizes from ofdm_rx_workspace_bytes) */
+    void*   workspace;
+    size_t  workspace_bytes;
+    /* outputs (device) */
+    uint32_t* status;          /* [1]  OFDM_ST_* bits                                   */
+    int32_t* n_trig;           /* [1]  triggers found by ofdm_sync_pn's peak detector   */
+    int64_t* trig_idx;         /* [max_frames] sample index of each trigger             */
+    float*   trig_ang;         /* [max_frames] angle(P) latched at the trigger          */
+    int32_t* n_frames;         /* [1]  frames the sampler emits                         */
+    int64_t* frame_start;      /* [max_frames] first sample of the preamble vector      */
+    int32_t* frame_ndata;      /* [max_frames] data vectors emitted after the preamble  */
+    uint8_t* frame_live;       /* [max_frames] 1: the frame sink started on this preamble */
+    uint8_t* frame_status;     /* [max_frames] 0 none, 1 bad header, 2 message, 3 stream ended */
+    int32_t* pkt_len;          /* [max_frames] header length field (payload + 4)        */
+    uint8_t* pkt_ok;           /* [max_frames] CRC-32 verdict of the message            */
+    uint8_t* pkt_bytes;        /* [max_frames*pkt_stride] dewhitened payload || crc     */
+    int64_t* counters;         /* [8] 0:frames 1:messages 2:crc_ok 3:payload bytes ok 4:samples 5:triggers */
+    /* optional taps for parity debugging (may be NULL); indexed by vector = position in the
+     * sampler's output stream */
+    float*   eq_syms;          /* [max_vectors*occ*2] ofdm_frame_acquisition output      */
+    uint8_t* sym_idx;          /* [max_vectors*ncar]  slicer decisions                   */
+    float*   derot_syms;       /* [max_vectors*ncar*2] frame-sink derotated symbols      */
+    int64_t  max_vectors;
+} ofdm_rx_io;
+
+size_t ofdm_rx_workspace_bytes(const ofdm_handle* h, int64_t n_samples, int32_t max_frames);
+
+/* gr.fft_filter_ccc(1, firdes.low_pass(...))  (ofdm_receiver.py~:69-76,131) */
+int ofdm_rx_chan_filter(ofdm_handle* h, const float* x_iq, int64_t n, float* y_iq, void* stream);
+/* upstream ofdm_sync_pn up to add_const_ff(-1) (ofdm_receiver.py~:97-101): mf[n]; first_nan[0] gets
+ * the first index whose metric is NaN (INT64_MAX if none) */
+int ofdm_rx_sync_metric(ofdm_handle* h, const float* y_iq, int64_t n, float* mf, int64_t* first_nan,
+                        void* stream);
+/* gr.peak_detector_fb(0.20,0.20,30,0.001) + complex_to_arg + sample_and_hold (ofdm_sync_pn) */
+int ofdm_rx_peak_detect(ofdm_handle* h, const float* y_iq, const float* mf, int64_t n, const int64_t* first_nan,
+                        ofdm_rx_io* io, void* stream);
+/* gr.frequency_modulator_fc + digital.ofdm_sampler (ofdm_receiver.py~:123-125,133-136) as a frame table */
+int ofdm_rx_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, void* stream);
+/* multiply_cc (derotation) + fft_vcc(forward) + ofdm_frame_acquisition + ofdm_frame_sink
+ * (ofdm_receiver.py~:124-129, ofdm.py:240-243) */
+int ofdm_rx_demod(ofdm_handle* h, const float* y_iq, int64_t n, ofdm_rx_io* io, void* stream);
+/* frame-sink liveness (which preambles the sink accepted), unmake_packet (dewhiten + CRC,
+ * ofdm.py:300-305) and the counters */
+int ofdm_rx_finish(ofdm_handle* h, ofdm_rx_io* io, void* stream);
+/* all of the above in order, no host synchronisation */
+int ofdm_rx_demodulate(ofdm_handle* h, const float* x_iq, int64_t n, ofdm_rx_io* io, void* stream);
+/* pointers into the workspace for parity tests: which = 0 filtered stream y (2n floats), 1 metric mf (n floats) */
+void* ofdm_rx_workspace_ptr(const ofdm_handle* h, const ofdm_rx_io* io, int64_t n, int which);
+
+/* ---- synthetic channel used by the loopback drivers and the bench (not a reference block) ----
+ * y[n] = x[n]*exp(j*(phase0 + 2*pi*cfo/N*n)) + sigma*(gauss+j*gauss), counter-based noise */
+int ofdm_channel(ofdm_handle* h, const float* x_iq, int64_t n, float cfo_subcarriers, double phase0,
+                 float sigma, uint64_t seed, float* y_iq, void* stream);
+
+/* ---- spectrum sensing: stream_to_vector -> fft_vcc(N,True,blackmanharris[,shift]) ->
+ *      complex_to_mag_squared -> bin_statistics_f  (secondary_tx.py:163-202, usrp_fft_save.py:58-62) ---- */
+ofdm_sense_handle* ofdm_sense_create(int32_t fft_size, int32_t device);
+void ofdm_sense_destroy(ofdm_sense_handle* s);
+/* max-hold power per dwell: maxhold[d][N], d < n_frames / (tune_delay+dwell_delay) */
+int ofdm_sense(ofdm_sense_handle* s, const float* x_iq, int64_t n_frames, int shift, int32_t tune_delay,
+               int32_t dwell_delay, float* maxhold, void* stream);
+/* raw windowed spectra (usrp_fft_save.py:61): out[frame][N] complex */
+int ofdm_sense_fft(ofdm_sense_handle* s, const float* x_iq, int64_t n_frames, int shift, float* out_iq,
+                   void* stream);
+/* sense_loop decision (secondary_tx.py:237-266,306-331): mean of n_avg dwell vectors, free = !(avg > thr),
+ * halves swapped into frequency order, nibble-packed hex (first bit = LSB).  avg_inorder: double[N],
+ * free_bits: uint8[N], hex: char[N/4] (no terminator) */
+int ofdm_sense_decide(ofdm_sense_handle* s, const float* maxhold, int32_t n_avg, double threshold,
+                      double* avg_inorder, uint8_t* free_bits, char* hex, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFDM_B200_H */

@@ -1,0 +1,120 @@
+// Shared-memory Stockham FFT core (no cuFFT), radix 4/8/16 register butterflies.
+//
+// One FFT of length N is executed by T = N/E cooperating threads, each owning E
+// points per pass.  The first pass pulls its points through a Load functor (global
+// memory, window/derotation/constellation mapping fused there) and the last pass
+// hands its results to a Store functor (scaling, cyclic prefix, |X|^2, ... fused
+// there), so only the NP-1 inter-pass exchanges touch shared memory.  Both the
+// first-pass loads and the last-pass stores are stride-1 across the threads of a
+// warp (index j + r*N/R), i.e. coalesced.
+//
+// Replaces gr.fft_vcc (FFTW) at /root/reference/ofdm.py:112 (backward, ifftshift in the
+// Load functor), ofdm_receiver.py~:126 (forward + shift) and the sensing FFTs at
+// secondary_tx.py:165 / usrp_fft_save.py:61.
+#pragma once
+#include "common.cuh"
+
+#define FFT_PAD(i) ((i) + ((i) >> 4))
+
+template <int N> struct FftPlan;
+template <> struct FftPlan<64>   { static constexpr int E = 8,  NP = 2; static constexpr int R[4] = {8, 8, 1, 1}; };
+template <> struct FftPlan<128>  { static constexpr int E = 16, NP = 2; static constexpr int R[4] = {8, 16, 1, 1}; };
+template <> struct FftPlan<256>  { static constexpr int E = 16, NP = 2; static constexpr int R[4] = {16, 16, 1, 1}; };
+template <> struct FftPlan<512>  { static constexpr int E = 8,  NP = 3; static constexpr int R[4] = {8, 8, 8, 1}; };
+template <> struct FftPlan<1024> { static constexpr int E = 16, NP = 3; static constexpr int R[4] = {4, 16, 16, 1}; };
+template <> struct FftPlan<2048> { static constexpr int E = 16, NP = 3; static constexpr int R[4] = {8, 16, 16, 1}; };
+template <> struct FftPlan<4096> { static constexpr int E = 16, NP = 3; static constexpr int R[4] = {16, 16, 16, 1}; };
+
+template <int N> HD constexpr int fft_threads() { return N / FftPlan<N>::E; }
+template <int N> HD constexpr int fft_smem_elems() { return FFT_PAD(N) + 1; }   // float2 elements per buffer
+
+// multiply by e^{S*j*2*pi*k/R} for the compile-time cases used inside the register butterflies
+template <int R, int K, int S> HD float2 tw_const(float2 o) {
+    constexpr float C8 = 0.70710678118654752440f;
+    constexpr float C16a = 0.92387953251128675613f;   // cos(pi/8)
+    constexpr float C16b = 0.38268343236508977173f;   // sin(pi/8)
+    constexpr int Q = (16 / R) * K;                   // position on the 16-point circle
+    if (Q == 0) return o;
+    if (Q == 4) return S < 0 ? make_float2(o.y, -o.x) : make_float2(-o.y, o.x);
+    if (Q == 2) return make_float2(C8 * (o.x - S * o.y), C8 * (S * o.x + o.y));
+    if (Q == 6) return make_float2(C8 * (-o.x - S * o.y), C8 * (S * o.x - o.y));
+    float c = (Q == 1 || Q == 7) ? C16a : C16b;
+    float s = (Q == 1 || Q == 7) ? C16b : C16a;
+    if (Q == 5 || Q == 7) c = -c;
+    // (x + jy)(c + jSs)
+    return make_float2(o.x * c - S * o.y * s, S * o.x * s + o.y * c);
+}
+
+template <int R, int S> struct DftReg;
+template <int S> struct DftReg<2, S> {
+    HDM static void run(float2* v) { float2 a = v[0], b = v[1]; v[0] = cadd(a, b); v[1] = csub(a, b); }
+};
+template <int R, int S, int K> struct DftCombine {
+    HDM static void run(float2* v, const float2* e, const float2* o) {
+        float2 t = tw_const<R, K, S>(o[K]);
+        v[K] = cadd(e[K], t);
+        v[K + R / 2] = csub(e[K], t);
+        DftCombine<R, S, K + 1>::run(v, e, o);
+    }
+};
+template <int S, int K> struct DftCombine<4, S, K> {
+    HDM static void run(float2* v, const float2* e, const float2* o) {
+        float2 t0 = tw_const<4, 0, S>(o[0]), t1 = tw_const<4, 1, S>(o[1]);
+        v[0] = cadd(e[0], t0); v[2] = csub(e[0], t0);
+        v[1] = cadd(e[1], t1); v[3] = csub(e[1], t1);
+    }
+};
+template <int S> struct DftCombine<8, S, 4> { HDM static void run(float2*, const float2*, const float2*) {} };
+template <int S> struct DftCombine<16, S, 8> { HDM static void run(float2*, const float2*, const float2*) {} };
+
+// in-register DFT of size R (decimation in time, natural order in and out)
+template <int R, int S> struct DftReg {
+    HDM static void run(float2* v) {
+        float2 e[R / 2], o[R / 2];
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+        DftReg<R / 2, S>::run(e);
+        DftReg<R / 2, S>::run(o);
+        DftCombine<R, S, 0>::run(v, e, o);
+    }
+};
+
+// One Stockham pass of radix R with Ns = product of the previous radices.
+//   in(j + r*N/R), r<R  ->  twiddle by w^{r*(j mod Ns)*N/(Ns*R)}  ->  DFT_R  ->  out((j/Ns)*Ns*R + j mod Ns + r*Ns)
+// Functors also receive the compile-time register slot q*R + r of the point, so a caller can keep
+// first-pass inputs / last-pass outputs in a register array (slot <-> index tid + q*T + r*N/R).
+template <int N, int R, int NS, int S, class In, class Out>
+HD void fft_pass(int tid, const float2* __restrict__ tw, In in, Out out) {
+    constexpr int E = FftPlan<N>::E;
+    constexpr int T = N / E;
+#pragma unroll
+    for (int q = 0; q < E / R; ++q) {
+        const int j = tid + q * T;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = in(j + r * (N / R), q * R + r);
+        const int k = j & (NS - 1);
+        if (NS > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                float2 w = LDG(tw + r * k * (N / (NS * R)));
+                if (S > 0) w.y = -w.y;
+                v[r] = cmul(v[r], w);
+            }
+        }
+        DftReg<R, S>::run(v);
+        const int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) out(j0 + r * NS, v[r], q * R + r);
+    }
+}
+
+struct SmemIn {
+    const float2* p;
+    HDM float2 operator()(int i, int) const { return p[FFT_PAD(i)]; }
+};
+struct SmemOut {
+    float2* p;
+    HDM void operator()(int i, float2 v, int) const { p[FFT_PAD(i)] = v; }
+};
+

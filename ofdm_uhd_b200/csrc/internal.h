@@ -1,0 +1,90 @@
+// Internal declarations shared by the translation units of libofdm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/ofdm_b200.h"
+
+#define OFDM_MAX_TAPS 512
+#define OFDM_SAMPLER_TIMEOUT 1000       // digital_swig.py:4719-4720
+#define OFDM_ACQ_MAX_SYMBOLS 1000       // upstream MAX_NUM_SYMBOLS
+#define OFDM_MAX_SHIFT 4                // digital_swig.py:4320 (max_fft_shift_len)
+#define OFDM_PEAK_WARM 24576            // samples of IIR warm-up before a detector segment
+#define OFDM_SEG_CAP_SHIFT 6            // detector segment slot list: seg_len >> 6 triggers
+
+struct ofdm_handle {
+    int device;
+    int N, occ, cp, L, zl, M, nbits, ncar, ntaps, NOS, pkt_stride;
+    float amp;
+    uint64_t pad_seed;
+    // device tables
+    float2* d_const;       // [M]
+    int16_t* d_bin2car;    // [N]  FFT-vector index -> data-carrier ordinal, -1 if unused (A.3 mapper map)
+    int16_t* d_sinkmap;    // [ncar] index into the occ-wide equalised vector (A.3 sink map)
+    float* d_ks;           // [occ] known symbol with odd bins zeroed
+    float* d_kd;           // [occ] |ks[i]-ks[i+2]|^2 on even i
+    float2* d_tw;          // [N]   exp(-2*pi*j*i/N)
+    float2* d_tw_os;       // [NOS]
+    float2* d_Hos;         // [NOS] FFT of the channel taps / NOS
+    float2* d_pre_time;    // [N+cp] time-domain preamble incl. CP, scaled by 1/sqrt(N)
+    uint8_t* d_mask;       // [4096] whitening mask
+    uint32_t* d_crctab;    // [256]
+    float h_taps[OFDM_MAX_TAPS];
+};
+
+struct ofdm_sense_handle {
+    int device;
+    int N;
+    float* d_win;          // [N] Blackman-Harris
+    float2* d_tw;          // [N]
+};
+
+void ofdm_set_error(const char* fmt, ...);
+#define OFDM_CUDA_CHECK(call)                                                               \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            ofdm_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return OFDM_E_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+#define OFDM_LAUNCH_CHECK() OFDM_CUDA_CHECK(cudaGetLastError())
+
+// workspace carve-out (rx.cu)
+struct RxWorkspace {
+    float2* y;             // [n]
+    float* mf;             // [n]
+    int64_t* first_nan;    // [1]
+    int32_t* seg_count;    // [n_seg]
+    int64_t* seg_trig;     // [n_seg * seg_cap]
+    double* phi0;          // [max_frames] NCO phase just before each trigger takes effect
+    double* step;          // [max_frames] NCO phase step per sample after each trigger
+    int32_t* first_ok;     // [1] index of the first trigger the sampler can see
+    int64_t* vbase;        // [max_frames] position of each frame's preamble vector in the vector stream
+    int32_t* sess_nvec;    // [max_frames] vectors consumed by a sink session started at this frame
+    int32_t* next_frame;   // [max_frames] scratch of the liveness walk
+    int32_t* exit_frame;   // [max_frames] scratch of the liveness walk
+    int32_t* seg_off;      // [n_seg+1] exclusive scan of seg_count
+    int64_t n_seg, seg_len, seg_cap;
+};
+int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, void* base, size_t bytes,
+                        RxWorkspace* ws, size_t* need);
+
+// launchers
+int launch_make_packets(ofdm_handle* h, const uint8_t* payload, const int64_t* payload_off, int32_t n_pkts,
+                        int whitening, uint8_t* pkts, const int64_t* pkt_off, cudaStream_t st);
+int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames, int64_t first_frame,
+              const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms, float2* out, cudaStream_t st);
+int launch_chan_filter(ofdm_handle* h, const float2* x, int64_t n, float2* y, cudaStream_t st);
+int launch_sync_metric(ofdm_handle* h, const float2* y, int64_t n, float* mf, int64_t* first_nan, cudaStream_t st);
+int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t n, const int64_t* first_nan,
+                       ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_channel(ofdm_handle* h, const float2* x, int64_t n, float cfo, double phase0, float sigma,
+                   uint64_t seed, float2* y, cudaStream_t st);
+int launch_sense(ofdm_sense_handle* s, const float2* x, int64_t n_frames, int shift, int32_t tune_delay,
+                 int32_t dwell_delay, float* maxhold, float2* spectra, cudaStream_t st);
+int launch_sense_decide(ofdm_sense_handle* s, const float* maxhold, int32_t n_avg, double threshold,
+                        double* avg_inorder, uint8_t* free_bits, char* hex, cudaStream_t st);

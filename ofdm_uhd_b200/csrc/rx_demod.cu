@@ -1,0 +1,465 @@
+// Receive back end: derotation + forward FFT + ofdm_frame_acquisition + ofdm_frame_sink as one
+// CTA per frame-sink session, then the sink's liveness walk, dewhitening and CRC.
+// Reference wiring: ofdm_receiver.py~:124-129 (sigmix, fft_demod, ofdm_frame_acq), ofdm.py:238-247
+// (ofdm_frame_sink), ofdm.py:300-305 + ofdm_packet_utils.py:169-191 (unmake_packet).
+#include "internal.h"
+#include "fft.cuh"
+#include <limits.h>
+
+struct DemodParams {
+    const float2* y;
+    int64_t n;
+    const int64_t* trig_idx;
+    const double* phi0;
+    const double* step;
+    const int32_t* n_trig;
+    const int32_t* first_ok;
+    const int32_t* n_frames;
+    const int32_t* frame_ndata;
+    const int64_t* vbase;
+    const float2* tw;
+    const float2* cst;
+    const int16_t* sinkmap;
+    const float* ks;
+    const float* kd;
+    int occ, cp, zl, ncar, nbits, M, L, max_frames, pkt_stride;
+    uint8_t* frame_status;
+    int32_t* pkt_len;
+    int32_t* sess_nvec;
+    uint8_t* pkt_bytes;
+    float2* eq_syms;
+    uint8_t* sym_idx;
+    float2* derot_syms;
+    int64_t max_vectors;
+};
+
+// multiply_cc(chan_filt, frequency_modulator_fc(-2/N)(sample_and_hold(angle))) evaluated at the
+// samples of one sampler vector: phi[s] = phi0[k] + step[k]*(s - t_k + 1) for t_k <= s < t_{k+1}  (A.8)
+struct DemodLoad {
+    const float2* y;
+    int64_t st;
+    const int64_t* trig;
+    const double* phi0;
+    const double* step;
+    int K, kseg0;
+    __device__ __forceinline__ float2 operator()(int idx, int) const {
+        const int64_t s = st + idx;
+        int kk = kseg0;
+        while (kk + 1 < K && LDG(trig + kk + 1) <= s) ++kk;
+        float2 v = LDG(y + s);
+        if (kk < 0) return v;
+        const double ph = LDG(phi0 + kk) + LDG(step + kk) * (double)(s - LDG(trig + kk) + 1);
+        double r = ph * 0.15915494309189533577;
+        r -= rint(r);
+        float sn, cs;
+        sincospif(2.0f * (float)r, &sn, &cs);
+        return cmul_x(v, make_float2(cs, sn));
+    }
+};
+
+template <int N>
+struct ShiftStore {                       // fft_vcc(..., shift=True): bin idx lands at (idx + N/2) mod N
+    float2* S;
+    __device__ __forceinline__ void operator()(int idx, float2 v, int) const { S[(idx + N / 2) & (N - 1)] = v; }
+};
+
+__device__ __forceinline__ float2 expj_f32(float ph) {
+    double s, c;
+    sincos((double)ph, &s, &c);
+    return make_float2((float)c, (float)s);
+}
+
+// coarse_freq_comp(delta, count) = expj(float(-2*pi*delta*cp) / N * count)   (A.10)
+__device__ __forceinline__ float2 coarse_comp(int delta, int cp, int N, int cnt) {
+    const float a = (float)(-2.0 * 3.14159265358979323846 * (double)delta * (double)cp);
+    const float ph = fmul_rn(fdiv_rn(a, (float)N), (float)cnt);
+    return expj_f32(ph);
+}
+
+template <int N>
+__global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E)) demod_kernel(const DemodParams p) {
+    using P = FftPlan<N>;
+    constexpr int T = N / P::E;
+    constexpr int BT = T < 64 ? 64 : T;
+    constexpr int NW = BT / 32;
+    constexpr int SB = fft_smem_elems<N>();
+    constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
+    extern __shared__ double smem_d[];
+    double* red = smem_d;                                   // [8*NW]
+    float2* bufA = (float2*)(red + 8 * NW);
+    float2* bufB = bufA + SB;
+    float2* H = bufB + SB;                                  // [occ]
+    float2* dfe = H + p.occ;                                // [ncar]
+    float2* eq = dfe + p.occ;                               // [occ]
+    float2* s_cst = eq + p.occ;                             // [M]
+    uint8_t* sym = (uint8_t*)(s_cst + p.M);                 // [ncar]
+    uint8_t* vb = sym + ((p.ncar + 15) & ~15);              // bytes of the current vector
+    __shared__ int s_delta, s_hdr_ok, s_len;
+    __shared__ float2 s_c, s_car;
+    __shared__ float s_phase, s_freq;
+    __shared__ unsigned s_carry;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int F = *p.n_frames;
+    int K = *p.n_trig;
+    if (K > p.max_frames) K = p.max_frames;
+    const int first_ok = *p.first_ok;
+    const int occ = p.occ, ncar = p.ncar, nbits = p.nbits, zl = p.zl, L = p.L;
+    for (int i = tid; i < p.M; i += BT) s_cst[i] = p.cst[i];
+    float2* S = (P::NP == 2) ? bufB : bufA;                 // shifted spectrum of the current vector
+    const int bits_this = ncar * nbits;
+
+    for (int f = blockIdx.x; f < F; f += gridDim.x) {
+        int g = f, m = 0, vi = 0, cnt = 1, delta = 0, bit_base = 0;
+        int status = 3, nvec = INT_MAX / 2, len = 0;
+        __syncthreads();
+        while (g < F) {
+            const int kg = first_ok + g;
+            const int64_t t = p.trig_idx[kg];
+            const int64_t st = t - N + 1 + (int64_t)m * L;
+            const bool flag = (m == 0);
+            const int64_t vglob = p.vbase[g] + m;
+            const bool tap = (g == f) && vglob < p.max_vectors;
+            // ---- sigmix + fft_demod ----
+            int kseg0 = kg;
+            if (flag) {
+                kseg0 = kg - 1;
+                while (kseg0 >= 0 && p.trig_idx[kseg0] > st) --kseg0;
+            }
+            DemodLoad ld{p.y, st, p.trig_idx, p.phi0, p.step, K, kseg0};
+            if (tid < T) fft_pass<N, R0, 1, -1>(tid, p.tw, ld, SmemOut{bufA});
+            __syncthreads();
+            if constexpr (P::NP == 2) {
+                if (tid < T) fft_pass<N, R1, R0, -1>(tid, p.tw, SmemIn{bufA}, ShiftStore<N>{S});
+            } else {
+                if (tid < T) fft_pass<N, R1, R0, -1>(tid, p.tw, SmemIn{bufA}, SmemOut{bufB});
+                __syncthreads();
+                if (tid < T) fft_pass<N, R2, R0 * R1, -1>(tid, p.tw, SmemIn{bufB}, ShiftStore<N>{S});
+            }
+            __syncthreads();
+            // ---- ofdm_frame_acquisition: correlate + calculate_equalizer on a flagged vector ----
+            if (flag) {
+                double acc[2 * OFDM_MAX_SHIFT];
+#pragma unroll
+                for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) acc[s] = 0.0;
+                for (int j = 2 * tid; j < occ - 2; j += 2 * BT) {
+                    const float kdj = LDG(p.kd + j);
+#pragma unroll
+                    for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) {
+                        const int pi = zl - OFDM_MAX_SHIFT + s + j;
+                        const float2 a = S[pi], b = S[pi + 2];
+                        const float2 d = make_float2(fsub_rn(a.x, b.x), fsub_rn(a.y, b.y));
+                        acc[s] += (double)kdj * (double)norm_x(d);
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) {
+                    double v = acc[s];
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                    if (lane == 0) red[w * 8 + s] = v;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    float best = 0.f;
+                    int index = 0;
+                    for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) {
+                        double v = 0.0;
+                        for (int ww = 0; ww < NW; ++ww) v += red[ww * 8 + s];
+                        const float sf = (float)v;
+                        if (sf > best) { best = sf; index = zl - OFDM_MAX_SHIFT + s; }
+                    }
+                    s_delta = index - zl;
+                    s_c = coarse_comp(index - zl, p.cp, N, 1);
+                }
+                __syncthreads();
+                delta = s_delta;
+                cnt = 1;
+                const float2 c1 = s_c;
+                for (int i = 2 * tid; i < occ; i += 2 * BT) {
+                    const float2 b = cmul_x(c1, S[i + zl + delta]);
+                    H[i] = cdiv_x(make_float2(LDG(p.ks + i), 0.f), b);
+                }
+                __syncthreads();
+                for (int i = 2 * tid + 1; i + 1 < occ; i += 2 * BT) {
+                    const float2 a = H[i + 1], b = H[i - 1];
+                    H[i] = make_float2(fmul_rn(fadd_rn(a.x, b.x), 0.5f), fmul_rn(fadd_rn(a.y, b.y), 0.5f));
+                }
+                if (tid == 0 && (occ & 1) == 0) H[occ - 1] = H[occ - 2];
+                __syncthreads();
+            }
+            // ---- one-tap equaliser with the coarse-offset CP phase compensation ----
+            if (tid == 0) s_c = coarse_comp(delta, p.cp, N, cnt);
+            __syncthreads();
+            {
+                const float2 c = s_c;
+                for (int i = tid; i < occ; i += BT) {
+                    const float2 v = cmul_x(cmul_x(H[i], c), S[i + zl + delta]);
+                    eq[i] = v;
+                    if (tap && p.eq_syms) p.eq_syms[vglob * occ + i] = v;
+                }
+            }
+            ++cnt;
+            if (cnt == OFDM_ACQ_MAX_SYMBOLS) cnt = 1;
+            __syncthreads();
+            // ---- ofdm_frame_sink ----
+            if (vi == 0) {
+                // enter_have_sync: the flagged vector itself is not demapped
+                for (int c = tid; c < ncar; c += BT) dfe[c] = make_float2(1.f, 0.f);
+                if (tid == 0) { s_phase = 0.f; s_freq = 0.f; s_carry = 0u; s_hdr_ok = 0; s_len = 0; }
+                __syncthreads();
+            } else {
+                if (tid == 0) s_car = expj_f32(s_phase);
+                __syncthreads();
+                const float2 car = s_car;
+                double er = 0.0, ei = 0.0;
+                for (int c = tid; c < ncar; c += BT) {
+                    const float2 d0 = dfe[c];
+                    const float2 r = cmul_x(cmul_x(eq[LDG(p.sinkmap + c)], car), d0);
+                    // slicer: first minimum of |r - const[k]|^2
+                    int b = 0;
+                    float best;
+                    {
+                        const float2 c0 = s_cst[0];
+                        const float dx = fsub_rn(r.x, c0.x), dy = fsub_rn(r.y, c0.y);
+                        best = fadd_rn(fmul_rn(dx, dx), fmul_rn(dy, dy));
+                    }
+                    for (int k = 1; k < p.M; ++k) {
+                        const float2 ck = s_cst[k];
+                        const float dx = fsub_rn(r.x, ck.x), dy = fsub_rn(r.y, ck.y);
+                        const float dd = fadd_rn(fmul_rn(dx, dx), fmul_rn(dy, dy));
+                        if (dd < best) { best = dd; b = k; }
+                    }
+                    const float2 cl = s_cst[b];
+                    const float2 e = cmulc_x(r, cl);
+                    er += (double)e.x;
+                    ei += (double)e.y;
+                    if (norm_x(r) > 0.001f) {
+                        const float2 q = cdiv_x(cl, r);
+                        dfe[c] = make_float2(fadd_rn(d0.x, fmul_rn(0.05f, fsub_rn(q.x, d0.x))),
+                                             fadd_rn(d0.y, fmul_rn(0.05f, fsub_rn(q.y, d0.y))));
+                    }
+                    sym[c] = (uint8_t)b;
+                    if (tap) {
+                        if (p.sym_idx) p.sym_idx[vglob * ncar + c] = (uint8_t)b;
+                        if (p.derot_syms) p.derot_syms[vglob * ncar + c] = r;
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    er += __shfl_xor_sync(0xffffffffu, er, d);
+                    ei += __shfl_xor_sync(0xffffffffu, ei, d);
+                }
+                if (lane == 0) { red[w * 8] = er; red[w * 8 + 1] = ei; }
+                __syncthreads();
+                const int B0 = bit_base >> 3, B1 = (bit_base + bits_this) >> 3;
+                if (tid == 0) {
+                    double sr = 0.0, si = 0.0;
+                    for (int ww = 0; ww < NW; ++ww) { sr += red[ww * 8]; si += red[ww * 8 + 1]; }
+                    const float angle = (float)atan2((double)(float)si, (double)(float)sr);
+                    const float freq = fsub_rn(s_freq, fmul_rn(0.015625f, angle));       // freq_gain = 0.25^2/4
+                    float ph = fsub_rn(fadd_rn(s_phase, freq), fmul_rn(0.25f, angle));   // phase_gain = 0.25
+                    if ((double)ph >= 6.283185307179586) ph = (float)((double)ph - 6.283185307179586);
+                    if ((double)ph < 0.0) ph = (float)((double)ph + 6.283185307179586);
+                    s_freq = freq;
+                    s_phase = ph;
+                }
+                // LSB-first byte packing; bits left over from the previous vector sit in s_carry
+                const unsigned carry = s_carry;
+                for (int q = B0 + tid; q < B1; q += BT) {
+                    unsigned byte = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rel = 8 * q + i - bit_base;
+                        unsigned bit;
+                        if (rel < 0) bit = (carry >> i) & 1u;
+                        else bit = ((unsigned)sym[rel / nbits] >> (rel % nbits)) & 1u;
+                        byte |= bit << i;
+                    }
+                    vb[q - B0] = (uint8_t)byte;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    if (vi == 1) {
+                        const unsigned hdr = ((unsigned)vb[0] << 24) | ((unsigned)vb[1] << 16) | ((unsigned)vb[2] << 8) | vb[3];
+                        s_hdr_ok = (((hdr >> 16) ^ (hdr & 0xFFFFu)) == 0u) ? 1 : 0;
+                        s_len = (int)((hdr >> 16) & 0x0FFFu);
+                    }
+                    const int nrb = bit_base + bits_this - 8 * B1;
+                    unsigned nc = 0;
+                    for (int i = 0; i < nrb; ++i) {
+                        const int rel = 8 * B1 + i - bit_base;
+                        nc |= (((unsigned)sym[rel / nbits] >> (rel % nbits)) & 1u) << i;
+                    }
+                    s_carry = nc;
+                }
+                __syncthreads();
+                const bool hdr_ok = s_hdr_ok != 0;
+                len = s_len;
+                if (vi == 1 && !hdr_ok) { status = 1; nvec = 2; len = 0; break; }
+                for (int q = B0 + tid; q < B1; q += BT) {
+                    const int pq = q - 4;
+                    if (pq >= 0 && pq < len && pq < p.pkt_stride) p.pkt_bytes[(size_t)f * p.pkt_stride + pq] = vb[q - B0];
+                }
+                bit_base += bits_this;
+                if (B1 >= 4 + len) { status = 2; nvec = vi + 1; break; }
+            }
+            ++vi;
+            ++m;
+            if (m > p.frame_ndata[g]) { ++g; m = 0; }
+        }
+        if (tid == 0) {
+            p.frame_status[f] = (uint8_t)status;
+            p.pkt_len[f] = status == 2 ? len : 0;
+            p.sess_nvec[f] = nvec;
+        }
+    }
+}
+
+template <int N>
+static int launch_demod_n(ofdm_handle* h, const DemodParams& p, int max_frames, cudaStream_t st) {
+    constexpr int T = N / FftPlan<N>::E;
+    constexpr int BT = T < 64 ? 64 : T;
+    constexpr int NW = BT / 32;
+    size_t smem = sizeof(double) * 8 * NW + sizeof(float2) * (2 * (size_t)fft_smem_elems<N>() + 3 * (size_t)p.occ + p.M) +
+                  ((p.ncar + 15) & ~15) + (size_t)(p.ncar * p.nbits / 8 + 16);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        OFDM_CUDA_CHECK(cudaFuncSetAttribute(demod_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    int grid = sms * 32;
+    if (grid > max_frames) grid = max_frames;
+    if (grid < 1) grid = 1;
+    demod_kernel<N><<<grid, BT, smem, st>>>(p);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
+int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+    DemodParams p;
+    p.y = y; p.n = n; p.trig_idx = io->trig_idx; p.phi0 = ws->phi0; p.step = ws->step; p.n_trig = io->n_trig;
+    p.first_ok = ws->first_ok; p.n_frames = io->n_frames; p.frame_ndata = io->frame_ndata; p.vbase = ws->vbase;
+    p.tw = h->d_tw; p.cst = h->d_const; p.sinkmap = h->d_sinkmap; p.ks = h->d_ks; p.kd = h->d_kd;
+    p.occ = h->occ; p.cp = h->cp; p.zl = h->zl; p.ncar = h->ncar; p.nbits = h->nbits; p.M = h->M; p.L = h->L;
+    p.max_frames = io->max_frames; p.pkt_stride = io->pkt_stride;
+    p.frame_status = io->frame_status; p.pkt_len = io->pkt_len; p.sess_nvec = ws->sess_nvec; p.pkt_bytes = io->pkt_bytes;
+    p.eq_syms = (float2*)io->eq_syms; p.sym_idx = io->sym_idx; p.derot_syms = (float2*)io->derot_syms;
+    p.max_vectors = io->max_vectors;
+    switch (h->N) {
+        case 64:   return launch_demod_n<64>(h, p, io->max_frames, st);
+        case 128:  return launch_demod_n<128>(h, p, io->max_frames, st);
+        case 256:  return launch_demod_n<256>(h, p, io->max_frames, st);
+        case 512:  return launch_demod_n<512>(h, p, io->max_frames, st);
+        case 1024: return launch_demod_n<1024>(h, p, io->max_frames, st);
+        case 2048: return launch_demod_n<2048>(h, p, io->max_frames, st);
+        case 4096: return launch_demod_n<4096>(h, p, io->max_frames, st);
+    }
+    ofdm_set_error("demod: unsupported fft_length %d", h->N);
+    return OFDM_E_INVAL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame-sink liveness: the sink only starts on a preamble it sees in SYNC_SEARCH; a session started at
+// frame f swallows sess_nvec[f] vectors of the sampler's stream, flagged ones included (A.11).  The live
+// frames are the orbit of frame 0 under next(f) = first frame whose preamble lies at or after the end of
+// f's session.  One CTA: parallel next[], per-chunk backward sweep for chunk exits, a serial hop over at
+// most 1024 chunk entries, then a parallel per-chunk walk that marks the live frames.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) liveness_kernel(const int32_t* __restrict__ n_frames,
+                                                        const int64_t* __restrict__ vbase,
+                                                        const int32_t* __restrict__ sess_nvec,
+                                                        int32_t* __restrict__ next, int32_t* __restrict__ exitf,
+                                                        uint8_t* __restrict__ live) {
+    __shared__ int s_entry[1024];
+    const int tid = threadIdx.x;
+    const int F = *n_frames;
+    s_entry[tid] = -1;
+    if (F <= 0) return;
+    for (int f = tid; f < F; f += 1024) {
+        const int64_t target = vbase[f] + (int64_t)sess_nvec[f];
+        int nx;
+        if (f + 1 >= F) nx = F;
+        else if (vbase[f + 1] >= target) nx = f + 1;
+        else {
+            int lo = f + 1, hi = F;                 // first g in (f, F) with vbase[g] >= target, else F
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (vbase[mid] >= target) hi = mid; else lo = mid + 1;
+            }
+            nx = lo;
+        }
+        next[f] = nx;
+    }
+    __syncthreads();
+    const int Kc = (F + 1023) / 1024;
+    const int cs = tid * Kc;
+    const int ce = (cs + Kc < F) ? cs + Kc : F;
+    for (int f = ce - 1; f >= cs; --f) {
+        const int nx = next[f];
+        exitf[f] = (nx < ce) ? exitf[nx] : nx;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int e = 0;
+        while (e < F) {
+            s_entry[e / Kc] = e;
+            e = exitf[e];
+        }
+    }
+    __syncthreads();
+    int f = s_entry[tid];
+    if (f >= 0)
+        while (f < ce) {
+            live[f] = 1;
+            f = next[f];
+        }
+}
+
+// unmake_packet: dewhiten (offset 0) + check_crc32 for every delivered message; counters for the stats
+__global__ void __launch_bounds__(128) crc_kernel(const int32_t* __restrict__ n_frames, const uint8_t* __restrict__ live,
+                                                  const uint8_t* __restrict__ status, const int32_t* __restrict__ pkt_len,
+                                                  uint8_t* __restrict__ pkt_bytes, int stride, uint8_t* __restrict__ pkt_ok,
+                                                  const uint8_t* __restrict__ mask, const uint32_t* __restrict__ crctab,
+                                                  int64_t* __restrict__ counters) {
+    __shared__ uint32_t s_crc[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = crctab[i];
+    __syncthreads();
+    const int F = *n_frames;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+        uint8_t ok = 0;
+        if (live[f] && status[f] == 2) {
+            const int len = pkt_len[f];
+            uint8_t* b = pkt_bytes + (size_t)f * stride;
+            const int nst = len < stride ? len : stride;
+            uint32_t crc = 0xFFFFFFFFu, tail = 0;
+            for (int i = 0; i < nst; ++i) {
+                const uint8_t v = (uint8_t)(b[i] ^ mask[i & 4095]);
+                b[i] = v;
+                if (i < len - 4) crc = s_crc[(v ^ (crc >> 24)) & 0xFF] ^ (crc << 8);
+                else tail = (tail << 8) | v;
+            }
+            ok = (len >= 4 && len <= stride && (~crc) == tail) ? 1 : 0;
+            atomicAdd((unsigned long long*)&counters[1], 1ull);
+            if (ok) {
+                atomicAdd((unsigned long long*)&counters[2], 1ull);
+                atomicAdd((unsigned long long*)&counters[3], (unsigned long long)(len - 4));
+            }
+        }
+        pkt_ok[f] = ok;
+    }
+}
+
+int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+    OFDM_CUDA_CHECK(cudaMemsetAsync(io->frame_live, 0, (size_t)io->max_frames, st));
+    liveness_kernel<<<1, 1024, 0, st>>>(io->n_frames, ws->vbase, ws->sess_nvec, ws->next_frame, ws->exit_frame, io->frame_live);
+    OFDM_LAUNCH_CHECK();
+    int grid = (io->max_frames + 127) / 128;
+    if (grid > 148 * 16) grid = 148 * 16;
+    crc_kernel<<<grid, 128, 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len, io->pkt_bytes,
+                                      io->pkt_stride, io->pkt_ok, h->d_mask, h->d_crctab, io->counters);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}

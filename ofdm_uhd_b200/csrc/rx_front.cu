@@ -1,0 +1,672 @@
+// Receive front end: channel filter, ofdm_sync_pn (Schmidl-Cox metric + peak detector + angle latch),
+// and the sampler / NCO plan.  Reference wiring: ofdm_receiver.py~:69-76,97-101,123-125,131-136.
+#include "internal.h"
+#include "fft.cuh"
+#include <limits.h>
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, void* base, size_t bytes,
+                        RxWorkspace* ws, size_t* need) {
+    (void)h;
+    if (n < 0) n = 0;
+    if (max_frames < 1) max_frames = 1;
+    int64_t seg_len = (n + 148 * 32 - 1) / (148 * 32);
+    if (seg_len < 65536) seg_len = 65536;
+    seg_len = (seg_len + 31) / 32 * 32;
+    ws->seg_len = seg_len;
+    ws->n_seg = n > 0 ? (n + seg_len - 1) / seg_len : 0;
+    ws->seg_cap = seg_len >> OFDM_SEG_CAP_SHIFT;
+    size_t off = 0;
+    char* b = (char*)base;
+    auto take = [&](size_t sz) { size_t o = off; off = align_up(off + sz, 256); return b ? (void*)(b + o) : nullptr; };
+    // fixed-size part first, so that the pointers do not depend on n
+    ws->first_nan = (int64_t*)take(sizeof(int64_t));
+    ws->first_ok = (int32_t*)take(sizeof(int32_t));
+    ws->phi0 = (double*)take(sizeof(double) * max_frames);
+    ws->step = (double*)take(sizeof(double) * max_frames);
+    ws->vbase = (int64_t*)take(sizeof(int64_t) * ((size_t)max_frames + 1));
+    ws->sess_nvec = (int32_t*)take(sizeof(int32_t) * max_frames);
+    ws->next_frame = (int32_t*)take(sizeof(int32_t) * max_frames);
+    ws->exit_frame = (int32_t*)take(sizeof(int32_t) * max_frames);
+    ws->seg_count = (int32_t*)take(sizeof(int32_t) * (size_t)(ws->n_seg + 1));
+    ws->seg_off = (int32_t*)take(sizeof(int32_t) * (size_t)(ws->n_seg + 1));
+    ws->seg_trig = (int64_t*)take(sizeof(int64_t) * (size_t)(ws->n_seg * ws->seg_cap));
+    ws->mf = (float*)take(sizeof(float) * (size_t)n);
+    ws->y = (float2*)take(sizeof(float2) * (size_t)n);
+    *need = off;
+    if (b && bytes < off) return OFDM_E_NOMEM;
+    return OFDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_RX1: gr.fft_filter_ccc(1, firdes.low_pass(...)) as overlap-save on the shared FFT core.
+// Block b: forward FFT of x[b*V-(ntaps-1) .. +NOS), multiply by H/NOS in registers, inverse FFT with the
+// reversed radix order (so the forward pass's register slots are exactly the inverse pass's inputs),
+// keep the last V = NOS-(ntaps-1) points.  x is read once (+8% halo), y written once.
+// ---------------------------------------------------------------------------------------------
+struct FiltParams {
+    const float2* x;
+    float2* y;
+    int64_t n;
+    int64_t nblk;
+    int V, hist;
+    const float2* tw;
+    const float2* H;
+};
+
+template <int NOS, int G>
+__global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E)) chan_filter_kernel(const FiltParams p) {
+    using P = FftPlan<NOS>;
+    constexpr int E = P::E;
+    constexpr int T = NOS / E;
+    constexpr int SB = fft_smem_elems<NOS>();
+    constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
+    static_assert(P::NP == 3 && R2 == E && R1 == E, "overlap-save plan must end with full-width radices");
+    extern __shared__ float2 smem[];
+    const int g = threadIdx.x / T;
+    const int tid = threadIdx.x - g * T;
+    float2* bufA = smem + (size_t)g * 2 * SB;
+    float2* bufB = bufA + SB;
+    for (int64_t base = (int64_t)blockIdx.x * G; base < p.nblk; base += (int64_t)gridDim.x * G) {
+        const int64_t blk = base + g;
+        const bool active = blk < p.nblk;
+        const int64_t in0 = blk * p.V - p.hist;
+        float2 regs[E];
+        auto ld = [&](int idx, int) -> float2 {
+            int64_t gi = in0 + idx;
+            return (gi >= 0 && gi < p.n) ? LDG(p.x + gi) : make_float2(0.f, 0.f);
+        };
+        auto mulH = [&](int idx, float2 v, int slot) { regs[slot] = cmul(v, LDG(p.H + idx)); };
+        auto fromRegs = [&](int, int slot) -> float2 { return regs[slot]; };
+        auto st = [&](int idx, float2 v, int) {
+            if (idx >= p.hist) {
+                int64_t o = blk * p.V + (idx - p.hist);
+                if (o < p.n) p.y[o] = v;
+            }
+        };
+        if (active) fft_pass<NOS, R0, 1, -1>(tid, p.tw, ld, SmemOut{bufA});
+        __syncthreads();
+        if (active) fft_pass<NOS, R1, R0, -1>(tid, p.tw, SmemIn{bufA}, SmemOut{bufB});
+        __syncthreads();
+        if (active) fft_pass<NOS, R2, R0 * R1, -1>(tid, p.tw, SmemIn{bufB}, mulH);
+        // inverse, radix order reversed: R2, R1, R0
+        if (active) fft_pass<NOS, R2, 1, 1>(tid, p.tw, fromRegs, SmemOut{bufA});
+        __syncthreads();
+        if (active) fft_pass<NOS, R1, R2, 1>(tid, p.tw, SmemIn{bufA}, SmemOut{bufB});
+        __syncthreads();
+        if (active) fft_pass<NOS, R0, R2 * R1, 1>(tid, p.tw, SmemIn{bufB}, st);
+    }
+}
+
+template <int NOS, int G>
+static int launch_filter_n(ofdm_handle* h, const FiltParams& p, cudaStream_t st) {
+    constexpr int T = NOS / FftPlan<NOS>::E;
+    size_t smem = ((size_t)G * 2 * fft_smem_elems<NOS>()) * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        OFDM_CUDA_CHECK(cudaFuncSetAttribute(chan_filter_kernel<NOS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    int64_t want = (p.nblk + G - 1) / G;
+    int64_t cap = (int64_t)sms * 8;
+    int grid = (int)(want < cap ? want : cap);
+    chan_filter_kernel<NOS, G><<<grid, G * T, smem, st>>>(p);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
+int launch_chan_filter(ofdm_handle* h, const float2* x, int64_t n, float2* y, cudaStream_t st) {
+    FiltParams p;
+    p.x = x; p.y = y; p.n = n; p.hist = h->ntaps - 1; p.V = h->NOS - p.hist;
+    p.nblk = (n + p.V - 1) / p.V; p.tw = h->d_tw_os; p.H = h->d_Hos;
+    if (h->NOS == 2048) return launch_filter_n<2048, 2>(h, p, st);
+    if (h->NOS == 4096) return launch_filter_n<4096, 1>(h, p, st);
+    ofdm_set_error("chan_filter: unsupported overlap-save size %d", h->NOS);
+    return OFDM_E_INVAL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_RX2a: Schmidl-Cox timing metric (upstream ofdm_sync_pn up to add_const_ff(-1); A.6).
+// The three moving sums (the reference runs them as 256/256/128-tap FIRs) are differences of
+// tile-local float64 prefix sums of the float32 products, rounded once to float32 -- the oracle's
+// precision policy -- so an all-zero window gives exactly 0 (and 0/0 = NaN like the reference).
+// ---------------------------------------------------------------------------------------------
+constexpr int SM_THREADS = 512;
+
+__device__ __forceinline__ double block_excl_scan_f64(double v, double* s_warp, double* total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        double o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < (SM_THREADS / 32) ? s_warp[lane] : 0.0;
+        double ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            double o = __shfl_up_sync(0xffffffffu, ti, d);
+            if (lane >= d) ti += o;
+        }
+        if (lane < SM_THREADS / 32) s_warp[lane] = ti - t;     // exclusive warp offsets
+        if (lane == SM_THREADS / 32 - 1) s_warp[32] = ti;      // block total
+    }
+    __syncthreads();
+    double r = s_warp[w] + (inc - v);
+    if (total) *total = s_warp[32];
+    __syncthreads();
+    return r;
+}
+
+template <int K>
+__global__ void __launch_bounds__(SM_THREADS) sync_metric_kernel(const float2* __restrict__ y, int64_t n, int N, int cp,
+                                                                 float tapf, float* __restrict__ mf,
+                                                                 int64_t* __restrict__ first_nan) {
+    constexpr int C = SM_THREADS * K;
+#define PADK(e) ((e) + (e) / K)
+    extern __shared__ double S[];                  // PADK(C) doubles, later reused as float staging
+    __shared__ double s_warp[33];
+    const int h = N / 2;
+    const int T = C - cp - h;                      // outputs per tile
+    const int64_t t0 = (int64_t)blockIdx.x * T;
+    const int64_t a = t0 - cp - h;                 // global index of tile element 0
+    const int tid = threadIdx.x;
+    const int e0 = tid * K;
+
+    float cre[K], cim[K], en[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const int64_t u = a + e0 + i;
+        float2 v = (u >= 0 && u < n) ? LDG(y + u) : make_float2(0.f, 0.f);
+        const int64_t ud = u - h;
+        float2 d = (ud >= 0 && ud < n) ? LDG(y + ud) : make_float2(0.f, 0.f);
+        float2 c = cmulc_x(v, d);                   // y[n] * conj(y[n-N/2])
+        cre[i] = c.x; cim[i] = c.y;
+        en[i] = norm_x(v);
+    }
+    float Pr[K], Pi[K], R[K];
+    // three moving sums of width h
+#pragma unroll
+    for (int arr = 0; arr < 3; ++arr) {
+        const float* src = arr == 0 ? cre : (arr == 1 ? cim : en);
+        float* dst = arr == 0 ? Pr : (arr == 1 ? Pi : R);
+        double loc[K];
+        double run = 0.0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) { run += (double)src[i]; loc[i] = run; }
+        const double base = block_excl_scan_f64(run, s_warp, nullptr);
+#pragma unroll
+        for (int i = 0; i < K; ++i) { loc[i] += base; S[PADK(e0 + i)] = loc[i]; }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const int e = e0 + i - h;
+            const double prev = e >= 0 ? S[PADK(e)] : 0.0;
+            dst[i] = (float)(loc[i] - prev);
+        }
+        __syncthreads();
+    }
+    // normalised metric, then the cp-wide average
+    float Mt[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const int e = e0 + i;
+        const int64_t m = a + e;
+        float num = fadd_rn(fmul_rn(Pr[i], Pr[i]), fmul_rn(Pi[i], Pi[i]));
+        float den = fmul_rn(R[i], R[i]);
+        float q = fdiv_rn(num, den);                // 0/0 -> NaN exactly like divide_ff
+        Mt[i] = (e > h && m >= 0) ? q : 0.f;        // below: window not inside the tile / before the stream
+    }
+    {
+        double loc[K];
+        double run = 0.0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) { run += (double)Mt[i]; loc[i] = run; }
+        const double base = block_excl_scan_f64(run, s_warp, nullptr);
+#pragma unroll
+        for (int i = 0; i < K; ++i) { loc[i] += base; S[PADK(e0 + i)] = loc[i]; }
+        __syncthreads();
+        float out[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const int e = e0 + i - cp;
+            const double prev = e >= 0 ? S[PADK(e)] : 0.0;
+            float s = (float)((loc[i] - prev) * (double)tapf);
+            out[i] = fadd_rn(s, -1.0f);
+        }
+        __syncthreads();
+        float* stage = (float*)S;                   // coalesced write-out through shared memory
+#pragma unroll
+        for (int i = 0; i < K; ++i) stage[e0 + i] = out[i];
+        __syncthreads();
+        for (int o = tid; o < T; o += SM_THREADS) {
+            const int64_t gi = t0 + o;
+            if (gi < n) {
+                float v = stage[o + cp + h];
+                mf[gi] = v;
+                if (v != v) atomicMin((unsigned long long*)first_nan, (unsigned long long)gi);
+            }
+        }
+    }
+#undef PADK
+}
+
+__global__ void init_i64_kernel(int64_t* p, int64_t v) { *p = v; }
+
+int launch_sync_metric(ofdm_handle* h, const float2* y, int64_t n, float* mf, int64_t* first_nan, cudaStream_t st) {
+    init_i64_kernel<<<1, 1, 0, st>>>(first_nan, LLONG_MAX);
+    OFDM_LAUNCH_CHECK();
+    if (n <= 0) return OFDM_OK;
+    const int need = h->cp + h->N / 2;
+    const float tapf = (float)(1.0 / (double)h->cp);
+    if (2 * need <= SM_THREADS * 8) {
+        constexpr int K = 8;
+        const int T = SM_THREADS * K - need;
+        size_t smem = sizeof(double) * (size_t)(SM_THREADS * K + SM_THREADS + 8);
+        static bool attr_done = false;
+        if (!attr_done) {
+            OFDM_CUDA_CHECK(cudaFuncSetAttribute(sync_metric_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        sync_metric_kernel<K><<<(unsigned)((n + T - 1) / T), SM_THREADS, smem, st>>>(y, n, h->N, h->cp, tapf, mf, first_nan);
+    } else if (2 * need <= SM_THREADS * 16 + 4096) {
+        constexpr int K = 16;
+        const int T = SM_THREADS * K - need;
+        size_t smem = sizeof(double) * (size_t)(SM_THREADS * K + SM_THREADS + 8);
+        static bool attr_done = false;
+        if (!attr_done) {
+            OFDM_CUDA_CHECK(cudaFuncSetAttribute(sync_metric_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        sync_metric_kernel<K><<<(unsigned)((n + T - 1) / T), SM_THREADS, smem, st>>>(y, n, h->N, h->cp, tapf, mf, first_nan);
+    } else {
+        ofdm_set_error("sync_metric: fft_length/cp_length too large for the tile");
+        return OFDM_E_INVAL;
+    }
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_RX2b: gr.peak_detector_fb(0.20, 0.20, 30, 0.001) (A.7).  Every sample updates the IIR average
+// exactly once, so avg is a pure linear recurrence of mf; one warp walks one contiguous segment,
+// 32 samples per step: warp scan for the recurrence (float64 state like the oracle), a ballot for
+// `mf > 0.2*avg_prev`, and a warp-uniform state machine over the ballot for the run / arg-max logic.
+// A segment starts OFDM_PEAK_WARM samples early so that the average has converged (0.999^24576 ~ 2e-11)
+// and keeps going past its end until an open run closes; a run belongs to the segment it started in.
+// ---------------------------------------------------------------------------------------------
+struct PeakParams {
+    const float* mf;
+    int64_t n;
+    const int64_t* first_nan;
+    int64_t seg_len, n_seg;
+    int seg_cap;
+    int32_t* seg_count;
+    int64_t* seg_trig;
+    uint32_t* status;
+};
+
+__global__ void __launch_bounds__(128) peak_detect_kernel(const PeakParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (seg >= p.n_seg) return;
+    const int64_t s0 = seg * p.seg_len;
+    const int64_t s1 = (s0 + p.seg_len < p.n) ? s0 + p.seg_len : p.n;
+    int64_t w0 = s0 - OFDM_PEAK_WARM;
+    if (w0 < 0) w0 = 0;
+    w0 &= ~(int64_t)31;
+    const int64_t fnan = *p.first_nan;
+    int count = 0;
+    if (fnan >= w0) {                               // else: average already poisoned, nothing can fire (C.1)
+        const double a1 = (double)0.001f;
+        const double a2 = 1.0 - a1;
+        // a2^(2^k) for the scan steps and a2^(lane+1) for the carry
+        double pw[5];
+        pw[0] = a2;
+#pragma unroll
+        for (int k = 1; k < 5; ++k) pw[k] = pw[k - 1] * pw[k - 1];
+        double plane = 1.0;
+        for (int k = 0; k <= lane; ++k) plane *= a2;
+        double carry = 0.0;                         // avg after the last consumed sample
+        int state = 0;
+        float peak = -INFINITY;
+        int64_t ind = 0, run_start = 0;
+        for (int64_t i0 = w0; i0 < p.n; i0 += 32) {
+            if (i0 >= s1 && state == 0) break;
+            const int64_t gi = i0 + lane;
+            const int nv = (p.n - i0 < 32) ? (int)(p.n - i0) : 32;
+            const float v = lane < nv ? p.mf[gi] : 0.f;
+            double b = a1 * (double)v;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                double o = __shfl_up_sync(0xffffffffu, b, 1 << k);
+                if (lane >= (1 << k)) b = b + pw[k] * o;
+            }
+            const double avg = b + plane * carry;   // average after consuming sample gi
+            double prev = __shfl_up_sync(0xffffffffu, avg, 1);
+            if (lane == 0) prev = carry;
+            carry = __shfl_sync(0xffffffffu, avg, 31);
+            const float thr = fmul_rn((float)prev, 0.2f);
+            const bool a = lane < nv && v > thr;
+            const unsigned mask = __ballot_sync(0xffffffffu, a);
+            int j = 0;
+            while (j < nv) {
+                if (state == 0) {
+                    unsigned rest = mask & (0xffffffffu << j);
+                    if (!rest) break;
+                    j = __ffs(rest) - 1;
+                    state = 1;
+                    peak = -INFINITY;
+                    run_start = i0 + j;
+                } else if ((mask >> j) & 1u) {
+                    // bulk: the rest of this run of `a` inside the block
+                    unsigned zeros = ~mask & (0xffffffffu << j);
+                    int e = zeros ? (__ffs(zeros) - 1) : 32;
+                    if (e > nv) e = nv;
+                    float bv = (lane >= j && lane < e) ? v : -INFINITY;
+                    int bl = lane;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) {
+                        float ov = __shfl_xor_sync(0xffffffffu, bv, d);
+                        int ol = __shfl_xor_sync(0xffffffffu, bl, d);
+                        if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+                    }
+                    if (bv > peak) { peak = bv; ind = i0 + bl; }
+                    j = e;
+                } else {
+                    const float vj = __shfl_sync(0xffffffffu, v, j);
+                    if (vj > peak) {                // a later sample beats the peak: the run stays alive
+                        peak = vj; ind = i0 + j;
+                        ++j;
+                    } else {
+                        if (run_start >= s0 && run_start < s1) {
+                            if (count < p.seg_cap) {
+                                if (lane == 0) p.seg_trig[seg * p.seg_cap + count] = ind;
+                            } else if (lane == 0) {
+                                atomicOr(p.status, OFDM_ST_SEG_OVERFLOW);
+                            }
+                            ++count;
+                        }
+                        state = 0;
+                        ++j;                        // the closing sample is consumed in state 0 (it failed the test)
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) p.seg_count[seg] = count < p.seg_cap ? count : p.seg_cap;
+}
+
+// exclusive scan of the segment counts (one CTA), then gather + angle
+__global__ void __launch_bounds__(1024) seg_scan_kernel(const int32_t* __restrict__ seg_count, int64_t n_seg,
+                                                        int32_t* __restrict__ seg_off, int32_t* __restrict__ n_trig,
+                                                        int max_frames, uint32_t* status) {
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_seg; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const int v = i < n_seg ? seg_count[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) s_w[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            int t = s_w[lane];
+            int ti = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int o = __shfl_up_sync(0xffffffffu, ti, d);
+                if (lane >= d) ti += o;
+            }
+            s_w[lane] = ti - t;
+        }
+        __syncthreads();
+        const int excl = s_carry + s_w[w] + inc - v;
+        if (i < n_seg) seg_off[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int total = s_carry;
+        if (total > max_frames) { total = max_frames; atomicOr(status, OFDM_ST_TRIG_OVERFLOW); }
+        *n_trig = total;
+    }
+}
+
+// one warp per trigger slot: copy the index, recompute P = sum_{k<N/2} y[t-k] conj(y[t-k-N/2]) (float64
+// accumulation of float32 products, rounded to float32) and latch angle = atan2(Im P, Re P)
+__global__ void __launch_bounds__(256) trig_gather_kernel(const float2* __restrict__ y, int64_t n, int N,
+                                                          const int32_t* __restrict__ seg_count,
+                                                          const int32_t* __restrict__ seg_off,
+                                                          const int64_t* __restrict__ seg_trig, int64_t n_seg, int seg_cap,
+                                                          int max_frames, int64_t* __restrict__ trig_idx,
+                                                          float* __restrict__ trig_ang) {
+    const int lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (seg >= n_seg) return;
+    const int cnt = seg_count[seg];
+    const int off = seg_off[seg];
+    const int h = N / 2;
+    for (int c = 0; c < cnt; ++c) {
+        const int dst = off + c;
+        if (dst >= max_frames) break;
+        const int64_t t = seg_trig[seg * seg_cap + c];
+        double pr = 0.0, pi = 0.0;
+        for (int k = lane; k < h; k += 32) {
+            const int64_t u = t - k, ud = u - h;
+            float2 v = (u >= 0 && u < n) ? LDG(y + u) : make_float2(0.f, 0.f);
+            float2 d = (ud >= 0 && ud < n) ? LDG(y + ud) : make_float2(0.f, 0.f);
+            float2 cc = cmulc_x(v, d);
+            pr += (double)cc.x;
+            pi += (double)cc.y;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            pr += __shfl_xor_sync(0xffffffffu, pr, d);
+            pi += __shfl_xor_sync(0xffffffffu, pi, d);
+        }
+        if (lane == 0) {
+            trig_idx[dst] = t;
+            trig_ang[dst] = (float)atan2((double)(float)pi, (double)(float)pr);
+        }
+    }
+}
+
+int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t n, const int64_t* first_nan,
+                       ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+    OFDM_CUDA_CHECK(cudaMemsetAsync(io->status, 0, sizeof(uint32_t), st));
+    if (ws->n_seg == 0) {
+        OFDM_CUDA_CHECK(cudaMemsetAsync(io->n_trig, 0, sizeof(int32_t), st));
+        return OFDM_OK;
+    }
+    PeakParams p;
+    p.mf = mf; p.n = n; p.first_nan = first_nan; p.seg_len = ws->seg_len; p.n_seg = ws->n_seg; p.seg_cap = (int)ws->seg_cap;
+    p.seg_count = ws->seg_count; p.seg_trig = ws->seg_trig; p.status = io->status;
+    const int wpb = 4;
+    peak_detect_kernel<<<(unsigned)((ws->n_seg + wpb - 1) / wpb), wpb * 32, 0, st>>>(p);
+    OFDM_LAUNCH_CHECK();
+    seg_scan_kernel<<<1, 1024, 0, st>>>(ws->seg_count, ws->n_seg, ws->seg_off, io->n_trig, io->max_frames, io->status);
+    OFDM_LAUNCH_CHECK();
+    trig_gather_kernel<<<(unsigned)((ws->n_seg + 7) / 8), 256, 0, st>>>(y, n, h->N, ws->seg_count, ws->seg_off, ws->seg_trig,
+                                                                        ws->n_seg, (int)ws->seg_cap, io->max_frames,
+                                                                        io->trig_idx, io->trig_ang);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_RX3: gr.frequency_modulator_fc(-2/N) phase bookkeeping (A.8) and digital.ofdm_sampler (A.9) in closed
+// form per trigger.  One CTA; the two prefix sums are chunked block scans.
+// ---------------------------------------------------------------------------------------------
+struct PlanParams {
+    int64_t n;
+    int N, L, max_frames;
+    const int32_t* n_trig;
+    const int64_t* trig_idx;
+    const float* trig_ang;
+    double* phi0;
+    double* step;
+    int32_t* first_ok;
+    int32_t* n_frames;
+    int64_t* frame_start;
+    int32_t* frame_ndata;
+    int64_t* vbase;
+    int64_t* counters;
+};
+
+__device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__global__ void __launch_bounds__(1024) plan_kernel(const PlanParams p) {
+    __shared__ double s_wd[32];
+    __shared__ long long s_wi[32];
+    __shared__ double s_carry_d;
+    __shared__ long long s_carry_i;
+    __shared__ int s_first_ok, s_nfr;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int K = *p.n_trig;
+    if (K > p.max_frames) K = p.max_frames;
+    const int64_t N = p.N, L = p.L, n = p.n;
+    if (tid == 0) { s_carry_d = 0.0; s_carry_i = 0; s_first_ok = K; s_nfr = INT_MAX; }
+    __syncthreads();
+    // (1) NCO: step_k = -2/N * ang_k ; phi0_k = sum_{j<k} step_j * (t_{j+1} - t_j)
+    for (int base = 0; base < K; base += 1024) {
+        const int k = base + tid;
+        double d = 0.0;
+        if (k < K) {
+            const double stp = (-2.0 / (double)N) * (double)p.trig_ang[k];
+            p.step[k] = stp;
+            if (k + 1 < K) d = stp * (double)(p.trig_idx[k + 1] - p.trig_idx[k]);
+        }
+        double inc = d;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            double o = __shfl_up_sync(0xffffffffu, inc, s);
+            if (lane >= s) inc += o;
+        }
+        if (lane == 31) s_wd[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            double t = s_wd[lane], ti = t;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                double o = __shfl_up_sync(0xffffffffu, ti, s);
+                if (lane >= s) ti += o;
+            }
+            s_wd[lane] = ti - t;
+        }
+        __syncthreads();
+        const double excl = s_carry_d + s_wd[w] + (inc - d);
+        if (k < K) p.phi0[k] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry_d = excl + d;
+        __syncthreads();
+    }
+    // (2) the sampler never looks at indices < N: first visible trigger
+    for (int k = tid; k < K; k += 1024)
+        if (p.trig_idx[k] >= N) { atomicMin(&s_first_ok, k); break; }
+    __syncthreads();
+    const int first_ok = s_first_ok;
+    // (3) can the call that finds trigger k run?  (a call at read pointer pos needs pos+L+N < n)
+    for (int k = first_ok + tid; k < K; k += 1024) {
+        const int64_t t = p.trig_idx[k];
+        bool ok;
+        if (k == first_ok) {
+            const int64_t c = (t - N) / (L + 1);
+            ok = c * (L + 1) + L + N < n;
+        } else {
+            const int64_t tp = p.trig_idx[k - 1];
+            int64_t mm = ceil_div64(t - tp - 1, L);
+            if (mm < 1) mm = 1;
+            if (mm <= OFDM_SAMPLER_TIMEOUT) {
+                ok = tp + 1 + mm * L < n;
+            } else {
+                const int64_t q0 = tp + 1 + (int64_t)OFDM_SAMPLER_TIMEOUT * L;   // pos + N of the first NO_SIG call
+                const int64_t c = (t - q0) / (L + 1);
+                ok = q0 + c * (L + 1) + L < n;
+            }
+        }
+        if (!ok) { atomicMin(&s_nfr, k - first_ok); break; }   // later ones fail too (pos only grows)
+    }
+    __syncthreads();
+    int F = K - first_ok;
+    if (s_nfr < F) F = s_nfr;
+    if (F < 0) F = 0;
+    // (4) data vectors per frame and the vector-stream prefix
+    for (int base = 0; base < F; base += 1024) {
+        const int f = base + tid;
+        long long v = 0;
+        if (f < F) {
+            const int k = first_ok + f;
+            const int64_t t = p.trig_idx[k];
+            int64_t J = OFDM_SAMPLER_TIMEOUT;
+            if (k + 1 < K) {
+                int64_t mm = ceil_div64(p.trig_idx[k + 1] - t - 1, L);
+                if (mm < 1) mm = 1;
+                if (mm - 1 < J) J = mm - 1;
+            }
+            int64_t room = (n - 2 - t >= 0) ? (n - 2 - t) / L : 0;
+            if (room < J) J = room;
+            if (J < 0) J = 0;
+            p.frame_start[f] = t - N + 1;
+            p.frame_ndata[f] = (int)J;
+            v = 1 + J;
+        }
+        long long inc = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            long long o = __shfl_up_sync(0xffffffffu, inc, s);
+            if (lane >= s) inc += o;
+        }
+        if (lane == 31) s_wi[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            long long t = s_wi[lane], ti = t;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                long long o = __shfl_up_sync(0xffffffffu, ti, s);
+                if (lane >= s) ti += o;
+            }
+            s_wi[lane] = ti - t;
+        }
+        __syncthreads();
+        const long long excl = s_carry_i + s_wi[w] + (inc - v);
+        if (f < F) p.vbase[f] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry_i = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        p.vbase[F] = s_carry_i;                     // total vectors
+        *p.first_ok = first_ok;
+        *p.n_frames = F;
+        p.counters[0] = F;
+        p.counters[4] = n;
+        p.counters[5] = K;
+        p.counters[6] = s_carry_i;
+    }
+}
+
+int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+    PlanParams p;
+    p.n = n; p.N = h->N; p.L = h->L; p.max_frames = io->max_frames; p.n_trig = io->n_trig; p.trig_idx = io->trig_idx;
+    p.trig_ang = io->trig_ang; p.phi0 = ws->phi0; p.step = ws->step; p.first_ok = ws->first_ok; p.n_frames = io->n_frames;
+    p.frame_start = io->frame_start; p.frame_ndata = io->frame_ndata; p.vbase = ws->vbase; p.counters = io->counters;
+    OFDM_CUDA_CHECK(cudaMemsetAsync(io->counters, 0, 8 * sizeof(int64_t), st));
+    plan_kernel<<<1, 1024, 0, st>>>(p);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}

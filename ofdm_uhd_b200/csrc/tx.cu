@@ -1,0 +1,251 @@
+// Transmit side: packet framing, the fused mapper + preamble + IFFT + cyclic-prefix kernel,
+// and the synthetic channel used by the loopback drivers.
+#include "internal.h"
+#include "fft.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// make_packet (ofdm_packet_utils.py:99-143): one thread per packet.  CRC-32 is the upstream
+// digital.crc32 (MSB-first 0x04C11DB7, init/final all ones; digital_swig.py:3151-3168).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) make_packets_kernel(const uint8_t* __restrict__ payload,
+                                                            const int64_t* __restrict__ payload_off, int n_pkts,
+                                                            int whitening, uint8_t* __restrict__ pkts,
+                                                            const int64_t* __restrict__ pkt_off,
+                                                            const uint8_t* __restrict__ mask,
+                                                            const uint32_t* __restrict__ crctab) {
+    __shared__ uint32_t s_crc[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = crctab[i];
+    __syncthreads();
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pkts) return;
+    const uint8_t* src = payload + payload_off[p];
+    const int plen = (int)(payload_off[p + 1] - payload_off[p]);
+    uint8_t* dst = pkts + pkt_off[p];
+    const int total = (int)(pkt_off[p + 1] - pkt_off[p]);
+    const int L = plen + 4;
+    const uint32_t v = (uint32_t)(L & 0x0FFF);                 // whitener offset 0 (ofdm.py:143)
+    dst[0] = (uint8_t)(v >> 8); dst[1] = (uint8_t)v; dst[2] = (uint8_t)(v >> 8); dst[3] = (uint8_t)v;
+    uint32_t crc = 0xFFFFFFFFu;
+    int o = 0;                                                  // offset into the whitened body
+    for (int i = 0; i < plen; ++i, ++o) {
+        uint8_t b = src[i];
+        crc = s_crc[(b ^ (crc >> 24)) & 0xFF] ^ (crc << 8);
+        dst[4 + o] = whitening ? (uint8_t)(b ^ mask[o]) : b;
+    }
+    crc = ~crc;
+    for (int i = 0; i < 4; ++i, ++o) {
+        uint8_t b = (uint8_t)(crc >> (24 - 8 * i));
+        dst[4 + o] = whitening ? (uint8_t)(b ^ mask[o]) : b;
+    }
+    for (; 4 + o < total; ++o) dst[4 + o] = whitening ? (uint8_t)(0x55 ^ mask[o & 4095]) : (uint8_t)0x55;
+}
+
+int launch_make_packets(ofdm_handle* h, const uint8_t* payload, const int64_t* payload_off, int32_t n_pkts,
+                        int whitening, uint8_t* pkts, const int64_t* pkt_off, cudaStream_t st) {
+    make_packets_kernel<<<(n_pkts + 127) / 128, 128, 0, st>>>(payload, payload_off, n_pkts, whitening, pkts, pkt_off,
+                                                             h->d_mask, h->d_crctab);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_TX: ofdm_mapper_bcv + ofdm_insert_preamble + fft_vcc(inverse, shifted) + ofdm_cyclic_prefixer
+//       + multiply_const(1/sqrt N) + multiply_const(amp)      (ofdm.py:106-117, transmit_path.py:48)
+// One group of T = N/E threads builds one OFDM symbol; G groups per CTA.
+// ---------------------------------------------------------------------------------------------
+struct TxParams {
+    const uint8_t* pkts;
+    const int64_t* pkt_off;
+    const int64_t* sym_off;
+    int n_frames;
+    int uniform_syms;
+    int64_t total_syms;
+    int64_t first_frame;
+    uint64_t seed;
+    float2* out;
+    const float2* cst;
+    const int16_t* bin2car;
+    const float2* tw;
+    const float2* pre_time;
+    int cp, ncar, nbits, M;
+    float s1, amp;
+};
+
+template <int N>
+struct TxLoad {
+    const TxParams& p;
+    const uint8_t* pkt;
+    int64_t pkt_bits;
+    int64_t frame_id;
+    int dsym;                    // data symbol number inside the frame
+    const float2* s_cst;
+    __device__ __forceinline__ float2 operator()(int idx, int) const {
+        const int v = (idx + N / 2) & (N - 1);          // ifftshift: IFFT input idx holds vector bin v
+        const int c = LDG(p.bin2car + v);
+        if (c < 0) return make_float2(0.f, 0.f);
+        const int64_t bit0 = ((int64_t)dsym * p.ncar + c) * p.nbits;
+        uint32_t val;
+        if (bit0 + p.nbits <= pkt_bits) val = extract_bits(pkt, bit0, p.nbits);
+        else val = pad_index(p.seed, (uint64_t)frame_id, (uint32_t)dsym, (uint32_t)c, (uint32_t)p.M);
+        return s_cst[val];
+    }
+};
+
+template <int N>
+struct TxStore {
+    float2* dst;                 // start of this symbol (its cyclic prefix)
+    int cp;
+    float s1, amp;
+    __device__ __forceinline__ void operator()(int n, float2 v, int) const {
+        // float32 after each multiply_const, like the two upstream blocks
+        float2 o = make_float2(fmul_rn(fmul_rn(v.x, s1), amp), fmul_rn(fmul_rn(v.y, s1), amp));
+        dst[cp + n] = o;
+        if (n >= N - cp) dst[n - (N - cp)] = o;
+    }
+};
+
+template <int N, int G>
+__global__ void __launch_bounds__(G * (N / FftPlan<N>::E)) tx_kernel(const TxParams p) {
+    constexpr int T = N / FftPlan<N>::E;
+    constexpr int SB = fft_smem_elems<N>();
+    extern __shared__ float2 smem[];
+    float2* s_cst = smem;                                  // [M]
+    float2* bufs = smem + 256;                             // G * 2 * SB
+    const int g = threadIdx.x / T;
+    const int tid = threadIdx.x - g * T;
+    for (int i = threadIdx.x; i < p.M; i += blockDim.x) s_cst[i] = p.cst[i];
+    __syncthreads();
+    float2* bufA = bufs + (size_t)g * 2 * SB;
+    float2* bufB = bufA + SB;
+    const int L = N + p.cp;
+    auto bar = [] { __syncthreads(); };
+    for (int64_t base = (int64_t)blockIdx.x * G; base < p.total_syms; base += (int64_t)gridDim.x * G) {
+        const int64_t s = base + g;
+        const bool active = s < p.total_syms;
+        int f = 0;
+        int m = 0;
+        if (active) {
+            if (p.uniform_syms > 0) {
+                f = (int)(s / p.uniform_syms);
+                m = (int)(s - (int64_t)f * p.uniform_syms);
+            } else {
+                int lo = 0, hi = p.n_frames;              // last f with sym_off[f] <= s
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (LDG(p.sym_off + mid) <= s) lo = mid; else hi = mid;
+                }
+                f = lo;
+                m = (int)(s - LDG(p.sym_off + f));
+            }
+        }
+        float2* dst = p.out + s * L;
+        const bool data = active && m > 0;
+        if (active && m == 0) {
+            // ofdm_insert_preamble: the pre-modulated known symbol
+            for (int i = tid; i < L; i += T) {
+                float2 v = LDG(p.pre_time + i);
+                dst[i] = make_float2(fmul_rn(v.x, p.amp), fmul_rn(v.y, p.amp));
+            }
+        }
+        const int64_t o0 = active ? LDG(p.pkt_off + f) : 0;
+        const int64_t o1 = active ? LDG(p.pkt_off + f + 1) : 0;
+        TxLoad<N> ld{p, p.pkts + o0, (o1 - o0) * 8, p.first_frame + f, m - 1, s_cst};
+        TxStore<N> st{dst, p.cp, p.s1, p.amp};
+        using P = FftPlan<N>;
+        constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
+        if (data) fft_pass<N, R0, 1, 1>(tid, p.tw, ld, SmemOut{bufA});
+        bar();
+        if constexpr (P::NP == 2) {
+            if (data) fft_pass<N, R1, R0, 1>(tid, p.tw, SmemIn{bufA}, st);
+            bar();
+        } else {
+            if (data) fft_pass<N, R1, R0, 1>(tid, p.tw, SmemIn{bufA}, SmemOut{bufB});
+            bar();
+            if (data) fft_pass<N, R2, R0 * R1, 1>(tid, p.tw, SmemIn{bufB}, st);
+        }
+    }
+}
+
+template <int N, int G>
+static int launch_tx_n(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
+    constexpr int T = N / FftPlan<N>::E;
+    size_t smem = (256 + (size_t)G * 2 * fft_smem_elems<N>()) * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        OFDM_CUDA_CHECK(cudaFuncSetAttribute(tx_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    int64_t want = (p.total_syms + G - 1) / G;
+    int64_t cap = (int64_t)sms * 16;
+    int grid = (int)(want < cap ? want : cap);
+    tx_kernel<N, G><<<grid, G * T, smem, st>>>(p);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
+int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames, int64_t first_frame,
+              const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms, float2* out, cudaStream_t st) {
+    TxParams p;
+    p.pkts = pkts; p.pkt_off = pkt_off; p.sym_off = sym_off; p.n_frames = n_frames; p.uniform_syms = uniform_syms;
+    p.first_frame = first_frame; p.seed = h->pad_seed; p.out = out; p.cst = h->d_const; p.bin2car = h->d_bin2car;
+    p.tw = h->d_tw; p.pre_time = h->d_pre_time; p.cp = h->cp; p.ncar = h->ncar; p.nbits = h->nbits; p.M = h->M;
+    p.s1 = (float)(1.0 / sqrt((double)h->N)); p.amp = h->amp;
+    p.total_syms = uniform_syms > 0 ? (int64_t)n_frames * uniform_syms : total_syms;
+    switch (h->N) {
+        case 64:   return launch_tx_n<64, 8>(h, p, st);
+        case 128:  return launch_tx_n<128, 8>(h, p, st);
+        case 256:  return launch_tx_n<256, 8>(h, p, st);
+        case 512:  return launch_tx_n<512, 4>(h, p, st);
+        case 1024: return launch_tx_n<1024, 4>(h, p, st);
+        case 2048: return launch_tx_n<2048, 2>(h, p, st);
+        case 4096: return launch_tx_n<4096, 1>(h, p, st);
+    }
+    ofdm_set_error("tx: unsupported fft_length %d", h->N);
+    return OFDM_E_INVAL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic channel (test / bench infrastructure): CFO rotation + counter-based Gaussian noise.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) channel_kernel(const float2* __restrict__ x, int64_t n, double w, double phase0,
+                                                       float sigma, uint64_t seed, float2* __restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double ph = phase0 + w * (double)i;              // radians
+        double r = ph * 0.15915494309189533577;          // turns
+        r -= rint(r);
+        float s, c;
+        sincospif(2.0f * (float)r, &s, &c);
+        float2 v = x[i];
+        float2 o = make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+        if (sigma > 0.f) {
+            uint64_t hsh = mix64(seed ^ (uint64_t)i * 0xD6E8FEB86659FD93ull);
+            float u1 = ((float)(uint32_t)(hsh >> 40) + 0.5f) * (1.0f / 16777216.0f);
+            float u2 = ((float)(uint32_t)((hsh >> 8) & 0xFFFFFF) + 0.5f) * (1.0f / 16777216.0f);
+            float rad = sigma * sqrtf(-2.0f * logf(u1));
+            float sn, cs;
+            sincospif(2.0f * u2, &sn, &cs);
+            o.x += rad * cs;
+            o.y += rad * sn;
+        }
+        y[i] = o;
+    }
+}
+
+int launch_channel(ofdm_handle* h, const float2* x, int64_t n, float cfo, double phase0, float sigma, uint64_t seed,
+                   float2* y, cudaStream_t st) {
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    double w = 2.0 * M_PI * (double)cfo / (double)h->N;
+    channel_kernel<<<(int)blocks, 256, 0, st>>>(x, n, w, phase0, sigma, seed, y);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}

@@ -1,0 +1,321 @@
+"""Device engine: owns an ``ofdm_handle`` and the torch buffers handed to libofdm_b200.so.
+
+This is the host-side glue the reference-facing classes in ofdm.py share.  It never computes
+samples or bits itself -- every stage is a CUDA kernel behind the C ABI (include/ofdm_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+try:
+    from . import _lib, psk, qam
+except ImportError:                      # flat import (directory on sys.path, like the reference)
+    import _lib
+    import psk
+    import qam
+
+MODS = {"bpsk": 2, "qpsk": 4, "8psk": 8, "qam8": 8, "qam16": 16, "qam64": 64, "qam256": 256}   # ofdm.py:88
+
+
+def rotated_constellation(modulation: str) -> List[complex]:
+    """The constellation exactly as the reference builds it (ofdm.py:88-101)."""
+    arity = MODS[modulation]                          # KeyError for unknown names, like the reference
+    rot = 1
+    if modulation == "qpsk":
+        rot = (0.707 + 0.707j)
+    if modulation.find("psk") >= 0:
+        return [pt * rot for pt in psk.gray_constellation[arity]]
+    return [pt * rot for pt in qam.constellation[arity]]
+
+
+@dataclass
+class RxBatch:
+    """Host view of one ofdm_rx_demodulate call."""
+    n_trig: int
+    n_frames: int
+    status_bits: int
+    trig_idx: np.ndarray
+    trig_ang: np.ndarray
+    frame_start: np.ndarray
+    frame_ndata: np.ndarray
+    frame_live: np.ndarray
+    frame_status: np.ndarray
+    pkt_len: np.ndarray
+    pkt_ok: np.ndarray
+    counters: np.ndarray
+    packets: List[Tuple[bool, bytes]]          # (ok, payload) in arrival order, what the callback sees
+
+
+class OfdmEngine:
+    def __init__(self, fft_length=512, occupied_tones=200, cp_length=128, modulation="bpsk", tx_amplitude=0.25,
+                 device: Optional[int] = None, pad_seed: int = 0, max_pkt_bytes: int = 4096):
+        import torch
+        self.torch = torch
+        self.L_ = _lib.lib()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.dev = torch.device("cuda", self.device)
+        self.modulation = modulation
+        const = np.array(rotated_constellation(modulation), dtype=np.complex128).astype(np.complex64)
+        self.constellation = const
+        flat = np.ascontiguousarray(const.view(np.float32))
+        cfg = _lib.OfdmCfg(fft_length, occupied_tones, cp_length, len(const),
+                           flat.ctypes.data_as(C.POINTER(C.c_float)), float(tx_amplitude), self.device,
+                           int(pad_seed) & 0xFFFFFFFFFFFFFFFF, int(max_pkt_bytes))
+        h = self.L_.ofdm_create(C.byref(cfg))
+        if not h:
+            raise ValueError("ofdm_create: " + self.L_.ofdm_last_error().decode())
+        self.h = C.c_void_p(h)
+        lay = (C.c_int32 * 8)()
+        _lib.check(self.L_.ofdm_get_layout(self.h, lay), "get_layout")
+        self.N, self.occ, self.cp = fft_length, occupied_tones, cp_length
+        self.zl, self.ncar, self.nbits, self.L, self.ntaps, self.nos, self.pkt_stride = [int(v) for v in lay[:7]]
+        self._ws = None
+        self._ws_key = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L_.ofdm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+    def set_tx_amplitude(self, ampl: float):
+        _lib.check(self.L_.ofdm_set_tx_amplitude(self.h, float(ampl)))
+
+    def chan_taps(self) -> np.ndarray:
+        buf = (C.c_float * 512)()
+        n = _lib.check(self.L_.ofdm_get_chan_taps(self.h, buf, 512))
+        return np.array(buf[:n], dtype=np.float32)
+
+    def frame_symbols(self, pkt_len: int) -> int:
+        return int(self.L_.ofdm_frame_symbols(self.h, int(pkt_len)))
+
+    # ------------------------------------------------------------------ transmit
+    def make_packets(self, payload, payload_off: np.ndarray, pad_for_usrp: bool = False, whitening: bool = True):
+        """payload: uint8 cuda tensor of the concatenated payloads; payload_off: host int64 [F+1].
+        Returns (pkts uint8 cuda tensor, pkt_off host int64 [F+1])."""
+        torch = self.torch
+        payload_off = np.ascontiguousarray(payload_off, dtype=np.int64)
+        plen = np.diff(payload_off)
+        if len(plen) and int(plen.max()) + 4 > 4095 + 1:
+            raise ValueError("len(payload) must be in [0, 4092]")
+        klen = plen + 9
+        if pad_for_usrp:
+            klen = (klen + 15) // 16 * 16
+        pkt_off = np.zeros(len(plen) + 1, dtype=np.int64)
+        np.cumsum(klen, out=pkt_off[1:])
+        pkts = torch.empty(int(pkt_off[-1]), dtype=torch.uint8, device=self.dev)
+        d_poff = torch.from_numpy(payload_off).to(self.dev, non_blocking=True)
+        d_koff = torch.from_numpy(pkt_off).to(self.dev, non_blocking=True)
+        _lib.check(self.L_.ofdm_make_packets(self.h, self._p(payload), self._p(d_poff), len(plen), int(whitening),
+                                             self._p(pkts), self._p(d_koff), self._stream()), "make_packets")
+        return pkts, pkt_off, d_koff
+
+    def modulate(self, pkts, pkt_off: np.ndarray, d_pkt_off=None, first_frame: int = 0, out=None):
+        """pkts: uint8 cuda tensor of concatenated packets; pkt_off: host int64 [F+1].
+        Returns complex64 cuda tensor with all frames back to back."""
+        torch = self.torch
+        pkt_off = np.ascontiguousarray(pkt_off, dtype=np.int64)
+        F = len(pkt_off) - 1
+        if F <= 0:
+            return torch.zeros(0, dtype=torch.complex64, device=self.dev)
+        plen = np.diff(pkt_off)
+        per = self.ncar * self.nbits
+        nsym = 1 + np.maximum(1, -(-(8 * plen) // per))
+        uniform = int(nsym[0]) if bool((nsym == nsym[0]).all()) else 0
+        total = int(nsym.sum())
+        if d_pkt_off is None:
+            d_pkt_off = torch.from_numpy(pkt_off).to(self.dev, non_blocking=True)
+        d_sym_off = None
+        if not uniform:
+            sym_off = np.zeros(F + 1, dtype=np.int64)
+            np.cumsum(nsym, out=sym_off[1:])
+            d_sym_off = torch.from_numpy(sym_off).to(self.dev, non_blocking=True)
+        if out is None:
+            out = torch.empty(total * self.L, dtype=torch.complex64, device=self.dev)
+        elif out.numel() < total * self.L:
+            raise ValueError("modulate: output buffer too small")
+        _lib.check(self.L_.ofdm_tx_modulate_batch(self.h, self._p(pkts), self._p(d_pkt_off), F, int(first_frame),
+                                                  self._p(d_sym_off), total, uniform, self._p(out), self._stream()),
+                   "tx_modulate_batch")
+        return out[:total * self.L]
+
+    def channel(self, x, cfo: float = 0.0, sigma: float = 0.0, seed: int = 0, phase0: float = 0.0, out=None):
+        torch = self.torch
+        if out is None:
+            out = torch.empty_like(x)
+        _lib.check(self.L_.ofdm_channel(self.h, self._p(x), x.numel(), float(cfo), float(phase0), float(sigma),
+                                        int(seed) & 0xFFFFFFFFFFFFFFFF, self._p(out), self._stream()), "channel")
+        return out
+
+    # ------------------------------------------------------------------ receive
+    def rx_alloc(self, n: int, max_frames: Optional[int] = None, taps: bool = False, max_vectors: int = 0):
+        """Allocate (and cache) the output arrays + workspace of one receive call."""
+        torch = self.torch
+        if max_frames is None:
+            max_frames = max(64, int(n // self.L) + 64)
+        key = (int(n), int(max_frames), bool(taps), int(max_vectors))
+        if self._ws_key == key:
+            return self._ws
+        dev = self.dev
+        need = int(self.L_.ofdm_rx_workspace_bytes(self.h, int(n), int(max_frames)))
+        b = {}
+        b["workspace"] = torch.empty(need, dtype=torch.uint8, device=dev)
+        b["status"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        b["n_trig"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        b["trig_idx"] = torch.zeros(max_frames, dtype=torch.int64, device=dev)
+        b["trig_ang"] = torch.zeros(max_frames, dtype=torch.float32, device=dev)
+        b["n_frames"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        b["frame_start"] = torch.zeros(max_frames, dtype=torch.int64, device=dev)
+        b["frame_ndata"] = torch.zeros(max_frames, dtype=torch.int32, device=dev)
+        b["frame_live"] = torch.zeros(max_frames, dtype=torch.uint8, device=dev)
+        b["frame_status"] = torch.zeros(max_frames, dtype=torch.uint8, device=dev)
+        b["pkt_len"] = torch.zeros(max_frames, dtype=torch.int32, device=dev)
+        b["pkt_ok"] = torch.zeros(max_frames, dtype=torch.uint8, device=dev)
+        b["pkt_bytes"] = torch.zeros(max_frames * self.pkt_stride, dtype=torch.uint8, device=dev)
+        b["counters"] = torch.zeros(8, dtype=torch.int64, device=dev)
+        if taps:
+            b["eq_syms"] = torch.zeros(max_vectors * self.occ, dtype=torch.complex64, device=dev)
+            b["sym_idx"] = torch.zeros(max_vectors * self.ncar, dtype=torch.uint8, device=dev)
+            b["derot_syms"] = torch.zeros(max_vectors * self.ncar, dtype=torch.complex64, device=dev)
+        io = _lib.RxIo()
+        io.max_frames = int(max_frames)
+        io.pkt_stride = self.pkt_stride
+        io.workspace = b["workspace"].data_ptr()
+        io.workspace_bytes = need
+        for k in ("status", "n_trig", "trig_idx", "trig_ang", "n_frames", "frame_start", "frame_ndata", "frame_live",
+                  "frame_status", "pkt_len", "pkt_ok", "pkt_bytes", "counters"):
+            setattr(io, k, b[k].data_ptr())
+        io.eq_syms = b["eq_syms"].data_ptr() if taps else None
+        io.sym_idx = b["sym_idx"].data_ptr() if taps else None
+        io.derot_syms = b["derot_syms"].data_ptr() if taps else None
+        io.max_vectors = int(max_vectors) if taps else 0
+        b["io"] = io
+        b["n"] = int(n)
+        self._ws, self._ws_key = b, key
+        return b
+
+    def demodulate_async(self, x, bufs=None, **kw):
+        """Run the whole receive chain on the current stream; returns the buffer dict (no sync)."""
+        n = int(x.numel())
+        if bufs is None:
+            bufs = self.rx_alloc(n, **kw)
+        _lib.check(self.L_.ofdm_rx_demodulate(self.h, self._p(x), n, C.byref(bufs["io"]), self._stream()),
+                   "rx_demodulate")
+        return bufs
+
+    def ws_view(self, bufs, which: int, n: int):
+        """Tensor views of the workspace taps (0: filtered stream y, 1: timing metric mf)."""
+        torch = self.torch
+        ptr = self.L_.ofdm_rx_workspace_ptr(self.h, C.byref(bufs["io"]), int(n), int(which))
+        base = bufs["workspace"].data_ptr()
+        off = int(ptr) - base
+        if which == 0:
+            return bufs["workspace"][off:off + 8 * n].view(torch.complex64)
+        if which == 1:
+            return bufs["workspace"][off:off + 4 * n].view(torch.float32)
+        raise ValueError(which)
+
+    def collect(self, bufs) -> RxBatch:
+        """Synchronise and bring one receive call's results to the host."""
+        torch = self.torch
+        torch.cuda.current_stream(self.dev).synchronize()
+        nt = int(bufs["n_trig"].item())
+        nf = int(bufs["n_frames"].item())
+        st = int(bufs["status"].item())
+        if st:
+            raise RuntimeError("receive: capacity overflow (status bits 0x%x): raise max_frames" % st)
+        g = lambda k, m: bufs[k][:m].cpu().numpy()
+        live, fstat = g("frame_live", nf), g("frame_status", nf)
+        plen, pok = g("pkt_len", nf), g("pkt_ok", nf)
+        sel = np.flatnonzero((live == 1) & (fstat == 2))
+        packets: List[Tuple[bool, bytes]] = []
+        if len(sel):
+            idx = torch.from_numpy(sel).to(self.dev)
+            rows = bufs["pkt_bytes"].view(-1, self.pkt_stride)[idx].cpu().numpy()
+            for r, f in enumerate(sel):
+                ln = int(plen[f])
+                body = rows[r, :min(ln, self.pkt_stride)].tobytes()
+                packets.append((bool(pok[f]), body[:-4] if ln >= 4 else b""))
+        return RxBatch(nt, nf, st, g("trig_idx", nt), g("trig_ang", nt), g("frame_start", nf), g("frame_ndata", nf),
+                       live, fstat, plen, pok, bufs["counters"].cpu().numpy(), packets)
+
+    def demodulate(self, x, **kw) -> RxBatch:
+        return self.collect(self.demodulate_async(x, **kw))
+
+
+class SenseEngine:
+    """stream_to_vector -> fft_vcc(N, True, blackmanharris) -> complex_to_mag_squared -> bin_statistics_f."""
+
+    def __init__(self, fft_size: int, device: Optional[int] = None):
+        import torch
+        self.torch = torch
+        self.L_ = _lib.lib()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.dev = torch.device("cuda", self.device)
+        self.N = int(fft_size)
+        s = self.L_.ofdm_sense_create(self.N, self.device)
+        if not s:
+            raise ValueError("ofdm_sense_create: " + self.L_.ofdm_last_error().decode())
+        self.s = C.c_void_p(s)
+
+    def close(self):
+        if getattr(self, "s", None):
+            self.L_.ofdm_sense_destroy(self.s)
+            self.s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def maxhold(self, x, tune_delay: int, dwell_delay: int, shift: bool = False, out=None):
+        torch = self.torch
+        nfr = int(x.numel()) // self.N
+        nd = nfr // (tune_delay + dwell_delay)
+        if out is None:
+            out = torch.empty((nd, self.N), dtype=torch.float32, device=self.dev)
+        _lib.check(self.L_.ofdm_sense(self.s, C.c_void_p(x.data_ptr()), nfr, int(shift), int(tune_delay),
+                                      int(dwell_delay), C.c_void_p(out.data_ptr()), self._stream()), "sense")
+        return out
+
+    def spectra(self, x, shift: bool = True):
+        torch = self.torch
+        nfr = int(x.numel()) // self.N
+        out = torch.empty((nfr, self.N), dtype=torch.complex64, device=self.dev)
+        _lib.check(self.L_.ofdm_sense_fft(self.s, C.c_void_p(x.data_ptr()), nfr, int(shift),
+                                          C.c_void_p(out.data_ptr()), self._stream()), "sense_fft")
+        return out
+
+    def decide(self, maxhold, threshold: float = 0.001):
+        """Mean of the dwell vectors, threshold, frequency-order swap, hex map (secondary_tx.py:237-266)."""
+        torch = self.torch
+        n_avg = int(maxhold.shape[0])
+        avg = torch.empty(self.N, dtype=torch.float64, device=self.dev)
+        free = torch.empty(self.N, dtype=torch.uint8, device=self.dev)
+        hx = torch.empty(self.N // 4, dtype=torch.uint8, device=self.dev)
+        _lib.check(self.L_.ofdm_sense_decide(self.s, C.c_void_p(maxhold.data_ptr()), n_avg, float(threshold),
+                                             C.c_void_p(avg.data_ptr()), C.c_void_p(free.data_ptr()),
+                                             C.c_void_p(hx.data_ptr()), self._stream()), "sense_decide")
+        return avg.cpu().numpy(), free.cpu().numpy(), bytes(hx.cpu().numpy()).decode("ascii")

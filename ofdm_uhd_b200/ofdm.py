@@ -1,0 +1,381 @@
+"""ofdm_mod / ofdm_demod with the constructor options, ``send_pkt`` and rx-callback semantics of the
+reference's ofdm.py (/root/reference/ofdm.py:38-305), running on B200 kernels instead of a GNU Radio
+flowgraph.
+
+The reference classes are ``gr.hier_block2`` objects with one complex stream port; a scheduler thread per
+block moves the samples.  Here there is no flowgraph: packets queued by ``send_pkt`` are modulated as one
+batch by ``flush()`` (also triggered when the queue is full and by ``eof``) and pushed to whatever was
+``connect()``-ed; ``ofdm_demod.feed(samples)`` runs the receiver on a buffer and delivers
+``callback(ok, payload)`` from a daemon watcher thread, in arrival order -- as ofdm.py:290-305 does.
+"""
+from __future__ import annotations
+
+import math
+import queue
+import threading
+
+import numpy as np
+
+try:
+    from . import ofdm_packet_utils
+    from .engine import OfdmEngine, MODS
+except ImportError:                      # flat import, like the reference's script directory
+    import ofdm_packet_utils
+    from engine import OfdmEngine, MODS
+
+
+# ------------------------------------------------------------------------------------------------
+# the sliver of gr.message / gr.msg_queue the callers touch (ofdm.py:139-148)
+# ------------------------------------------------------------------------------------------------
+class message:
+    def __init__(self, type=0, arg1=0.0, arg2=0.0, data=b""):
+        self._type, self._arg1, self._arg2, self._data = type, arg1, arg2, bytes(data)
+
+    def type(self):
+        return self._type
+
+    def arg1(self):
+        return self._arg1
+
+    def arg2(self):
+        return self._arg2
+
+    def length(self):
+        return len(self._data)
+
+    def to_string(self):
+        return self._data
+
+
+def message_from_string(s, type=0, arg1=0.0, arg2=0.0):
+    return message(type, arg1, arg2, s)
+
+
+class msg_queue:
+    """Thread-safe FIFO with gr.msg_queue's method names; ``limit`` 0 means unbounded."""
+
+    def __init__(self, limit=0, on_full=None):
+        self._q = queue.Queue()
+        self._limit = limit
+        self._on_full = on_full
+
+    def limit(self):
+        return self._limit
+
+    def count(self):
+        return self._q.qsize()
+
+    def empty_p(self):
+        return self._q.empty()
+
+    def full_p(self):
+        return self._limit != 0 and self._q.qsize() >= self._limit
+
+    def insert_tail(self, msg):
+        # gr.msg_queue blocks the producer here until the mapper has drained a slot; the drain is ours to run
+        if self.full_p() and self._on_full is not None:
+            self._on_full()
+        self._q.put(msg)
+
+    def delete_head(self):
+        return self._q.get()
+
+    def delete_head_nowait(self):
+        try:
+            return self._q.get_nowait()
+        except queue.Empty:
+            return None
+
+    def flush(self):
+        while self.delete_head_nowait() is not None:
+            pass
+
+
+class _pkt_input:
+    """Stands where digital.ofdm_mapper_bcv stood: callers only reach ``_pkt_input.msgq()`` (ofdm.py:148)."""
+
+    def __init__(self, msgq_limit, on_full):
+        self._msgq = msg_queue(msgq_limit, on_full)
+
+    def msgq(self):
+        return self._msgq
+
+
+def _known_preamble(fft_length, occupied_tones):
+    """ofdm.py:70-87: the known symbol with odd absolute bins zeroed, and its padded vector."""
+    zeros_on_left = int(math.ceil((fft_length - occupied_tones) / 2.0))
+    ksfreq = list(known_symbols_4512_3[0:occupied_tones])
+    for i in range(len(ksfreq)):
+        if (zeros_on_left + i) & 1:
+            ksfreq[i] = 0
+    padded = fft_length * [0, ]
+    padded[zeros_on_left: zeros_on_left + occupied_tones] = ksfreq
+    return ksfreq, padded
+
+
+# /////////////////////////////////////////////////////////////////////////////
+#                   mod/demod with packets as i/o
+# /////////////////////////////////////////////////////////////////////////////
+
+class ofdm_mod:
+    """
+    Modulates an OFDM stream. Based on the options fft_length, occupied_tones, and cp_length, this
+    creates OFDM symbols using a specified modulation option.  Send packets by calling send_pkt.
+    """
+
+    def __init__(self, options, msgq_limit=2, pad_for_usrp=True, batch_limit=4096, device=None, pad_seed=0):
+        """
+        @param options: pass modulation options from higher layers (fft length, occupied tones, etc.)
+        @param msgq_limit: maximum number of messages in message queue (kept for compatibility: the queue is
+               drained by ``flush()``, which runs automatically every ``batch_limit`` packets and on eof)
+        @param pad_for_usrp: If true, packets are padded such that they end up a multiple of 128 samples
+        """
+        self._pad_for_usrp = pad_for_usrp
+        self._modulation = options.modulation
+        self._fft_length = options.fft_length
+        self._occupied_tones = options.occupied_tones
+        self._cp_length = options.cp_length
+        self._msgq_limit = msgq_limit
+        self._batch_limit = max(1, int(batch_limit))
+
+        ksfreq, padded = _known_preamble(self._fft_length, self._occupied_tones)
+        self.preambles = (padded,)
+        arity = MODS[self._modulation]                      # KeyError for an unknown modulation (ofdm.py:92)
+        self._arity = arity
+        # ofdm_mod scales by 1/sqrt(N) only; transmit_path owns the amplitude stage (transmit_path.py:48)
+        self._engine = OfdmEngine(self._fft_length, self._occupied_tones, self._cp_length, self._modulation,
+                                  tx_amplitude=1.0, device=device, pad_seed=pad_seed)
+        self._pkt_input = _pkt_input(self._batch_limit, self.flush)
+        self._sinks = []
+        self._frames_sent = 0
+        self._eof = False
+        self._lock = threading.Lock()
+        # attribute names of the reference blocks (ofdm.py:111-114): the stages are fused into one kernel
+        self.ifft = self.cp_adder = self.scale = self._engine
+        if options.verbose:
+            self._print_verbage()
+        self._log = bool(getattr(options, "log", False))
+
+    # -- flowgraph replacement ------------------------------------------------------------------
+    def connect(self, sink):
+        """sink: callable(samples) or object with .feed(samples); samples is a complex64 cuda tensor."""
+        self._sinks.append(sink)
+        return sink
+
+    def modulate(self):
+        """Drain the packet queue: returns a complex64 cuda tensor (frames back to back), or None."""
+        import torch
+        with self._lock:
+            pkts = []
+            q = self._pkt_input.msgq()
+            while True:
+                m = q.delete_head_nowait()
+                if m is None:
+                    break
+                if m.type() == 1:
+                    self._eof = True
+                    continue
+                pkts.append(m.to_string())
+            if not pkts:
+                return None
+            off = np.zeros(len(pkts) + 1, dtype=np.int64)
+            np.cumsum([len(p) for p in pkts], out=off[1:])
+            host = torch.frombuffer(bytearray(b"".join(pkts)), dtype=torch.uint8)
+            dev = host.to(self._engine.dev, non_blocking=False)
+            out = self._engine.modulate(dev, off, first_frame=self._frames_sent)
+            self._frames_sent += len(pkts)
+            if self._log:
+                out.cpu().numpy().tofile("ofdm_cp_adder_c.dat")        # same name/format as ofdm.py:130-131
+            return out
+
+    def flush(self):
+        out = self.modulate()
+        if out is not None:
+            for s in self._sinks:
+                (s.feed if hasattr(s, "feed") else s)(out)
+        return out
+
+    def send_pkt(self, payload='', eof=False):
+        """
+        Send the payload.
+
+        @param payload: data to send
+        @type payload: bytes (str is encoded latin-1)
+        """
+        if eof:
+            msg = message(1)          # tell self._pkt_input we're not sending any more packets
+        else:
+            pkt = ofdm_packet_utils.make_packet(payload, 1, 1, self._pad_for_usrp, whitening=True)
+            msg = message_from_string(pkt)
+        self._pkt_input.msgq().insert_tail(msg)
+        if eof:
+            self.flush()
+
+    @staticmethod
+    def add_options(normal, expert):
+        """
+        Adds OFDM-specific options to the Options Parser
+        """
+        normal.add_option("-m", "--modulation", type="string", default="bpsk",
+                          help="set modulation type (bpsk, qpsk, 8psk, qam{16,64}) [default=%default]")
+        expert.add_option("", "--fft-length", type="int", default=512,
+                          help="set the number of FFT bins [default=%default]")
+        expert.add_option("", "--occupied-tones", type="int", default=200,
+                          help="set the number of occupied FFT bins [default=%default]")
+        expert.add_option("", "--cp-length", type="int", default=128,
+                          help="set the number of bits in the cyclic prefix [default=%default]")
+
+    def _print_verbage(self):
+        """
+        Prints information about the OFDM modulator
+        """
+        print("\nOFDM Modulator:")
+        print("Modulation Type: %s" % (self._modulation))
+        print("FFT length:      %3d" % (self._fft_length))
+        print("Occupied Tones:  %3d" % (self._occupied_tones))
+        print("CP length:       %3d" % (self._cp_length))
+
+
+class ofdm_demod:
+    """
+    Demodulates a received OFDM stream. Based on the options fft_length, occupied_tones, and cp_length,
+    this performs synchronization, FFT, and demodulation of incoming OFDM symbols and passes packets up
+    to a higher layer via the callback.
+    """
+
+    def __init__(self, options, callback=None, device=None, max_pkt_bytes=4096):
+        """
+        @param options: pass modulation options from higher layers (fft length, occupied tones, etc.)
+        @param callback:  function of two args: ok, payload
+        @type callback: ok: bool; payload: bytes
+        """
+        self._rcvd_pktq = msg_queue()          # holds packets from the PHY
+        self._modulation = options.modulation
+        self._fft_length = options.fft_length
+        self._occupied_tones = options.occupied_tones
+        self._cp_length = options.cp_length
+        self._snr = options.snr                # parsed, unused by the live "pn" synchroniser (ofdm.py:208)
+
+        ksfreq, _ = _known_preamble(self._fft_length, self._occupied_tones)
+        self.preambles = (ksfreq,)
+        self._arity = MODS[self._modulation]
+        self._engine = OfdmEngine(self._fft_length, self._occupied_tones, self._cp_length, self._modulation,
+                                  device=device, max_pkt_bytes=max_pkt_bytes)
+        self.ofdm_recv = self.ofdm_demod = self._engine
+        self._log = bool(getattr(options, "log", False))
+        if options.verbose:
+            self._print_verbage()
+        self._watcher = _queue_watcher_thread(self._rcvd_pktq, callback)
+        self.last = None
+
+    def feed(self, samples, max_frames=None):
+        """Run the receiver on one buffer of complex64 samples (cuda tensor, or host array copied to the
+        device) and queue every packet the frame sink produced for the watcher thread.  Each call is a
+        self-contained stream (filter history, detector average and NCO phase start from zero)."""
+        import torch
+        if not isinstance(samples, torch.Tensor):
+            samples = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.complex64))
+        if samples.device.type != "cuda":
+            samples = samples.to(self._engine.dev)
+        res = self._engine.demodulate(samples.contiguous(), max_frames=max_frames)
+        self.last = res
+        for ok, payload in res.packets:
+            self._rcvd_pktq.insert_tail(message(0, 0, 0, payload) if False else _rx_message(ok, payload))
+        return res
+
+    def wait(self, timeout=None):
+        """Block until the watcher has delivered everything queued so far."""
+        self._watcher.drain(timeout)
+
+    @staticmethod
+    def add_options(normal, expert):
+        """
+        Adds OFDM-specific options to the Options Parser
+        """
+        normal.add_option("-m", "--modulation", type="string", default="bpsk",
+                          help="set modulation type (bpsk or qpsk) [default=%default]")
+        expert.add_option("", "--fft-length", type="int", default=512,
+                          help="set the number of FFT bins [default=%default]")
+        expert.add_option("", "--occupied-tones", type="int", default=200,
+                          help="set the number of occupied FFT bins [default=%default]")
+        expert.add_option("", "--cp-length", type="int", default=128,
+                          help="set the number of bits in the cyclic prefix [default=%default]")
+
+    def _print_verbage(self):
+        """
+        Prints information about the OFDM demodulator
+        """
+        print("\nOFDM Demodulator:")
+        print("Modulation Type: %s" % (self._modulation))
+        print("FFT length:      %3d" % (self._fft_length))
+        print("Occupied Tones:  %3d" % (self._occupied_tones))
+        print("CP length:       %3d" % (self._cp_length))
+
+
+class _rx_message(message):
+    """A received packet whose dewhitening and CRC check already ran on the device (ofdm_rx_finish)."""
+
+    def __init__(self, ok, payload):
+        message.__init__(self, 0, 0, 0, payload)
+        self.ok = bool(ok)
+
+
+class _queue_watcher_thread(threading.Thread):
+    """ofdm.py:290-305: pops received packets and fires callback(ok, payload), one at a time, in order,
+    for bad CRCs too."""
+
+    def __init__(self, rcvd_pktq, callback):
+        threading.Thread.__init__(self)
+        self.daemon = True
+        self.rcvd_pktq = rcvd_pktq
+        self.callback = callback
+        self.keep_running = True
+        self._pending = 0
+        self._cv = threading.Condition()
+        _insert = rcvd_pktq.insert_tail
+
+        def counted_insert(msg):
+            with self._cv:
+                self._pending += 1
+            _insert(msg)
+        rcvd_pktq.insert_tail = counted_insert
+        self.start()
+
+    def run(self):
+        while self.keep_running:
+            msg = self.rcvd_pktq.delete_head()
+            try:
+                if isinstance(msg, _rx_message):
+                    ok, payload = msg.ok, msg.to_string()
+                else:
+                    ok, payload = ofdm_packet_utils.unmake_packet(msg.to_string())
+                if self.callback:
+                    self.callback(ok, payload)
+            finally:
+                with self._cv:
+                    self._pending -= 1
+                    self._cv.notify_all()
+
+    def drain(self, timeout=None):
+        with self._cv:
+            self._cv.wait_for(lambda: self._pending == 0, timeout)
+
+
+# The reference's 4512 known symbols (ofdm.py:310-325, "i = [2*random.randint(0,1)-1 for i in range(4512)]"),
+# kept as a packed bit string (bit = 1 <=> +1, LSB first); tests/test_tables.py pins the SHA-256 of the
+# expanded list against the reference file.
+def _expand_known_symbols():
+    import base64
+    packed = np.frombuffer(base64.b85decode(
+        "G%Yn+z+C((y^1&>9SHr$Q%^4)KPP8_N!hz@_mT_hMPvTxbqaQkWSi~Wu8B!QR)zkQ)?zPm4aH;<^;58S?h8z>gq=eL_VMpm?DBrxa2xPsU>54"
+        ";i5Ru+gfA;GH$bMdh_xJhbN6kQ9)ryE|IZ?)lhgjCkOlAekgb&5m$FbNK%Pmv|0=(<v(p0LR%@q-)c0D`wL6(X^8?*2YAJeZE+~CFpi;G2eEiD"
+        "Odn=*7&a>x+PX~&MIuu~7%bh%cQomBX^95JLBM0i)MRP!ug~mrlXB7BpNLLXlee6tz#FW&H?aNNkYkly63%RC$RBee%Aat=1+U^cPDrIKt|8XH"
+        "S3gA?LIbFBq63Ljc%e$T{6tVZn#a|2pXi-U}YxJByY%$CtU{u*{3~>*h>h31-=c!WIGcg<p3~_<>J_8m%OCM-bl@>7_oL&`GTCGH;-X2I3?Yl"
+        "}b)m2yTpd5)>DM{#Xip|l$!o3)kCK`q9U<LEsg-M(yP~uH(k4z5oFj20cdCeIh^m;Gcvohp>V6iA65@;>N%zpw7P<7^|Fg@F7nw$CRx~H&uR!"
+        "4k~i5XL-hcE<7jm>uHxDL<<8tR3xCLADjp691EO9&P=s~@I7i>0L!lW5T9Zhj22RarGG8+Ti-M`_e;Xci|P-7!lnOKc(gdR8LNP`45$hx8#Hay"
+        "1_Nc3F)TUXg|=B}+BSL*;>0dPw{g&!t;!18_z1Te0emdM_YY"), dtype=np.uint8)
+    bits = np.unpackbits(packed, bitorder="little")[:4512]
+    return [int(2 * int(b) - 1) for b in bits]
+
+
+known_symbols_4512_3 = _expand_known_symbols()

@@ -1,0 +1,1060 @@
+"""CPU oracle (NumPy) for the OFDM baseband hot path of rubiruchi/ofdm_uhd.
+
+TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this
+module; the product (``ofdm_uhd_b200``) never does.
+
+PARITY UNPINNED: the arithmetic of this path lives in GNU Radio 3.6.0 C++
+blocks (gr-digital / gnuradio-core; version evidence /root/reference/ofdm.py:29,
+output.txt:1-3) that are not vendored in the reference tree, and neither
+GNU Radio nor Python 2 exists in this environment.  This file restates the
+published algorithm of those blocks as wired by the reference's own Python
+(ofdm.py:62-118,202-261; ofdm_receiver.py~:69-142; ofdm_packet_utils.py:84-191;
+secondary_tx.py:163-331), following SURVEY.md Appendix A.  The only in-tree
+data that pin tables exactly (whitening mask, known symbols, docstring
+examples) are checked in tests/test_oracle_tables.py.
+
+Precision policy: every inter-block stream is float32 /
+complex64; FIR / sliding sums, correlation sums, the slicer error sum and the
+NCO phase accumulate in float64 and are rounded once; every comparison is made
+on the rounded float32 values.  Elementwise float32 products/sums are rounded
+individually (no fused multiply-add), which is what the CUDA kernels
+reproduce with __fmul_rn/__fadd_rn.
+"""
+from __future__ import annotations
+
+import base64
+import math
+import struct
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+F32 = np.float32
+C64 = np.complex64
+
+# --------------------------------------------------------------------------
+# Tables pinned by the reference tree
+# --------------------------------------------------------------------------
+
+_KNOWN_B85 = (
+    "G%Yn+z+C((y^1&>9SHr$Q%^4)KPP8_N!hz@_mT_hMPvTxbqaQkWSi~Wu8B!QR)zkQ)?zPm4aH;<^;58S?h8z>gq=eL_VMpm?DBrxa2xPsU>54"
+    ";i5Ru+gfA;GH$bMdh_xJhbN6kQ9)ryE|IZ?)lhgjCkOlAekgb&5m$FbNK%Pmv|0=(<v(p0LR%@q-)c0D`wL6(X^8?*2YAJeZE+~CFpi;G2eEiD"
+    "Odn=*7&a>x+PX~&MIuu~7%bh%cQomBX^95JLBM0i)MRP!ug~mrlXB7BpNLLXlee6tz#FW&H?aNNkYkly63%RC$RBee%Aat=1+U^cPDrIKt|8XH"
+    "S3gA?LIbFBq63Ljc%e$T{6tVZn#a|2pXi-U}YxJByY%$CtU{u*{3~>*h>h31-=c!WIGcg<p3~_<>J_8m%OCM-bl@>7_oL&`GTCGH;-X2I3?Yl"
+    "}b)m2yTpd5)>DM{#Xip|l$!o3)kCK`q9U<LEsg-M(yP~uH(k4z5oFj20cdCeIh^m;Gcvohp>V6iA65@;>N%zpw7P<7^|Fg@F7nw$CRx~H&uR!"
+    "4k~i5XL-hcE<7jm>uHxDL<<8tR3xCLADjp691EO9&P=s~@I7i>0L!lW5T9Zhj22RarGG8+Ti-M`_e;Xci|P-7!lnOKc(gdR8LNP`45$hx8#Hay"
+    "1_Nc3F)TUXg|=B}+BSL*;>0dPw{g&!t;!18_z1Te0emdM_YY"
+)
+
+
+def known_symbols_4512() -> np.ndarray:
+    """The 4512 +/-1 preamble symbols of ofdm.py:310-325 (``known_symbols_4512_3``),
+    stored here as a packed bit string (bit=1 <=> +1, LSB-first)."""
+    packed = np.frombuffer(base64.b85decode(_KNOWN_B85), dtype=np.uint8)
+    bits = np.unpackbits(packed, bitorder="little")[:4512]
+    return (2 * bits.astype(np.int32) - 1).astype(np.int32)
+
+
+def whitening_mask() -> np.ndarray:
+    """``random_mask_tuple`` of ofdm_packet_utils.py:195-451 (4096 bytes).
+
+    The reference comment (:194) says it is a 15-bit LFSR output: it is PN15
+    (x^15+x^14+1) seeded with 14 ones, packed LSB-first, for 4094 bytes, after
+    which the generator of the table restarted (the last two bytes repeat the
+    first two)."""
+    nbits = 4094 * 8
+    g = np.zeros(nbits, dtype=np.uint8)
+    g[:14] = 1
+    for n in range(15, nbits):
+        g[n] = g[n - 14] ^ g[n - 15]
+    m = np.packbits(g, bitorder="little")
+    return np.concatenate([m, m[:2]]).astype(np.uint8)
+
+
+_MASK: Optional[np.ndarray] = None
+
+
+def _mask() -> np.ndarray:
+    global _MASK
+    if _MASK is None:
+        _MASK = whitening_mask()
+    return _MASK
+
+
+# --------------------------------------------------------------------------
+# A.1 packet framing  (ofdm_packet_utils.py:84-191, upstream crc.py / crc32)
+# --------------------------------------------------------------------------
+
+def _crc_table() -> np.ndarray:
+    t = np.zeros(256, dtype=np.uint32)
+    for i in range(256):
+        c = i << 24
+        for _ in range(8):
+            c = ((c << 1) ^ 0x04C11DB7) & 0xFFFFFFFF if c & 0x80000000 else (c << 1) & 0xFFFFFFFF
+        t[i] = c
+    return t
+
+
+_CRC_T = _crc_table()
+
+
+def crc32_gr(data: bytes) -> int:
+    """digital.crc32 (digital_swig.py:3151-3168): init all ones, MSB-first
+    polynomial 0x04C11DB7, unreflected, final one's complement (CRC-32/BZIP2)."""
+    crc = 0xFFFFFFFF
+    tab = _CRC_T
+    for b in data:
+        crc = (int(tab[(b ^ (crc >> 24)) & 0xFF]) ^ (crc << 8)) & 0xFFFFFFFF
+    return crc ^ 0xFFFFFFFF
+
+
+def whiten(data: bytes, offset: int = 0) -> bytes:
+    """ofdm_packet_utils.py:84-90."""
+    a = np.frombuffer(data, dtype=np.uint8)
+    return (a ^ _mask()[offset:offset + len(a)]).tobytes()
+
+
+def make_header(payload_len: int, whitener_offset: int = 0) -> bytes:
+    """ofdm_packet_utils.py:93-97."""
+    v = ((whitener_offset & 0xF) << 12) | (payload_len & 0x0FFF)
+    return struct.pack("!HH", v, v)
+
+
+def npadding_bytes(pkt_byte_len: int, sps: int, bps: int) -> int:
+    """ofdm_packet_utils.py:145-166."""
+    byte_modulus = (math.lcm(128 // 8, sps) * bps) // sps
+    r = pkt_byte_len % byte_modulus
+    return 0 if r == 0 else byte_modulus - r
+
+
+def make_packet(payload: bytes, sps: int = 1, bps: int = 1, pad_for_usrp: bool = True,
+                whitener_offset: int = 0, whitening: bool = True) -> bytes:
+    """ofdm_packet_utils.py:99-143."""
+    pw = payload + struct.pack("!I", crc32_gr(payload))
+    L = len(pw)
+    if L > 4096:
+        raise ValueError("len(payload) must be in [0, 4096]")
+    hdr = make_header(L, whitener_offset)
+    body = pw + b"\x55"
+    if pad_for_usrp:
+        body += b"\x55" * npadding_bytes(len(hdr) + len(body), sps, bps)
+    return hdr + (whiten(body, whitener_offset) if whitening else body)
+
+
+def unmake_packet(data: bytes, whitener_offset: int = 0, dewhitening: bool = True) -> Tuple[bool, bytes]:
+    """ofdm_packet_utils.py:169-191 + upstream crc.check_crc32."""
+    s = whiten(data, whitener_offset) if dewhitening else data
+    if len(s) < 4:
+        return False, b""
+    body, tail = s[:-4], s[-4:]
+    return crc32_gr(body) == struct.unpack("!I", tail)[0], body
+
+
+# --------------------------------------------------------------------------
+# A.2 constellations  (psk.py:26-43, qam.py:28-64, ofdm.py:88-101)
+# --------------------------------------------------------------------------
+
+def psk_gray_constellation(m: int) -> List[complex]:
+    k = int(round(math.log2(m)))
+    out = []
+    for i in range(m):
+        b = [0, 0, 0]
+        for j in range(k):
+            b[3 - k + j] = (i >> (k - j - 1)) & 1
+        theta = -(2 * b[0] - 1) * (2 * math.pi / m) * (b[0] + abs(b[1] - b[2]) + 2 * b[1])
+        out.append(complex(math.cos(theta), math.sin(theta)))
+    return out
+
+
+def qam_constellation(m: int) -> List[complex]:
+    k = int(round(math.log2(m)))
+
+    def level(bits: Sequence[int]) -> float:
+        ss = 0.0
+        n = len(bits)
+        for ii in range(n):
+            rr = 0
+            for jj in range(n - ii):
+                rr = abs(bits[jj] - rr)
+            ss += rr * 2.0 ** (ii + 1)
+        return ss + 1
+
+    pts, coeff = [], 1
+    for i in range(m):
+        a = (i >> (k - 1)) & 1
+        b = (i >> (k - 2)) & 1
+        bi = [(i >> (k - j - 1)) & 1 for j in range(2, k, 2)]
+        bq = [(i >> (k - j - 1)) & 1 for j in range(3, k, 2)]
+        re = (2 * a - 1) * level(bi)
+        im = (2 * b - 1) * level(bq)
+        coeff = max(coeff, re, im)
+        pts.append(complex(re, im))
+    return [complex(p.real / coeff, p.imag / coeff) for p in pts]
+
+
+MODS = {"bpsk": 2, "qpsk": 4, "8psk": 8, "qam8": 8, "qam16": 16, "qam64": 64, "qam256": 256}
+
+
+def constellation_for(modulation: str) -> np.ndarray:
+    """Rotated constellation exactly as ofdm.py:88-101 builds it, as complex64."""
+    arity = MODS[modulation]            # KeyError for unknown names, like ofdm.py:92
+    rot = (0.707 + 0.707j) if modulation == "qpsk" else 1
+    if "psk" in modulation:
+        base = psk_gray_constellation(arity)
+    else:
+        base = qam_constellation(arity)
+    return np.array([p * rot for p in base], dtype=np.complex128).astype(C64)
+
+
+# --------------------------------------------------------------------------
+# Layout
+# --------------------------------------------------------------------------
+
+@dataclass
+class Layout:
+    fft_length: int = 512
+    occupied_tones: int = 200
+    cp_length: int = 128
+    modulation: str = "bpsk"
+    zl: int = field(init=False)
+    ncar: int = field(init=False)
+    nbits: int = field(init=False)
+    M: int = field(init=False)
+
+    def __post_init__(self):
+        N, occ = self.fft_length, self.occupied_tones
+        if occ > N:
+            raise ValueError("occupied_tones > fft_length")   # upstream std::invalid_argument
+        self.zl = int(math.ceil((N - occ) / 2.0))            # ofdm.py:71
+        self.M = MODS[self.modulation]
+        self.nbits = int(round(math.log2(self.M)))
+        self.const = constellation_for(self.modulation)
+        self.sink_map = sink_carrier_map(occ)                 # indices into the occ-wide vector
+        self.tx_map = mapper_carrier_map(N, occ)              # indices into the N-wide vector
+        self.ncar = len(self.sink_map)
+        ks = known_symbols_4512()[:occ].astype(np.float64)
+        for i in range(occ):
+            if (self.zl + i) & 1:
+                ks[i] = 0                                    # ofdm.py:73-77
+        self.ks = ks.astype(F32)
+
+    @property
+    def sym_len(self) -> int:
+        return self.fft_length + self.cp_length
+
+    def n_data_syms(self, pkt_len: int) -> int:
+        return n_data_symbols(pkt_len, self.ncar, self.nbits)
+
+
+def _carrier_hex(occ: int) -> str:
+    """A.3: the default "FE7F" map widened to ``occ`` tones (upstream mapper/sink ctor)."""
+    carriers = "FE7F"
+    diff = occ - 4 * len(carriers)
+    while diff > 7:
+        carriers = "f" + carriers + "f"
+        diff -= 8
+    if diff > 0:
+        diff_left = int(math.ceil(diff / 2.0))
+        diff_right = diff - diff_left
+        left = "%x" % ((1 << diff_left) - 1)
+        right = "%x" % (0xF ^ ((1 << diff_right) - 1))
+        carriers = left + carriers + right
+    return carriers
+
+
+def sink_carrier_map(occ: int) -> np.ndarray:
+    idx = []
+    for i, ch in enumerate(_carrier_hex(occ)):
+        c = int(ch, 16)
+        for j in range(4):
+            if (c >> (3 - j)) & 1:
+                idx.append(4 * i + j)
+    return np.array(idx, dtype=np.int32)
+
+
+def mapper_carrier_map(N: int, occ: int) -> np.ndarray:
+    hexs = _carrier_hex(occ)
+    pad = (N // 4 - len(hexs)) // 2
+    idx = []
+    for i, ch in enumerate(hexs):
+        c = int(ch, 16)
+        for j in range(4):
+            if (c >> (3 - j)) & 1:
+                idx.append(4 * (i + pad) + j)
+    return np.array(idx, dtype=np.int32)
+
+
+def n_data_symbols(pkt_len: int, ncar: int, nbits: int) -> int:
+    """Number of OFDM data symbols the mapper emits for a packet (A.4)."""
+    return max(1, -(-(8 * pkt_len) // (ncar * nbits))) if pkt_len > 0 else 1
+
+
+# --------------------------------------------------------------------------
+# pad symbols (the reference uses libc rand(); the oracle takes explicit indices)
+# --------------------------------------------------------------------------
+
+_U64 = np.uint64
+
+
+def pad_index(seed: int, frame, symbol, carrier, M: int):
+    """splitmix64(seed ^ frame<<32 ^ symbol<<16 ^ carrier) & (M-1); vectorised."""
+    with np.errstate(over="ignore"):
+        x = (_U64(seed) ^ (np.asarray(frame, dtype=_U64) << _U64(32))
+             ^ (np.asarray(symbol, dtype=_U64) << _U64(16)) ^ np.asarray(carrier, dtype=_U64))
+        z = x + _U64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> _U64(30))) * _U64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> _U64(27))) * _U64(0x94D049BB133111EB)
+        z = z ^ (z >> _U64(31))
+    return (z & _U64(M - 1)).astype(np.int64)
+
+
+# --------------------------------------------------------------------------
+# A.4 mapper (upstream ofdm_mapper_bcv::work; call site ofdm.py:106-107)
+# --------------------------------------------------------------------------
+
+def mapper_sequential(pkt: bytes, lay: Layout, frame: int, seed: int) -> np.ndarray:
+    """Line-by-line restatement of the upstream residue state machine.
+    Returns symbol indices [n_syms, ncar] (pad carriers included)."""
+    ncar, nbits = lay.ncar, lay.nbits
+    out = []
+    msg_offset = 0
+    bit_offset = 0
+    resid = 0
+    nresid = 0
+    msgbyte = 0
+    n = len(pkt)
+    sym = 0
+    done = False
+    while not done:
+        row = np.zeros(ncar, dtype=np.int64)
+        i = 0
+        while msg_offset < n and i < ncar:
+            if bit_offset == 0:
+                msgbyte = pkt[msg_offset]
+            if nresid > 0:
+                resid |= (((1 << nresid) - 1) & msgbyte) << (nbits - nresid)
+                row[i] = resid
+                i += 1
+                bit_offset += nresid
+                nresid = 0
+                resid = 0
+            else:
+                if 8 - bit_offset >= nbits:
+                    row[i] = ((1 << nbits) - 1) & (msgbyte >> bit_offset)
+                    bit_offset += nbits
+                    i += 1
+                else:
+                    extra = 8 - bit_offset
+                    resid = ((1 << extra) - 1) & (msgbyte >> bit_offset)
+                    bit_offset += extra
+                    nresid = nbits - extra
+            if bit_offset == 8:
+                bit_offset = 0
+                msg_offset += 1
+        if msg_offset == n:
+            nresid = 0
+            resid = 0
+            if i < ncar:
+                c = np.arange(i, ncar)
+                row[i:] = pad_index(seed, frame, sym, c, lay.M)
+            done = True
+        out.append(row)
+        sym += 1
+    return np.array(out, dtype=np.int64)
+
+
+def mapper_indices(pkt: bytes, lay: Layout, frame: int, seed: int) -> np.ndarray:
+    """Closed form of the mapper: LSB-first bitstream cut into nbits groups."""
+    ncar, nbits = lay.ncar, lay.nbits
+    nsym = lay.n_data_syms(len(pkt))
+    bits = np.unpackbits(np.frombuffer(pkt, dtype=np.uint8), bitorder="little")
+    ngroups = len(bits) // nbits
+    g = bits[:ngroups * nbits].reshape(ngroups, nbits).astype(np.int64)
+    vals = (g << np.arange(nbits, dtype=np.int64)).sum(axis=1)
+    total = nsym * ncar
+    out = np.empty(total, dtype=np.int64)
+    ng = min(ngroups, total)
+    out[:ng] = vals[:ng]
+    if ng < total:
+        k = np.arange(ng, total)
+        out[ng:] = pad_index(seed, frame, k // ncar, k % ncar, lay.M)
+    return out.reshape(nsym, ncar)
+
+
+def preamble_freq(lay: Layout) -> np.ndarray:
+    """N-wide frequency-domain preamble vector (ofdm.py:82-87)."""
+    X = np.zeros(lay.fft_length, dtype=C64)
+    X[lay.zl:lay.zl + lay.occupied_tones] = lay.ks
+    return X
+
+
+def _ifft_unnorm(X: np.ndarray) -> np.ndarray:
+    """gr.fft_vcc(N, False, [], True): ifftshift then unnormalised backward FFT."""
+    N = X.shape[-1]
+    return (np.fft.ifft(np.fft.ifftshift(X.astype(np.complex128), axes=-1), axis=-1) * N).astype(C64)
+
+
+def _fft_shift(v: np.ndarray) -> np.ndarray:
+    """gr.fft_vcc(N, True, [1]*N, True): forward FFT then fftshift."""
+    return np.fft.fftshift(np.fft.fft(v.astype(np.complex128), axis=-1), axes=-1).astype(C64)
+
+
+def tx_symbols_freq(pkt: bytes, lay: Layout, frame: int, seed: int) -> np.ndarray:
+    """[1 + n_data, N] frequency-domain vectors of one frame (preamble first)."""
+    idx = mapper_indices(pkt, lay, frame, seed)
+    X = np.zeros((idx.shape[0] + 1, lay.fft_length), dtype=C64)
+    X[0] = preamble_freq(lay)
+    X[1:, lay.tx_map] = lay.const[idx]
+    return X
+
+
+def tx_modulate(pkts: Sequence[bytes], lay: Layout, amp: float = 0.25, seed: int = 0,
+                first_frame: int = 0) -> np.ndarray:
+    """mapper -> insert_preamble -> IFFT -> cyclic prefix -> *1/sqrt(N) -> *amp
+    (ofdm.py:106-117, transmit_path.py:48-62).  Frames are concatenated."""
+    N, cp = lay.fft_length, lay.cp_length
+    s1 = F32(1.0 / math.sqrt(N))
+    s2 = F32(max(0.0, min(amp, 1)))
+    outs = []
+    for f, pkt in enumerate(pkts):
+        X = tx_symbols_freq(pkt, lay, first_frame + f, seed)
+        x = _ifft_unnorm(X)
+        x = np.concatenate([x[:, N - cp:], x], axis=1).reshape(-1)
+        re = (x.real.astype(F32) * s1) * s2
+        im = (x.imag.astype(F32) * s1) * s2
+        outs.append((re + 1j * im).astype(C64))
+    return np.concatenate(outs) if outs else np.zeros(0, dtype=C64)
+
+
+# --------------------------------------------------------------------------
+# A.5 channel filter  (ofdm_receiver.py~:69-76)
+# --------------------------------------------------------------------------
+
+def firdes_low_pass_hamming(gain: float, fs: float, fc: float, tw: float) -> np.ndarray:
+    """gr.firdes.low_pass(gain, fs, fc, tw, WIN_HAMMING)."""
+    ntaps = int(53.0 * fs / (22.0 * tw))
+    if ntaps % 2 == 0:
+        ntaps += 1
+    M0 = (ntaps - 1) // 2
+    w = 0.54 - 0.46 * np.cos(2 * np.pi * np.arange(ntaps) / (ntaps - 1))
+    fw = 2 * np.pi * fc / fs
+    taps = np.zeros(ntaps, dtype=np.float64)
+    for n in range(-M0, M0 + 1):
+        if n == 0:
+            taps[n + M0] = fw / np.pi * w[n + M0]
+        else:
+            taps[n + M0] = math.sin(n * fw) / (n * np.pi) * w[n + M0]
+    fmax = taps[M0]
+    for n in range(1, M0 + 1):
+        fmax += 2 * taps[n + M0]
+    taps *= gain / fmax
+    return taps.astype(F32)
+
+
+def chan_filter_taps(lay: Layout) -> np.ndarray:
+    bw = (float(lay.occupied_tones) / float(lay.fft_length)) / 2.0
+    tb = bw * 0.08
+    return firdes_low_pass_hamming(1.0, 1.0, bw + tb, tb)
+
+
+def chan_filter(x: np.ndarray, taps: np.ndarray) -> np.ndarray:
+    """gr.fft_filter_ccc(1, taps): causal linear convolution, zero history."""
+    from scipy.signal import oaconvolve
+    if len(x) == 0:
+        return np.zeros(0, dtype=C64)
+    y = oaconvolve(x.astype(np.complex128), taps.astype(np.float64))[:len(x)]
+    return y.astype(C64)
+
+
+# --------------------------------------------------------------------------
+# A.6 Schmidl-Cox metric  (upstream ofdm_sync_pn.py; call site ofdm_receiver.py~:97-101)
+# --------------------------------------------------------------------------
+
+def _sliding_sum64(v: np.ndarray, w: int) -> np.ndarray:
+    """sum_{k<w} v[n-k] with zero history, accumulated in float64."""
+    c = np.cumsum(v.astype(np.float64))
+    out = c.copy()
+    out[w:] -= c[:-w]
+    return out
+
+
+def sync_pn_metric(y: np.ndarray, N: int, cp: int):
+    """Returns (mf, P_re, P_im) as float32 arrays."""
+    n = len(y)
+    h = N // 2
+    yr = y.real.astype(F32)
+    yi = y.imag.astype(F32)
+    dr = np.zeros(n, dtype=F32)
+    di = np.zeros(n, dtype=F32)
+    if n > h:
+        dr[h:] = yr[:n - h]
+        di[h:] = yi[:n - h]
+    cre = yr * dr + yi * di                      # y * conj(delayed y), float32 ops
+    cim = yi * dr - yr * di
+    e = yr * yr + yi * yi
+    Pr = _sliding_sum64(cre, h).astype(F32)
+    Pi = _sliding_sum64(cim, h).astype(F32)
+    R = _sliding_sum64(e, h).astype(F32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        num = Pr * Pr + Pi * Pi
+        den = R * R
+        Mt = (num / den).astype(F32)
+    tap = np.float64(F32(1.0 / cp))
+    with np.errstate(invalid="ignore"):
+        s = (_sliding_sum64(Mt, cp) * tap).astype(F32)
+        mf = (s + F32(-1.0)).astype(F32)
+    # a windowed FIR recovers from NaN after cp samples; the cumulative form does not.
+    # Nothing downstream can fire after the first NaN (A.7 / C.1), so only mark it.
+    return mf, Pr, Pi
+
+
+# --------------------------------------------------------------------------
+# A.7 peak detector
+# --------------------------------------------------------------------------
+
+ALPHA_F = F32(0.001)
+RISE_F = F32(0.20)
+
+
+def peak_avg(mf: np.ndarray) -> np.ndarray:
+    """IIR average after consuming each sample, float64 state, returned as float32."""
+    from scipy.signal import lfilter
+    a1 = np.float64(ALPHA_F)
+    a2 = 1.0 - a1
+    with np.errstate(invalid="ignore"):
+        avg = lfilter([a1], [1.0, -a2], mf.astype(np.float64))
+    return avg.astype(F32)
+
+
+def peak_detect_sequential(mf: np.ndarray) -> np.ndarray:
+    """The upstream state machine (peak_detector_fb(0.2, 0.2, 30, 0.001)) verbatim,
+    whole-stream semantics.  Pure-Python: small inputs only."""
+    a1 = float(np.float64(ALPHA_F))
+    a2 = 1.0 - a1
+    avg = 0.0
+    state = 0
+    peak = -math.inf
+    ind = 0
+    trig = []
+    i = 0
+    n = len(mf)
+    while i < n:
+        v = mf[i]
+        thr = F32(avg) * RISE_F
+        if state == 0:
+            if v > thr:
+                state = 1
+            else:
+                avg = a1 * float(v) + a2 * avg
+                i += 1
+        else:
+            if v > peak:
+                peak = v
+                ind = i
+                avg = a1 * float(v) + a2 * avg
+                i += 1
+            elif v > thr:
+                avg = a1 * float(v) + a2 * avg
+                i += 1
+            else:
+                trig.append(ind)
+                state = 0
+                peak = -math.inf
+    return np.array(trig, dtype=np.int64)
+
+
+def peak_detect(mf: np.ndarray) -> np.ndarray:
+    """Vectorised equivalent of :func:`peak_detect_sequential`: every sample updates the
+    average exactly once, so ``a[i] = mf[i] > 0.2*avg[i-1]`` is a pure function of the input;
+    a trigger is the first arg-max of each run of ``a`` (extended while a later sample beats
+    the running peak), and a run still open at the end of the stream emits nothing."""
+    n = len(mf)
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    avg = peak_avg(mf)
+    prev = np.concatenate([[F32(0)], avg[:-1]]).astype(F32)
+    with np.errstate(invalid="ignore"):
+        a = mf > prev * RISE_F
+    ai = a.astype(np.int8)
+    d = np.diff(ai)
+    starts = np.flatnonzero(d == 1) + 1
+    ends = np.flatnonzero(d == -1) + 1
+    if a[0]:
+        starts = np.concatenate([[0], starts])
+    if a[-1]:
+        ends = np.concatenate([ends, [n]])
+    trig = []
+    r = 0
+    nr = len(starts)
+    while r < nr:
+        i, e = int(starts[r]), int(ends[r])
+        seg = mf[i:e]
+        k = int(np.argmax(seg))
+        peak = seg[k]
+        ind = i + k
+        j = e
+        while j < n and (mf[j] > peak or a[j]):
+            if mf[j] > peak:
+                peak = mf[j]
+                ind = j
+            j += 1
+        if j >= n:
+            break
+        trig.append(ind)
+        r = int(np.searchsorted(starts, j + 1, side="left"))
+    return np.array(trig, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------
+# A.8 / A.9  NCO phase and sampler plan
+# --------------------------------------------------------------------------
+
+@dataclass
+class Plan:
+    trig: np.ndarray          # all trigger indices
+    ang: np.ndarray           # float32 angle latched at each trigger
+    phi0: np.ndarray          # float64 NCO phase just before each trigger takes effect
+    vec_start: np.ndarray     # first sample of every vector the sampler emits
+    vec_flag: np.ndarray      # 1 = preamble vector
+    frame_trig: np.ndarray    # index into trig of each frame the sampler emits
+    n_data: np.ndarray        # data vectors emitted after each frame's preamble vector
+
+
+def sampler_sim(trig: np.ndarray, n: int, N: int, L: int, timeout_max: int = 1000):
+    """digital.ofdm_sampler(N, N+cp, timeout=1000) (ofdm_receiver.py~:125; digital_swig.py:4717-4726)
+    run call by call over a whole stream of ``n`` samples.  A call at read pointer ``pos`` reads
+    trigger[pos+N .. pos+L+N], so it runs only while pos+L+N < n."""
+    trig = np.asarray(trig, dtype=np.int64)
+    starts, flags, ftrig, ndata = [], [], [], []
+    pos = 0
+    state = 0            # 0 NO_SIG, 2 FRAME
+    timeout = 0
+    while pos + L + N < n:
+        lo = int(np.searchsorted(trig, pos + N, side="left"))
+        if lo < len(trig) and trig[lo] <= pos + L + N:
+            t = int(trig[lo])
+            starts.append(t - N + 1)
+            flags.append(1)
+            ftrig.append(lo)
+            ndata.append(0)
+            timeout = timeout_max
+            state = 2
+            pos = t - N + 1
+        elif state == 2:
+            starts.append(pos + L)
+            flags.append(0)
+            ndata[-1] += 1
+            timeout -= 1
+            if timeout == 0:
+                state = 0
+            pos += L
+        else:
+            pos += L + 1
+    return (np.array(starts, dtype=np.int64), np.array(flags, dtype=np.uint8),
+            np.array(ftrig, dtype=np.int64), np.array(ndata, dtype=np.int64))
+
+
+def plan_frames(trig: np.ndarray, ang: np.ndarray, n: int, N: int, L: int, timeout: int = 1000) -> Plan:
+    trig = np.asarray(trig, dtype=np.int64)
+    ang = np.asarray(ang, dtype=F32)
+    T = len(trig)
+    step = (-2.0 / N) * ang.astype(np.float64)
+    phi0 = np.zeros(T, dtype=np.float64)
+    for k in range(1, T):
+        phi0[k] = phi0[k - 1] + step[k - 1] * float(trig[k] - trig[k - 1])
+    vs, vf, ft, nd = sampler_sim(trig, n, N, L, timeout)
+    return Plan(trig, ang, phi0, vs, vf, ft, nd)
+
+
+def nco_phase_at(plan: Plan, idx: np.ndarray, N: int) -> np.ndarray:
+    """float64 NCO phase phi[n] for sample indices ``idx`` (A.8, closed form)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    if len(plan.trig) == 0:
+        return np.zeros(idx.shape, dtype=np.float64)
+    k = np.searchsorted(plan.trig, idx, side="right") - 1
+    step = (-2.0 / N) * plan.ang.astype(np.float64)
+    kk = np.maximum(k, 0)
+    ph = plan.phi0[kk] + step[kk] * (idx - plan.trig[kk] + 1).astype(np.float64)
+    return np.where(k >= 0, ph, 0.0)
+
+
+def derotate(y: np.ndarray, idx: np.ndarray, plan: Plan, N: int) -> np.ndarray:
+    ph = nco_phase_at(plan, idx, N)
+    cs = np.cos(ph).astype(F32)
+    sn = np.sin(ph).astype(F32)
+    yr = y[idx].real.astype(F32)
+    yi = y[idx].imag.astype(F32)
+    zr = yr * cs - yi * sn
+    zi = yr * sn + yi * cs
+    return (zr + 1j * zi).astype(C64)
+
+
+# --------------------------------------------------------------------------
+# A.10 frame acquisition, A.11 frame sink
+# --------------------------------------------------------------------------
+
+def _cmul(ar, ai, br, bi):
+    return (ar * br - ai * bi).astype(F32), (ar * bi + ai * br).astype(F32)
+
+
+def _cdiv(ar, ai, br, bi):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = (br * br + bi * bi).astype(F32)
+        re = ((ar * br + ai * bi).astype(F32) / t).astype(F32)
+        im = ((ai * br - ar * bi).astype(F32) / t).astype(F32)
+    return re, im
+
+
+def _expj32(ph32) -> Tuple[np.float32, np.float32]:
+    p = np.float64(ph32)
+    return F32(np.cos(p)), F32(np.sin(p))
+
+
+class FrameAcquisition:
+    """digital.ofdm_frame_acquisition(occ, N, cp, ks[0], max_fft_shift_len=4)
+    (ofdm_receiver.py~:127-129; digital_swig.py:4316-4330)."""
+
+    MAX_NUM_SYMBOLS = 1000
+
+    def __init__(self, lay: Layout, max_shift: int = 4):
+        self.lay = lay
+        self.max_shift = max_shift
+        occ = lay.occupied_tones
+        ks = lay.ks
+        kd = np.zeros(occ, dtype=F32)
+        for i in range(0, occ - 2, 2):
+            d = ks[i] - ks[i + 2]
+            kd[i] = d * d
+        self.kd = kd
+        self.Hr = np.ones(occ, dtype=F32)
+        self.Hi = np.zeros(occ, dtype=F32)
+        self.delta = 0
+        self.cnt = 1
+
+    def _comp(self, cnt: int):
+        lay = self.lay
+        a = F32(-2.0 * math.pi * self.delta * lay.cp_length)
+        ph = F32(F32(a / F32(lay.fft_length)) * F32(cnt))
+        return _expj32(ph)
+
+    def work(self, S: np.ndarray, flag: int) -> np.ndarray:
+        lay = self.lay
+        N, occ, zl = lay.fft_length, lay.occupied_tones, lay.zl
+        Sr = S.real.astype(F32)
+        Si = S.imag.astype(F32)
+        if flag:
+            self.cnt = 1
+            dr = Sr[:N - 2] - Sr[2:]
+            di = Si[:N - 2] - Si[2:]
+            sd = np.zeros(N, dtype=F32)
+            sd[:N - 2] = dr * dr + di * di
+            best, index = F32(0), 0
+            kd64 = self.kd.astype(np.float64)
+            for i in range(zl - self.max_shift, zl + self.max_shift):
+                s = F32(np.dot(kd64, sd[i:i + occ].astype(np.float64)))
+                if s > best:
+                    best, index = s, i
+            self.delta = index - zl
+            c_r, c_i = self._comp(1)
+            sel_r = Sr[zl + self.delta: zl + self.delta + occ]
+            sel_i = Si[zl + self.delta: zl + self.delta + occ]
+            br, bi = _cmul(np.full(occ, c_r, F32), np.full(occ, c_i, F32), sel_r, sel_i)
+            ev = np.arange(0, occ, 2)
+            hr, hi = _cdiv(lay.ks[ev], np.zeros(len(ev), F32), br[ev], bi[ev])
+            self.Hr[ev] = hr
+            self.Hi[ev] = hi
+            od = np.arange(1, occ - 1, 2)
+            self.Hr[od] = ((self.Hr[od + 1] + self.Hr[od - 1]) * F32(0.5)).astype(F32)
+            self.Hi[od] = ((self.Hi[od + 1] + self.Hi[od - 1]) * F32(0.5)).astype(F32)
+            if occ % 2 == 0:
+                self.Hr[occ - 1] = self.Hr[occ - 2]
+                self.Hi[occ - 1] = self.Hi[occ - 2]
+        c_r, c_i = self._comp(self.cnt)
+        tr, ti = _cmul(self.Hr, self.Hi, np.full(occ, c_r, F32), np.full(occ, c_i, F32))
+        sel_r = Sr[zl + self.delta: zl + self.delta + occ]
+        sel_i = Si[zl + self.delta: zl + self.delta + occ]
+        o_r, o_i = _cmul(tr, ti, sel_r, sel_i)
+        self.cnt += 1
+        if self.cnt == self.MAX_NUM_SYMBOLS:
+            self.cnt = 1
+        return (o_r + 1j * o_i).astype(C64)
+
+
+STATE_SEARCH, STATE_HAVE_SYNC, STATE_HAVE_HEADER = 0, 1, 2
+
+
+class FrameSink:
+    """digital.ofdm_frame_sink(const, range(M), queue, occ, 0.25, 0.25**2/4)
+    (ofdm.py:238-243; digital_swig.py:4415-4428)."""
+
+    def __init__(self, lay: Layout, phase_gain: float = 0.25, freq_gain: float = 0.25 * 0.25 / 4.0):
+        self.lay = lay
+        self.pg = F32(phase_gain)
+        self.fg = F32(freq_gain)
+        self.eq_gain = F32(0.05)
+        self.cr = lay.const.real.astype(F32)
+        self.ci = lay.const.imag.astype(F32)
+        self.state = STATE_SEARCH
+        self.messages: List[Tuple[int, bytes]] = []
+        self.sym_log: List[np.ndarray] = []          # slicer indices per demapped vector
+        self.rot_log: List[np.ndarray] = []          # derotated symbols per demapped vector
+        self._enter_sync()
+        self.state = STATE_SEARCH
+
+    def _enter_sync(self):
+        self.state = STATE_HAVE_SYNC
+        self.bitbuf = 0
+        self.nbitbuf = 0
+        self.header = 0
+        self.hdr_cnt = 0
+        self.freq = F32(0)
+        self.phase = F32(0)
+        ncar = self.lay.ncar
+        self.dr = np.ones(ncar, dtype=F32)
+        self.di = np.zeros(ncar, dtype=F32)
+
+    def slicer(self, rr: np.ndarray, ri: np.ndarray) -> np.ndarray:
+        dre = rr[:, None] - self.cr[None, :]
+        dim = ri[:, None] - self.ci[None, :]
+        d = (dre * dre + dim * dim).astype(F32)
+        return np.argmin(d, axis=1)                   # first minimum, like the upstream loop
+
+    def demapper(self, vec: np.ndarray) -> bytes:
+        lay = self.lay
+        v = vec[lay.sink_map]
+        car_r, car_i = _expj32(self.phase)
+        n = lay.ncar
+        tr, ti = _cmul(v.real.astype(F32), v.imag.astype(F32), np.full(n, car_r, F32), np.full(n, car_i, F32))
+        rr, ri = _cmul(tr, ti, self.dr, self.di)
+        b = self.slicer(rr, ri)
+        cr, ci = self.cr[b], self.ci[b]
+        er = (rr * cr + ri * ci).astype(F32)
+        ei = (ri * cr - rr * ci).astype(F32)
+        err_r = F32(np.sum(er.astype(np.float64)))
+        err_i = F32(np.sum(ei.astype(np.float64)))
+        nrm = (rr * rr + ri * ri).astype(F32)
+        qr, qi = _cdiv(cr, ci, rr, ri)
+        upd = nrm > F32(0.001)
+        ndr = (self.dr + self.eq_gain * (qr - self.dr)).astype(F32)
+        ndi = (self.di + self.eq_gain * (qi - self.di)).astype(F32)
+        self.dr = np.where(upd, ndr, self.dr).astype(F32)
+        self.di = np.where(upd, ndi, self.di).astype(F32)
+        self.sym_log.append(b.astype(np.uint8))
+        self.rot_log.append((rr + 1j * ri).astype(C64))
+        # LSB-first packing with residue carried to the next vector
+        nb = lay.nbits
+        out = bytearray()
+        for s in b.tolist():
+            self.bitbuf |= s << self.nbitbuf
+            self.nbitbuf += nb
+            while self.nbitbuf >= 8:
+                out.append(self.bitbuf & 0xFF)
+                self.bitbuf >>= 8
+                self.nbitbuf -= 8
+        angle = F32(math.atan2(float(err_i), float(err_r)))
+        self.freq = F32(self.freq - F32(self.fg * angle))
+        ph = F32(F32(self.phase + self.freq) - F32(self.pg * angle))
+        if float(ph) >= 2 * math.pi:
+            ph = F32(float(ph) - 2 * math.pi)
+        if float(ph) < 0:
+            ph = F32(float(ph) + 2 * math.pi)
+        self.phase = ph
+        return bytes(out)
+
+    def work(self, vec: np.ndarray, flag: int):
+        if self.state == STATE_SEARCH:
+            if flag:
+                self._enter_sync()
+            return
+        data = self.demapper(vec)
+        if self.state == STATE_HAVE_SYNC:
+            j = 0
+            while j < len(data):
+                self.header = ((self.header << 8) | data[j]) & 0xFFFFFFFF
+                j += 1
+                self.hdr_cnt += 1
+                if self.hdr_cnt == 4:
+                    if ((self.header >> 16) ^ (self.header & 0xFFFF)) == 0:
+                        self.state = STATE_HAVE_HEADER
+                        self.pktlen = (self.header >> 16) & 0x0FFF
+                        self.woff = (self.header >> 28) & 0xF
+                        self.pkt = bytearray()
+                        while j < len(data) and len(self.pkt) < self.pktlen:
+                            self.pkt.append(data[j])
+                            j += 1
+                        if len(self.pkt) == self.pktlen:
+                            self.messages.append((self.woff, bytes(self.pkt)))
+                            self.state = STATE_SEARCH
+                    else:
+                        self.state = STATE_SEARCH
+                    break
+        else:
+            j = 0
+            while j < len(data):
+                self.pkt.append(data[j])
+                j += 1
+                if len(self.pkt) == self.pktlen:
+                    self.messages.append((self.woff, bytes(self.pkt)))
+                    self.state = STATE_SEARCH
+                    break
+
+
+# --------------------------------------------------------------------------
+# Whole receiver
+# --------------------------------------------------------------------------
+
+@dataclass
+class RxResult:
+    packets: List[Tuple[bool, bytes]]          # what the callback sees, in order
+    raw_messages: List[bytes]                  # whitened packet bodies from the sink
+    trig: np.ndarray
+    ang: np.ndarray
+    frame_start: np.ndarray                    # s0 of each emitted frame
+    n_data: np.ndarray
+    y: Optional[np.ndarray] = None
+    mf: Optional[np.ndarray] = None
+    eq: Optional[np.ndarray] = None            # equalised vectors [n_vec, occ]
+    flags: Optional[np.ndarray] = None
+    sym_idx: Optional[List[np.ndarray]] = None
+    derot: Optional[List[np.ndarray]] = None
+    vec_start: Optional[np.ndarray] = None
+
+
+def rx_demodulate(x: np.ndarray, lay: Layout, keep: bool = False) -> RxResult:
+    """chan_filt -> sync_pn -> NCO -> sampler -> FFT -> frame_acq -> frame_sink -> unmake_packet
+    (ofdm_receiver.py~:131-142, ofdm.py:245-247,300-305), whole-stream semantics."""
+    N, cp, L = lay.fft_length, lay.cp_length, lay.sym_len
+    x = np.asarray(x, dtype=C64)
+    n = len(x)
+    taps = chan_filter_taps(lay)
+    y = chan_filter(x, taps)
+    mf, Pr, Pi = sync_pn_metric(y, N, cp)
+    trig = peak_detect(mf)
+    ang = np.arctan2(Pi[trig].astype(np.float64), Pr[trig].astype(np.float64)).astype(F32)
+    plan = plan_frames(trig, ang, n, N, L)
+    acq = FrameAcquisition(lay)
+    sink = FrameSink(lay)
+    eqs, flags, vstart = [], [], []
+    ar = np.arange(N, dtype=np.int64)
+    for st, flag in zip(plan.vec_start.tolist(), plan.vec_flag.tolist()):
+        v = derotate(y, st + ar, plan, N)
+        S = _fft_shift(v)
+        o = acq.work(S, flag)
+        sink.work(o, flag)
+        if keep:
+            eqs.append(o)
+            flags.append(flag)
+            vstart.append(st)
+    raw = [m for (_, m) in sink.messages]
+    pkts = [unmake_packet(m) for m in raw]
+    fs = plan.trig[plan.frame_trig] - N + 1 if len(plan.frame_trig) else np.zeros(0, np.int64)
+    res = RxResult(pkts, raw, trig, ang, fs, plan.n_data)
+    if keep:
+        res.y, res.mf = y, mf
+        res.eq = np.array(eqs, dtype=C64) if eqs else np.zeros((0, lay.occupied_tones), C64)
+        res.flags = np.array(flags, dtype=np.uint8)
+        res.sym_idx, res.derot = sink.sym_log, sink.rot_log
+        res.vec_start = np.array(vstart, dtype=np.int64)
+    return res
+
+
+# --------------------------------------------------------------------------
+# Channel model used by the loopback tests (not part of the reference path)
+# --------------------------------------------------------------------------
+
+def channel(x: np.ndarray, snr_db: float, cfo: float, N: int, seed: int, sig_power: Optional[float] = None,
+            phase0: float = 0.0) -> np.ndarray:
+    """AWGN at ``snr_db`` relative to the mean signal power, plus a frequency offset of
+    ``cfo`` subcarrier spacings (phase-continuous), complex64 out."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    n = len(x)
+    p = float(np.mean(np.abs(x.astype(np.complex128)) ** 2)) if sig_power is None else sig_power
+    sigma = math.sqrt(p / (10 ** (snr_db / 10.0)) / 2.0)
+    noise = rng.standard_normal(n) * sigma + 1j * rng.standard_normal(n) * sigma
+    rot = np.exp(1j * (phase0 + 2 * np.pi * cfo / N * np.arange(n)))
+    return (x.astype(np.complex128) * rot + noise).astype(C64)
+
+
+# --------------------------------------------------------------------------
+# A.13 sensing  (secondary_tx.py:163-202,228-331; usrp_fft_save.py:58-62)
+# --------------------------------------------------------------------------
+
+def blackmanharris(n: int) -> np.ndarray:
+    """gnuradio window.blackmanharris(n) (4-term, GNU Radio 3.x (i+0.5)/(n-1) argument)."""
+    i = np.arange(n, dtype=np.float64)
+    a = 2 * np.pi * (i + 0.5) / (n - 1)
+    w = 0.35875 - 0.48829 * np.cos(a) + 0.14128 * np.cos(2 * a) - 0.01168 * np.cos(3 * a)
+    return w.astype(F32)
+
+
+def sense_fft(x: np.ndarray, N: int, shift: bool = False) -> np.ndarray:
+    """stream_to_vector(N) -> fft_vcc(N, True, blackmanharris(N), shift): complex64 [frames, N]."""
+    nf = len(x) // N
+    v = np.asarray(x[:nf * N], dtype=C64).reshape(nf, N)
+    w = blackmanharris(N)
+    vr = (v.real.astype(F32) * w).astype(F32)
+    vi = (v.imag.astype(F32) * w).astype(F32)
+    X = np.fft.fft(vr.astype(np.float64) + 1j * vi.astype(np.float64), axis=1)
+    if shift:
+        X = np.fft.fftshift(X, axes=1)
+    return X.astype(C64)
+
+
+def sense_maxhold(x: np.ndarray, N: int, tune_delay: int, dwell_delay: int, shift: bool = False) -> np.ndarray:
+    """complex_to_mag_squared -> bin_statistics_f: per-bin max over ``dwell_delay`` frames after
+    skipping ``tune_delay`` frames, repeated; float32 [n_dwell, N]."""
+    X = sense_fft(x, N, shift)
+    p = (X.real.astype(F32) ** 2 + X.imag.astype(F32) ** 2).astype(F32)
+    per = tune_delay + dwell_delay
+    nd = p.shape[0] // per
+    p = p[:nd * per].reshape(nd, per, N)[:, tune_delay:, :]
+    return np.maximum(p.max(axis=1), F32(0)).astype(F32)
+
+
+def hex_conv(bits: Sequence[int]) -> str:
+    """secondary_tx.py:306-331: nibble pack, first bit = LSB, uppercase hex."""
+    abc = "0123456789ABCDEF"
+    out = []
+    n = len(bits)
+    i = 0
+    while i < n and n - i >= 4:
+        v = 0
+        for j in range(4):
+            if bits[i + j] == 1:
+                v += 1 << j
+        out.append(abc[v])
+        i += 4
+    return "".join(out)
+
+
+def sense_decide(dwells: np.ndarray, threshold: float = 0.001):
+    """secondary_tx.py:237-266: mean of the dwell vectors (Python floats), free = not (avg > thr),
+    halves swapped into frequency order, hex map.  Returns (avg_inorder, free_inorder, hex)."""
+    d = np.asarray(dwells, dtype=F32)
+    k, N = d.shape
+    acc = np.zeros(N, dtype=np.float64)
+    for i in range(k):
+        acc = acc + d[i].astype(np.float64)
+    avg = acc / float(k)
+    free = np.where(avg > threshold, 0, 1).astype(np.uint8)
+    h = N // 2
+    free_in = np.concatenate([free[h:], free[:h]])
+    avg_in = np.concatenate([avg[h:], avg[:h]])
+    return avg_in, free_in, hex_conv(free_in.tolist())
+
+
+def best_band(avg_inorder: np.ndarray, lo: int = 200, span: int = 17) -> int:
+    """secondary_tx.py:284-295: start index of the quietest ``span``-bin window; returns index+8."""
+    size = len(avg_inorder)
+    power_temp = 50.0
+    index = -1
+    for i in range(lo, size - 217):
+        power = 0.0
+        for j in range(span):
+            power = power + float(avg_inorder[i + j])
+        if power < power_temp:
+            power_temp = power
+            index = i + 8
+    return index
