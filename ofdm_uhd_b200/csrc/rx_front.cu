@@ -119,6 +119,7 @@ static int launch_filter_n(ofdm_handle* h, const FiltParams& p, cudaStream_t st)
 }
 
 int launch_chan_filter(ofdm_handle* h, const float2* x, int64_t n, float2* y, cudaStream_t st) {
+    if (n <= 0) return OFDM_OK;
     FiltParams p;
     p.x = x; p.y = y; p.n = n; p.hist = h->ntaps - 1; p.V = h->NOS - p.hist;
     p.nblk = (n + p.V - 1) / p.V; p.tw = h->d_tw_os; p.H = h->d_Hos;
@@ -130,12 +131,14 @@ int launch_chan_filter(ofdm_handle* h, const float2* x, int64_t n, float2* y, cu
 
 // ---------------------------------------------------------------------------------------------
 // K_RX2a: Schmidl-Cox timing metric (upstream ofdm_sync_pn up to add_const_ff(-1); A.6).
-// The three moving sums (the reference runs them as 256/256/128-tap FIRs) are differences of
-// tile-local float64 prefix sums of the float32 products, rounded once to float32 -- the oracle's
-// precision policy -- so an all-zero window gives exactly 0 (and 0/0 = NaN like the reference).
+// The three N/2-wide moving sums (the reference runs them as brute-force FIRs) accumulate the float32
+// products in float64 and round once to float32 -- the oracle's precision policy; the cp-wide average of
+// the (non-negative) metric is a difference of tile-local float64 prefix sums.
 // ---------------------------------------------------------------------------------------------
 constexpr int SM_THREADS = 512;
 
+// Exclusive block scan.  Exclusive values are taken by shuffling the inclusive ones (never as
+// "inclusive - own"), so a NaN/inf element only affects the elements after it.
 __device__ __forceinline__ double block_excl_scan_f64(double v, double* s_warp, double* total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double inc = v;
@@ -144,24 +147,52 @@ __device__ __forceinline__ double block_excl_scan_f64(double v, double* s_warp, 
         double o = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += o;
     }
+    double exc = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) exc = 0.0;
     if (lane == 31) s_warp[w] = inc;
     __syncthreads();
     if (w == 0) {
-        double t = lane < (SM_THREADS / 32) ? s_warp[lane] : 0.0;
-        double ti = t;
+        double ti = lane < (SM_THREADS / 32) ? s_warp[lane] : 0.0;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             double o = __shfl_up_sync(0xffffffffu, ti, d);
             if (lane >= d) ti += o;
         }
-        if (lane < SM_THREADS / 32) s_warp[lane] = ti - t;     // exclusive warp offsets
+        double te = __shfl_up_sync(0xffffffffu, ti, 1);
+        if (lane == 0) te = 0.0;
+        if (lane < SM_THREADS / 32) s_warp[lane] = te;         // exclusive warp offsets
         if (lane == SM_THREADS / 32 - 1) s_warp[32] = ti;      // block total
     }
     __syncthreads();
-    double r = s_warp[w] + (inc - v);
+    double r = s_warp[w] + exc;
     if (total) *total = s_warp[32];
     __syncthreads();
     return r;
+}
+
+// Exclusive scan of one value per thread inside segments of G consecutive threads (G a power of two),
+// forwards (sum of the segment's earlier threads) or backwards (later threads).  Only additions.
+template <bool FWD>
+__device__ __forceinline__ double seg_excl_scan(double v, int G, double* s_wt) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int width = G < 32 ? G : 32;
+    const int pos = lane & (width - 1);
+    double inc = v;
+    for (int d = 1; d < width; d <<= 1) {
+        const double o = FWD ? __shfl_up_sync(0xffffffffu, inc, d, width) : __shfl_down_sync(0xffffffffu, inc, d, width);
+        if (FWD ? (pos >= d) : (pos + d < width)) inc += o;
+    }
+    double exc = FWD ? __shfl_up_sync(0xffffffffu, inc, 1, width) : __shfl_down_sync(0xffffffffu, inc, 1, width);
+    if (FWD ? (pos == 0) : (pos == width - 1)) exc = 0.0;
+    if (G > 32) {
+        if (lane == (FWD ? 31 : 0)) s_wt[w] = inc;                        // warp total
+        __syncthreads();
+        const int wps = G >> 5, wseg = w & (wps - 1), w0 = w - wseg;
+        if (FWD) { for (int j = 0; j < wseg; ++j) exc += s_wt[w0 + j]; }
+        else     { for (int j = wseg + 1; j < wps; ++j) exc += s_wt[w0 + j]; }
+        __syncthreads();
+    }
+    return exc;
 }
 
 template <int K>
@@ -191,24 +222,36 @@ __global__ void __launch_bounds__(SM_THREADS) sync_metric_kernel(const float2* _
         en[i] = norm_x(v);
     }
     float Pr[K], Pi[K], R[K];
-    // three moving sums of width h
+    // Three moving sums of width h WITHOUT subtraction (van Herk / Gil-Werman): the tile is cut into blocks of
+    // h samples (G = h/K threads); a window ending at e is  suffix(e-h+1 .. end of the previous block) +
+    // prefix(start of e's block .. e).  Only terms inside the window are ever added, so an all-zero window
+    // gives exactly 0 (-> 0/0 = NaN like the reference's FIR sums) and there is no cancellation noise when
+    // the signal level drops.
+    const int G = h / K;
 #pragma unroll
     for (int arr = 0; arr < 3; ++arr) {
         const float* src = arr == 0 ? cre : (arr == 1 ? cim : en);
         float* dst = arr == 0 ? Pr : (arr == 1 ? Pi : R);
-        double loc[K];
+        double pre[K], suf[K];
         double run = 0.0;
 #pragma unroll
-        for (int i = 0; i < K; ++i) { run += (double)src[i]; loc[i] = run; }
-        const double base = block_excl_scan_f64(run, s_warp, nullptr);
+        for (int i = 0; i < K; ++i) { run += (double)src[i]; pre[i] = run; }
+        const double tot = run;
+        run = 0.0;
 #pragma unroll
-        for (int i = 0; i < K; ++i) { loc[i] += base; S[PADK(e0 + i)] = loc[i]; }
+        for (int i = K - 1; i >= 0; --i) { run += (double)src[i]; suf[i] = run; }
+        const double fwd = seg_excl_scan<true>(tot, G, s_warp);
+        const double bwd = seg_excl_scan<false>(tot, G, s_warp);
+#pragma unroll
+        for (int i = 0; i < K; ++i) { pre[i] += fwd; suf[i] += bwd; S[PADK(e0 + i)] = suf[i]; }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            const int e = e0 + i - h;
-            const double prev = e >= 0 ? S[PADK(e)] : 0.0;
-            dst[i] = (float)(loc[i] - prev);
+            const int e = e0 + i;
+            const int sidx = e - h + 1;                                   // first sample of the window
+            const bool whole = ((e + 1) & (h - 1)) == 0;                  // the window is exactly one block
+            const double tail = (sidx >= 0 && !whole) ? S[PADK(sidx)] : 0.0;
+            dst[i] = (float)(tail + pre[i]);
         }
         __syncthreads();
     }

@@ -34,6 +34,22 @@ def rotated_constellation(modulation: str) -> List[complex]:
 
 
 @dataclass
+class TxPlan:
+    """Offsets of one batch of frames, resident on the device (built once, reused every step)."""
+    n_frames: int
+    payload_off: np.ndarray
+    pkt_off: np.ndarray
+    d_payload_off: object
+    d_pkt_off: object
+    d_sym_off: object
+    pkts: object                 # uint8 cuda tensor holding the framed packets
+    total_syms: int
+    uniform_syms: int
+    n_samples: int
+    pad_for_usrp: bool
+
+
+@dataclass
 class RxBatch:
     """Host view of one ofdm_rx_demodulate call."""
     n_trig: int
@@ -49,6 +65,10 @@ class RxBatch:
     pkt_ok: np.ndarray
     counters: np.ndarray
     packets: List[Tuple[bool, bytes]]          # (ok, payload) in arrival order, what the callback sees
+    msg_frames: Optional[np.ndarray] = None    # frame index of every delivered message
+    payload_rows: Optional[np.ndarray] = None  # uint8 [n_messages, pkt_stride] dewhitened payload || crc
+    payload_bytes_copied: int = 0
+    meta_bytes_copied: int = 0
 
 
 class OfdmEngine:
@@ -108,6 +128,51 @@ class OfdmEngine:
         return int(self.L_.ofdm_frame_symbols(self.h, int(pkt_len)))
 
     # ------------------------------------------------------------------ transmit
+    def tx_plan(self, payload_off: np.ndarray, pad_for_usrp: bool = False) -> TxPlan:
+        """Everything about a batch that does not depend on the payload bytes."""
+        torch = self.torch
+        payload_off = np.ascontiguousarray(payload_off, dtype=np.int64)
+        plen = np.diff(payload_off)
+        F = len(plen)
+        if F and int(plen.max()) > 4092:
+            raise ValueError("len(payload) must be in [0, 4092]")
+        klen = plen + 9
+        if pad_for_usrp:
+            klen = (klen + 15) // 16 * 16
+        pkt_off = np.zeros(F + 1, dtype=np.int64)
+        np.cumsum(klen, out=pkt_off[1:])
+        per = self.ncar * self.nbits
+        nsym = 1 + np.maximum(1, -(-(8 * klen) // per))
+        uniform = int(nsym[0]) if F and bool((nsym == nsym[0]).all()) else 0
+        total = int(nsym.sum())
+        d_sym_off = None
+        if not uniform and F:
+            sym_off = np.zeros(F + 1, dtype=np.int64)
+            np.cumsum(nsym, out=sym_off[1:])
+            d_sym_off = torch.from_numpy(sym_off).to(self.dev)
+        return TxPlan(F, payload_off, pkt_off, torch.from_numpy(payload_off).to(self.dev),
+                      torch.from_numpy(pkt_off).to(self.dev), d_sym_off,
+                      torch.empty(int(pkt_off[-1]), dtype=torch.uint8, device=self.dev), total, uniform,
+                      total * self.L, bool(pad_for_usrp))
+
+    def tx_run(self, plan: TxPlan, payload, out=None, first_frame: int = 0, whitening: bool = True):
+        """make_packets + K_TX for a prepared batch: two kernel launches, nothing else."""
+        torch = self.torch
+        if plan.n_frames == 0:
+            return torch.zeros(0, dtype=torch.complex64, device=self.dev)
+        if out is None:
+            out = torch.empty(plan.n_samples, dtype=torch.complex64, device=self.dev)
+        elif out.numel() < plan.n_samples:
+            raise ValueError("tx_run: output buffer too small")
+        st = self._stream()
+        _lib.check(self.L_.ofdm_make_packets(self.h, self._p(payload), self._p(plan.d_payload_off), plan.n_frames,
+                                             int(whitening), self._p(plan.pkts), self._p(plan.d_pkt_off), st),
+                   "make_packets")
+        _lib.check(self.L_.ofdm_tx_modulate_batch(self.h, self._p(plan.pkts), self._p(plan.d_pkt_off), plan.n_frames,
+                                                  int(first_frame), self._p(plan.d_sym_off), plan.total_syms,
+                                                  plan.uniform_syms, self._p(out), st), "tx_modulate_batch")
+        return out[:plan.n_samples]
+
     def make_packets(self, payload, payload_off: np.ndarray, pad_for_usrp: bool = False, whitening: bool = True):
         """payload: uint8 cuda tensor of the concatenated payloads; payload_off: host int64 [F+1].
         Returns (pkts uint8 cuda tensor, pkt_off host int64 [F+1])."""
@@ -233,29 +298,41 @@ class OfdmEngine:
             return bufs["workspace"][off:off + 4 * n].view(torch.float32)
         raise ValueError(which)
 
-    def collect(self, bufs) -> RxBatch:
+    def collect(self, bufs, want_packets: bool = True, want_payload: bool = True) -> RxBatch:
         """Synchronise and bring one receive call's results to the host."""
         torch = self.torch
         torch.cuda.current_stream(self.dev).synchronize()
-        nt = int(bufs["n_trig"].item())
-        nf = int(bufs["n_frames"].item())
-        st = int(bufs["status"].item())
+        head = torch.stack([bufs["n_trig"][0], bufs["n_frames"][0], bufs["status"][0]]).cpu().numpy()
+        nt, nf, st = int(head[0]), int(head[1]), int(head[2])
         if st:
             raise RuntimeError("receive: capacity overflow (status bits 0x%x): raise max_frames" % st)
         g = lambda k, m: bufs[k][:m].cpu().numpy()
         live, fstat = g("frame_live", nf), g("frame_status", nf)
         plen, pok = g("pkt_len", nf), g("pkt_ok", nf)
+        meta = 4 * nf + 2 * nf + nf + 64 + 12
         sel = np.flatnonzero((live == 1) & (fstat == 2))
         packets: List[Tuple[bool, bytes]] = []
-        if len(sel):
-            idx = torch.from_numpy(sel).to(self.dev)
-            rows = bufs["pkt_bytes"].view(-1, self.pkt_stride)[idx].cpu().numpy()
-            for r, f in enumerate(sel):
-                ln = int(plen[f])
-                body = rows[r, :min(ln, self.pkt_stride)].tobytes()
-                packets.append((bool(pok[f]), body[:-4] if ln >= 4 else b""))
-        return RxBatch(nt, nf, st, g("trig_idx", nt), g("trig_ang", nt), g("frame_start", nf), g("frame_ndata", nf),
-                       live, fstat, plen, pok, bufs["counters"].cpu().numpy(), packets)
+        rows = None
+        copied = 0
+        if len(sel) and (want_payload or want_packets):
+            mat = bufs["pkt_bytes"].view(-1, self.pkt_stride)
+            if len(sel) == nf:
+                rows = mat[:nf].cpu().numpy()
+            else:
+                rows = mat[torch.from_numpy(sel).to(self.dev)].cpu().numpy()
+            copied = int(rows.size)
+            if want_packets:
+                for r, f in enumerate(sel):
+                    ln = int(plen[f])
+                    body = rows[r, :min(ln, self.pkt_stride)].tobytes()
+                    packets.append((bool(pok[f]), body[:-4] if ln >= 4 else b""))
+        if want_packets:
+            trig_idx, trig_ang = g("trig_idx", nt), g("trig_ang", nt)
+            fstart, fnd = g("frame_start", nf), g("frame_ndata", nf)
+        else:
+            trig_idx = trig_ang = fstart = fnd = np.zeros(0)
+        return RxBatch(nt, nf, st, trig_idx, trig_ang, fstart, fnd, live, fstat, plen, pok,
+                       bufs["counters"].cpu().numpy(), packets, sel, rows, copied, meta)
 
     def demodulate(self, x, **kw) -> RxBatch:
         return self.collect(self.demodulate_async(x, **kw))

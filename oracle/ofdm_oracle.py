@@ -473,7 +473,27 @@ def chan_filter(x: np.ndarray, taps: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------
 
 def _sliding_sum64(v: np.ndarray, w: int) -> np.ndarray:
-    """sum_{k<w} v[n-k] with zero history, accumulated in float64."""
+    """sum_{k<w} v[n-k] with zero history, accumulated in float64 WITHOUT subtraction (van Herk / Gil-Werman
+    blocks of w: suffix of the previous block + prefix of the current one).  Like the reference's brute-force
+    FIR sums, only terms inside the window are added: an all-zero window is exactly 0 and there is no
+    cancellation noise when the signal level drops."""
+    n = len(v)
+    if n == 0:
+        return np.zeros(0, dtype=np.float64)
+    nb = -(-n // w)
+    a = np.zeros(nb * w, dtype=np.float64)
+    a[:n] = v
+    a = a.reshape(nb, w)
+    pre = np.cumsum(a, axis=1)
+    suf = np.cumsum(a[:, ::-1], axis=1)[:, ::-1]
+    out = pre.copy()
+    out[1:, :w - 1] += suf[:-1, 1:]
+    return out.reshape(-1)[:n]
+
+
+def _sliding_mean_prefix64(v: np.ndarray, w: int) -> np.ndarray:
+    """Moving sum as a difference of float64 prefix sums (used for the cp-wide average of the non-negative
+    metric, where cancellation is harmless and a NaN must stay NaN)."""
     c = np.cumsum(v.astype(np.float64))
     out = c.copy()
     out[w:] -= c[:-w]
@@ -503,7 +523,7 @@ def sync_pn_metric(y: np.ndarray, N: int, cp: int):
         Mt = (num / den).astype(F32)
     tap = np.float64(F32(1.0 / cp))
     with np.errstate(invalid="ignore"):
-        s = (_sliding_sum64(Mt, cp) * tap).astype(F32)
+        s = (_sliding_mean_prefix64(Mt, cp) * tap).astype(F32)
         mf = (s + F32(-1.0)).astype(F32)
     # a windowed FIR recovers from NaN after cp samples; the cumulative form does not.
     # Nothing downstream can fire after the first NaN (A.7 / C.1), so only mark it.

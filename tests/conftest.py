@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_tables.npz"))
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """libofdm_b200.so, built if needed (nvcc cross-compiles without a GPU)."""
+    from ofdm_uhd_b200 import _build
+    return _build.build()

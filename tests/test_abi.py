@@ -1,0 +1,52 @@
+"""The C-ABI library builds for sm_100a without a GPU, loads, and exports every symbol include/ofdm_b200.h
+declares (no compute call is made here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "ofdm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ofdm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from ofdm_uhd_b200 import _lib
+    L = _lib.load_library(built_lib)
+    names = declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), "libofdm_b200.so does not export %s" % n
+    assert sorted(_lib.EXPORTS) == names
+    assert L.ofdm_version() >= 100
+
+
+def test_host_only_entry_points(built_lib):
+    from ofdm_uhd_b200 import _lib
+    L = _lib.load_library(built_lib)
+    # header(4) + payload + crc(4) + 0x55, optionally padded to 16 (ofdm_packet_utils.py:128-135,145-166)
+    assert L.ofdm_packet_len(402, 0) == 411 and L.ofdm_packet_len(402, 1) == 416 and L.ofdm_packet_len(0, 0) == 9
+
+
+def test_sass_has_no_library_fft(built_lib):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--undefined-only", built_lib], capture_output=True, text=True).stdout
+    assert "cufft" not in out.lower()
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from types import SimpleNamespace
+    from ofdm_uhd_b200 import ofdm
+    opt = SimpleNamespace(modulation="bpsk", fft_length=512, occupied_tones=200, cp_length=128, verbose=False,
+                          log=False, snr=30)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ofdm.ofdm_mod(opt)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ofdm.ofdm_demod(opt)

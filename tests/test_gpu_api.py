@@ -1,0 +1,90 @@
+"""The reference-facing Python surface on the GPU: transmit_path.send_pkt -> channel_model -> receive_path
+callback, driven the way benchmark_ofdm_tx.py / benchmark_ofdm_rx.py drive the reference."""
+import struct
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from oracle import ofdm_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def options(**kw):
+    d = dict(modulation="bpsk", fft_length=512, occupied_tones=200, cp_length=128, snr=30, verbose=False, log=False,
+             tx_amplitude=0.25, samples_per_symbol=2)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+@pytest.mark.parametrize("mod", ["bpsk", "qpsk", "qam16"])
+def test_send_pkt_to_rx_callback(mod):
+    from ofdm_uhd_b200 import transmit_path, receive_path, channel_model
+    opts = options(modulation=mod)
+    got = []
+
+    def rx_callback(ok, payload):                                  # benchmark_ofdm_rx.py:50-61
+        (pktno,) = struct.unpack("!H", payload[0:2])
+        got.append((ok, pktno, payload))
+
+    tx = transmit_path.transmit_path(opts, pad_seed=21)
+    rx = receive_path.receive_path(rx_callback, opts)
+    lay = o.Layout(512, 200, 128, mod)
+    chan = channel_model.channel_model(tx.ofdm_tx._engine, noise_voltage=0.003, frequency_offset=0.2, seed=4,
+                                       lead_in=1200, tail=2600)
+    caps = []
+    tx.connect(chan)
+    chan.connect(lambda smp: caps.append(smp.cpu().numpy()))
+    chan.connect(rx)
+    rng = np.random.default_rng(5)
+    sent = []
+    for pktno in range(30):
+        data = bytes(rng.integers(0, 256, 398, dtype=np.uint8))
+        payload = struct.pack("!H", pktno & 0xFFFF) + struct.pack("!H", 0) + data       # benchmark_ofdm_tx.py:117
+        sent.append(payload)
+        tx.send_pkt(payload, False, "FE7F")                                             # 3 positional args (:60)
+    tx.send_pkt(eof=True)
+    rx.wait(timeout=60)
+    good = [g for g in got if g[0]]
+    # the first frame after the CFO step may be lost and a bogus header can swallow followers (C.2): the
+    # callbacks must be exactly what the oracle's receiver delivers for the same capture, in the same order
+    ref = o.rx_demodulate(np.concatenate(caps), lay)
+    assert [(g[0], g[2]) for g in got] == ref.packets
+    assert len(good) >= 22 and [g[1] for g in good] == sorted(g[1] for g in good)
+    for ok, pktno, payload in good:
+        assert payload == sent[pktno]
+    # the samples the transmit path produced are the oracle's
+    x = tx.ofdm_tx._engine
+    assert tx.carrier_map_old == "FE7F" and tx._tx_amplitude == 0.25
+    tx.set_tx_amplitude(7.0)
+    assert tx._tx_amplitude == 1
+
+
+def test_constructor_errors():
+    from ofdm_uhd_b200 import ofdm
+    with pytest.raises(KeyError):
+        ofdm.ofdm_mod(options(modulation="qam4"))                  # ofdm.py:92
+    with pytest.raises(ValueError):
+        ofdm.ofdm_mod(options(occupied_tones=600))                 # upstream std::invalid_argument
+    m = ofdm.ofdm_mod(options(modulation="qam8"))                  # "qam8" is accepted (ofdm.py:88)
+    assert m._arity == 8
+    with pytest.raises(ValueError):
+        m.send_pkt(bytes(4093))                                    # ofdm_packet_utils.py:124-126
+
+
+def test_ofdm_mod_samples_equal_oracle():
+    import torch
+    from ofdm_uhd_b200 import ofdm
+    opts = options(modulation="qpsk")
+    m = ofdm.ofdm_mod(opts, msgq_limit=2, pad_for_usrp=True, pad_seed=33)
+    pay = [bytes([i]) * (50 + 7 * i) for i in range(6)]
+    chunks = []
+    m.connect(lambda s: chunks.append(s.cpu().numpy()))
+    for p in pay:
+        m.send_pkt(p)
+    m.send_pkt(eof=True)
+    got = np.concatenate(chunks)
+    lay = o.Layout(512, 200, 128, "qpsk")
+    want = o.tx_modulate([o.make_packet(p, 1, 1, True) for p in pay], lay, 1.0, seed=33)   # ofdm_mod: 1/sqrt(N) only
+    assert got.shape == want.shape and float(np.max(np.abs(got - want))) < 1e-5

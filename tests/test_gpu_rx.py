@@ -1,0 +1,229 @@
+"""Receive chain against the oracle, stage by stage and end to end, through the C ABI.
+
+Bit-exact: decoded bytes, CRC verdicts, trigger / frame tables, slicer decisions (on the oracle's filtered
+stream, which isolates the stage from the 1e-7 differences of the FFT-based channel filter).  Tolerance 1e-4
+relative L2 (north star) for float32 samples: filtered stream, equalised symbols."""
+import ctypes as C
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import ofdm_oracle as o
+from helpers import payloads, rel_l2, loopback_capture
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+CASES = [(512, 200, 128, "bpsk", 8, 40, 0.0), (512, 200, 128, "qpsk", 24, 20, 0.3), (512, 200, 128, "qam16", 24, 25, -0.4),
+         (512, 200, 128, "8psk", 12, 30, 0.2), (512, 200, 128, "qam64", 10, 32, 0.1), (1024, 400, 256, "qam64", 12, 30, 1.3),
+         (1024, 800, 256, "qam64", 10, 30, -2.2), (4096, 3200, 512, "qam256", 6, 38, 0.3), (256, 104, 64, "qpsk", 12, 30, 0.1),
+         (2048, 800, 512, "qam16", 6, 30, 0.2), (128, 56, 32, "qpsk", 20, 30, 0.05)]
+
+
+def stage_run(eng, xc, r, lay):
+    """Runs every stage on the ORACLE's intermediate of the previous stage and returns the GPU outputs."""
+    import torch
+    from ofdm_uhd_b200 import _lib
+    from gpu_helpers import processed_vectors
+    n = len(xc)
+    L_, st = eng.L_, eng._stream()
+    nvec = len(r.vec_start) + 64
+    bufs = eng.rx_alloc(n, taps=True, max_vectors=nvec)
+    io = bufs["io"]
+    out = {}
+    d_x = torch.from_numpy(xc).cuda()
+    y_g = torch.empty(n, dtype=torch.complex64, device="cuda")
+    _lib.check(L_.ofdm_rx_chan_filter(eng.h, eng._p(d_x), n, eng._p(y_g), st))
+    out["y"] = y_g.cpu().numpy()
+    d_y = torch.from_numpy(r.y).cuda()
+    mf_g = torch.empty(n, dtype=torch.float32, device="cuda")
+    fnan = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.check(L_.ofdm_rx_sync_metric(eng.h, eng._p(d_y), n, eng._p(mf_g), eng._p(fnan), st))
+    out["mf"] = mf_g.cpu().numpy()
+    out["first_nan"] = int(fnan.item())
+    d_mf = torch.from_numpy(r.mf).cuda()
+    _lib.check(L_.ofdm_rx_peak_detect(eng.h, eng._p(d_y), eng._p(d_mf), n, eng._p(fnan), C.byref(io), st))
+    _lib.check(L_.ofdm_rx_plan(eng.h, n, C.byref(io), st))
+    _lib.check(L_.ofdm_rx_demod(eng.h, eng._p(d_y), n, C.byref(io), st))
+    _lib.check(L_.ofdm_rx_finish(eng.h, C.byref(io), st))
+    res = eng.collect(bufs)
+    out["res"] = res
+    nf = res.n_frames
+    vb_ptr = L_.ofdm_rx_workspace_ptr(eng.h, C.byref(io), n, 5)
+    nv_ptr = L_.ofdm_rx_workspace_ptr(eng.h, C.byref(io), n, 6)
+    base = bufs["workspace"].data_ptr()
+    ws = bufs["workspace"]
+    out["vbase"] = ws[vb_ptr - base: vb_ptr - base + 8 * (nf + 1)].view(torch.int64).cpu().numpy()
+    out["nvec"] = ws[nv_ptr - base: nv_ptr - base + 4 * nf].view(torch.int32).cpu().numpy()
+    nv = len(r.vec_start)
+    out["eq"] = bufs["eq_syms"][:nv * lay.occupied_tones].cpu().numpy().reshape(nv, lay.occupied_tones)
+    out["sym"] = bufs["sym_idx"][:nv * lay.ncar].cpu().numpy().reshape(nv, lay.ncar)
+    out["rows"] = processed_vectors(out["vbase"], res.frame_ndata, out["nvec"])
+    return out
+
+
+@pytest.mark.parametrize("N,occ,cp,mod,nfr,snr,cfo", CASES)
+def test_stage_parity(N, occ, cp, mod, nfr, snr, cfo):
+    from ofdm_uhd_b200.engine import OfdmEngine
+    from gpu_helpers import oracle_demapped
+    rng = np.random.default_rng(N + nfr)
+    lay = o.Layout(N, occ, cp, mod)
+    pay = payloads(rng, nfr)
+    _, xc = loopback_capture(lay, pay, snr, cfo, seed=N + 1)
+    r = o.rx_demodulate(xc, lay, keep=True)
+    assert len(r.packets) >= nfr - 6
+    eng = OfdmEngine(N, occ, cp, mod)
+    assert np.array_equal(eng.chan_taps(), o.chan_filter_taps(lay))
+    g = stage_run(eng, xc, r, lay)
+    # channel filter: float32 samples within tolerance
+    assert rel_l2(g["y"], r.y) < TOL
+    # timing metric on identical input: same op order -> equal up to the last bit of the float64 prefix sums
+    finite = np.isfinite(r.mf)
+    assert np.array_equal(np.isfinite(g["mf"]), finite)
+    assert float(np.max(np.abs(g["mf"][finite] - r.mf[finite]) / (1 + np.abs(r.mf[finite])))) < 1e-5
+    assert float(np.mean(g["mf"][finite] != r.mf[finite])) < 0.01
+    # peak detector / angle latch / sampler plan on identical input: exact
+    res = g["res"]
+    assert np.array_equal(res.trig_idx, r.trig)
+    assert float(np.max(np.abs(res.trig_ang - r.ang))) < 1e-6
+    assert np.array_equal(res.frame_start, r.frame_start) and np.array_equal(res.frame_ndata, r.n_data)
+    # demod on identical input: packets and CRC verdicts exact, equalised symbols within tolerance
+    assert res.packets == r.packets
+    rows = g["rows"]
+    assert rel_l2(g["eq"][rows], r.eq[rows]) < TOL
+    # slicer decisions of the live sessions' own vectors
+    dem = oracle_demapped(r, lay)
+    own = set(rows.tolist())
+    live_rows = set()
+    for f in np.flatnonzero(res.frame_live):
+        k = int(min(int(g["nvec"][f]), 1 + int(res.frame_ndata[f])))
+        live_rows.update(range(int(g["vbase"][f]), int(g["vbase"][f]) + k))
+    checked = 0
+    for k, v in enumerate(dem):
+        if v in live_rows and v in own:
+            assert np.array_equal(g["sym"][v], r.sym_idx[k]), (v,)
+            checked += 1
+    assert checked >= len(r.packets)
+    eng.close()
+
+
+@pytest.mark.parametrize("N,occ,cp,mod,nfr,snr,cfo", CASES)
+def test_full_chain_equals_oracle(N, occ, cp, mod, nfr, snr, cfo):
+    """The whole GPU chain (its own FFT-based filter output feeding the detector) against the oracle."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    rng = np.random.default_rng(7 * N + nfr)
+    lay = o.Layout(N, occ, cp, mod)
+    pay = payloads(rng, nfr)
+    _, xc = loopback_capture(lay, pay, snr, cfo, seed=N + 2)
+    r = o.rx_demodulate(xc, lay, keep=True)
+    eng = OfdmEngine(N, occ, cp, mod)
+    res = eng.demodulate(torch.from_numpy(xc).cuda())
+    # a trigger may move by one sample where two neighbouring metric values tie to ~1e-7 (flat plateau);
+    # decoded bytes and CRC verdicts must still be identical
+    assert len(res.trig_idx) == len(r.trig) and int(np.max(np.abs(res.trig_idx - r.trig))) <= 1
+    assert res.packets == r.packets
+    c = res.counters
+    assert c[1] == len(r.packets) and c[2] == sum(1 for ok, _ in r.packets if ok)
+    eng.close()
+
+
+def test_edge_streams():
+    """Empty, shorter-than-one-symbol and noise-only inputs; a zero gap (NaN poisoning, C.1)."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    lay = o.Layout(512, 200, 128, "bpsk")
+    eng = OfdmEngine(512, 200, 128, "bpsk")
+    rng = np.random.default_rng(8)
+    for n in (0, 1, 100, 700):
+        x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.01).astype(np.complex64)
+        res = eng.demodulate(torch.from_numpy(x).cuda() if n else torch.zeros(0, dtype=torch.complex64, device="cuda"))
+        assert res.packets == [] and res.n_frames == 0
+    noise = ((rng.standard_normal(200000) + 1j * rng.standard_normal(200000)) * 0.05).astype(np.complex64)
+    res = eng.demodulate(torch.from_numpy(noise).cuda())
+    ref = o.rx_demodulate(noise, lay)
+    assert res.packets == ref.packets == [] and np.array_equal(res.trig_idx, ref.trig)
+    eng.close()
+
+
+def test_zero_gap_nan_poisoning_stage_parity():
+    """C.1: an all-zero span makes the metric 0/0 = NaN and the detector's average never recovers.  Whether a
+    zero INPUT span yields exactly-zero filter output depends on the FFT block alignment of the channel filter
+    (true of gr.fft_filter_ccc as well), so the quirk is pinned per stage on the oracle's filtered stream: same
+    first NaN index, same triggers (none after the gap); end to end, everything before the gap is identical."""
+    import torch
+    from ofdm_uhd_b200 import _lib
+    from ofdm_uhd_b200.engine import OfdmEngine
+    lay = o.Layout(512, 200, 128, "bpsk")
+    eng = OfdmEngine(512, 200, 128, "bpsk")
+    rng = np.random.default_rng(8)
+    x = o.tx_modulate([o.make_packet(p, 1, 1, False) for p in payloads(rng, 2)], lay, 0.25, seed=1)
+    burst = o.channel(x, 40, 0.0, 512, seed=1)
+    cap = np.concatenate([burst, np.zeros(3000, np.complex64), burst, np.zeros(1500, np.complex64)])
+    ref = o.rx_demodulate(cap, lay, keep=True)
+    assert np.isnan(ref.mf).any()
+    want_nan = int(np.flatnonzero(np.isnan(ref.mf))[0])
+    n = len(cap)
+    L_, st = eng.L_, eng._stream()
+    bufs = eng.rx_alloc(n)
+    d_y = torch.from_numpy(ref.y).cuda()
+    mf_g = torch.empty(n, dtype=torch.float32, device="cuda")
+    fnan = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.check(L_.ofdm_rx_sync_metric(eng.h, eng._p(d_y), n, eng._p(mf_g), eng._p(fnan), st))
+    assert int(fnan.item()) == want_nan
+    got = mf_g.cpu().numpy()
+    fin = np.isfinite(ref.mf[:want_nan])
+    assert np.array_equal(np.isfinite(got[:want_nan]), fin) and np.array_equal(got[:want_nan][~fin], ref.mf[:want_nan][~fin])
+    assert float(np.max(np.abs(got[:want_nan][fin] - ref.mf[:want_nan][fin]) / (1 + np.abs(ref.mf[:want_nan][fin])))) < 1e-5
+    d_mf = torch.from_numpy(ref.mf).cuda()
+    _lib.check(L_.ofdm_rx_peak_detect(eng.h, eng._p(d_y), eng._p(d_mf), n, eng._p(fnan), C.byref(bufs["io"]), st))
+    torch.cuda.synchronize()
+    nt = int(bufs["n_trig"].item())
+    assert np.array_equal(bufs["trig_idx"][:nt].cpu().numpy(), ref.trig) and (ref.trig < want_nan).all()
+    res = eng.demodulate(torch.from_numpy(cap).cuda())
+    k = len(ref.packets)
+    assert k >= 1 and res.packets[:k] == ref.packets
+    eng.close()
+
+
+def test_large_stream_round_trip():
+    """Size-independent properties at scale (5 000 QAM16 frames, noise + CFO): every delivered payload with a
+    good CRC equals what was sent, almost all frames are delivered, a second run is bit-identical."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    F, psize = 5000, 402
+    eng = OfdmEngine(512, 200, 128, "qam16", 0.25, pad_seed=3, max_pkt_bytes=416)
+    rng = np.random.default_rng(9)
+    body = rng.integers(0, 256, size=(F, psize), dtype=np.uint8)
+    body[:, 0] = np.arange(F) >> 8
+    body[:, 1] = np.arange(F) & 0xFF
+    off = np.arange(F + 1, dtype=np.int64) * psize
+    plan = eng.tx_plan(off)
+    x = eng.tx_run(plan, torch.from_numpy(body.reshape(-1)).cuda())
+    lead = torch.zeros(1300, dtype=torch.complex64, device="cuda")
+    cap = torch.cat([lead, x, lead])
+    p_sig = float((x.abs() ** 2).mean())
+    sigma = (p_sig / 10 ** 2.5 / 2) ** 0.5                                             # 25 dB
+    xc = eng.channel(cap, cfo=0.31, sigma=sigma, seed=17)
+    res = eng.demodulate(xc)
+    ok = [(g, p) for g, p in res.packets if g]
+    assert len(res.packets) >= F - 10 and len(ok) >= 0.93 * F          # LS channel estimate from one preamble
+    # the oracle on a prefix of the same capture delivers the same packets (ok or not), in the same order
+    npre = 1300 + 200 * 6 * 640
+    ref = o.rx_demodulate(xc[:npre].cpu().numpy(), o.Layout(512, 200, 128, "qam16"))
+    k = len(ref.packets) - 3
+    # The first frame after the CFO step decodes to garbage (C.2) and its bogus header length sits on slicer
+    # boundaries, where the 1e-7 differences of the FFT-based filter show; from then on the two receivers must
+    # deliver the same good packets in the same order.
+    assert k > 150
+    good_g = [p for g, p in res.packets if g and 10 <= ((p[0] << 8) | p[1]) < k]
+    good_o = [p for g, p in ref.packets if g and 10 <= ((p[0] << 8) | p[1]) < k]
+    assert good_g == good_o and len(good_o) > 0.9 * (k - 10)
+    for _, p in ok:
+        k = (p[0] << 8) | p[1]
+        assert p == body[k].tobytes()
+    res2 = eng.demodulate(xc)
+    assert res2.packets == res.packets and np.array_equal(res2.trig_idx, res.trig_idx)
+    assert res.counters[2] == len(ok) and res.counters[3] == len(ok) * psize
+    eng.close()

@@ -1,0 +1,68 @@
+"""K_SENSE (window + FFT + |X|^2 + max-hold) and the decision kernel against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import ofdm_oracle as o
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def capture(N, nfr, seed, tone=0.13, amp=0.01):
+    rng = np.random.default_rng(seed)
+    x = ((rng.standard_normal(nfr * N) + 1j * rng.standard_normal(nfr * N)) * 1e-3).astype(np.complex64)
+    x += (amp * np.exp(2j * np.pi * tone * np.arange(nfr * N))).astype(np.complex64)
+    return x
+
+
+@pytest.mark.parametrize("N", [64, 128, 256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("shift", [False, True])
+def test_maxhold_and_decision(N, shift):
+    import torch
+    from ofdm_uhd_b200.engine import SenseEngine
+    x = capture(N, 130, N)
+    se = SenseEngine(N)
+    dx = torch.from_numpy(x).cuda()
+    for tune, dwell in ((0, 12), (3, 10), (0, 1)):
+        mh = se.maxhold(dx, tune, dwell, shift=shift)
+        ref = o.sense_maxhold(x, N, tune, dwell, shift=shift)
+        assert tuple(mh.shape) == ref.shape
+        assert rel_l2(mh.cpu().numpy(), ref) < 1e-4
+    mh = se.maxhold(dx, 0, 12, shift=False)
+    avg, free, hx = se.decide(mh[:10], 1e-3)
+    a2, f2, h2 = o.sense_decide(mh[:10].cpu().numpy(), 1e-3)           # same dwell vectors -> exact
+    assert np.array_equal(avg, a2) and np.array_equal(free, f2) and hx == h2
+    sp = se.spectra(dx[:6 * N], shift=shift).cpu().numpy()
+    assert rel_l2(sp, o.sense_fft(x[:6 * N], N, shift)) < 1e-4
+    se.close()
+
+
+def test_wideband_capture_bands_detected():
+    """BASELINE configs[3] in miniature: 1024-pt sensing of white noise plus three occupied bands; the hex carrier
+    map must flag exactly those bands, and must equal the oracle's map computed from the same capture."""
+    import torch
+    from ofdm_uhd_b200.engine import SenseEngine
+    N, nfr = 1024, 12 * 10 * 4
+    rng = np.random.default_rng(5)
+    sig = np.sqrt(5e-6 / 1024 / 2)
+    X = (rng.standard_normal((nfr, N)) + 1j * rng.standard_normal((nfr, N))) * sig * np.sqrt(N)
+    bands = [(100, 140), (400, 416), (800, 900)]                      # in shifted (frequency) order
+    for lo, hi in bands:
+        X[:, lo:hi] *= 10.0                                           # +20 dB
+    x = np.fft.ifft(np.fft.ifftshift(X, axes=1), axis=1).reshape(-1).astype(np.complex64)
+    se = SenseEngine(N)
+    mh = se.maxhold(torch.from_numpy(x).cuda(), 0, 12, shift=False)
+    assert mh.shape[0] == 40
+    ref = o.sense_maxhold(x, N, 0, 12, shift=False)
+    assert rel_l2(mh.cpu().numpy(), ref) < 1e-4
+    thr = 2e-5
+    for g in range(4):
+        avg, free, hx = se.decide(mh[10 * g:10 * g + 10], thr)
+        _, f2, h2 = o.sense_decide(ref[10 * g:10 * g + 10], thr)
+        assert hx == h2 and np.array_equal(free, f2)
+        busy = np.flatnonzero(free == 0)
+        inside = np.zeros(N, bool)
+        for lo, hi in bands:
+            inside[lo:hi] = True
+        assert inside[busy].mean() > 0.9 and (free[inside] == 0).mean() > 0.7
+    se.close()

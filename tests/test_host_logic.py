@@ -1,0 +1,96 @@
+"""Host-side mirror of the reference interface: packet utils against the oracle, option parsing, queue shim,
+flat imports, sharding helpers (single process) -- nothing here needs a GPU."""
+import optparse
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ofdm_oracle as o
+from ofdm_uhd_b200 import ofdm_packet_utils as pu, sensing, sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_packet_utils_equal_oracle():
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 402, 1020, 4091):
+        p = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        for pad in (False, True):
+            if pad and n == 4091:
+                continue
+            assert pu.make_packet(p, 1, 1, pad) == o.make_packet(p, 1, 1, pad)
+        pkt = pu.make_packet(p, 1, 1, False)
+        assert pu.unmake_packet(pkt[4:-1]) == (True, p)
+        bad = bytearray(pkt[4:-1])
+        if bad:
+            bad[0] ^= 1
+            assert pu.unmake_packet(bytes(bad))[0] is False
+    assert pu.unmake_packet(b"abc") == (False, b"")
+    assert pu.whiten(pu.whiten(b"hello", 3), 3) == b"hello" and pu.dewhiten(pu.whiten(b"x", 0), 0) == b"x"
+    with pytest.raises(ValueError):
+        pu.make_packet(bytes(4093), 1, 1, False)
+    assert pu.make_packet("abc", 1, 1, False) == pu.make_packet(b"abc", 1, 1, False)   # py2-style str payloads
+    assert pu._npadding_bytes(411, 1, 1) == 5 and pu._npadding_bytes(416, 1, 1) == 0
+
+
+def test_add_options_like_the_reference_scripts():
+    pytest.importorskip("torch")
+    from ofdm_uhd_b200 import ofdm, transmit_path, receive_path
+    parser = optparse.OptionParser(conflict_handler="resolve")
+    expert = parser.add_option_group("Expert")
+    parser.add_option("", "--snr", type="float", default=30)
+    transmit_path.transmit_path.add_options(parser, expert)
+    receive_path.receive_path.add_options(parser, expert)
+    ofdm.ofdm_mod.add_options(parser, expert)
+    ofdm.ofdm_demod.add_options(parser, expert)
+    opts, args = parser.parse_args([])
+    assert (opts.modulation, opts.fft_length, opts.occupied_tones, opts.cp_length) == ("bpsk", 512, 200, 128)
+    assert opts.tx_amplitude == 0.25 and opts.samples_per_symbol == 2 and opts.log is False and opts.verbose is False
+    opts, _ = parser.parse_args(["-m", "qam16", "--fft-length", "1024", "--tx-amplitude", "0.5", "-v"])
+    assert opts.modulation == "qam16" and opts.fft_length == 1024 and opts.tx_amplitude == 0.5 and opts.verbose
+
+
+def test_msg_queue_shim():
+    pytest.importorskip("torch")
+    from ofdm_uhd_b200 import ofdm
+    hits = []
+    q = ofdm.msg_queue(2, on_full=lambda: hits.append(q.count()) or q.flush())
+    for i in range(5):
+        q.insert_tail(ofdm.message_from_string(bytes([i])))
+    assert hits == [2, 2] and q.count() == 1 and q.delete_head().to_string() == b"\x04" and q.empty_p()
+    m = ofdm.message(1)
+    assert m.type() == 1 and m.length() == 0
+
+
+def test_flat_import_like_the_reference_directory():
+    code = ("import sys; sys.path.insert(0, %r); import psk, qam, ofdm_packet_utils, ofdm, transmit_path, receive_path;"
+            "print(ofdm.ofdm_mod.__name__, transmit_path.transmit_path.__name__, len(ofdm.known_symbols_4512_3))"
+            % os.path.join(ROOT, "ofdm_uhd_b200"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["ofdm_mod", "transmit_path", "4512"]
+
+
+def test_sensing_decision_helpers():
+    assert sensing.hex_conv([0, 0, 0, 0] + [1] * 12) == "0FFF"
+    rng = np.random.default_rng(1)
+    bits = rng.integers(0, 2, 256).tolist()
+    assert sensing.hex_conv(bits) == o.hex_conv(bits)
+    avg = rng.random(1024) * 1e-5
+    avg[400:430] = 1e-7
+    assert sensing.best_band(avg) == o.best_band(avg)
+    assert sensing.busy_count([1] * 1024, 905e6, 25e6, 1024) == 0
+
+
+def test_sharding_helpers():
+    assert sharding.streams_of_rank(64, 8, 3) == list(range(3, 64, 8))
+    cover = []
+    for r in range(3):
+        lo, hi = sharding.split_frames(10, 3, r)
+        cover += list(range(lo, hi))
+    assert cover == list(range(10))
+    assert sharding.as_dict(range(8))["crc_ok"] == 2
