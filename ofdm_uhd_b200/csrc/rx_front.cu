@@ -11,7 +11,7 @@ int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, voi
     (void)h;
     if (n < 0) n = 0;
     if (max_frames < 1) max_frames = 1;
-    int64_t seg_len = (n + 148 * 32 - 1) / (148 * 32);
+    int64_t seg_len = (n + 148 * 24 - 1) / (148 * 24);
     if (seg_len < 65536) seg_len = 65536;
     seg_len = (seg_len + 31) / 32 * 32;
     ws->seg_len = seg_len;
@@ -211,15 +211,34 @@ __global__ void __launch_bounds__(SM_THREADS) sync_metric_kernel(const float2* _
     const int e0 = tid * K;
 
     float cre[K], cim[K], en[K];
+    {
+        float2 yv[K], yd[K];
+        const int64_t u0 = a + e0;
+        // interior tiles: 16-byte vector loads, no bounds checks (block-uniform branch)
+        const bool fast = (a - h >= 0) && (a + C <= n) && ((((uintptr_t)(y + a)) & 15) == 0);
+        if (fast) {
+            const float4* pv = (const float4*)(y + u0);
+            const float4* pd = (const float4*)(y + u0 - h);
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-        const int64_t u = a + e0 + i;
-        float2 v = (u >= 0 && u < n) ? LDG(y + u) : make_float2(0.f, 0.f);
-        const int64_t ud = u - h;
-        float2 d = (ud >= 0 && ud < n) ? LDG(y + ud) : make_float2(0.f, 0.f);
-        float2 c = cmulc_x(v, d);                   // y[n] * conj(y[n-N/2])
-        cre[i] = c.x; cim[i] = c.y;
-        en[i] = norm_x(v);
+            for (int i = 0; i < K / 2; ++i) {
+                const float4 q = __ldg(pv + i), r = __ldg(pd + i);
+                yv[2 * i] = make_float2(q.x, q.y); yv[2 * i + 1] = make_float2(q.z, q.w);
+                yd[2 * i] = make_float2(r.x, r.y); yd[2 * i + 1] = make_float2(r.z, r.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const int64_t u = u0 + i, ud = u - h;
+                yv[i] = (u >= 0 && u < n) ? LDG(y + u) : make_float2(0.f, 0.f);
+                yd[i] = (ud >= 0 && ud < n) ? LDG(y + ud) : make_float2(0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const float2 c = cmulc_x(yv[i], yd[i]);   // y[n] * conj(y[n-N/2])
+            cre[i] = c.x; cim[i] = c.y;
+            en[i] = norm_x(yv[i]);
+        }
     }
     float Pr[K], Pi[K], R[K];
     // Three moving sums of width h WITHOUT subtraction (van Herk / Gil-Werman): the tile is cut into blocks of
@@ -355,6 +374,8 @@ struct PeakParams {
     uint32_t* status;
 };
 
+constexpr int PK = 8;                        // consecutive samples per lane and step (256 per warp step)
+
 __global__ void __launch_bounds__(128) peak_detect_kernel(const PeakParams p) {
     const int lane = threadIdx.x & 31;
     const int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -363,71 +384,79 @@ __global__ void __launch_bounds__(128) peak_detect_kernel(const PeakParams p) {
     const int64_t s1 = (s0 + p.seg_len < p.n) ? s0 + p.seg_len : p.n;
     int64_t w0 = s0 - OFDM_PEAK_WARM;
     if (w0 < 0) w0 = 0;
-    w0 &= ~(int64_t)31;
+    w0 &= ~(int64_t)(32 * PK - 1);
     const int64_t fnan = *p.first_nan;
+    const bool vec_ok = (((uintptr_t)p.mf) & 15) == 0;
     int count = 0;
     if (fnan >= w0) {                               // else: average already poisoned, nothing can fire (C.1)
         const double a1 = (double)0.001f;
         const double a2 = 1.0 - a1;
-        // a2^(2^k) for the scan steps and a2^(lane+1) for the carry
-        double pw[5];
-        pw[0] = a2;
+        double a2k = 1.0;                           // a2^PK: multiplier of one lane's block
+#pragma unroll
+        for (int k = 0; k < PK; ++k) a2k *= a2;
+        double pw[5];                               // (a2^PK)^(2^k) for the scan steps
+        pw[0] = a2k;
 #pragma unroll
         for (int k = 1; k < 5; ++k) pw[k] = pw[k - 1] * pw[k - 1];
-        double plane = 1.0;
-        for (int k = 0; k <= lane; ++k) plane *= a2;
+        const double p32 = pw[4] * pw[4];           // (a2^PK)^32
+        double plane = 1.0;                         // (a2^PK)^lane: weight of the carry at the start of this lane
+        for (int k = 0; k < lane; ++k) plane *= a2k;
         double carry = 0.0;                         // avg after the last consumed sample
         int state = 0;
         float peak = -INFINITY;
         int64_t ind = 0, run_start = 0;
-        for (int64_t i0 = w0; i0 < p.n; i0 += 32) {
+        for (int64_t i0 = w0; i0 < p.n; i0 += 32 * PK) {
             if (i0 >= s1 && state == 0) break;
-            const int64_t gi = i0 + lane;
-            const int nv = (p.n - i0 < 32) ? (int)(p.n - i0) : 32;
-            const float v = lane < nv ? p.mf[gi] : 0.f;
-            double b = a1 * (double)v;
+            const int64_t b0 = i0 + (int64_t)lane * PK;
+            float v[PK];
+            if (vec_ok && i0 + 32 * PK <= p.n) {
+                const float4 q0 = __ldg((const float4*)(p.mf + b0));
+                const float4 q1 = __ldg((const float4*)(p.mf + b0) + 1);
+                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
+                v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < PK; ++i) v[i] = (b0 + i < p.n) ? p.mf[b0 + i] : 0.f;
+            }
+            // lane-local recurrence from a zero state, then the affine scan across lanes
+            double loc = 0.0;
+#pragma unroll
+            for (int i = 0; i < PK; ++i) loc = a2 * loc + a1 * (double)v[i];
+            double b = loc;
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                double o = __shfl_up_sync(0xffffffffu, b, 1 << k);
+                const double o = __shfl_up_sync(0xffffffffu, b, 1 << k);
                 if (lane >= (1 << k)) b = b + pw[k] * o;
             }
-            const double avg = b + plane * carry;   // average after consuming sample gi
-            double prev = __shfl_up_sync(0xffffffffu, avg, 1);
-            if (lane == 0) prev = carry;
-            carry = __shfl_sync(0xffffffffu, avg, 31);
-            const float thr = fmul_rn((float)prev, 0.2f);
-            const bool a = lane < nv && v > thr;
-            const unsigned mask = __ballot_sync(0xffffffffu, a);
-            int j = 0;
-            while (j < nv) {
-                if (state == 0) {
-                    unsigned rest = mask & (0xffffffffu << j);
-                    if (!rest) break;
-                    j = __ffs(rest) - 1;
-                    state = 1;
-                    peak = -INFINITY;
-                    run_start = i0 + j;
-                } else if ((mask >> j) & 1u) {
-                    // bulk: the rest of this run of `a` inside the block
-                    unsigned zeros = ~mask & (0xffffffffu << j);
-                    int e = zeros ? (__ffs(zeros) - 1) : 32;
-                    if (e > nv) e = nv;
-                    float bv = (lane >= j && lane < e) ? v : -INFINITY;
-                    int bl = lane;
+            double prev = __shfl_up_sync(0xffffffffu, b, 1);      // state after the previous lane's block (zero carry)
+            if (lane == 0) prev = 0.0;
+            prev = prev + plane * carry;                          // avg just before this lane's first sample
+            carry = __shfl_sync(0xffffffffu, b, 31) + p32 * carry;      // state after the 256th sample
+            unsigned mk = 0;
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) {
-                        float ov = __shfl_xor_sync(0xffffffffu, bv, d);
-                        int ol = __shfl_xor_sync(0xffffffffu, bl, d);
-                        if (ov > bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
-                    }
-                    if (bv > peak) { peak = bv; ind = i0 + bl; }
-                    j = e;
-                } else {
-                    const float vj = __shfl_sync(0xffffffffu, v, j);
-                    if (vj > peak) {                // a later sample beats the peak: the run stays alive
-                        peak = vj; ind = i0 + j;
-                        ++j;
-                    } else {
+            for (int i = 0; i < PK; ++i) {
+                const float thr = fmul_rn((float)prev, 0.2f);
+                if (b0 + i < p.n && v[i] > thr) mk |= 1u << i;
+                prev = a2 * prev + a1 * (double)v[i];
+            }
+            const unsigned any = __ballot_sync(0xffffffffu, mk != 0);
+            if (state == 0 && any == 0) continue;
+            // slow path (a run is open or starts in this step): walk the 256 samples in order
+            for (int l = (state == 0 ? __ffs(any) - 1 : 0); l < 32; ++l) {
+                const unsigned m = __shfl_sync(0xffffffffu, mk, l);
+                if (state == 0 && m == 0) continue;
+                const int64_t base = i0 + (int64_t)l * PK;
+#pragma unroll
+                for (int i = 0; i < PK; ++i) {
+                    const float vi = __shfl_sync(0xffffffffu, v[i], l);
+                    const int64_t idx = base + i;
+                    if (idx >= p.n) break;                        // end of stream: an open run emits nothing
+                    const bool bit = (m >> i) & 1u;
+                    if (state == 0) {
+                        if (bit) { state = 1; peak = vi; ind = idx; run_start = idx; }
+                    } else if (vi > peak) {
+                        peak = vi; ind = idx;                     // also keeps the run alive when !bit
+                    } else if (!bit) {
                         if (run_start >= s0 && run_start < s1) {
                             if (count < p.seg_cap) {
                                 if (lane == 0) p.seg_trig[seg * p.seg_cap + count] = ind;
@@ -436,8 +465,7 @@ __global__ void __launch_bounds__(128) peak_detect_kernel(const PeakParams p) {
                             }
                             ++count;
                         }
-                        state = 0;
-                        ++j;                        // the closing sample is consumed in state 0 (it failed the test)
+                        state = 0;                                // the closing sample is consumed in state 0
                     }
                 }
             }
