@@ -34,26 +34,35 @@ struct DemodParams {
 };
 
 // multiply_cc(chan_filt, frequency_modulator_fc(-2/N)(sample_and_hold(angle))) evaluated at the
-// samples of one sampler vector: phi[s] = phi0[k] + step[k]*(s - t_k + 1) for t_k <= s < t_{k+1}  (A.8)
+// samples of one sampler vector: phi[s] = phi0[k] + step[k]*(s - t_k + 1) for t_k <= s < t_{k+1}  (A.8).
+// Inside one trigger segment the phasor of point tid + d is  e^{j phi(st+tid)} * e^{j step d}: one sincos per
+// thread and vector plus a per-segment table of the E compile-time offsets d; samples at or after the next
+// trigger (the last sample of a preamble vector) take the exact per-sample path.
+__device__ __forceinline__ float2 phasor_f64(double ph) {
+    double r = ph * 0.15915494309189533577;
+    r -= rint(r);
+    float sn, cs;
+    sincospif(2.0f * (float)r, &sn, &cs);
+    return make_float2(cs, sn);
+}
+
 struct DemodLoad {
     const float2* y;
-    int64_t st;
+    int64_t st, t_next;
     const int64_t* trig;
     const double* phi0;
     const double* step;
-    int K, kseg0;
-    __device__ __forceinline__ float2 operator()(int idx, int) const {
+    int K, kk0;
+    float2 ph0;
+    const float2* Wt;
+    __device__ __forceinline__ float2 operator()(int idx, int slot) const {
         const int64_t s = st + idx;
-        int kk = kseg0;
+        const float2 v = LDG(y + s);
+        if (s < t_next) return cmul_x(v, cmul(ph0, Wt[slot]));
+        int kk = kk0;
         while (kk + 1 < K && LDG(trig + kk + 1) <= s) ++kk;
-        float2 v = LDG(y + s);
-        if (kk < 0) return v;
         const double ph = LDG(phi0 + kk) + LDG(step + kk) * (double)(s - LDG(trig + kk) + 1);
-        double r = ph * 0.15915494309189533577;
-        r -= rint(r);
-        float sn, cs;
-        sincospif(2.0f * (float)r, &sn, &cs);
-        return cmul_x(v, make_float2(cs, sn));
+        return cmul_x(v, phasor_f64(ph));
     }
 };
 
@@ -76,10 +85,29 @@ __device__ __forceinline__ float2 coarse_comp(int delta, int cp, int N, int cnt)
     return expj_f32(ph);
 }
 
-template <int N>
+// LSB-first packing of the slicer decisions of one vector into bytes q in [B0, B1)
+template <int NB>
+__device__ __forceinline__ void pack_bytes(const uint8_t* sym, uint8_t* vb, int B0, int B1, int bit_base, unsigned carry,
+                                           int tid, int nthreads) {
+    for (int q = B0 + tid; q < B1; q += nthreads) {
+        unsigned byte = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rel = 8 * q + i - bit_base;
+            unsigned bit;
+            if (rel < 0) bit = (carry >> i) & 1u;
+            else bit = ((unsigned)sym[rel / NB] >> (rel % NB)) & 1u;
+            byte |= bit << i;
+        }
+        vb[q - B0] = (uint8_t)byte;
+    }
+}
+
+template <int N, bool TAPS>
 __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E)) demod_kernel(const DemodParams p) {
     using P = FftPlan<N>;
-    constexpr int T = N / P::E;
+    constexpr int E = P::E;
+    constexpr int T = N / E;
     constexpr int BT = T < 64 ? 64 : T;
     constexpr int NW = BT / 32;
     constexpr int SB = fft_smem_elems<N>();
@@ -90,12 +118,11 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     float2* bufB = bufA + SB;
     float2* H = bufB + SB;                                  // [occ]
     float2* dfe = H + p.occ;                                // [ncar]
-    float2* eq = dfe + p.occ;                               // [occ]
-    float2* s_cst = eq + p.occ;                             // [M]
+    float2* s_cst = dfe + p.occ;                            // [M]
     uint8_t* sym = (uint8_t*)(s_cst + p.M);                 // [ncar]
     uint8_t* vb = sym + ((p.ncar + 15) & ~15);              // bytes of the current vector
     __shared__ int s_delta, s_hdr_ok, s_len;
-    __shared__ float2 s_c, s_car;
+    __shared__ float2 s_cc[2], s_car[2], s_W[E];
     __shared__ float s_phase, s_freq;
     __shared__ unsigned s_carry;
 
@@ -112,21 +139,39 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     for (int f = blockIdx.x; f < F; f += gridDim.x) {
         int g = f, m = 0, vi = 0, cnt = 1, delta = 0, bit_base = 0;
         int status = 3, nvec = INT_MAX / 2, len = 0;
+        int kk_w = INT_MIN;                                 // trigger segment the table s_W belongs to
         __syncthreads();
         while (g < F) {
             const int kg = first_ok + g;
             const int64_t t = p.trig_idx[kg];
             const int64_t st = t - N + 1 + (int64_t)m * L;
             const bool flag = (m == 0);
-            const int64_t vglob = p.vbase[g] + m;
-            const bool tap = (g == f) && vglob < p.max_vectors;
+            const int64_t vglob = TAPS ? p.vbase[g] + m : 0;
+            const bool tap = TAPS && (g == f) && vglob < p.max_vectors;
+            const int par = vi & 1;
             // ---- sigmix + fft_demod ----
-            int kseg0 = kg;
+            int kk = kg;
             if (flag) {
-                kseg0 = kg - 1;
-                while (kseg0 >= 0 && p.trig_idx[kseg0] > st) --kseg0;
+                kk = kg - 1;
+                while (kk >= 0 && p.trig_idx[kk] > st) --kk;
             }
-            DemodLoad ld{p.y, st, p.trig_idx, p.phi0, p.step, K, kseg0};
+            const int64_t t_next = (kk + 1 < K) ? p.trig_idx[kk + 1] : LLONG_MAX;
+            double stp = 0.0, ph_base = 0.0;
+            if (kk >= 0) {
+                stp = p.step[kk];
+                ph_base = p.phi0[kk] + stp * (double)(st + tid - p.trig_idx[kk] + 1);
+            }
+            if (kk != kk_w) {                               // block-uniform
+                __syncthreads();
+                if (tid < E) {
+                    const int d = (tid / R0) * T + (tid % R0) * (N / R0);     // slot q*R0 + r  <->  offset q*T + r*N/R0
+                    s_W[tid] = phasor_f64(stp * (double)d);
+                }
+                kk_w = kk;
+                __syncthreads();
+            }
+            DemodLoad ld{p.y, st, t_next, p.trig_idx, p.phi0, p.step, K, kk < 0 ? 0 : kk, phasor_f64(ph_base), s_W};
+            if (kk < 0) ld.t_next = (K > 0) ? p.trig_idx[0] : LLONG_MAX;
             if (tid < T) fft_pass<N, R0, 1, -1>(tid, p.tw, ld, SmemOut{bufA});
             __syncthreads();
             if constexpr (P::NP == 2) {
@@ -170,12 +215,12 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                         if (sf > best) { best = sf; index = zl - OFDM_MAX_SHIFT + s; }
                     }
                     s_delta = index - zl;
-                    s_c = coarse_comp(index - zl, p.cp, N, 1);
+                    s_cc[par] = coarse_comp(index - zl, p.cp, N, 1);
                 }
                 __syncthreads();
                 delta = s_delta;
                 cnt = 1;
-                const float2 c1 = s_c;
+                const float2 c1 = s_cc[par];
                 for (int i = 2 * tid; i < occ; i += 2 * BT) {
                     const float2 b = cmul_x(c1, S[i + zl + delta]);
                     H[i] = cdiv_x(make_float2(LDG(p.ks + i), 0.f), b);
@@ -188,34 +233,34 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 if (tid == 0 && (occ & 1) == 0) H[occ - 1] = H[occ - 2];
                 __syncthreads();
             }
-            // ---- one-tap equaliser with the coarse-offset CP phase compensation ----
-            if (tid == 0) s_c = coarse_comp(delta, p.cp, N, cnt);
-            __syncthreads();
-            {
-                const float2 c = s_c;
-                for (int i = tid; i < occ; i += BT) {
-                    const float2 v = cmul_x(cmul_x(H[i], c), S[i + zl + delta]);
-                    eq[i] = v;
-                    if (tap && p.eq_syms) p.eq_syms[vglob * occ + i] = v;
-                }
+            // one-tap equaliser with the coarse-offset CP phase compensation: comp(delta, cnt) is in s_cc[par]
+            // (written by the acquisition above, or during the previous vector's serial section)
+            const float2 cc = s_cc[par];
+            if (TAPS) {
+                if (tap && p.eq_syms)
+                    for (int i = tid; i < occ; i += BT)
+                        p.eq_syms[vglob * occ + i] = cmul_x(cmul_x(H[i], cc), S[i + zl + delta]);
             }
-            ++cnt;
-            if (cnt == OFDM_ACQ_MAX_SYMBOLS) cnt = 1;
-            __syncthreads();
+            int cnt_next = cnt + 1;
+            if (cnt_next == OFDM_ACQ_MAX_SYMBOLS) cnt_next = 1;
             // ---- ofdm_frame_sink ----
             if (vi == 0) {
                 // enter_have_sync: the flagged vector itself is not demapped
                 for (int c = tid; c < ncar; c += BT) dfe[c] = make_float2(1.f, 0.f);
-                if (tid == 0) { s_phase = 0.f; s_freq = 0.f; s_carry = 0u; s_hdr_ok = 0; s_len = 0; }
+                if (tid == 0) {
+                    s_phase = 0.f; s_freq = 0.f; s_carry = 0u; s_hdr_ok = 0; s_len = 0;
+                    s_car[par ^ 1] = make_float2(1.f, 0.f);                       // expj(0)
+                }
+                if (tid == 32) s_cc[par ^ 1] = coarse_comp(delta, p.cp, N, cnt_next);
                 __syncthreads();
             } else {
-                if (tid == 0) s_car = expj_f32(s_phase);
-                __syncthreads();
-                const float2 car = s_car;
+                const float2 car = s_car[par];
                 double er = 0.0, ei = 0.0;
                 for (int c = tid; c < ncar; c += BT) {
                     const float2 d0 = dfe[c];
-                    const float2 r = cmul_x(cmul_x(eq[LDG(p.sinkmap + c)], car), d0);
+                    const int i = LDG(p.sinkmap + c);
+                    const float2 eqv = cmul_x(cmul_x(H[i], cc), S[i + zl + delta]);
+                    const float2 r = cmul_x(cmul_x(eqv, car), d0);
                     // slicer: first minimum of |r - const[k]|^2
                     int b = 0;
                     float best;
@@ -240,7 +285,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                                              fadd_rn(d0.y, fmul_rn(0.05f, fsub_rn(q.y, d0.y))));
                     }
                     sym[c] = (uint8_t)b;
-                    if (tap) {
+                    if (TAPS && tap) {
                         if (p.sym_idx) p.sym_idx[vglob * ncar + c] = (uint8_t)b;
                         if (p.derot_syms) p.derot_syms[vglob * ncar + c] = r;
                     }
@@ -254,6 +299,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 __syncthreads();
                 const int B0 = bit_base >> 3, B1 = (bit_base + bits_this) >> 3;
                 if (tid == 0) {
+                    // PLL update, and the carrier of the next vector while we are at it
                     double sr = 0.0, si = 0.0;
                     for (int ww = 0; ww < NW; ++ww) { sr += red[ww * 8]; si += red[ww * 8 + 1]; }
                     const float angle = (float)atan2((double)(float)si, (double)(float)sr);
@@ -263,20 +309,20 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                     if ((double)ph < 0.0) ph = (float)((double)ph + 6.283185307179586);
                     s_freq = freq;
                     s_phase = ph;
+                    s_car[par ^ 1] = expj_f32(ph);
                 }
+                if (tid == 32) s_cc[par ^ 1] = coarse_comp(delta, p.cp, N, cnt_next);
                 // LSB-first byte packing; bits left over from the previous vector sit in s_carry
                 const unsigned carry = s_carry;
-                for (int q = B0 + tid; q < B1; q += BT) {
-                    unsigned byte = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rel = 8 * q + i - bit_base;
-                        unsigned bit;
-                        if (rel < 0) bit = (carry >> i) & 1u;
-                        else bit = ((unsigned)sym[rel / nbits] >> (rel % nbits)) & 1u;
-                        byte |= bit << i;
-                    }
-                    vb[q - B0] = (uint8_t)byte;
+                switch (nbits) {
+                    case 1: pack_bytes<1>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
+                    case 2: pack_bytes<2>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
+                    case 3: pack_bytes<3>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
+                    case 4: pack_bytes<4>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
+                    case 5: pack_bytes<5>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
+                    case 6: pack_bytes<6>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
+                    case 7: pack_bytes<7>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
+                    default: pack_bytes<8>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
                 }
                 __syncthreads();
                 if (tid == 0) {
@@ -304,6 +350,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 bit_base += bits_this;
                 if (B1 >= 4 + len) { status = 2; nvec = vi + 1; break; }
             }
+            cnt = cnt_next;
             ++vi;
             ++m;
             if (m > p.frame_ndata[g]) { ++g; m = 0; }
@@ -316,16 +363,16 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     }
 }
 
-template <int N>
-static int launch_demod_n(ofdm_handle* h, const DemodParams& p, int max_frames, cudaStream_t st) {
+template <int N, bool TAPS>
+static int launch_demod_nt(ofdm_handle* h, const DemodParams& p, int max_frames, cudaStream_t st) {
     constexpr int T = N / FftPlan<N>::E;
     constexpr int BT = T < 64 ? 64 : T;
     constexpr int NW = BT / 32;
-    size_t smem = sizeof(double) * 8 * NW + sizeof(float2) * (2 * (size_t)fft_smem_elems<N>() + 3 * (size_t)p.occ + p.M) +
+    size_t smem = sizeof(double) * 8 * NW + sizeof(float2) * (2 * (size_t)fft_smem_elems<N>() + 2 * (size_t)p.occ + p.M) +
                   ((p.ncar + 15) & ~15) + (size_t)(p.ncar * p.nbits / 8 + 16);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        OFDM_CUDA_CHECK(cudaFuncSetAttribute(demod_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OFDM_CUDA_CHECK(cudaFuncSetAttribute(demod_kernel<N, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
     int sms = 148;
@@ -333,9 +380,15 @@ static int launch_demod_n(ofdm_handle* h, const DemodParams& p, int max_frames, 
     int grid = sms * 32;
     if (grid > max_frames) grid = max_frames;
     if (grid < 1) grid = 1;
-    demod_kernel<N><<<grid, BT, smem, st>>>(p);
+    demod_kernel<N, TAPS><<<grid, BT, smem, st>>>(p);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
+}
+
+template <int N>
+static int launch_demod_n(ofdm_handle* h, const DemodParams& p, int max_frames, cudaStream_t st) {
+    const bool taps = p.eq_syms || p.sym_idx || p.derot_syms;
+    return taps ? launch_demod_nt<N, true>(h, p, max_frames, st) : launch_demod_nt<N, false>(h, p, max_frames, st);
 }
 
 int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {

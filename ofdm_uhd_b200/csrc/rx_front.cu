@@ -56,7 +56,7 @@ struct FiltParams {
 };
 
 template <int NOS, int G>
-__global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E)) chan_filter_kernel(const FiltParams p) {
+__global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 2) chan_filter_kernel(const FiltParams p) {
     using P = FftPlan<NOS>;
     constexpr int E = P::E;
     constexpr int T = NOS / E;

@@ -75,7 +75,7 @@ template <int N>
 struct TxLoad {
     const TxParams& p;
     const uint8_t* pkt;
-    int64_t pkt_bits;
+    int pkt_bits;
     int64_t frame_id;
     int dsym;                    // data symbol number inside the frame
     const float2* s_cst;
@@ -83,9 +83,9 @@ struct TxLoad {
         const int v = (idx + N / 2) & (N - 1);          // ifftshift: IFFT input idx holds vector bin v
         const int c = LDG(p.bin2car + v);
         if (c < 0) return make_float2(0.f, 0.f);
-        const int64_t bit0 = ((int64_t)dsym * p.ncar + c) * p.nbits;
+        const int bit0 = (dsym * p.ncar + c) * p.nbits;          // < 8 * 4112: 32-bit math
         uint32_t val;
-        if (bit0 + p.nbits <= pkt_bits) val = extract_bits(pkt, bit0, p.nbits);
+        if (bit0 + p.nbits <= pkt_bits) val = extract_bits32(pkt, bit0, p.nbits);
         else val = pad_index(p.seed, (uint64_t)frame_id, (uint32_t)dsym, (uint32_t)c, (uint32_t)p.M);
         return s_cst[val];
     }
@@ -105,7 +105,7 @@ struct TxStore {
 };
 
 template <int N, int G>
-__global__ void __launch_bounds__(G * (N / FftPlan<N>::E)) tx_kernel(const TxParams p) {
+__global__ void __launch_bounds__(G * (N / FftPlan<N>::E), FftPlan<N>::E == 8 ? 4 : 1) tx_kernel(const TxParams p) {
     constexpr int T = N / FftPlan<N>::E;
     constexpr int SB = fft_smem_elems<N>();
     extern __shared__ float2 smem[];
@@ -119,26 +119,27 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E)) tx_kernel(const TxPar
     float2* bufB = bufA + SB;
     const int L = N + p.cp;
     auto bar = [] { __syncthreads(); };
-    for (int64_t base = (int64_t)blockIdx.x * G; base < p.total_syms; base += (int64_t)gridDim.x * G) {
-        const int64_t s = base + g;
-        const bool active = s < p.total_syms;
+    const unsigned total = (unsigned)p.total_syms;               // launcher guarantees < 2^31
+    for (unsigned base = blockIdx.x * G; base < total; base += gridDim.x * G) {
+        const unsigned s = base + g;
+        const bool active = s < total;
         int f = 0;
         int m = 0;
         if (active) {
             if (p.uniform_syms > 0) {
-                f = (int)(s / p.uniform_syms);
-                m = (int)(s - (int64_t)f * p.uniform_syms);
+                f = (int)(s / (unsigned)p.uniform_syms);
+                m = (int)(s - (unsigned)f * (unsigned)p.uniform_syms);
             } else {
                 int lo = 0, hi = p.n_frames;              // last f with sym_off[f] <= s
                 while (hi - lo > 1) {
                     int mid = (lo + hi) >> 1;
-                    if (LDG(p.sym_off + mid) <= s) lo = mid; else hi = mid;
+                    if (LDG(p.sym_off + mid) <= (int64_t)s) lo = mid; else hi = mid;
                 }
                 f = lo;
                 m = (int)(s - LDG(p.sym_off + f));
             }
         }
-        float2* dst = p.out + s * L;
+        float2* dst = p.out + (size_t)s * L;
         const bool data = active && m > 0;
         if (active && m == 0) {
             // ofdm_insert_preamble: the pre-modulated known symbol
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E)) tx_kernel(const TxPar
         }
         const int64_t o0 = active ? LDG(p.pkt_off + f) : 0;
         const int64_t o1 = active ? LDG(p.pkt_off + f + 1) : 0;
-        TxLoad<N> ld{p, p.pkts + o0, (o1 - o0) * 8, p.first_frame + f, m - 1, s_cst};
+        TxLoad<N> ld{p, p.pkts + o0, (int)(o1 - o0) * 8, p.first_frame + f, m - 1, s_cst};
         TxStore<N> st{dst, p.cp, p.s1, p.amp};
         using P = FftPlan<N>;
         constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
@@ -193,6 +194,7 @@ int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32
     p.tw = h->d_tw; p.pre_time = h->d_pre_time; p.cp = h->cp; p.ncar = h->ncar; p.nbits = h->nbits; p.M = h->M;
     p.s1 = (float)(1.0 / sqrt((double)h->N)); p.amp = h->amp;
     p.total_syms = uniform_syms > 0 ? (int64_t)n_frames * uniform_syms : total_syms;
+    if (p.total_syms >= (1ll << 31)) { ofdm_set_error("tx: more than 2^31 OFDM symbols in one batch"); return OFDM_E_INVAL; }
     switch (h->N) {
         case 64:   return launch_tx_n<64, 8>(h, p, st);
         case 128:  return launch_tx_n<128, 8>(h, p, st);
