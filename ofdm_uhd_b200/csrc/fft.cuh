@@ -95,12 +95,22 @@ HD void fft_pass(int tid, const float2* __restrict__ tw, In in, Out out) {
         for (int r = 0; r < R; ++r) v[r] = in(j + r * (N / R), q * R + r);
         const int k = j & (NS - 1);
         if (NS > 1) {
+            // twiddles w^r, r < R: only the power-of-two exponents are loaded (3-4 loads instead of R-1, which
+            // were the long-scoreboard stalls of every FFT kernel); the others are products of two loaded ones
+            float2 w[R];
 #pragma unroll
-            for (int r = 1; r < R; ++r) {
-                float2 w = LDG(tw + r * k * (N / (NS * R)));
-                if (S > 0) w.y = -w.y;
-                v[r] = cmul(v[r], w);
+            for (int r = 1; r < R; r <<= 1) {
+                w[r] = LDG(tw + r * k * (N / (NS * R)));
+                if (S > 0) w[r].y = -w[r].y;
             }
+#pragma unroll
+            for (int r = 3; r < R; ++r)
+                if (r & (r - 1)) {                                   // not a power of two
+                    const int hi = (r >= 8) ? 8 : ((r >= 4) ? 4 : 2);
+                    w[r] = cmul(w[hi], w[r - hi]);
+                }
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
         }
         DftReg<R, S>::run(v);
         const int j0 = (j - k) * R + k;
