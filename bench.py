@@ -213,7 +213,7 @@ def run_b200(args):
         fn()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
+        reps = 10
         a.record()
         for _ in range(reps):
             fn()

@@ -172,12 +172,13 @@ __device__ __forceinline__ double block_excl_scan_f64(double v, double* s_warp, 
 
 // Exclusive scan of one value per thread inside segments of G consecutive threads (G a power of two),
 // forwards (sum of the segment's earlier threads) or backwards (later threads).  Only additions.
-template <bool FWD>
-__device__ __forceinline__ double seg_excl_scan(double v, int G, double* s_wt) {
+template <bool FWD, int G>
+__device__ __forceinline__ double seg_excl_scan(double v, double* s_wt) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int width = G < 32 ? G : 32;
+    constexpr int width = G < 32 ? G : 32;
     const int pos = lane & (width - 1);
     double inc = v;
+#pragma unroll
     for (int d = 1; d < width; d <<= 1) {
         const double o = FWD ? __shfl_up_sync(0xffffffffu, inc, d, width) : __shfl_down_sync(0xffffffffu, inc, d, width);
         if (FWD ? (pos >= d) : (pos + d < width)) inc += o;
@@ -187,7 +188,8 @@ __device__ __forceinline__ double seg_excl_scan(double v, int G, double* s_wt) {
     if (G > 32) {
         if (lane == (FWD ? 31 : 0)) s_wt[w] = inc;                        // warp total
         __syncthreads();
-        const int wps = G >> 5, wseg = w & (wps - 1), w0 = w - wseg;
+        constexpr int wps = G >> 5;
+        const int wseg = w & (wps - 1), w0 = w - wseg;
         if (FWD) { for (int j = 0; j < wseg; ++j) exc += s_wt[w0 + j]; }
         else     { for (int j = wseg + 1; j < wps; ++j) exc += s_wt[w0 + j]; }
         __syncthreads();
@@ -195,15 +197,15 @@ __device__ __forceinline__ double seg_excl_scan(double v, int G, double* s_wt) {
     return exc;
 }
 
-template <int K>
-__global__ void __launch_bounds__(SM_THREADS) sync_metric_kernel(const float2* __restrict__ y, int64_t n, int N, int cp,
+template <int K, int G>
+__global__ void __launch_bounds__(SM_THREADS, (K <= 8 ? 2 : 1)) sync_metric_kernel(const float2* __restrict__ y, int64_t n, int cp,
                                                                  float tapf, float* __restrict__ mf,
                                                                  int64_t* __restrict__ first_nan) {
     constexpr int C = SM_THREADS * K;
 #define PADK(e) ((e) + (e) / K)
     extern __shared__ double S[];                  // PADK(C) doubles, later reused as float staging
     __shared__ double s_warp[33];
-    const int h = N / 2;
+    constexpr int h = G * K;                       // N/2
     const int T = C - cp - h;                      // outputs per tile
     const int64_t t0 = (int64_t)blockIdx.x * T;
     const int64_t a = t0 - cp - h;                 // global index of tile element 0
@@ -246,31 +248,35 @@ __global__ void __launch_bounds__(SM_THREADS) sync_metric_kernel(const float2* _
     // prefix(start of e's block .. e).  Only terms inside the window are ever added, so an all-zero window
     // gives exactly 0 (-> 0/0 = NaN like the reference's FIR sums) and there is no cancellation noise when
     // the signal level drops.
-    const int G = h / K;
+    // A window ending at e0+i starts at (e0-h)+(i+1): elements i+1.. of thread tid-G, or (i = K-1) element 0 of
+    // thread tid-G+1; that last window is a whole block (no tail) exactly when e0+K is a multiple of h.
+    const bool has_prev = tid >= G;
+    const bool whole_last = ((e0 + K) & (h - 1)) == 0;
+    const int pb = e0 + tid;                                       // PADK(e0)
+    const int qb = pb - (h + G);                                   // PADK(e0 - h)
 #pragma unroll
     for (int arr = 0; arr < 3; ++arr) {
         const float* src = arr == 0 ? cre : (arr == 1 ? cim : en);
         float* dst = arr == 0 ? Pr : (arr == 1 ? Pi : R);
-        double pre[K], suf[K];
+        double x[K], pre[K];
         double run = 0.0;
 #pragma unroll
-        for (int i = 0; i < K; ++i) { run += (double)src[i]; pre[i] = run; }
+        for (int i = 0; i < K; ++i) { x[i] = (double)src[i]; run += x[i]; pre[i] = run; }
         const double tot = run;
-        run = 0.0;
+        const double fwd = seg_excl_scan<true, G>(tot, s_warp);
+        const double bwd = seg_excl_scan<false, G>(tot, s_warp);
+        run = bwd;
 #pragma unroll
-        for (int i = K - 1; i >= 0; --i) { run += (double)src[i]; suf[i] = run; }
-        const double fwd = seg_excl_scan<true>(tot, G, s_warp);
-        const double bwd = seg_excl_scan<false>(tot, G, s_warp);
-#pragma unroll
-        for (int i = 0; i < K; ++i) { pre[i] += fwd; suf[i] += bwd; S[PADK(e0 + i)] = suf[i]; }
+        for (int i = K - 1; i >= 0; --i) { run += x[i]; S[pb + i] = run; }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            const int e = e0 + i;
-            const int sidx = e - h + 1;                                   // first sample of the window
-            const bool whole = ((e + 1) & (h - 1)) == 0;                  // the window is exactly one block
-            const double tail = (sidx >= 0 && !whole) ? S[PADK(sidx)] : 0.0;
-            dst[i] = (float)(tail + pre[i]);
+            double tail = 0.0;
+            if (has_prev) {
+                if (i < K - 1) tail = S[qb + i + 1];
+                else if (!whole_last) tail = S[qb + K + 1];
+            }
+            dst[i] = (float)(tail + (pre[i] + fwd));
         }
         __syncthreads();
     }
@@ -321,38 +327,38 @@ __global__ void __launch_bounds__(SM_THREADS) sync_metric_kernel(const float2* _
 
 __global__ void init_i64_kernel(int64_t* p, int64_t v) { *p = v; }
 
+template <int K, int G>
+static int launch_metric_kg(ofdm_handle* h, const float2* y, int64_t n, float* mf, int64_t* first_nan, cudaStream_t st) {
+    const int need = h->cp + h->N / 2;
+    const float tapf = (float)(1.0 / (double)h->cp);
+    const int T = SM_THREADS * K - need;
+    if (T < 256) { ofdm_set_error("sync_metric: cp_length too large for the tile"); return OFDM_E_INVAL; }
+    size_t smem = sizeof(double) * (size_t)(SM_THREADS * K + SM_THREADS + 8);
+    static bool attr_done = false;
+    if (!attr_done) {
+        OFDM_CUDA_CHECK(cudaFuncSetAttribute(sync_metric_kernel<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    sync_metric_kernel<K, G><<<(unsigned)((n + T - 1) / T), SM_THREADS, smem, st>>>(y, n, h->cp, tapf, mf, first_nan);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
 int launch_sync_metric(ofdm_handle* h, const float2* y, int64_t n, float* mf, int64_t* first_nan, cudaStream_t st) {
     init_i64_kernel<<<1, 1, 0, st>>>(first_nan, LLONG_MAX);
     OFDM_LAUNCH_CHECK();
     if (n <= 0) return OFDM_OK;
-    const int need = h->cp + h->N / 2;
-    const float tapf = (float)(1.0 / (double)h->cp);
-    if (2 * need <= SM_THREADS * 8) {
-        constexpr int K = 8;
-        const int T = SM_THREADS * K - need;
-        size_t smem = sizeof(double) * (size_t)(SM_THREADS * K + SM_THREADS + 8);
-        static bool attr_done = false;
-        if (!attr_done) {
-            OFDM_CUDA_CHECK(cudaFuncSetAttribute(sync_metric_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
-        }
-        sync_metric_kernel<K><<<(unsigned)((n + T - 1) / T), SM_THREADS, smem, st>>>(y, n, h->N, h->cp, tapf, mf, first_nan);
-    } else if (2 * need <= SM_THREADS * 16 + 4096) {
-        constexpr int K = 16;
-        const int T = SM_THREADS * K - need;
-        size_t smem = sizeof(double) * (size_t)(SM_THREADS * K + SM_THREADS + 8);
-        static bool attr_done = false;
-        if (!attr_done) {
-            OFDM_CUDA_CHECK(cudaFuncSetAttribute(sync_metric_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
-        }
-        sync_metric_kernel<K><<<(unsigned)((n + T - 1) / T), SM_THREADS, smem, st>>>(y, n, h->N, h->cp, tapf, mf, first_nan);
-    } else {
-        ofdm_set_error("sync_metric: fft_length/cp_length too large for the tile");
-        return OFDM_E_INVAL;
+    switch (h->N) {                                   // G = (N/2) / K threads per N/2-sample block
+        case 64:   return launch_metric_kg<8, 4>(h, y, n, mf, first_nan, st);
+        case 128:  return launch_metric_kg<8, 8>(h, y, n, mf, first_nan, st);
+        case 256:  return launch_metric_kg<8, 16>(h, y, n, mf, first_nan, st);
+        case 512:  return launch_metric_kg<8, 32>(h, y, n, mf, first_nan, st);
+        case 1024: return launch_metric_kg<8, 64>(h, y, n, mf, first_nan, st);
+        case 2048: return launch_metric_kg<16, 64>(h, y, n, mf, first_nan, st);
+        case 4096: return launch_metric_kg<16, 128>(h, y, n, mf, first_nan, st);
     }
-    OFDM_LAUNCH_CHECK();
-    return OFDM_OK;
+    ofdm_set_error("sync_metric: unsupported fft_length %d", h->N);
+    return OFDM_E_INVAL;
 }
 
 // ---------------------------------------------------------------------------------------------
