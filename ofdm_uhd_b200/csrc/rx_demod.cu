@@ -80,6 +80,7 @@ __device__ __forceinline__ float2 expj_f32(float ph) {
 
 // coarse_freq_comp(delta, count) = expj(float(-2*pi*delta*cp) / N * count)   (A.10)
 __device__ __forceinline__ float2 coarse_comp(int delta, int cp, int N, int cnt) {
+    if (delta == 0) return make_float2(1.0f, -0.0f);     // ph = -0.0: (cos, sin) without the float64 sincos
     const float a = (float)(-2.0 * 3.14159265358979323846 * (double)delta * (double)cp);
     const float ph = fmul_rn(fdiv_rn(a, (float)N), (float)cnt);
     return expj_f32(ph);
@@ -104,7 +105,7 @@ __device__ __forceinline__ void pack_bytes(const uint8_t* sym, uint8_t* vb, int 
 }
 
 template <int N, bool TAPS>
-__global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E)) demod_kernel(const DemodParams p) {
+__global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E), (FftPlan<N>::E == 8 && !TAPS) ? 16 : 1) demod_kernel(const DemodParams p) {
     using P = FftPlan<N>;
     constexpr int E = P::E;
     constexpr int T = N / E;
