@@ -26,8 +26,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-KERNELS_PER_STEP = 12   # make_packets, tx, chan_filter, init, sync_metric, peak_detect, seg_scan, trig_gather,
-                        # plan, demod, liveness, crc
+KERNELS_PER_STEP = 11   # make_packets, tx, chan_filter, stream_init, sync_stream, seg_scan, trig_gather, plan,
+                        # demod, liveness, crc
 
 
 def peaks():
@@ -204,8 +204,7 @@ def run_b200(args):
         "tx_kernel": lambda: L_.ofdm_tx_modulate_batch(eng.h, eng._p(plan.pkts), eng._p(plan.d_pkt_off), F, 0, None,
                                                        plan.total_syms, plan.uniform_syms, eng._p(xs), st),
         "chan_filter_kernel": lambda: L_.ofdm_rx_chan_filter(eng.h, eng._p(xc), n, eng._p(y), st),
-        "sync_metric_kernel": lambda: L_.ofdm_rx_sync_metric(eng.h, eng._p(y), n, eng._p(mf), eng._p(fnan), st),
-        "peak_detect(+scan,gather)": lambda: L_.ofdm_rx_peak_detect(eng.h, eng._p(y), eng._p(mf), n, eng._p(fnan), C.byref(io), st),
+        "sync_stream_kernel(+scan,gather)": lambda: L_.ofdm_rx_sync(eng.h, eng._p(y), n, C.byref(io), st),
         "plan_kernel": lambda: L_.ofdm_rx_plan(eng.h, n, C.byref(io), st),
         "demod_kernel": lambda: L_.ofdm_rx_demod(eng.h, eng._p(y), n, C.byref(io), st),
         "liveness+crc": lambda: L_.ofdm_rx_finish(eng.h, C.byref(io), st),

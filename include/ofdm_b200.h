@@ -116,6 +116,10 @@ int ofdm_rx_sync_metric(ofdm_handle* h, const float* y_iq, int64_t n, float* mf,
 /* gr.peak_detector_fb(0.20,0.20,30,0.001) + complex_to_arg + sample_and_hold (ofdm_sync_pn) */
 int ofdm_rx_peak_detect(ofdm_handle* h, const float* y_iq, const float* mf, int64_t n, const int64_t* first_nan,
                         ofdm_rx_io* io, void* stream);
+/* the whole ofdm_sync_pn hier-block (ofdm_receiver.py~:97-101) in one pass: y -> io->n_trig / trig_idx / trig_ang.
+ * Uses the fused streaming kernel when 32*K = N/2 (N = 128, 256, 512) and cp <= N/2, else the two stages above
+ * (ofdm_rx_demodulate also falls back to them for streams too short to fill the GPU with one warp per segment). */
+int ofdm_rx_sync(ofdm_handle* h, const float* y_iq, int64_t n, ofdm_rx_io* io, void* stream);
 /* gr.frequency_modulator_fc + digital.ofdm_sampler (ofdm_receiver.py~:123-125,133-136) as a frame table */
 int ofdm_rx_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, void* stream);
 /* multiply_cc (derotation) + fft_vcc(forward) + ofdm_frame_acquisition + ofdm_frame_sink

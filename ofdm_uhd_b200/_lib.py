@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libofdm_b200.so")
 EXPORTS = [
     "ofdm_last_error", "ofdm_version", "ofdm_create", "ofdm_destroy", "ofdm_set_tx_amplitude", "ofdm_get_layout",
     "ofdm_get_chan_taps", "ofdm_packet_len", "ofdm_make_packets", "ofdm_frame_symbols", "ofdm_tx_modulate_batch",
-    "ofdm_rx_workspace_bytes", "ofdm_rx_chan_filter", "ofdm_rx_sync_metric", "ofdm_rx_peak_detect", "ofdm_rx_plan",
+    "ofdm_rx_workspace_bytes", "ofdm_rx_chan_filter", "ofdm_rx_sync_metric", "ofdm_rx_peak_detect", "ofdm_rx_sync",
+    "ofdm_rx_plan",
     "ofdm_rx_demod", "ofdm_rx_finish", "ofdm_rx_demodulate", "ofdm_rx_workspace_ptr", "ofdm_channel",
     "ofdm_sense_create", "ofdm_sense_destroy", "ofdm_sense", "ofdm_sense_fft", "ofdm_sense_decide",
 ]
@@ -69,6 +70,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.ofdm_rx_chan_filter.argtypes = [vp, vp, i64, vp, vp]
     L.ofdm_rx_sync_metric.argtypes = [vp, vp, i64, vp, vp, vp]
     L.ofdm_rx_peak_detect.argtypes = [vp, vp, vp, i64, vp, C.POINTER(RxIo), vp]
+    L.ofdm_rx_sync.argtypes = [vp, vp, i64, C.POINTER(RxIo), vp]
     L.ofdm_rx_plan.argtypes = [vp, i64, C.POINTER(RxIo), vp]
     L.ofdm_rx_demod.argtypes = [vp, vp, i64, C.POINTER(RxIo), vp]
     L.ofdm_rx_finish.argtypes = [vp, C.POINTER(RxIo), vp]

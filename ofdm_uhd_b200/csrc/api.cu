@@ -369,6 +369,26 @@ extern "C" int ofdm_rx_finish(ofdm_handle* h, ofdm_rx_io* io, void* stream) {
     return launch_finish(h, io, &ws, (cudaStream_t)stream);
 }
 
+// ofdm_sync_pn: the fused streaming kernel where the layout allows it (32*K = N/2, cp <= N/2), else the
+// metric kernel followed by the detector kernel
+static int rx_sync(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, int force_fused,
+                   cudaStream_t st) {
+    OFDM_CUDA_CHECK(cudaMemsetAsync(io->status, 0, sizeof(uint32_t), st));
+    int rc = launch_sync_stream(h, y, n, io, ws, force_fused, st);
+    if (rc == 0) return launch_trig_compact(h, y, n, io, ws, st);
+    if (rc < 0) return rc;
+    if ((rc = launch_sync_metric(h, y, n, ws->mf, ws->first_nan, st))) return rc;
+    return launch_peak_detect(h, y, ws->mf, n, ws->first_nan, io, ws, st);
+}
+
+extern "C" int ofdm_rx_sync(ofdm_handle* h, const float* y, int64_t n, ofdm_rx_io* io, void* stream) {
+    NEED(h);
+    RxWorkspace ws;
+    int rc = get_ws(h, n, io, &ws);
+    if (rc) return rc;
+    return rx_sync(h, (const float2*)y, n, io, &ws, 1, (cudaStream_t)stream);
+}
+
 extern "C" int ofdm_rx_demodulate(ofdm_handle* h, const float* x, int64_t n, ofdm_rx_io* io, void* stream) {
     NEED(h);
     RxWorkspace ws;
@@ -376,8 +396,7 @@ extern "C" int ofdm_rx_demodulate(ofdm_handle* h, const float* x, int64_t n, ofd
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = launch_chan_filter(h, (const float2*)x, n, ws.y, st))) return rc;
-    if ((rc = launch_sync_metric(h, ws.y, n, ws.mf, ws.first_nan, st))) return rc;
-    if ((rc = launch_peak_detect(h, ws.y, ws.mf, n, ws.first_nan, io, &ws, st))) return rc;
+    if ((rc = rx_sync(h, ws.y, n, io, &ws, 0, st))) return rc;
     if ((rc = launch_plan(h, n, io, &ws, st))) return rc;
     if ((rc = launch_demod(h, ws.y, n, io, &ws, st))) return rc;
     return launch_finish(h, io, &ws, st);

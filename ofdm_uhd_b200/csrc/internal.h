@@ -79,6 +79,9 @@ int launch_chan_filter(ofdm_handle* h, const float2* x, int64_t n, float2* y, cu
 int launch_sync_metric(ofdm_handle* h, const float2* y, int64_t n, float* mf, int64_t* first_nan, cudaStream_t st);
 int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t n, const int64_t* first_nan,
                        ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_trig_compact(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_sync_stream(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, int force,
+                       cudaStream_t st);
 int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
 int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
 int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);

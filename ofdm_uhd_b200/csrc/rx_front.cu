@@ -563,9 +563,21 @@ __global__ void __launch_bounds__(256) trig_gather_kernel(const float2* __restri
     }
 }
 
+int launch_trig_compact(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+    seg_scan_kernel<<<1, 1024, 0, st>>>(ws->seg_count, ws->n_seg, ws->seg_off, io->n_trig, io->max_frames, io->status);
+    OFDM_LAUNCH_CHECK();
+    trig_gather_kernel<<<(unsigned)((ws->n_seg + 7) / 8), 256, 0, st>>>(y, n, h->N, ws->seg_count, ws->seg_off, ws->seg_trig,
+                                                                        ws->n_seg, (int)ws->seg_cap, io->max_frames,
+                                                                        io->trig_idx, io->trig_ang);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
 int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t n, const int64_t* first_nan,
                        ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
     OFDM_CUDA_CHECK(cudaMemsetAsync(io->status, 0, sizeof(uint32_t), st));
+    if (first_nan != ws->first_nan)                  // the plan reads it from the workspace
+        OFDM_CUDA_CHECK(cudaMemcpyAsync(ws->first_nan, first_nan, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     if (ws->n_seg == 0) {
         OFDM_CUDA_CHECK(cudaMemsetAsync(io->n_trig, 0, sizeof(int32_t), st));
         return OFDM_OK;
@@ -576,13 +588,7 @@ int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t
     const int wpb = 4;
     peak_detect_kernel<<<(unsigned)((ws->n_seg + wpb - 1) / wpb), wpb * 32, 0, st>>>(p);
     OFDM_LAUNCH_CHECK();
-    seg_scan_kernel<<<1, 1024, 0, st>>>(ws->seg_count, ws->n_seg, ws->seg_off, io->n_trig, io->max_frames, io->status);
-    OFDM_LAUNCH_CHECK();
-    trig_gather_kernel<<<(unsigned)((ws->n_seg + 7) / 8), 256, 0, st>>>(y, n, h->N, ws->seg_count, ws->seg_off, ws->seg_trig,
-                                                                        ws->n_seg, (int)ws->seg_cap, io->max_frames,
-                                                                        io->trig_idx, io->trig_ang);
-    OFDM_LAUNCH_CHECK();
-    return OFDM_OK;
+    return launch_trig_compact(h, y, n, io, ws, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -592,7 +598,8 @@ int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t
 struct PlanParams {
     int64_t n;
     int N, L, max_frames;
-    const int32_t* n_trig;
+    int32_t* n_trig;
+    const int64_t* first_nan;
     const int64_t* trig_idx;
     const float* trig_ang;
     double* phi0;
@@ -616,8 +623,20 @@ __global__ void __launch_bounds__(1024) plan_kernel(const PlanParams p) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     int K = *p.n_trig;
     if (K > p.max_frames) K = p.max_frames;
+    {
+        // nothing fires after the first NaN of the timing metric (C.1): a run that was open closes there with
+        // its arg-max before it, so exactly the triggers at indices < first_nan survive
+        const int64_t fn = *p.first_nan;
+        int lo = 0, hi = K;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (p.trig_idx[mid] < fn) lo = mid + 1; else hi = mid;
+        }
+        K = lo;
+    }
     const int64_t N = p.N, L = p.L, n = p.n;
-    if (tid == 0) { s_carry_d = 0.0; s_carry_i = 0; s_first_ok = K; s_nfr = INT_MAX; }
+    __syncthreads();
+    if (tid == 0) { s_carry_d = 0.0; s_carry_i = 0; s_first_ok = K; s_nfr = INT_MAX; *p.n_trig = K; }
     __syncthreads();
     // (1) NCO: step_k = -2/N * ang_k ; phi0_k = sum_{j<k} step_j * (t_{j+1} - t_j)
     for (int base = 0; base < K; base += 1024) {
@@ -739,7 +758,8 @@ __global__ void __launch_bounds__(1024) plan_kernel(const PlanParams p) {
 
 int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
     PlanParams p;
-    p.n = n; p.N = h->N; p.L = h->L; p.max_frames = io->max_frames; p.n_trig = io->n_trig; p.trig_idx = io->trig_idx;
+    p.n = n; p.N = h->N; p.L = h->L; p.max_frames = io->max_frames; p.n_trig = io->n_trig; p.first_nan = ws->first_nan;
+    p.trig_idx = io->trig_idx;
     p.trig_ang = io->trig_ang; p.phi0 = ws->phi0; p.step = ws->step; p.first_ok = ws->first_ok; p.n_frames = io->n_frames;
     p.frame_start = io->frame_start; p.frame_ndata = io->frame_ndata; p.vbase = ws->vbase; p.counters = io->counters;
     OFDM_CUDA_CHECK(cudaMemsetAsync(io->counters, 0, 8 * sizeof(int64_t), st));

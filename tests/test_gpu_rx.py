@@ -227,3 +227,50 @@ def test_large_stream_round_trip():
     assert res2.packets == res.packets and np.array_equal(res2.trig_idx, res.trig_idx)
     assert res.counters[2] == len(ok) and res.counters[3] == len(ok) * psize
     eng.close()
+
+
+@pytest.mark.parametrize("N,occ,cp,mod,nfr,snr,cfo", CASES)
+def test_fused_sync_equals_oracle(N, occ, cp, mod, nfr, snr, cfo):
+    """ofdm_rx_sync (the fused streaming ofdm_sync_pn kernel for N = 128..512, the two-stage path otherwise) on the
+    oracle's filtered stream: trigger indices exact, latched angles within float32 rounding."""
+    import torch
+    from ofdm_uhd_b200 import _lib
+    from ofdm_uhd_b200.engine import OfdmEngine
+    rng = np.random.default_rng(3 * N + nfr)
+    lay = o.Layout(N, occ, cp, mod)
+    _, xc = loopback_capture(lay, payloads(rng, nfr), snr, cfo, seed=N + 5)
+    r = o.rx_demodulate(xc, lay, keep=True)
+    eng = OfdmEngine(N, occ, cp, mod)
+    n = len(xc)
+    bufs = eng.rx_alloc(n)
+    d_y = torch.from_numpy(r.y).cuda()
+    _lib.check(eng.L_.ofdm_rx_sync(eng.h, eng._p(d_y), n, C.byref(bufs["io"]), eng._stream()))
+    torch.cuda.synchronize()
+    nt = int(bufs["n_trig"].item())
+    assert int(bufs["status"].item()) == 0
+    assert np.array_equal(bufs["trig_idx"][:nt].cpu().numpy(), r.trig)
+    assert float(np.max(np.abs(bufs["trig_ang"][:nt].cpu().numpy() - r.ang))) < 1e-6
+    eng.close()
+
+
+def test_fused_sync_long_stream_segments():
+    """Several detector segments (seg_len 65 536) with warm-up and priming steps: 600 QAM16 frames, triggers must
+    equal the oracle's sequential detector on the same filtered stream."""
+    import torch
+    from ofdm_uhd_b200 import _lib
+    from ofdm_uhd_b200.engine import OfdmEngine
+    lay = o.Layout(512, 200, 128, "qam16")
+    rng = np.random.default_rng(77)
+    _, xc = loopback_capture(lay, payloads(rng, 600), 22, 0.17, seed=78)
+    y = o.chan_filter(xc, o.chan_filter_taps(lay))
+    mf, Pr, Pi = o.sync_pn_metric(y, 512, 128)
+    trig = o.peak_detect(mf)
+    eng = OfdmEngine(512, 200, 128, "qam16")
+    n = len(xc)
+    assert n > 30 * 65536
+    bufs = eng.rx_alloc(n)
+    _lib.check(eng.L_.ofdm_rx_sync(eng.h, eng._p(torch.from_numpy(y).cuda()), n, C.byref(bufs["io"]), eng._stream()))
+    torch.cuda.synchronize()
+    nt = int(bufs["n_trig"].item())
+    assert nt == len(trig) and np.array_equal(bufs["trig_idx"][:nt].cpu().numpy(), trig)
+    eng.close()
