@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(1024) liveness_kernel(const int32_t* __restric
                                                         int32_t* __restrict__ next, int32_t* __restrict__ exitf,
                                                         uint8_t* __restrict__ live) {
     __shared__ int s_entry[1024];
+    __shared__ int s_first_exit[1024];
     const int tid = threadIdx.x;
     const int F = *n_frames;
     s_entry[tid] = -1;
@@ -455,12 +456,16 @@ __global__ void __launch_bounds__(1024) liveness_kernel(const int32_t* __restric
         const int nx = next[f];
         exitf[f] = (nx < ce) ? exitf[nx] : nx;
     }
+    // exit of each chunk when entered at its first frame (the common case) -> shared memory, so that the
+    // serial hop over the chunks below is a chain of shared-memory reads, not of global-memory round trips
+    s_first_exit[tid] = (cs < F) ? exitf[cs] : F;
     __syncthreads();
     if (tid == 0) {
         int e = 0;
         while (e < F) {
-            s_entry[e / Kc] = e;
-            e = exitf[e];
+            const int c = e / Kc;
+            s_entry[c] = e;
+            e = (e == c * Kc) ? s_first_exit[c] : exitf[e];
         }
     }
     __syncthreads();
@@ -472,37 +477,80 @@ __global__ void __launch_bounds__(1024) liveness_kernel(const int32_t* __restric
         }
 }
 
-// unmake_packet: dewhiten (offset 0) + check_crc32 for every delivered message; counters for the stats
-__global__ void __launch_bounds__(128) crc_kernel(const int32_t* __restrict__ n_frames, const uint8_t* __restrict__ live,
-                                                  const uint8_t* __restrict__ status, const int32_t* __restrict__ pkt_len,
-                                                  uint8_t* __restrict__ pkt_bytes, int stride, uint8_t* __restrict__ pkt_ok,
-                                                  const uint8_t* __restrict__ mask, const uint32_t* __restrict__ crctab,
-                                                  int64_t* __restrict__ counters) {
+// unmake_packet: dewhiten (offset 0) + check_crc32 for every delivered message; counters for the stats.
+// One warp per 32 consecutive packet slots: when 32 slots fit, they are staged through shared memory (coalesced
+// word copies, rows padded by one word against bank conflicts) and each lane works on its own row there.
+constexpr int CRC_SMEM_WORDS = 3456;      // 32 rows of up to 107 words (stride <= 424 bytes)
+
+__device__ __forceinline__ uint8_t dewhiten_crc_row(uint8_t* b, int len, int stride, const uint8_t* __restrict__ mask,
+                                                    const uint32_t* s_crc) {
+    const int nst = len < stride ? len : stride;
+    uint32_t crc = 0xFFFFFFFFu, tail = 0;
+    for (int i = 0; i < nst; ++i) {
+        const uint8_t v = (uint8_t)(b[i] ^ mask[i & 4095]);
+        b[i] = v;
+        if (i < len - 4) crc = s_crc[(v ^ (crc >> 24)) & 0xFF] ^ (crc << 8);
+        else tail = (tail << 8) | v;
+    }
+    return (len >= 4 && len <= stride && (~crc) == tail) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(32) crc_kernel(const int32_t* __restrict__ n_frames, const uint8_t* __restrict__ live,
+                                                 const uint8_t* __restrict__ status, const int32_t* __restrict__ pkt_len,
+                                                 uint8_t* __restrict__ pkt_bytes, int stride, uint8_t* __restrict__ pkt_ok,
+                                                 const uint8_t* __restrict__ mask, const uint32_t* __restrict__ crctab,
+                                                 int64_t* __restrict__ counters) {
     __shared__ uint32_t s_crc[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = crctab[i];
-    __syncthreads();
+    __shared__ uint32_t s_rows[CRC_SMEM_WORDS];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 256; i += 32) s_crc[i] = crctab[i];
+    __syncwarp();
     const int F = *n_frames;
-    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+    const int wpr = stride >> 2, spr = wpr + 1;                   // words per row in global / shared memory
+    const bool staged = (stride & 3) == 0 && 32 * spr <= CRC_SMEM_WORDS && ((((uintptr_t)pkt_bytes) & 3) == 0);
+    for (int f0 = blockIdx.x * 32; f0 < F; f0 += gridDim.x * 32) {
+        const int f = f0 + lane;
+        const bool mine = f < F && live[f] && status[f] == 2;
+        const unsigned any = __ballot_sync(0xffffffffu, mine);
         uint8_t ok = 0;
-        if (live[f] && status[f] == 2) {
-            const int len = pkt_len[f];
-            uint8_t* b = pkt_bytes + (size_t)f * stride;
-            const int nst = len < stride ? len : stride;
-            uint32_t crc = 0xFFFFFFFFu, tail = 0;
-            for (int i = 0; i < nst; ++i) {
-                const uint8_t v = (uint8_t)(b[i] ^ mask[i & 4095]);
-                b[i] = v;
-                if (i < len - 4) crc = s_crc[(v ^ (crc >> 24)) & 0xFF] ^ (crc << 8);
-                else tail = (tail << 8) | v;
-            }
-            ok = (len >= 4 && len <= stride && (~crc) == tail) ? 1 : 0;
-            atomicAdd((unsigned long long*)&counters[1], 1ull);
-            if (ok) {
-                atomicAdd((unsigned long long*)&counters[2], 1ull);
-                atomicAdd((unsigned long long*)&counters[3], (unsigned long long)(len - 4));
+        int len = 0;
+        if (any) {
+            if (staged) {
+                const int nf = (F - f0 < 32) ? F - f0 : 32;
+                uint32_t* g = (uint32_t*)(pkt_bytes + (size_t)f0 * stride);
+                const int nw = nf * wpr;                          // the 32 slots are contiguous in global memory
+#pragma unroll 4
+                for (int i = lane; i < nw; i += 32) {
+                    const int r = i / wpr;
+                    s_rows[i + r] = g[i];                         // row r starts at r*spr = r*wpr + r
+                }
+                __syncwarp();
+                if (mine) { len = pkt_len[f]; ok = dewhiten_crc_row((uint8_t*)(s_rows + lane * spr), len, stride, mask, s_crc); }
+                __syncwarp();
+#pragma unroll 4
+                for (int i = lane; i < nw; i += 32) {
+                    const int r = i / wpr;
+                    if ((any >> r) & 1u) g[i] = s_rows[i + r];
+                }
+                __syncwarp();
+            } else if (mine) {
+                len = pkt_len[f];
+                ok = dewhiten_crc_row(pkt_bytes + (size_t)f * stride, len, stride, mask, s_crc);
             }
         }
-        pkt_ok[f] = ok;
+        if (f < F) pkt_ok[f] = ok;
+        // warp-aggregated counters: messages, CRC ok, payload bytes of the good ones
+        const unsigned okm = __ballot_sync(0xffffffffu, ok != 0);
+        int pay = ok ? len - 4 : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) pay += __shfl_xor_sync(0xffffffffu, pay, d);
+        if (lane == 0 && any) {
+            atomicAdd((unsigned long long*)&counters[1], (unsigned long long)__popc(any));
+            if (okm) {
+                atomicAdd((unsigned long long*)&counters[2], (unsigned long long)__popc(okm));
+                atomicAdd((unsigned long long*)&counters[3], (unsigned long long)pay);
+            }
+        }
     }
 }
 
@@ -510,9 +558,9 @@ int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t 
     OFDM_CUDA_CHECK(cudaMemsetAsync(io->frame_live, 0, (size_t)io->max_frames, st));
     liveness_kernel<<<1, 1024, 0, st>>>(io->n_frames, ws->vbase, ws->sess_nvec, ws->next_frame, ws->exit_frame, io->frame_live);
     OFDM_LAUNCH_CHECK();
-    int grid = (io->max_frames + 127) / 128;
-    if (grid > 148 * 16) grid = 148 * 16;
-    crc_kernel<<<grid, 128, 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len, io->pkt_bytes,
+    int grid = (io->max_frames + 31) / 32;
+    if (grid > 148 * 32) grid = 148 * 32;
+    crc_kernel<<<grid, 32, 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len, io->pkt_bytes,
                                       io->pkt_stride, io->pkt_ok, h->d_mask, h->d_crctab, io->counters);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;

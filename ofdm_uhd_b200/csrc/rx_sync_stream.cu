@@ -34,7 +34,7 @@ struct StreamParams {
 constexpr int SS_WARPS = 4;
 
 template <int K>
-__global__ void __launch_bounds__(SS_WARPS * 32) sync_stream_kernel(const StreamParams p) {
+__global__ void __launch_bounds__(SS_WARPS * 32, 3) sync_stream_kernel(const StreamParams p) {
     constexpr int SZ = 32 * K;                       // samples per step = N/2
     extern __shared__ double s_ring[];               // [SS_WARPS][2*SZ] prefix sums of the metric
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

@@ -7,43 +7,84 @@
 // make_packet (ofdm_packet_utils.py:99-143): one thread per packet.  CRC-32 is the upstream
 // digital.crc32 (MSB-first 0x04C11DB7, init/final all ones; digital_swig.py:3151-3168).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) make_packets_kernel(const uint8_t* __restrict__ payload,
-                                                            const int64_t* __restrict__ payload_off, int n_pkts,
-                                                            int whitening, uint8_t* __restrict__ pkts,
-                                                            const int64_t* __restrict__ pkt_off,
-                                                            const uint8_t* __restrict__ mask,
-                                                            const uint32_t* __restrict__ crctab) {
-    __shared__ uint32_t s_crc[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = crctab[i];
-    __syncthreads();
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pkts) return;
-    const uint8_t* src = payload + payload_off[p];
-    const int plen = (int)(payload_off[p + 1] - payload_off[p]);
-    uint8_t* dst = pkts + pkt_off[p];
-    const int total = (int)(pkt_off[p + 1] - pkt_off[p]);
-    const int L = plen + 4;
-    const uint32_t v = (uint32_t)(L & 0x0FFF);                 // whitener offset 0 (ofdm.py:143)
+__device__ __forceinline__ void frame_one_packet(const uint8_t* src, int plen, uint8_t* dst, int total, int whitening,
+                                                 const uint8_t* __restrict__ mask, const uint32_t* s_crc) {
+    const uint32_t v = (uint32_t)((plen + 4) & 0x0FFF);            // whitener offset 0 (ofdm.py:143)
     dst[0] = (uint8_t)(v >> 8); dst[1] = (uint8_t)v; dst[2] = (uint8_t)(v >> 8); dst[3] = (uint8_t)v;
     uint32_t crc = 0xFFFFFFFFu;
-    int o = 0;                                                  // offset into the whitened body
+    int o = 0;                                                      // offset into the whitened body
     for (int i = 0; i < plen; ++i, ++o) {
-        uint8_t b = src[i];
+        const uint8_t b = src[i];
         crc = s_crc[(b ^ (crc >> 24)) & 0xFF] ^ (crc << 8);
         dst[4 + o] = whitening ? (uint8_t)(b ^ mask[o]) : b;
     }
     crc = ~crc;
     for (int i = 0; i < 4; ++i, ++o) {
-        uint8_t b = (uint8_t)(crc >> (24 - 8 * i));
+        const uint8_t b = (uint8_t)(crc >> (24 - 8 * i));
         dst[4 + o] = whitening ? (uint8_t)(b ^ mask[o]) : b;
     }
     for (; 4 + o < total; ++o) dst[4 + o] = whitening ? (uint8_t)(0x55 ^ mask[o & 4095]) : (uint8_t)0x55;
 }
 
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* src, int nbytes, int lane) {
+    // src and dst have the same address phase modulo 4: byte head, word body, byte tail
+    int head = (int)((4 - ((uintptr_t)src & 3)) & 3);
+    if (head > nbytes) head = nbytes;
+    if (lane < head) dst[lane] = src[lane];
+    const uint32_t* s4 = (const uint32_t*)(src + head);
+    uint32_t* d4 = (uint32_t*)(dst + head);
+    const int nw = (nbytes - head) >> 2;
+    for (int i = lane; i < nw; i += 32) d4[i] = s4[i];
+    const int done = head + 4 * nw;
+    if (lane < nbytes - done) dst[done + lane] = src[done + lane];
+}
+
+// One warp per 32 consecutive packets: their payloads (contiguous in the input) are staged through shared
+// memory with coalesced word copies, each lane frames one packet there, and the 32 framed packets (contiguous
+// in the output) are written back coalesced.  Groups that do not fit the staging buffers are framed straight
+// from / to global memory by the same lanes.
+constexpr int MP_IN = 13312;      // 32 payloads (32 * 402 = 12 864 for the benchmark packet)
+constexpr int MP_OUT = 13824;     // 32 framed packets
+
+__global__ void __launch_bounds__(32) make_packets_kernel(const uint8_t* __restrict__ payload,
+                                                           const int64_t* __restrict__ payload_off, int n_pkts,
+                                                           int whitening, uint8_t* __restrict__ pkts,
+                                                           const int64_t* __restrict__ pkt_off,
+                                                           const uint8_t* __restrict__ mask,
+                                                           const uint32_t* __restrict__ crctab) {
+    __shared__ uint32_t s_crc[256];
+    __shared__ __align__(16) uint8_t s_in[MP_IN];
+    __shared__ __align__(16) uint8_t s_out[MP_OUT];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 256; i += 32) s_crc[i] = crctab[i];
+    __syncwarp();
+    const int f0 = blockIdx.x * 32;
+    if (f0 >= n_pkts) return;
+    const int nf = (n_pkts - f0 < 32) ? n_pkts - f0 : 32;
+    const int64_t in0 = payload_off[f0], out0 = pkt_off[f0];
+    const int64_t in_bytes = payload_off[f0 + nf] - in0, out_bytes = pkt_off[f0 + nf] - out0;
+    const int p = f0 + lane;
+    if (in_bytes + 4 > MP_IN || out_bytes + 4 > MP_OUT) {
+        if (lane < nf)
+            frame_one_packet(payload + payload_off[p], (int)(payload_off[p + 1] - payload_off[p]), pkts + pkt_off[p],
+                             (int)(pkt_off[p + 1] - pkt_off[p]), whitening, mask, s_crc);
+        return;
+    }
+    uint8_t* bi = s_in + ((uintptr_t)(payload + in0) & 3);       // same phase as the source / destination
+    uint8_t* bo = s_out + ((uintptr_t)(pkts + out0) & 3);
+    warp_copy_bytes(bi, payload + in0, (int)in_bytes, lane);
+    __syncwarp();
+    if (lane < nf)
+        frame_one_packet(bi + (int)(payload_off[p] - in0), (int)(payload_off[p + 1] - payload_off[p]),
+                         bo + (int)(pkt_off[p] - out0), (int)(pkt_off[p + 1] - pkt_off[p]), whitening, mask, s_crc);
+    __syncwarp();
+    warp_copy_bytes(pkts + out0, bo, (int)out_bytes, lane);
+}
+
 int launch_make_packets(ofdm_handle* h, const uint8_t* payload, const int64_t* payload_off, int32_t n_pkts,
                         int whitening, uint8_t* pkts, const int64_t* pkt_off, cudaStream_t st) {
-    make_packets_kernel<<<(n_pkts + 127) / 128, 128, 0, st>>>(payload, payload_off, n_pkts, whitening, pkts, pkt_off,
-                                                             h->d_mask, h->d_crctab);
+    make_packets_kernel<<<(n_pkts + 31) / 32, 32, 0, st>>>(payload, payload_off, n_pkts, whitening, pkts, pkt_off,
+                                                           h->d_mask, h->d_crctab);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
