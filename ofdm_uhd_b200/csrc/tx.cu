@@ -259,27 +259,41 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
+__device__ __forceinline__ float2 channel_sample(float2 v, int64_t i, double w, double phase0, float sigma, uint64_t seed) {
+    double r = (phase0 + w * (double)i) * 0.15915494309189533577;        // turns
+    r -= rint(r);
+    float s, c;
+    sincospif(2.0f * (float)r, &s, &c);
+    float2 o = make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+    if (sigma > 0.f) {
+        const uint64_t hsh = mix64(seed ^ (uint64_t)i * 0xD6E8FEB86659FD93ull);
+        const float u1 = ((float)(uint32_t)(hsh >> 40) + 0.5f) * (1.0f / 16777216.0f);
+        const float u2 = ((float)(uint32_t)((hsh >> 8) & 0xFFFFFF) + 0.5f) * (1.0f / 16777216.0f);
+        const float rad = sigma * sqrtf(-2.0f * __logf(u1));             // Box-Muller, fast intrinsics: noise only
+        float sn, cs;
+        __sincosf(6.283185307f * u2, &sn, &cs);
+        o.x += rad * cs;
+        o.y += rad * sn;
+    }
+    return o;
+}
+
 __global__ void __launch_bounds__(256) channel_kernel(const float2* __restrict__ x, int64_t n, double w, double phase0,
                                                        float sigma, uint64_t seed, float2* __restrict__ y) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double ph = phase0 + w * (double)i;              // radians
-        double r = ph * 0.15915494309189533577;          // turns
-        r -= rint(r);
-        float s, c;
-        sincospif(2.0f * (float)r, &s, &c);
-        float2 v = x[i];
-        float2 o = make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
-        if (sigma > 0.f) {
-            uint64_t hsh = mix64(seed ^ (uint64_t)i * 0xD6E8FEB86659FD93ull);
-            float u1 = ((float)(uint32_t)(hsh >> 40) + 0.5f) * (1.0f / 16777216.0f);
-            float u2 = ((float)(uint32_t)((hsh >> 8) & 0xFFFFFF) + 0.5f) * (1.0f / 16777216.0f);
-            float rad = sigma * sqrtf(-2.0f * logf(u1));
-            float sn, cs;
-            sincospif(2.0f * u2, &sn, &cs);
-            o.x += rad * cs;
-            o.y += rad * sn;
+    const bool vec = ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        const int64_t n2 = n >> 1;
+        for (int64_t k = t; k < n2; k += stride) {
+            const float4 q = __ldg((const float4*)x + k);
+            const float2 a = channel_sample(make_float2(q.x, q.y), 2 * k, w, phase0, sigma, seed);
+            const float2 b = channel_sample(make_float2(q.z, q.w), 2 * k + 1, w, phase0, sigma, seed);
+            ((float4*)y)[k] = make_float4(a.x, a.y, b.x, b.y);
         }
-        y[i] = o;
+        if ((n & 1) && t == 0) y[n - 1] = channel_sample(x[n - 1], n - 1, w, phase0, sigma, seed);
+    } else {
+        for (int64_t i = t; i < n; i += stride) y[i] = channel_sample(x[i], i, w, phase0, sigma, seed);
     }
 }
 

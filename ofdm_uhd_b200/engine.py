@@ -66,7 +66,7 @@ class RxBatch:
     counters: np.ndarray
     packets: List[Tuple[bool, bytes]]          # (ok, payload) in arrival order, what the callback sees
     msg_frames: Optional[np.ndarray] = None    # frame index of every delivered message
-    payload_rows: Optional[np.ndarray] = None  # uint8 [n_messages, pkt_stride] dewhitened payload || crc
+    payload_rows: Optional[np.ndarray] = None  # uint8 [n_frames, pkt_stride] dewhitened payload || crc, by frame slot
     payload_bytes_copied: int = 0
     meta_bytes_copied: int = 0
 
@@ -298,41 +298,75 @@ class OfdmEngine:
             return bufs["workspace"][off:off + 4 * n].view(torch.float32)
         raise ValueError(which)
 
+    def _pinned(self, bufs, key, like, count):
+        """Pinned host mirror of a result array (allocated once per buffer set): device->host copies into
+        pinned memory run at PCIe speed and can be queued asynchronously."""
+        pool = bufs.setdefault("_pinned", {})
+        t = pool.get(key)
+        if t is None or t.numel() < count or t.dtype != like.dtype:
+            t = self.torch.empty(max(count, 1), dtype=like.dtype, pin_memory=True)
+            pool[key] = t
+        return t
+
     def collect(self, bufs, want_packets: bool = True, want_payload: bool = True) -> RxBatch:
-        """Synchronise and bring one receive call's results to the host."""
+        """Synchronise and bring one receive call's results to the host.  The returned arrays are views of
+        pinned staging buffers that the next collect() on the same buffer set overwrites."""
         torch = self.torch
-        torch.cuda.current_stream(self.dev).synchronize()
-        head = torch.stack([bufs["n_trig"][0], bufs["n_frames"][0], bufs["status"][0]]).cpu().numpy()
-        nt, nf, st = int(head[0]), int(head[1]), int(head[2])
+        stream = torch.cuda.current_stream(self.dev)
+        hd = self._pinned(bufs, "head", bufs["n_trig"], 3)
+        hd[0:1].copy_(bufs["n_trig"], non_blocking=True)
+        hd[1:2].copy_(bufs["n_frames"], non_blocking=True)
+        hd[2:3].copy_(bufs["status"], non_blocking=True)
+        hc = self._pinned(bufs, "counters", bufs["counters"], 8)
+        hc.copy_(bufs["counters"], non_blocking=True)
+        stream.synchronize()
+        nt, nf, st = int(hd[0]), int(hd[1]), int(hd[2])
         if st:
             raise RuntimeError("receive: capacity overflow (status bits 0x%x): raise max_frames" % st)
-        g = lambda k, m: bufs[k][:m].cpu().numpy()
-        live, fstat = g("frame_live", nf), g("frame_status", nf)
-        plen, pok = g("pkt_len", nf), g("pkt_ok", nf)
-        meta = 4 * nf + 2 * nf + nf + 64 + 12
+        host = {}
+
+        def fetch(key, m):
+            t = self._pinned(bufs, key, bufs[key], m)
+            if m:
+                t[:m].copy_(bufs[key][:m], non_blocking=True)
+            host[key] = t[:m].numpy()
+
+        for k in ("frame_live", "frame_status", "pkt_len", "pkt_ok"):
+            fetch(k, nf)
+        if want_packets:
+            fetch("trig_idx", nt)
+            fetch("trig_ang", nt)
+            fetch("frame_start", nf)
+            fetch("frame_ndata", nf)
+        rows_all = None
+        if (want_payload or want_packets) and nf:
+            # every slot up to n_frames in one pinned copy; the (few) undelivered rows are dropped on the host
+            pb = self._pinned(bufs, "pkt_bytes", bufs["pkt_bytes"], nf * self.pkt_stride)
+            pb[:nf * self.pkt_stride].copy_(bufs["pkt_bytes"][:nf * self.pkt_stride], non_blocking=True)
+            rows_all = pb[:nf * self.pkt_stride].numpy().reshape(nf, self.pkt_stride)
+        stream.synchronize()
+        live, fstat = host["frame_live"], host["frame_status"]
+        plen, pok = host["pkt_len"], host["pkt_ok"]
+        meta = 4 * nf + 3 * nf + 64 + 12
         sel = np.flatnonzero((live == 1) & (fstat == 2))
         packets: List[Tuple[bool, bytes]] = []
         rows = None
         copied = 0
-        if len(sel) and (want_payload or want_packets):
-            mat = bufs["pkt_bytes"].view(-1, self.pkt_stride)
-            if len(sel) == nf:
-                rows = mat[:nf].cpu().numpy()
-            else:
-                rows = mat[torch.from_numpy(sel).to(self.dev)].cpu().numpy()
-            copied = int(rows.size)
+        if rows_all is not None:
+            copied = int(rows_all.size)
+            rows = rows_all                      # indexed by frame slot; msg_frames lists the delivered ones
             if want_packets:
-                for r, f in enumerate(sel):
+                for f in sel:
                     ln = int(plen[f])
-                    body = rows[r, :min(ln, self.pkt_stride)].tobytes()
+                    body = rows[f, :min(ln, self.pkt_stride)].tobytes()
                     packets.append((bool(pok[f]), body[:-4] if ln >= 4 else b""))
         if want_packets:
-            trig_idx, trig_ang = g("trig_idx", nt), g("trig_ang", nt)
-            fstart, fnd = g("frame_start", nf), g("frame_ndata", nf)
+            trig_idx, trig_ang = host["trig_idx"].copy(), host["trig_ang"].copy()
+            fstart, fnd = host["frame_start"].copy(), host["frame_ndata"].copy()
         else:
             trig_idx = trig_ang = fstart = fnd = np.zeros(0)
-        return RxBatch(nt, nf, st, trig_idx, trig_ang, fstart, fnd, live, fstat, plen, pok,
-                       bufs["counters"].cpu().numpy(), packets, sel, rows, copied, meta)
+        return RxBatch(nt, nf, st, trig_idx, trig_ang, fstart, fnd, live.copy(), fstat.copy(), plen.copy(), pok.copy(),
+                       hc.numpy().copy(), packets, sel, rows, copied, meta)
 
     def demodulate(self, x, **kw) -> RxBatch:
         return self.collect(self.demodulate_async(x, **kw))
