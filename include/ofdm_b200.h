@@ -41,6 +41,8 @@ typedef struct ofdm_cfg {
     int32_t device;            /* CUDA device ordinal                    */
     uint64_t pad_seed;         /* seed of the pad-symbol generator (upstream: libc rand()) */
     int32_t max_pkt_bytes;     /* bytes kept per received packet slot (<= 4096) */
+    const char* host_carrier_map; /* hex data-carrier mask, NULL = "FE7F" (ofdm_mapper_bcv / ofdm_frame_sink default;
+                                   the ctor argument of the commented call at ofdm.py:103-104) */
 } ofdm_cfg;
 
 const char* ofdm_last_error(void);

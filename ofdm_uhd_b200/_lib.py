@@ -27,7 +27,7 @@ class OfdmCfg(C.Structure):
     _fields_ = [("fft_length", C.c_int32), ("occupied_tones", C.c_int32), ("cp_length", C.c_int32),
                 ("constellation_size", C.c_int32), ("host_constellation", C.POINTER(C.c_float)),
                 ("tx_amplitude", C.c_float), ("device", C.c_int32), ("pad_seed", C.c_uint64),
-                ("max_pkt_bytes", C.c_int32)]
+                ("max_pkt_bytes", C.c_int32), ("host_carrier_map", C.c_char_p)]
 
 
 class RxIo(C.Structure):

@@ -2,6 +2,7 @@
 // Host-side table construction restates ofdm.py:71-101 (preamble / constellation wiring),
 // ofdm_receiver.py~:69-76 (firdes.low_pass design inputs) and SURVEY.md A.3/A.5/A.13.
 #include "internal.h"
+#include <ctype.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -77,9 +78,9 @@ static void crc_table(uint32_t* t) {
     }
 }
 
-static std::string carrier_hex(int occ) {
-    std::string c = "FE7F";
-    int diff = occ - 16;
+static std::string carrier_hex(int occ, const char* base) {
+    std::string c = (base && *base) ? base : "FE7F";
+    int diff = occ - 4 * (int)c.size();
     while (diff > 7) { c = "f" + c + "f"; diff -= 8; }
     if (diff > 0) {
         const char* hx = "0123456789abcdef";
@@ -150,7 +151,11 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
     h->pkt_stride = (mp + 15) & ~15;
 
     // carrier maps (A.3)
-    std::string hx = carrier_hex(occ);
+    if (cfg->host_carrier_map)
+        for (const char* q = cfg->host_carrier_map; *q; ++q)
+            if (!isxdigit((unsigned char)*q)) { ofdm_set_error("ofdm_create: carrier map is not a hex string"); delete h; return nullptr; }
+    std::string hx = carrier_hex(occ, cfg->host_carrier_map);
+    if ((int)hx.size() * 4 > occ + 3) { ofdm_set_error("ofdm_create: carrier map wider than occupied_tones"); delete h; return nullptr; }
     int pad = (N / 4 - (int)hx.size()) / 2;
     std::vector<int16_t> bin2car(N, -1), sinkmap;
     int ord = 0;

@@ -73,7 +73,8 @@ class RxBatch:
 
 class OfdmEngine:
     def __init__(self, fft_length=512, occupied_tones=200, cp_length=128, modulation="bpsk", tx_amplitude=0.25,
-                 device: Optional[int] = None, pad_seed: int = 0, max_pkt_bytes: int = 4096):
+                 device: Optional[int] = None, pad_seed: int = 0, max_pkt_bytes: int = 4096,
+                 carrier_map: Optional[str] = None):
         import torch
         self.torch = torch
         self.L_ = _lib.lib()
@@ -85,7 +86,9 @@ class OfdmEngine:
         flat = np.ascontiguousarray(const.view(np.float32))
         cfg = _lib.OfdmCfg(fft_length, occupied_tones, cp_length, len(const),
                            flat.ctypes.data_as(C.POINTER(C.c_float)), float(tx_amplitude), self.device,
-                           int(pad_seed) & 0xFFFFFFFFFFFFFFFF, int(max_pkt_bytes))
+                           int(pad_seed) & 0xFFFFFFFFFFFFFFFF, int(max_pkt_bytes),
+                           carrier_map.encode("ascii") if carrier_map else None)
+        self.carrier_map = carrier_map or "FE7F"
         h = self.L_.ofdm_create(C.byref(cfg))
         if not h:
             raise ValueError("ofdm_create: " + self.L_.ofdm_last_error().decode())

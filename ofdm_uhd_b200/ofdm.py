@@ -123,7 +123,8 @@ class ofdm_mod:
     creates OFDM symbols using a specified modulation option.  Send packets by calling send_pkt.
     """
 
-    def __init__(self, options, msgq_limit=2, pad_for_usrp=True, batch_limit=4096, device=None, pad_seed=0):
+    def __init__(self, options, msgq_limit=2, pad_for_usrp=True, batch_limit=4096, device=None, pad_seed=0,
+                 carrier_map=None):
         """
         @param options: pass modulation options from higher layers (fft length, occupied tones, etc.)
         @param msgq_limit: maximum number of messages in message queue (kept for compatibility: the queue is
@@ -144,7 +145,8 @@ class ofdm_mod:
         self._arity = arity
         # ofdm_mod scales by 1/sqrt(N) only; transmit_path owns the amplitude stage (transmit_path.py:48)
         self._engine = OfdmEngine(self._fft_length, self._occupied_tones, self._cp_length, self._modulation,
-                                  tx_amplitude=1.0, device=device, pad_seed=pad_seed)
+                                  tx_amplitude=1.0, device=device, pad_seed=pad_seed, carrier_map=carrier_map)
+        self._device, self._pad_seed = device, pad_seed
         self._pkt_input = _pkt_input(self._batch_limit, self.flush)
         self._sinks = []
         self._frames_sent = 0
@@ -157,6 +159,18 @@ class ofdm_mod:
         self._log = bool(getattr(options, "log", False))
 
     # -- flowgraph replacement ------------------------------------------------------------------
+    def reset_carrier_map(self, carrier_map):
+        """What the reference's custom mapper offered as ``_pkt_input.reset_carrier_map`` (the call commented
+        out at transmit_path.py:67): pending packets go out with the old map, later ones use the new one."""
+        self.flush()
+        amp = getattr(self, "_amp", 1.0)
+        old = self._engine
+        self._engine = OfdmEngine(self._fft_length, self._occupied_tones, self._cp_length, self._modulation,
+                                  tx_amplitude=amp, device=self._device, pad_seed=self._pad_seed,
+                                  carrier_map=carrier_map)
+        self.ifft = self.cp_adder = self.scale = self._engine
+        old.close()
+
     def connect(self, sink):
         """sink: callable(samples) or object with .feed(samples); samples is a complex64 cuda tensor."""
         self._sinks.append(sink)
@@ -243,7 +257,7 @@ class ofdm_demod:
     to a higher layer via the callback.
     """
 
-    def __init__(self, options, callback=None, device=None, max_pkt_bytes=4096):
+    def __init__(self, options, callback=None, device=None, max_pkt_bytes=4096, carrier_map=None):
         """
         @param options: pass modulation options from higher layers (fft length, occupied tones, etc.)
         @param callback:  function of two args: ok, payload
@@ -260,7 +274,7 @@ class ofdm_demod:
         self.preambles = (ksfreq,)
         self._arity = MODS[self._modulation]
         self._engine = OfdmEngine(self._fft_length, self._occupied_tones, self._cp_length, self._modulation,
-                                  device=device, max_pkt_bytes=max_pkt_bytes)
+                                  device=device, max_pkt_bytes=max_pkt_bytes, carrier_map=carrier_map)
         self.ofdm_recv = self.ofdm_demod = self._engine
         self._log = bool(getattr(options, "log", False))
         if options.verbose:

@@ -12,20 +12,21 @@ except ImportError:
 class _amp_stage:
     """Stands where ``gr.multiply_const_cc`` stood (transmit_path.py:48): ``set_k`` forwards to the kernel."""
 
-    def __init__(self, engine):
-        self._engine = engine
+    def __init__(self, owner):
+        self._owner = owner            # the ofdm_mod whose kernel applies the amplitude
         self._k = 1.0
 
     def set_k(self, k):
         self._k = k
-        self._engine.set_tx_amplitude(k)
+        self._owner._amp = k
+        self._owner._engine.set_tx_amplitude(k)
 
     def k(self):
         return self._k
 
 
 class transmit_path:
-    def __init__(self, options, device=None, pad_seed=0, batch_limit=4096):
+    def __init__(self, options, device=None, pad_seed=0, batch_limit=4096, honor_carrier_map=False):
         options = copy.copy(options)    # make a copy so we can destructively modify
 
         self._verbose = options.verbose
@@ -34,9 +35,10 @@ class transmit_path:
 
         self.ofdm_tx = ofdm.ofdm_mod(options, msgq_limit=4, pad_for_usrp=False, device=device, pad_seed=pad_seed,
                                      batch_limit=batch_limit)
-        self.amp = _amp_stage(self.ofdm_tx._engine)
+        self.amp = _amp_stage(self.ofdm_tx)
         self.set_tx_amplitude(self._tx_amplitude)
         self.carrier_map_old = ""
+        self._honor_carrier_map = bool(honor_carrier_map)
         if self._verbose:
             self._print_verbage()
 
@@ -55,8 +57,11 @@ class transmit_path:
         self.amp.set_k(self._tx_amplitude)
 
     def send_pkt(self, payload='', eof=False, carrier_map_new="FE7F"):
-        # the reference accepts the map and ignores it (reset_carrier_map is commented out, :66-70)
+        # the reference accepts the map and ignores it (reset_carrier_map is commented out, :66-70);
+        # honor_carrier_map=True restores the intended behaviour
         if carrier_map_new != self.carrier_map_old:
+            if self._honor_carrier_map and not eof:
+                self.ofdm_tx.reset_carrier_map(carrier_map_new)
             self.carrier_map_old = carrier_map_new
         return self.ofdm_tx.send_pkt(payload, eof)
 

@@ -218,6 +218,7 @@ class Layout:
     occupied_tones: int = 200
     cp_length: int = 128
     modulation: str = "bpsk"
+    carrier_map: str = "FE7F"            # hex data-carrier mask (upstream default; ofdm.py:103-104 shows the ctor arg)
     zl: int = field(init=False)
     ncar: int = field(init=False)
     nbits: int = field(init=False)
@@ -231,8 +232,8 @@ class Layout:
         self.M = MODS[self.modulation]
         self.nbits = int(round(math.log2(self.M)))
         self.const = constellation_for(self.modulation)
-        self.sink_map = sink_carrier_map(occ)                 # indices into the occ-wide vector
-        self.tx_map = mapper_carrier_map(N, occ)              # indices into the N-wide vector
+        self.sink_map = sink_carrier_map(occ, self.carrier_map)      # indices into the occ-wide vector
+        self.tx_map = mapper_carrier_map(N, occ, self.carrier_map)   # indices into the N-wide vector
         self.ncar = len(self.sink_map)
         ks = known_symbols_4512()[:occ].astype(np.float64)
         for i in range(occ):
@@ -248,9 +249,9 @@ class Layout:
         return n_data_symbols(pkt_len, self.ncar, self.nbits)
 
 
-def _carrier_hex(occ: int) -> str:
-    """A.3: the default "FE7F" map widened to ``occ`` tones (upstream mapper/sink ctor)."""
-    carriers = "FE7F"
+def _carrier_hex(occ: int, base: str = "FE7F") -> str:
+    """A.3: the hex data-carrier map (default "FE7F") widened to ``occ`` tones (upstream mapper/sink ctor)."""
+    carriers = base
     diff = occ - 4 * len(carriers)
     while diff > 7:
         carriers = "f" + carriers + "f"
@@ -264,9 +265,9 @@ def _carrier_hex(occ: int) -> str:
     return carriers
 
 
-def sink_carrier_map(occ: int) -> np.ndarray:
+def sink_carrier_map(occ: int, base: str = "FE7F") -> np.ndarray:
     idx = []
-    for i, ch in enumerate(_carrier_hex(occ)):
+    for i, ch in enumerate(_carrier_hex(occ, base)):
         c = int(ch, 16)
         for j in range(4):
             if (c >> (3 - j)) & 1:
@@ -274,8 +275,8 @@ def sink_carrier_map(occ: int) -> np.ndarray:
     return np.array(idx, dtype=np.int32)
 
 
-def mapper_carrier_map(N: int, occ: int) -> np.ndarray:
-    hexs = _carrier_hex(occ)
+def mapper_carrier_map(N: int, occ: int, base: str = "FE7F") -> np.ndarray:
+    hexs = _carrier_hex(occ, base)
     pad = (N // 4 - len(hexs)) // 2
     idx = []
     for i, ch in enumerate(hexs):

@@ -88,3 +88,46 @@ def test_ofdm_mod_samples_equal_oracle():
     lay = o.Layout(512, 200, 128, "qpsk")
     want = o.tx_modulate([o.make_packet(p, 1, 1, True) for p in pay], lay, 1.0, seed=33)   # ofdm_mod: 1/sqrt(N) only
     assert got.shape == want.shape and float(np.max(np.abs(got - want))) < 1e-5
+
+
+def test_custom_carrier_map_round_trip():
+    """a non-default hex data-carrier mask (the ctor argument of the commented call at
+    ofdm.py:103-104, honoured on request by transmit_path.send_pkt) -- samples and decoded packets equal the
+    oracle's for the same mask; by default send_pkt ignores the map like the reference."""
+    import torch
+    from ofdm_uhd_b200 import transmit_path, ofdm
+    from ofdm_uhd_b200.engine import OfdmEngine
+    cmap = "F00FF00F"
+    opts = options(modulation="qpsk")
+    lay = o.Layout(512, 200, 128, "qpsk", carrier_map=cmap)
+    assert lay.ncar == 184
+    rng = np.random.default_rng(8)
+    pay = [struct.pack("!HH", i, 0) + bytes(rng.integers(0, 256, 200, dtype=np.uint8)) for i in range(10)]
+    # default: map accepted and ignored
+    tx = transmit_path.transmit_path(opts, pad_seed=3)
+    out = []
+    tx.connect(lambda smp: out.append(smp.cpu().numpy()))
+    for p in pay:
+        tx.send_pkt(p, False, cmap)
+    tx.send_pkt(eof=True)
+    ref_default = o.tx_modulate([o.make_packet(p, 1, 1, False) for p in pay], o.Layout(512, 200, 128, "qpsk"), 0.25, seed=3)
+    assert float(np.max(np.abs(np.concatenate(out) - ref_default))) < 1e-5
+    # honoured
+    tx = transmit_path.transmit_path(opts, pad_seed=3, honor_carrier_map=True)
+    out = []
+    tx.connect(lambda smp: out.append(smp.cpu().numpy()))
+    for p in pay:
+        tx.send_pkt(p, False, cmap)
+    tx.send_pkt(eof=True)
+    x = np.concatenate(out)
+    want = o.tx_modulate([o.make_packet(p, 1, 1, False) for p in pay], lay, 0.25, seed=3)
+    assert x.shape == want.shape and float(np.max(np.abs(x - want))) < 1e-5
+    lead = np.zeros(700, np.complex64)
+    cap = o.channel(np.concatenate([lead, want, np.zeros(2600, np.complex64)]), 30, 0.15, 512, seed=4,
+                    sig_power=float(np.mean(np.abs(want) ** 2)))
+    ref = o.rx_demodulate(cap, lay)
+    eng = OfdmEngine(512, 200, 128, "qpsk", carrier_map=cmap)
+    got = eng.demodulate(torch.from_numpy(cap).cuda())
+    assert got.packets == ref.packets and sum(1 for g, _ in got.packets if g) >= 8
+    with pytest.raises(ValueError):
+        OfdmEngine(512, 200, 128, "qpsk", carrier_map="XYZ")
