@@ -291,10 +291,44 @@ class ofdm_demod:
             samples = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.complex64))
         if samples.device.type != "cuda":
             samples = samples.to(self._engine.dev)
-        res = self._engine.demodulate(samples.contiguous(), max_frames=max_frames)
+        samples = samples.contiguous()
+        if self._log:
+            res = self._feed_logged(samples, max_frames)
+        else:
+            res = self._engine.demodulate(samples, max_frames=max_frames)
         self.last = res
         for ok, payload in res.packets:
             self._rcvd_pktq.insert_tail(message(0, 0, 0, payload) if False else _rx_message(ok, payload))
+        return res
+
+    def _feed_logged(self, samples, max_frames):
+        """options.log: dump the stage taps with the reference's file names and raw layout (ofdm.py:253-254,
+        ofdm_receiver.py~:144-152; interleaved float32 I/Q, utils/read_complex_binary.m:39-46).  Files are
+        truncated by the first feed() and appended to afterwards.  sampler_c / fft_out_c / sigmix_c / nco_c are
+        not materialised by the fused kernels and are not written."""
+        eng = self._engine
+        n = int(samples.numel())
+        nvec = n // eng.L + 64
+        bufs = eng.rx_alloc(n, max_frames=max_frames, taps=True, max_vectors=nvec)
+        for k in ("eq_syms", "sym_idx", "derot_syms"):
+            bufs[k].zero_()
+        res = eng.collect(eng.demodulate_async(samples, bufs))
+        mode = "ab" if getattr(self, "_log_started", False) else "wb"
+        self._log_started = True
+        with open("ofdm_receiver-chan_filt_c.dat", mode) as f:
+            eng.ws_view(bufs, 0, n).cpu().numpy().tofile(f)
+        flags = np.concatenate([np.concatenate([[1], np.zeros(int(j), np.uint8)]) for j in res.frame_ndata]).astype(np.uint8) \
+            if res.n_frames else np.zeros(0, np.uint8)
+        nv = len(flags)
+        with open("ofdm_receiver-found_corr_b.dat", mode) as f:
+            flags.tofile(f)
+        with open("ofdm_receiver-frame_acq_c.dat", mode) as f:
+            bufs["eq_syms"][:nv * eng.occ].cpu().numpy().tofile(f)
+        derot = bufs["derot_syms"][:nv * eng.ncar].cpu().numpy().reshape(nv, eng.ncar)
+        wide = np.zeros((nv, eng.occ), dtype=np.complex64)
+        wide[:, :eng.ncar] = derot
+        with open("ofdm_frame_sink_c.dat", mode) as f:
+            wide[np.abs(derot).sum(axis=1) > 0].tofile(f)          # only the vectors the sink demapped
         return res
 
     def wait(self, timeout=None):

@@ -131,3 +131,31 @@ def test_custom_carrier_map_round_trip():
     assert got.packets == ref.packets and sum(1 for g, _ in got.packets if g) >= 8
     with pytest.raises(ValueError):
         OfdmEngine(512, 200, 128, "qpsk", carrier_map="XYZ")
+
+
+def test_log_option_dumps_stage_taps(tmp_path, monkeypatch):
+    """options.log (ofdm.py:123-131,253-254; ofdm_receiver.py~:144-152): raw float32 I/Q dumps under the
+    reference's file names; the channel-filter dump equals the oracle's filtered stream."""
+    import torch
+    from ofdm_uhd_b200 import ofdm
+    monkeypatch.chdir(tmp_path)
+    lay = o.Layout(512, 200, 128, "bpsk")
+    rng = np.random.default_rng(2)
+    pay = [struct.pack("!HH", i, 0) + bytes(rng.integers(0, 256, 100, dtype=np.uint8)) for i in range(4)]
+    x = o.tx_modulate([o.make_packet(p, 1, 1, False) for p in pay], lay, 0.25, seed=0)
+    cap = o.channel(np.concatenate([np.zeros(700, np.complex64), x, np.zeros(2600, np.complex64)]), 35, 0.0, 512, seed=3,
+                    sig_power=float(np.mean(np.abs(x) ** 2)))
+    got = []
+    d = ofdm.ofdm_demod(options(log=True), callback=lambda ok, p: got.append((ok, p)))
+    d.feed(cap)
+    d.wait(30)
+    ref = o.rx_demodulate(cap, lay, keep=True)
+    assert got == ref.packets
+    y = np.fromfile("ofdm_receiver-chan_filt_c.dat", dtype=np.complex64)
+    assert y.shape == ref.y.shape and np.linalg.norm(y - ref.y) / np.linalg.norm(ref.y) < 1e-4
+    flags = np.fromfile("ofdm_receiver-found_corr_b.dat", dtype=np.uint8)
+    assert np.array_equal(flags, ref.flags)
+    eq = np.fromfile("ofdm_receiver-frame_acq_c.dat", dtype=np.complex64).reshape(-1, 200)
+    assert eq.shape[0] == len(ref.flags)
+    sink = np.fromfile("ofdm_frame_sink_c.dat", dtype=np.complex64).reshape(-1, 200)
+    assert sink.shape[0] == len(ref.derot) and np.linalg.norm(sink[:, :198] - np.array(ref.derot)) / np.linalg.norm(np.array(ref.derot)) < 1e-4
