@@ -38,6 +38,20 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_label, n_samples):
+    """dram__bytes_read+write of one launch of the named kernel from the committed ncu capture (bytes)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            k = json.load(f)["kernels"]
+        for name, v in k.items():
+            if kernel_label.startswith(name):
+                return v["traffic_bytes"] * (n_samples / 640e6)
+    except Exception:
+        pass
+    return None
+
+
 def make_payloads(n_frames, size, seed):
     """payload = struct.pack('!HH', pktno, 0) + random bytes, like benchmark_ofdm_tx.py:117."""
     rng = np.random.Generator(np.random.Philox(seed))
@@ -265,6 +279,7 @@ def run_b200(args):
         dom = max(kern_ms, key=kern_ms.get)
         alg_bytes = 8.0 * n_sig          # every kernel of the chain streams the capture once: 8 B per sample
         dom_gbs = alg_bytes / (kern_ms[dom] * 1e-3) / 1e9
+        traffic = ncu_traffic(dom, n_sig)
         step_gbs = 16.0 * n_sig / (ms_per_step * 1e-3) / 1e9
         line = {
             "metric": "OFDM Msamples/s mod+demod (fft=512)", "value": value, "unit": "Msamples/s", "n_gpus": world,
@@ -277,7 +292,9 @@ def run_b200(args):
                        "l2": "inputs (%.1f GB per pass) larger than L2" % (8.0 * n_sig / 1e9)},
             "ms_mod": t_mod, "ms_demod": t_dem,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": dom_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram read+write of one launch at "
+                                           "640 M samples, scaled to this launch's samples)" if traffic else None,
                          "algorithmic_bytes_per_launch": alg_bytes},
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                               "algorithmic_bytes_per_sample": 16},
