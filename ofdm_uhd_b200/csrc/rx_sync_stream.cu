@@ -31,165 +31,163 @@ struct StreamParams {
     uint32_t* status;
 };
 
-constexpr int SS_WARPS = 4;
+constexpr int SS_WARPS = 1;       // one warp per CTA: segment index and loop bounds are CTA-uniform, so the
+                                   // compiler can prove the shuffles convergent (no WARPSYNC around each of them)
+
+// Warp scans of doubles.  A conditional add after a shuffle compiles to DADD + two FSEL; multiplying the shuffled
+// value by a per-lane 1.0 / 0.0 mask inside one DFMA is exact (x*1 = x, x*0 = 0 for finite x) and a single instruction.
+__device__ __forceinline__ double shfl_up_d(double x, int d) {
+    return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(x), d),
+                            __shfl_up_sync(0xffffffffu, __double2loint(x), d));
+}
+__device__ __forceinline__ double shfl_down_d(double x, int d) {
+    return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(x), d),
+                            __shfl_down_sync(0xffffffffu, __double2loint(x), d));
+}
+
+// one step's worth of per-lane history (ping-ponged between two instances so nothing is copied per step)
+template <int K>
+struct StepHist {
+    float2 y[K];                                     // samples            (y[n - N/2] of the next step)
+    float x[3][K];                                   // products Re c, Im c, |y|^2
+    double bwd[3];                                   // sum of the products of the later lanes
+};
 
 template <int K>
-__global__ void __launch_bounds__(SS_WARPS * 32, 3) sync_stream_kernel(const StreamParams p) {
-    constexpr int SZ = 32 * K;                       // samples per step = N/2
-    extern __shared__ double s_ring[];               // [SS_WARPS][2*SZ] prefix sums of the metric
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* ring = s_ring + (size_t)wib * 2 * SZ;
-    const int64_t seg = (int64_t)blockIdx.x * SS_WARPS + wib;
-    if (seg >= p.n_seg) return;
-    const int64_t s0 = seg * p.seg_len;
-    const int64_t s1 = (s0 + p.seg_len < p.n) ? s0 + p.seg_len : p.n;
-    int64_t w0 = s0 - OFDM_PEAK_WARM - 2 * SZ;
-    if (w0 < 0) w0 = 0;
-    w0 -= w0 % SZ;
-    const int cp = p.cp;
-    const double tap = (double)p.tapf;
-    const bool vec_ok = (((uintptr_t)p.y) & 15) == 0;
-
-    // detector constants
-    const double a1 = (double)0.001f, a2 = 1.0 - a1;
-    double a2k = 1.0;
-#pragma unroll
-    for (int k = 0; k < K; ++k) a2k *= a2;
-    double pw[5];
-    pw[0] = a2k;
-#pragma unroll
-    for (int k = 1; k < 5; ++k) pw[k] = pw[k - 1] * pw[k - 1];
-    const double p32 = pw[4] * pw[4];
-    double plane = 1.0;
-    for (int k = 0; k < lane; ++k) plane *= a2k;
-
-    // streaming state
-    float2 yprev[K];                                 // this lane's samples of the previous step (= y[n - N/2])
-    float xp[3][K];                                  // previous step's products (Re c, Im c, |y|^2)
-    double pbwd[3] = {0.0, 0.0, 0.0};                // previous step: sum over the later lanes
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        yprev[i] = make_float2(0.f, 0.f);
-        xp[0][i] = xp[1][i] = xp[2][i] = 0.f;
-    }
-    if (w0 > 0) {                                    // mid-stream start: the delayed samples exist
-#pragma unroll
-        for (int i = 0; i < K; ++i) yprev[i] = p.y[w0 - SZ + lane * K + i];
-    }
-    for (int i = lane; i < 2 * SZ; i += 32) ring[i] = 0.0;
-    __syncwarp();
+struct StreamCtx {
+    static constexpr int SZ = 32 * K;
+    const StreamParams& p;
+    double* ring;
+    int lane;
+    int64_t seg, s0, s1;
+    bool vec_ok, cp_aligned;
+    int prime, cpq;
+    double tap, a1, a2, p32, plane;
+    double pw[5];                                    // IIR scan weights, 0 where the source lane does not exist
+    double mu[5], md[5];                             // 1.0 where lane - 2^k / lane + 2^k exists, else 0.0
+    // running state
     double carry2 = 0.0;                             // prefix of the metric up to the previous step
     double carry = 0.0;                              // detector average after the last consumed sample
     int state = 0, count = 0;
     float peak = -INFINITY;
     int64_t ind = 0, run_start = 0;
-    const int prime = (w0 > 0) ? 2 : 0;              // steps whose sums still miss history
-    int step = 0;
 
-    for (int64_t i0 = w0; i0 < p.n; i0 += SZ, ++step) {
-        if (i0 >= s1 && state == 0) break;
+    __device__ __forceinline__ StreamCtx(const StreamParams& p_) : p(p_) {}
+
+    // samples [i0 + lane*K, +K) of the stream, zero past its end
+    __device__ __forceinline__ void load(float2 (&dst)[K], const int64_t i0) const {
         const int64_t b0 = i0 + (int64_t)lane * K;
-        float2 yv[K];
-        if (vec_ok && i0 + SZ <= p.n && (K % 2) == 0) {
+        if (i0 + SZ <= p.n && vec_ok) {                          // warp-uniform
             const float4* q = (const float4*)(p.y + b0);
 #pragma unroll
             for (int i = 0; i < K / 2; ++i) {
                 const float4 t = __ldg(q + i);
-                yv[2 * i] = make_float2(t.x, t.y);
-                yv[2 * i + 1] = make_float2(t.z, t.w);
+                dst[2 * i] = make_float2(t.x, t.y);
+                dst[2 * i + 1] = make_float2(t.z, t.w);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < K; ++i) yv[i] = (b0 + i < p.n) ? p.y[b0 + i] : make_float2(0.f, 0.f);
+            for (int i = 0; i < K; ++i) dst[i] = (b0 + i < p.n) ? p.y[b0 + i] : make_float2(0.f, 0.f);
+        }
+    }
+
+    // cur.y holds this step's samples on entry; prev.y is refilled with the next step's as soon as the products
+    // are formed (the two histories swap roles every step), so the loads fly during the rest of the step
+    __device__ __forceinline__ void step(StepHist<K>& prev, StepHist<K>& cur, const int64_t i0, const int stepno) {
+        const int64_t b0 = i0 + (int64_t)lane * K;
+        const bool full = i0 + SZ <= p.n;                        // warp-uniform
+        int nvalid = K;                                          // samples of this lane inside the stream
+        if (!full) {
+            const int64_t r = p.n - b0;
+            nvalid = r < 0 ? 0 : (r > K ? K : (int)r);
         }
         // products of this step
-        float x[3][K];
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            const float2 c = cmulc_x(yv[i], yprev[i]);          // y[n] * conj(y[n - N/2])
-            x[0][i] = c.x; x[1][i] = c.y; x[2][i] = norm_x(yv[i]);
-            yprev[i] = yv[i];
+            const float2 c = cmulc_x(cur.y[i], prev.y[i]);      // y[n] * conj(y[n - N/2])
+            cur.x[0][i] = c.x; cur.x[1][i] = c.y; cur.x[2][i] = norm_x(cur.y[i]);
         }
-        // three moving sums of width N/2 = SZ (van Herk: previous step's tail + this step's head)
+        if (i0 + SZ < p.n) load(prev.y, i0 + SZ);
+        // three moving sums of width N/2 = SZ (van Herk: previous step's tail + this step's head), no subtraction
         float PR[3][K];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             double pre[K];
             double run = 0.0;
 #pragma unroll
-            for (int i = 0; i < K; ++i) { run += (double)x[a][i]; pre[i] = run; }
-            // exclusive scans of the lane totals: earlier lanes (fwd), later lanes (bwd)
-            double fi = run, bi = run;
+            for (int i = 0; i < K; ++i) { run += (double)cur.x[a][i]; pre[i] = run; }
+            double fi = run, bi = run;                           // inclusive scans: earlier lanes, later lanes
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const double of = __shfl_up_sync(0xffffffffu, fi, d);
-                const double ob = __shfl_down_sync(0xffffffffu, bi, d);
-                if (lane >= d) fi += of;
-                if (lane + d < 32) bi += ob;
+            for (int k = 0; k < 5; ++k) {
+                fi = fma(shfl_up_d(fi, 1 << k), mu[k], fi);
+                bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
             }
-            double fwd = __shfl_up_sync(0xffffffffu, fi, 1);
-            double bwd = __shfl_down_sync(0xffffffffu, bi, 1);
-            if (lane == 0) fwd = 0.0;
-            if (lane == 31) bwd = 0.0;
+            const double fwd = shfl_up_d(fi, 1) * mu[0];
+            cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
             // previous step's part of each window: elements i+1.. of this lane, then the later lanes
             double tail[K];
-            double sfx = pbwd[a];
+            double sfx = prev.bwd[a];
             tail[K - 1] = sfx;
 #pragma unroll
-            for (int i = K - 2; i >= 0; --i) { sfx += (double)xp[a][i + 1]; tail[i] = sfx; }
+            for (int i = K - 2; i >= 0; --i) { sfx += (double)prev.x[a][i + 1]; tail[i] = sfx; }
 #pragma unroll
-            for (int i = 0; i < K; ++i) {
-                PR[a][i] = (float)(tail[i] + (pre[i] + fwd));
-                xp[a][i] = x[a][i];
-            }
-            pbwd[a] = bwd;
+            for (int i = 0; i < K; ++i) PR[a][i] = (float)(tail[i] + (pre[i] + fwd));
         }
         // normalised metric and its cp-wide average (float64 prefix difference)
-        float Mt[K];
+        const bool zero_first = prime && stepno == 0;            // mid-stream start: sums miss the previous block
         double mloc[K];
         double mrun = 0.0;
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             const float num = fadd_rn(fmul_rn(PR[0][i], PR[0][i]), fmul_rn(PR[1][i], PR[1][i]));
             const float den = fmul_rn(PR[2][i], PR[2][i]);
-            // mid-stream start: the first step's sums miss the previous block -> keep the prefix finite
-            Mt[i] = (prime && step == 0) ? 0.f : fdiv_rn(num, den);
-            mrun += (double)Mt[i];
+            float q = fdiv_rn(num, den);
+            asm volatile("" : "+f"(q));                          // keep the division out of a branch
+            q = zero_first ? 0.f : q;                            // keeps the prefix finite
+            mrun += (double)q;
             mloc[i] = mrun;
         }
         double mi = mrun;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double o = __shfl_up_sync(0xffffffffu, mi, d);
-            if (lane >= d) mi += o;
-        }
-        double mex = __shfl_up_sync(0xffffffffu, mi, 1);
-        if (lane == 0) mex = 0.0;
-        const double mtot = __shfl_sync(0xffffffffu, mi, 31);
-        const int rb = (step & 1) * SZ;                          // ring half of this step
+        for (int k = 0; k < 5; ++k) mi = fma(shfl_up_d(mi, 1 << k), mu[k], mi);
+        const double mex = fma(shfl_up_d(mi, 1), mu[0], carry2);
+        carry2 += __shfl_sync(0xffffffffu, mi, 31);
+        const int rb = (stepno & 1) * SZ;                        // ring half of this step
+        double* mine = ring + rb + lane * K;
 #pragma unroll
-        for (int i = 0; i < K; ++i) { mloc[i] += carry2 + mex; ring[rb + lane * K + i] = mloc[i]; }
-        carry2 += mtot;
+        for (int i = 0; i < K; i += 2) {
+            mloc[i] += mex; mloc[i + 1] += mex;
+            *(double2*)(mine + i) = make_double2(mloc[i], mloc[i + 1]);
+        }
         __syncwarp();
         float v[K];
+        if (cp_aligned) {
+            // n - cp sits cp/K lanes back: K consecutive ring slots, in this step's half or the previous one
+            const int ql = lane - cpq;
+            const double* src = ring + (ql >= 0 ? rb + ql * K : (rb ^ SZ) + (32 + ql) * K);
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-            const int e = lane * K + i - cp;                     // position of n - cp relative to this step
-            double prevS;
-            if (e >= 0) prevS = ring[rb + e];
-            else prevS = ring[(rb ^ SZ) + SZ + e];               // previous step's half (zeros before the stream)
-            const float s = (float)((mloc[i] - prevS) * tap);
-            v[i] = fadd_rn(s, -1.0f);
+            for (int i = 0; i < K; i += 2) {
+                const double2 pv = *(const double2*)(src + i);
+                v[i] = fadd_rn((float)((mloc[i] - pv.x) * tap), -1.0f);
+                v[i + 1] = fadd_rn((float)((mloc[i + 1] - pv.y) * tap), -1.0f);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const int e = lane * K + i - p.cp;               // position of n - cp relative to this step
+                const double prevS = ring[e >= 0 ? rb + e : (rb ^ SZ) + SZ + e];
+                v[i] = fadd_rn((float)((mloc[i] - prevS) * tap), -1.0f);
+            }
         }
         __syncwarp();
-        if (step < prime) continue;                              // priming: sums not yet valid, detector idle
+        if (stepno < prime) return;                              // priming: sums not yet valid, detector idle
         // first NaN of the metric (poisons the detector for the rest of the stream, C.1)
         if (v[K - 1] != v[K - 1]) {                              // a NaN poisons the prefix: the lane's last value shows it
             int first = K - 1;
 #pragma unroll
             for (int i = K - 2; i >= 0; --i)
                 if (v[i] != v[i]) first = i;
-            if (b0 + first < p.n) atomicMin((unsigned long long*)p.first_nan, (unsigned long long)(b0 + first));
+            if (first < nvalid) atomicMin((unsigned long long*)p.first_nan, (unsigned long long)(b0 + first));
         }
         // ---- peak_detector_fb: IIR average as an affine scan over lanes, threshold bits, run state machine ----
         double vd[K];
@@ -200,35 +198,32 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 3) sync_stream_kernel(const Str
         for (int i = 0; i < K; ++i) loc = a2 * loc + vd[i];
         double b = loc;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const double o = __shfl_up_sync(0xffffffffu, b, 1 << k);
-            if (lane >= (1 << k)) b = b + pw[k] * o;
-        }
-        double prev = __shfl_up_sync(0xffffffffu, b, 1);
-        if (lane == 0) prev = 0.0;
-        prev = prev + plane * carry;
+        for (int k = 0; k < 5; ++k) b = fma(shfl_up_d(b, 1 << k), pw[k], b);
+        double pavg = shfl_up_d(b, 1) * mu[0];
+        pavg = pavg + plane * carry;
         carry = __shfl_sync(0xffffffffu, b, 31) + p32 * carry;
         unsigned mk = 0;
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            const float thr = fmul_rn((float)prev, 0.2f);
-            if (b0 + i < p.n && v[i] > thr) mk |= 1u << i;
-            prev = a2 * prev + vd[i];
+            const float thr = fmul_rn((float)pavg, 0.2f);
+            if (v[i] > thr) mk |= 1u << i;
+            pavg = a2 * pavg + vd[i];
         }
+        constexpr unsigned FULLM = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
+        if (!full) mk &= (nvalid >= K) ? FULLM : ((1u << nvalid) - 1u);
         const unsigned any = __ballot_sync(0xffffffffu, mk != 0);
-        if (state == 0 && any == 0) continue;
+        if (state == 0 && any == 0) return;
         // lane summaries for the bulk path: a lane fully inside a run only contributes its maximum
         float lmax = v[0];
         int larg = 0;
 #pragma unroll
         for (int i = 1; i < K; ++i)
             if (v[i] > lmax) { lmax = v[i]; larg = i; }
-        constexpr unsigned FULL = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
         for (int l = (state == 0 ? __ffs(any) - 1 : 0); l < 32; ++l) {
             const unsigned m = __shfl_sync(0xffffffffu, mk, l);
             if (state == 0 && m == 0) continue;
             const int64_t base = i0 + (int64_t)l * K;
-            if (state == 1 && m == FULL && base + K <= p.n) {
+            if (state == 1 && m == FULLM && base + K <= p.n) {
                 const float bm = __shfl_sync(0xffffffffu, lmax, l);
                 const int ba = __shfl_sync(0xffffffffu, larg, l);
                 if (bm > peak) { peak = bm; ind = base + ba; }
@@ -257,8 +252,74 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 3) sync_stream_kernel(const Str
                 }
             }
         }
+        state = (int)__reduce_or_sync(0xffffffffu, (unsigned)state);   // warp-uniform by construction; says so to the compiler
     }
-    if (lane == 0) p.seg_count[seg] = count < p.seg_cap ? count : p.seg_cap;
+};
+
+template <int K>
+__global__ void __launch_bounds__(SS_WARPS * 32, 12) sync_stream_kernel(const StreamParams p) {
+    constexpr int SZ = 32 * K;                       // samples per step = N/2
+    extern __shared__ __align__(16) double s_ring[]; // [SS_WARPS][2*SZ] prefix sums of the metric
+    StreamCtx<K> c(p);
+    c.lane = threadIdx.x;
+    c.ring = s_ring;
+    c.seg = (int64_t)blockIdx.x;
+    if (c.seg >= p.n_seg) return;
+    c.s0 = c.seg * p.seg_len;
+    c.s1 = (c.s0 + p.seg_len < p.n) ? c.s0 + p.seg_len : p.n;
+    int64_t w0 = c.s0 - OFDM_PEAK_WARM - 2 * SZ;
+    if (w0 < 0) w0 = 0;
+    w0 -= w0 % SZ;
+    c.tap = (double)p.tapf;
+    c.vec_ok = (((uintptr_t)p.y) & 15) == 0;
+    c.cp_aligned = (p.cp % K) == 0;
+    c.cpq = p.cp / K;
+
+    // detector constants
+    c.a1 = (double)0.001f;
+    c.a2 = 1.0 - c.a1;
+    double a2k = 1.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) a2k *= c.a2;
+    c.pw[0] = a2k;
+#pragma unroll
+    for (int k = 1; k < 5; ++k) c.pw[k] = c.pw[k - 1] * c.pw[k - 1];
+    c.p32 = c.pw[4] * c.pw[4];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        c.mu[k] = (c.lane >= (1 << k)) ? 1.0 : 0.0;
+        c.md[k] = (c.lane + (1 << k) < 32) ? 1.0 : 0.0;
+        c.pw[k] *= c.mu[k];
+    }
+    c.plane = 1.0;
+    for (int k = 0; k < c.lane; ++k) c.plane *= a2k;
+
+    StepHist<K> A, B;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        A.y[i] = make_float2(0.f, 0.f);
+        A.x[0][i] = A.x[1][i] = A.x[2][i] = 0.f;
+    }
+    A.bwd[0] = A.bwd[1] = A.bwd[2] = 0.0;
+    if (w0 > 0) {                                    // mid-stream start: the delayed samples exist
+#pragma unroll
+        for (int i = 0; i < K; ++i) A.y[i] = p.y[w0 - SZ + c.lane * K + i];
+    }
+    for (int i = c.lane; i < 2 * SZ; i += 32) c.ring[i] = 0.0;
+    __syncwarp();
+    c.prime = (w0 > 0) ? 2 : 0;                      // steps whose sums still miss history
+
+    int step = 0;
+    if (w0 < p.n) c.load(B.y, w0);
+    for (int64_t i0 = w0; i0 < p.n;) {
+        if (i0 >= c.s1 && c.state == 0) break;
+        c.step(A, B, i0, step);
+        i0 += SZ; ++step;
+        if (i0 >= p.n || (i0 >= c.s1 && c.state == 0)) break;
+        c.step(B, A, i0, step);
+        i0 += SZ; ++step;
+    }
+    if (c.lane == 0) p.seg_count[c.seg] = c.count < p.seg_cap ? c.count : p.seg_cap;
 }
 
 __global__ void stream_init_kernel(int64_t* first_nan) { *first_nan = LLONG_MAX; }
