@@ -26,8 +26,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-KERNELS_PER_STEP = 11   # make_packets, tx, chan_filter, stream_init, sync_stream, seg_scan, trig_gather, plan,
-                        # demod, liveness, crc
+KERNELS_PER_STEP = 15   # make_packets, tx, chan_filter, stream_init, sync_stream, seg_scan, trig_gather, plan_init,
+                        # plan_local, plan_offset, demod, next, liveness_fast, liveness (general walk, idle), crc
 
 
 def peaks():

@@ -130,6 +130,13 @@ int ofdm_rx_demod(ofdm_handle* h, const float* y_iq, int64_t n, ofdm_rx_io* io, 
 /* frame-sink liveness (which preambles the sink accepted), unmake_packet (dewhiten + CRC,
  * ofdm.py:300-305) and the counters */
 int ofdm_rx_finish(ofdm_handle* h, ofdm_rx_io* io, void* stream);
+/* the liveness walk of ofdm_rx_finish on caller-supplied tables (stage-level entry, like ofdm_rx_sync_metric):
+ * which frames does an ofdm_frame_sink (ofdm.py:240-243) start a session on, when a session started at frame f
+ * consumes sess_nvec[f] vectors of a stream in which frame f's preamble vector sits at position vbase[f]?
+ * n_frames: device int32[1]; vbase: device int64[>= F]; sess_nvec: device int32[F]; scratch: device int32[2*max_frames+2];
+ * live: device uint8[max_frames].  force_general != 0 skips the short-exception-list fast path. */
+int ofdm_rx_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_t* sess_nvec, int32_t max_frames,
+                     int32_t* scratch, uint8_t* live, int force_general, void* stream);
 /* all of the above in order, no host synchronisation */
 int ofdm_rx_demodulate(ofdm_handle* h, const float* x_iq, int64_t n, ofdm_rx_io* io, void* stream);
 /* pointers into the workspace for parity tests: which = 0 filtered stream y (2n floats), 1 metric mf (n floats) */

@@ -374,6 +374,16 @@ extern "C" int ofdm_rx_finish(ofdm_handle* h, ofdm_rx_io* io, void* stream) {
     return launch_finish(h, io, &ws, (cudaStream_t)stream);
 }
 
+extern "C" int ofdm_rx_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_t* sess_nvec, int32_t max_frames,
+                                int32_t* scratch, uint8_t* live, int force_general, void* stream) {
+    if (!n_frames || !vbase || !sess_nvec || !scratch || !live || max_frames < 1) {
+        ofdm_set_error("ofdm_rx_liveness: null argument or max_frames < 1");
+        return OFDM_E_INVAL;
+    }
+    return launch_liveness(n_frames, vbase, sess_nvec, max_frames, scratch, scratch + max_frames, scratch + 2 * max_frames,
+                           live, force_general, (cudaStream_t)stream);
+}
+
 // ofdm_sync_pn: the fused streaming kernel where the layout allows it (32*K = N/2, cp <= N/2), else the
 // metric kernel followed by the detector kernel
 static int rx_sync(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, int force_fused,

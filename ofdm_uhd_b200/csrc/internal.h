@@ -60,6 +60,10 @@ struct RxWorkspace {
     double* phi0;          // [max_frames] NCO phase just before each trigger takes effect
     double* step;          // [max_frames] NCO phase step per sample after each trigger
     int32_t* first_ok;     // [1] index of the first trigger the sampler can see
+    int32_t* plan_hdr;     // [4] scratch of the two-launch plan
+    double* plan_blk_d;    // [1024]
+    int64_t* plan_blk_i;   // [1024]
+    int32_t* live_overflow;// [1] set when the liveness fast path hands over to the general walk
     int64_t* vbase;        // [max_frames] position of each frame's preamble vector in the vector stream
     int32_t* sess_nvec;    // [max_frames] vectors consumed by a sink session started at this frame
     int32_t* next_frame;   // [max_frames] scratch of the liveness walk
@@ -85,6 +89,8 @@ int launch_sync_stream(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* i
 int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
 int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
 int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_t* sess_nvec, int32_t max_frames,
+                    int32_t* next, int32_t* exitf, int32_t* overflow, uint8_t* live, int force_general, cudaStream_t st);
 int launch_channel(ofdm_handle* h, const float2* x, int64_t n, float cfo, double phase0, float sigma,
                    uint64_t seed, float2* y, cudaStream_t st);
 int launch_sense(ofdm_sense_handle* s, const float2* x, int64_t n_frames, int shift, int32_t tune_delay,

@@ -419,21 +419,21 @@ int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxW
 // Frame-sink liveness: the sink only starts on a preamble it sees in SYNC_SEARCH; a session started at
 // frame f swallows sess_nvec[f] vectors of the sampler's stream, flagged ones included (A.11).  The live
 // frames are the orbit of frame 0 under next(f) = first frame whose preamble lies at or after the end of
-// f's session.  One CTA: parallel next[], per-chunk backward sweep for chunk exits, a serial hop over at
-// most 1024 chunk entries, then a parallel per-chunk walk that marks the live frames.
+// f's session.
+//   next_kernel      (grid-wide)  next[f]; every frame presumed live; frames with next(f) != f+1 are flagged.
+//   liveness_fast    (one CTA)    ordered list of the flagged frames (normally a handful: a session only
+//                                 swallows a preamble after a bogus header or an early re-sync), serial hop
+//                                 over that list in shared memory, dead ranges cleared in parallel.
+//   liveness_kernel  (one CTA)    the general chunked pointer walk, run only if the list overflows.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) liveness_kernel(const int32_t* __restrict__ n_frames,
-                                                        const int64_t* __restrict__ vbase,
-                                                        const int32_t* __restrict__ sess_nvec,
-                                                        int32_t* __restrict__ next, int32_t* __restrict__ exitf,
-                                                        uint8_t* __restrict__ live) {
-    __shared__ int s_entry[1024];
-    __shared__ int s_first_exit[1024];
-    const int tid = threadIdx.x;
+constexpr int LIVE_CAP = 3072;
+
+__global__ void __launch_bounds__(256) next_kernel(const int32_t* __restrict__ n_frames, const int64_t* __restrict__ vbase,
+                                                   const int32_t* __restrict__ sess_nvec, int32_t* __restrict__ next,
+                                                   uint8_t* __restrict__ exc, uint8_t* __restrict__ live, int max_frames) {
     const int F = *n_frames;
-    s_entry[tid] = -1;
-    if (F <= 0) return;
-    for (int f = tid; f < F; f += 1024) {
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < max_frames; f += gridDim.x * blockDim.x) {
+        if (f >= F) { live[f] = 0; continue; }
         const int64_t target = vbase[f] + (int64_t)sess_nvec[f];
         int nx;
         if (f + 1 >= F) nx = F;
@@ -447,7 +447,94 @@ __global__ void __launch_bounds__(1024) liveness_kernel(const int32_t* __restric
             nx = lo;
         }
         next[f] = nx;
+        exc[f] = (nx != f + 1) ? 1 : 0;
+        live[f] = 1;
     }
+}
+
+__global__ void __launch_bounds__(1024) liveness_fast_kernel(const int32_t* __restrict__ n_frames,
+                                                             const int32_t* __restrict__ next,
+                                                             const uint8_t* __restrict__ exc, uint8_t* __restrict__ live,
+                                                             int32_t* __restrict__ overflow, int force_general) {
+    __shared__ int s_e[LIVE_CAP], s_nx[LIVE_CAP];   // flagged frames in order, and their next(); reused as dead ranges
+    __shared__ int s_w[32];
+    __shared__ int s_total, s_ndead;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int F = *n_frames;
+    if (force_general) {
+        if (tid == 0) *overflow = 1;
+        return;
+    }
+    if (tid == 0) { s_total = 0; s_ndead = 0; *overflow = 0; }
+    __syncthreads();
+    // ordered compaction of the flags, 8 frames per thread and pass
+    for (int base = 0; base < F; base += 1024 * 8) {
+        const int f0 = base + tid * 8;
+        unsigned bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (f0 + i < F && exc[f0 + i]) bits |= 1u << i;
+        const int cnt = __popc(bits);
+        int inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) s_w[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            const int t = s_w[lane];
+            int ti = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, ti, d);
+                if (lane >= d) ti += o;
+            }
+            s_w[lane] = ti - t;
+        }
+        __syncthreads();
+        int pos = s_total + s_w[w] + inc - cnt;
+        for (unsigned b = bits; b; b &= b - 1) {
+            if (pos < LIVE_CAP) { const int f = f0 + __ffs(b) - 1; s_e[pos] = f; s_nx[pos] = next[f]; }
+            ++pos;
+        }
+        __syncthreads();
+        if (tid == 1023) s_total = pos;             // the last thread's end = running total
+        __syncthreads();
+    }
+    const int total = s_total;
+    if (total > LIVE_CAP) {                         // the general walk takes over
+        if (tid == 0) *overflow = 1;
+        return;
+    }
+    if (tid == 0) {
+        int cur = 0, nd = 0;
+        for (int i = 0; i < total; ++i) {
+            const int e = s_e[i];
+            if (e < cur) continue;                  // swallowed by an earlier session: its own next() is moot
+            const int nx = s_nx[i];
+            if (nx > e + 1) { s_e[nd] = e + 1; s_nx[nd] = nx; ++nd; }   // nd <= i: never overtakes the read position
+            cur = nx;
+        }
+        s_ndead = nd;
+    }
+    __syncthreads();
+    for (int r = tid; r < s_ndead; r += 1024)
+        for (int f = s_e[r]; f < s_nx[r]; ++f) live[f] = 0;
+}
+
+__global__ void __launch_bounds__(1024) liveness_kernel(const int32_t* __restrict__ n_frames,
+                                                        const int32_t* __restrict__ run_flag,
+                                                        const int32_t* __restrict__ next, int32_t* __restrict__ exitf,
+                                                        uint8_t* __restrict__ live) {
+    __shared__ int s_entry[1024];
+    __shared__ int s_first_exit[1024];
+    const int tid = threadIdx.x;
+    const int F = *n_frames;
+    if (*run_flag == 0 || F <= 0) return;
+    s_entry[tid] = -1;
+    for (int f = tid; f < F; f += 1024) live[f] = 0;
     __syncthreads();
     const int Kc = (F + 1023) / 1024;
     const int cs = tid * Kc;
@@ -480,7 +567,7 @@ __global__ void __launch_bounds__(1024) liveness_kernel(const int32_t* __restric
 // unmake_packet: dewhiten (offset 0) + check_crc32 for every delivered message; counters for the stats.
 // One warp per 32 consecutive packet slots: when 32 slots fit, they are staged through shared memory (coalesced
 // word copies, rows padded by one word against bank conflicts) and each lane works on its own row there.
-constexpr int CRC_SMEM_WORDS = 3456;      // 32 rows of up to 107 words (stride <= 424 bytes)
+constexpr int CRC_SMEM_MAX = 160 * 1024;  // staging is used while 32 padded rows fit (any stride up to 4096 + 16 does)
 
 __device__ __forceinline__ uint8_t dewhiten_crc_row(uint8_t* b, int len, int stride, const uint8_t* __restrict__ mask,
                                                     const uint32_t* s_crc) {
@@ -499,15 +586,15 @@ __global__ void __launch_bounds__(32) crc_kernel(const int32_t* __restrict__ n_f
                                                  const uint8_t* __restrict__ status, const int32_t* __restrict__ pkt_len,
                                                  uint8_t* __restrict__ pkt_bytes, int stride, uint8_t* __restrict__ pkt_ok,
                                                  const uint8_t* __restrict__ mask, const uint32_t* __restrict__ crctab,
-                                                 int64_t* __restrict__ counters) {
+                                                 int64_t* __restrict__ counters, int staged_in) {
     __shared__ uint32_t s_crc[256];
-    __shared__ uint32_t s_rows[CRC_SMEM_WORDS];
+    extern __shared__ uint32_t s_rows[];                          // [32][stride/4 + 1] when staged, else empty
     const int lane = threadIdx.x;
     for (int i = lane; i < 256; i += 32) s_crc[i] = crctab[i];
     __syncwarp();
     const int F = *n_frames;
     const int wpr = stride >> 2, spr = wpr + 1;                   // words per row in global / shared memory
-    const bool staged = (stride & 3) == 0 && 32 * spr <= CRC_SMEM_WORDS && ((((uintptr_t)pkt_bytes) & 3) == 0);
+    const bool staged = staged_in != 0;
     for (int f0 = blockIdx.x * 32; f0 < F; f0 += gridDim.x * 32) {
         const int f = f0 + lane;
         const bool mine = f < F && live[f] && status[f] == 2;
@@ -554,14 +641,38 @@ __global__ void __launch_bounds__(32) crc_kernel(const int32_t* __restrict__ n_f
     }
 }
 
-int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
-    OFDM_CUDA_CHECK(cudaMemsetAsync(io->frame_live, 0, (size_t)io->max_frames, st));
-    liveness_kernel<<<1, 1024, 0, st>>>(io->n_frames, ws->vbase, ws->sess_nvec, ws->next_frame, ws->exit_frame, io->frame_live);
+int launch_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_t* sess_nvec, int32_t max_frames,
+                    int32_t* next, int32_t* exitf, int32_t* overflow, uint8_t* live, int force_general, cudaStream_t st) {
+    // exitf doubles as the flag bytes of next_kernel (the general walk overwrites it only after the fast path is done)
+    uint8_t* exc = (uint8_t*)exitf;
+    int ngrid = (max_frames + 255) / 256;
+    if (ngrid > 148 * 8) ngrid = 148 * 8;
+    if (ngrid < 1) ngrid = 1;
+    next_kernel<<<ngrid, 256, 0, st>>>(n_frames, vbase, sess_nvec, next, exc, live, max_frames);
     OFDM_LAUNCH_CHECK();
+    liveness_fast_kernel<<<1, 1024, 0, st>>>(n_frames, next, exc, live, overflow, force_general);
+    OFDM_LAUNCH_CHECK();
+    liveness_kernel<<<1, 1024, 0, st>>>(n_frames, overflow, next, exitf, live);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
+int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+    int rc = launch_liveness(io->n_frames, ws->vbase, ws->sess_nvec, io->max_frames, ws->next_frame, ws->exit_frame,
+                             ws->live_overflow, io->frame_live, 0, st);
+    if (rc) return rc;
     int grid = (io->max_frames + 31) / 32;
     if (grid > 148 * 32) grid = 148 * 32;
-    crc_kernel<<<grid, 32, 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len, io->pkt_bytes,
-                                      io->pkt_stride, io->pkt_ok, h->d_mask, h->d_crctab, io->counters);
+    const size_t row_smem = (size_t)32 * (io->pkt_stride / 4 + 1) * sizeof(uint32_t);
+    const int staged = (io->pkt_stride & 3) == 0 && row_smem <= (size_t)CRC_SMEM_MAX && ((((uintptr_t)io->pkt_bytes) & 3) == 0);
+    static size_t attr_smem = 0;
+    if (staged && row_smem > attr_smem) {
+        OFDM_CUDA_CHECK(cudaFuncSetAttribute(crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+        attr_smem = row_smem;
+    }
+    crc_kernel<<<grid, 32, staged ? row_smem : 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len,
+                                                        io->pkt_bytes, io->pkt_stride, io->pkt_ok, h->d_mask, h->d_crctab,
+                                                        io->counters, staged);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }

@@ -23,6 +23,10 @@ int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, voi
     // fixed-size part first, so that the pointers do not depend on n
     ws->first_nan = (int64_t*)take(sizeof(int64_t));
     ws->first_ok = (int32_t*)take(sizeof(int32_t));
+    ws->live_overflow = (int32_t*)take(sizeof(int32_t));
+    ws->plan_hdr = (int32_t*)take(4 * sizeof(int32_t));
+    ws->plan_blk_d = (double*)take(sizeof(double) * 1024);
+    ws->plan_blk_i = (int64_t*)take(sizeof(int64_t) * 1024);
     ws->phi0 = (double*)take(sizeof(double) * max_frames);
     ws->step = (double*)take(sizeof(double) * max_frames);
     ws->vbase = (int64_t*)take(sizeof(int64_t) * ((size_t)max_frames + 1));
@@ -593,7 +597,8 @@ int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t
 
 // ---------------------------------------------------------------------------------------------
 // K_RX3: gr.frequency_modulator_fc(-2/N) phase bookkeeping (A.8) and digital.ofdm_sampler (A.9) in closed
-// form per trigger.  One CTA; the two prefix sums are chunked block scans.
+// form per trigger.  Two grid-wide launches: CTA-local prefixes + totals, then offsets (the divisions of the
+// closed form were 0.3 ms on a single SM).
 // ---------------------------------------------------------------------------------------------
 struct PlanParams {
     int64_t n;
@@ -610,20 +615,58 @@ struct PlanParams {
     int32_t* frame_ndata;
     int64_t* vbase;
     int64_t* counters;
+    int32_t* hdr;          // [4] scratch: K, first_ok, frames before the first call that cannot run
+    double* blk_d;         // [nblk] CTA totals of the phase increments
+    long long* blk_i;      // [nblk] CTA totals of the vector counts
 };
 
 __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-__global__ void __launch_bounds__(1024) plan_kernel(const PlanParams p) {
-    __shared__ double s_wd[32];
-    __shared__ long long s_wi[32];
-    __shared__ double s_carry_d;
-    __shared__ long long s_carry_i;
-    __shared__ int s_first_ok, s_nfr;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    int K = *p.n_trig;
-    if (K > p.max_frames) K = p.max_frames;
-    {
+// exclusive block scan of one value per thread (1024 threads); total = sum over the block.  s_w: [33] scratch.
+template <typename T>
+__device__ __forceinline__ T plan_block_scan(T v, T* s_w, T& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const T o = __shfl_up_sync(0xffffffffu, inc, s);
+        if (lane >= s) inc += o;
+    }
+    T ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) ex = (T)0;
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const T t = s_w[lane];
+        T ti = t;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const T o = __shfl_up_sync(0xffffffffu, ti, s);
+            if (lane >= s) ti += o;
+        }
+        T te = __shfl_up_sync(0xffffffffu, ti, 1);
+        if (lane == 0) te = (T)0;
+        s_w[lane] = te;
+        if (lane == 31) s_w[32] = ti;
+    }
+    __syncthreads();
+    ex += s_w[w];
+    total = s_w[32];
+    __syncthreads();
+    return ex;
+}
+
+// P1 (grid-wide, one trigger per thread): per-trigger NCO step and phase increment, per-frame vector count, their
+// CTA-local exclusive prefixes and the CTA totals; hdr = {K after the NaN cut, first_ok, first trigger whose call cannot run}.
+__global__ void __launch_bounds__(1024) plan_local_kernel(const PlanParams p) {
+    __shared__ double s_wd[33];
+    __shared__ long long s_wi[33];
+    __shared__ int s_K, s_first_ok;
+    const int tid = threadIdx.x;
+    const int64_t N = p.N, L = p.L, n = p.n;
+    if (tid == 0) {
+        int K = *p.n_trig;
+        if (K > p.max_frames) K = p.max_frames;
         // nothing fires after the first NaN of the timing metric (C.1): a run that was open closes there with
         // its arg-max before it, so exactly the triggers at indices < first_nan survive
         const int64_t fn = *p.first_nan;
@@ -633,128 +676,111 @@ __global__ void __launch_bounds__(1024) plan_kernel(const PlanParams p) {
             if (p.trig_idx[mid] < fn) lo = mid + 1; else hi = mid;
         }
         K = lo;
+        // (2) the sampler never looks at indices < N: first visible trigger (the indices ascend)
+        lo = 0; hi = K;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (p.trig_idx[mid] < N) lo = mid + 1; else hi = mid;
+        }
+        s_K = K; s_first_ok = lo;
+        if (blockIdx.x == 0) { p.hdr[0] = K; p.hdr[1] = lo; }
     }
-    const int64_t N = p.N, L = p.L, n = p.n;
     __syncthreads();
-    if (tid == 0) { s_carry_d = 0.0; s_carry_i = 0; s_first_ok = K; s_nfr = INT_MAX; *p.n_trig = K; }
-    __syncthreads();
-    // (1) NCO: step_k = -2/N * ang_k ; phi0_k = sum_{j<k} step_j * (t_{j+1} - t_j)
-    for (int base = 0; base < K; base += 1024) {
-        const int k = base + tid;
-        double d = 0.0;
-        if (k < K) {
-            const double stp = (-2.0 / (double)N) * (double)p.trig_ang[k];
-            p.step[k] = stp;
-            if (k + 1 < K) d = stp * (double)(p.trig_idx[k + 1] - p.trig_idx[k]);
-        }
-        double inc = d;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            double o = __shfl_up_sync(0xffffffffu, inc, s);
-            if (lane >= s) inc += o;
-        }
-        if (lane == 31) s_wd[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            double t = s_wd[lane], ti = t;
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                double o = __shfl_up_sync(0xffffffffu, ti, s);
-                if (lane >= s) ti += o;
-            }
-            s_wd[lane] = ti - t;
-        }
-        __syncthreads();
-        const double excl = s_carry_d + s_wd[w] + (inc - d);
-        if (k < K) p.phi0[k] = excl;
-        __syncthreads();
-        if (tid == 1023) s_carry_d = excl + d;
-        __syncthreads();
-    }
-    // (2) the sampler never looks at indices < N: first visible trigger
-    for (int k = tid; k < K; k += 1024)
-        if (p.trig_idx[k] >= N) { atomicMin(&s_first_ok, k); break; }
-    __syncthreads();
-    const int first_ok = s_first_ok;
-    // (3) can the call that finds trigger k run?  (a call at read pointer pos needs pos+L+N < n)
-    for (int k = first_ok + tid; k < K; k += 1024) {
+    const int K = s_K, first_ok = s_first_ok;
+    const int k = blockIdx.x * 1024 + tid;
+    double d = 0.0;
+    long long v = 0;
+    if (k < K) {
         const int64_t t = p.trig_idx[k];
-        bool ok;
-        if (k == first_ok) {
-            const int64_t c = (t - N) / (L + 1);
-            ok = c * (L + 1) + L + N < n;
-        } else {
-            const int64_t tp = p.trig_idx[k - 1];
-            int64_t mm = ceil_div64(t - tp - 1, L);
-            if (mm < 1) mm = 1;
-            if (mm <= OFDM_SAMPLER_TIMEOUT) {
-                ok = tp + 1 + mm * L < n;
+        const int64_t tn = (k + 1 < K) ? p.trig_idx[k + 1] : 0;
+        // (1) NCO: step_k = -2/N * ang_k ; phi0_k = sum_{j<k} step_j * (t_{j+1} - t_j)
+        const double stp = (-2.0 / (double)N) * (double)p.trig_ang[k];
+        p.step[k] = stp;
+        if (k + 1 < K) d = stp * (double)(tn - t);
+        if (k >= first_ok) {
+            // (3) can the call that finds trigger k run?  (a call at read pointer pos needs pos+L+N < n)
+            bool ok;
+            if (k == first_ok) {
+                const int64_t c = (t - N) / (L + 1);
+                ok = c * (L + 1) + L + N < n;
             } else {
-                const int64_t q0 = tp + 1 + (int64_t)OFDM_SAMPLER_TIMEOUT * L;   // pos + N of the first NO_SIG call
-                const int64_t c = (t - q0) / (L + 1);
-                ok = q0 + c * (L + 1) + L < n;
+                const int64_t tp = p.trig_idx[k - 1];
+                int64_t mm = ceil_div64(t - tp - 1, L);
+                if (mm < 1) mm = 1;
+                if (mm <= OFDM_SAMPLER_TIMEOUT) {
+                    ok = tp + 1 + mm * L < n;
+                } else {
+                    const int64_t q0 = tp + 1 + (int64_t)OFDM_SAMPLER_TIMEOUT * L;   // pos + N of the first NO_SIG call
+                    const int64_t c = (t - q0) / (L + 1);
+                    ok = q0 + c * (L + 1) + L < n;
+                }
             }
-        }
-        if (!ok) { atomicMin(&s_nfr, k - first_ok); break; }   // later ones fail too (pos only grows)
-    }
-    __syncthreads();
-    int F = K - first_ok;
-    if (s_nfr < F) F = s_nfr;
-    if (F < 0) F = 0;
-    // (4) data vectors per frame and the vector-stream prefix
-    for (int base = 0; base < F; base += 1024) {
-        const int f = base + tid;
-        long long v = 0;
-        if (f < F) {
-            const int k = first_ok + f;
-            const int64_t t = p.trig_idx[k];
+            if (!ok) atomicMin(&p.hdr[2], k - first_ok);     // later ones fail too (pos only grows)
+            // (4) data vectors of the frame
             int64_t J = OFDM_SAMPLER_TIMEOUT;
             if (k + 1 < K) {
-                int64_t mm = ceil_div64(p.trig_idx[k + 1] - t - 1, L);
+                int64_t mm = ceil_div64(tn - t - 1, L);
                 if (mm < 1) mm = 1;
                 if (mm - 1 < J) J = mm - 1;
             }
-            int64_t room = (n - 2 - t >= 0) ? (n - 2 - t) / L : 0;
+            const int64_t room = (n - 2 - t >= 0) ? (n - 2 - t) / L : 0;
             if (room < J) J = room;
             if (J < 0) J = 0;
-            p.frame_start[f] = t - N + 1;
-            p.frame_ndata[f] = (int)J;
+            p.frame_start[k - first_ok] = t - N + 1;
+            p.frame_ndata[k - first_ok] = (int)J;
             v = 1 + J;
         }
-        long long inc = v;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            long long o = __shfl_up_sync(0xffffffffu, inc, s);
-            if (lane >= s) inc += o;
-        }
-        if (lane == 31) s_wi[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            long long t = s_wi[lane], ti = t;
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                long long o = __shfl_up_sync(0xffffffffu, ti, s);
-                if (lane >= s) ti += o;
-            }
-            s_wi[lane] = ti - t;
-        }
-        __syncthreads();
-        const long long excl = s_carry_i + s_wi[w] + (inc - v);
-        if (f < F) p.vbase[f] = excl;
-        __syncthreads();
-        if (tid == 1023) s_carry_i = excl + v;
-        __syncthreads();
     }
-    if (tid == 0) {
-        p.vbase[F] = s_carry_i;                     // total vectors
+    double tot_d;
+    long long tot_i;
+    const double ex_d = plan_block_scan<double>(d, s_wd, tot_d);
+    const long long ex_i = plan_block_scan<long long>(v, s_wi, tot_i);
+    if (k < K) {
+        p.phi0[k] = ex_d;
+        if (k >= first_ok) p.vbase[k - first_ok] = ex_i;
+    }
+    if (tid == 0) { p.blk_d[blockIdx.x] = tot_d; p.blk_i[blockIdx.x] = tot_i; }
+}
+
+// P2 (same grid): every CTA scans the CTA totals (at most 1024 of them), adds its own offset; CTA 0 publishes the scalars.
+__global__ void __launch_bounds__(1024) plan_offset_kernel(const PlanParams p, int nblk) {
+    __shared__ double s_wd[33];
+    __shared__ long long s_wi[33];
+    __shared__ double s_off_d;
+    __shared__ long long s_off_i;
+    const int tid = threadIdx.x;
+    const int K = p.hdr[0], first_ok = p.hdr[1];
+    int F = K - first_ok;
+    if (p.hdr[2] < F) F = p.hdr[2];
+    if (F < 0) F = 0;
+    double tot_d;
+    long long tot_i;
+    const double ex_d = plan_block_scan<double>(tid < nblk ? p.blk_d[tid] : 0.0, s_wd, tot_d);
+    const long long ex_i = plan_block_scan<long long>(tid < nblk ? p.blk_i[tid] : 0, s_wi, tot_i);
+    if (tid == blockIdx.x) { s_off_d = ex_d; s_off_i = ex_i; }
+    __syncthreads();
+    const int k = blockIdx.x * 1024 + tid;
+    if (k < K) {
+        p.phi0[k] = s_off_d + p.phi0[k];
+        const int f = k - first_ok;
+        if (f >= 0 && f <= F) {
+            const long long vb = s_off_i + p.vbase[f];
+            p.vbase[f] = vb;
+            if (f == F) p.counters[6] = vb;         // F < K - first_ok: vectors of the F frames
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        if (F == K - first_ok) { p.vbase[F] = tot_i; p.counters[6] = tot_i; }
+        *p.n_trig = K;
         *p.first_ok = first_ok;
         *p.n_frames = F;
         p.counters[0] = F;
-        p.counters[4] = n;
+        p.counters[4] = p.n;
         p.counters[5] = K;
-        p.counters[6] = s_carry_i;
     }
 }
+
+__global__ void plan_init_kernel(int32_t* hdr) { hdr[0] = 0; hdr[1] = 0; hdr[2] = INT_MAX; }
 
 int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
     PlanParams p;
@@ -762,8 +788,18 @@ int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cuda
     p.trig_idx = io->trig_idx;
     p.trig_ang = io->trig_ang; p.phi0 = ws->phi0; p.step = ws->step; p.first_ok = ws->first_ok; p.n_frames = io->n_frames;
     p.frame_start = io->frame_start; p.frame_ndata = io->frame_ndata; p.vbase = ws->vbase; p.counters = io->counters;
+    p.hdr = ws->plan_hdr; p.blk_d = ws->plan_blk_d; p.blk_i = (long long*)ws->plan_blk_i;
+    const int nblk = (io->max_frames + 1023) / 1024;
+    if (nblk > 1024) {
+        ofdm_set_error("plan: max_frames %d exceeds 1048576", io->max_frames);
+        return OFDM_E_INVAL;
+    }
     OFDM_CUDA_CHECK(cudaMemsetAsync(io->counters, 0, 8 * sizeof(int64_t), st));
-    plan_kernel<<<1, 1024, 0, st>>>(p);
+    plan_init_kernel<<<1, 1, 0, st>>>(p.hdr);
+    OFDM_LAUNCH_CHECK();
+    plan_local_kernel<<<nblk, 1024, 0, st>>>(p);
+    OFDM_LAUNCH_CHECK();
+    plan_offset_kernel<<<nblk, 1024, 0, st>>>(p, nblk);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }

@@ -300,3 +300,40 @@ def test_independent_streams_are_order_invariant():
     assert first[0] == refs[0] and first[1] == refs[1]
     assert all(sum(1 for g, _ in first[s] if g) >= 7 for s in range(6))
     eng.close()
+
+
+@pytest.mark.parametrize("F,p_exc", [(1, 0.0), (50, 0.3), (20000, 0.0), (20000, 0.002), (20000, 0.5), (100000, 0.01)])
+def test_liveness_walk_fast_and_general(F, p_exc):
+    """ofdm_rx_liveness (the sink-liveness stage of ofdm_rx_finish) on synthetic frame tables: the short-exception
+    fast path, its overflow hand-over (p_exc = 0.5 flags ~10 000 frames > LIVE_CAP) and the forced general walk all
+    equal the sequential orbit of frame 0 under next()."""
+    import torch
+    from ofdm_uhd_b200 import _lib
+    rng = np.random.default_rng(F + int(1000 * p_exc))
+    ndata = rng.integers(1, 6, size=F)
+    vbase = np.concatenate([[0], np.cumsum(1 + ndata)])[:F].astype(np.int64)
+    nvec = (1 + ndata).astype(np.int32)
+    exc = rng.random(F) < p_exc
+    nvec[exc] = rng.integers(1, 60, size=int(exc.sum())).astype(np.int32)
+    if F > 10:
+        nvec[F // 2] = np.iinfo(np.int32).max // 2          # a session that never ends swallows the rest
+        nvec[exc & (np.arange(F) >= F // 2)] = 3
+    live_ref = np.zeros(F, dtype=np.uint8)
+    f = 0
+    while f < F:
+        live_ref[f] = 1
+        f = max(f + 1, int(np.searchsorted(vbase, vbase[f] + int(nvec[f]), side="left")))
+    L = _lib.lib()
+    maxf = F + 7
+    d_n = torch.tensor([F], dtype=torch.int32, device="cuda")
+    d_vb = torch.from_numpy(vbase).cuda()
+    d_nv = torch.from_numpy(nvec).cuda()
+    for force in (0, 1):
+        scratch = torch.zeros(2 * maxf + 2, dtype=torch.int32, device="cuda")
+        live = torch.full((maxf,), 7, dtype=torch.uint8, device="cuda")
+        _lib.check(L.ofdm_rx_liveness(d_n.data_ptr(), d_vb.data_ptr(), d_nv.data_ptr(), maxf, scratch.data_ptr(),
+                                      live.data_ptr(), force, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        got = live.cpu().numpy()
+        assert np.array_equal(got[:F], live_ref), (force, int(np.flatnonzero(got[:F] != live_ref)[0]))
+        assert not got[F:].any()
