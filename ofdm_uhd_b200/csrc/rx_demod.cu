@@ -46,6 +46,15 @@ __device__ __forceinline__ float2 phasor_f64(double ph) {
     return make_float2(cs, sn);
 }
 
+// a sample at or after the next trigger (the last sample of a preamble vector): exact per-sample NCO phase.
+// Out of line: it is inlined E times otherwise and the per-vector loop must stay small.
+__device__ __noinline__ float2 derot_slow(float2 v, int64_t s, const int64_t* trig, const double* phi0, const double* step,
+                                          int K, int kk) {
+    while (kk + 1 < K && LDG(trig + kk + 1) <= s) ++kk;
+    const double ph = LDG(phi0 + kk) + LDG(step + kk) * (double)(s - LDG(trig + kk) + 1);
+    return cmul_x(v, phasor_f64(ph));
+}
+
 struct DemodLoad {
     const float2* y;
     int64_t st, t_next;
@@ -59,10 +68,7 @@ struct DemodLoad {
         const int64_t s = st + idx;
         const float2 v = LDG(y + s);
         if (s < t_next) return cmul_x(v, cmul(ph0, Wt[slot]));
-        int kk = kk0;
-        while (kk + 1 < K && LDG(trig + kk + 1) <= s) ++kk;
-        const double ph = LDG(phi0 + kk) + LDG(step + kk) * (double)(s - LDG(trig + kk) + 1);
-        return cmul_x(v, phasor_f64(ph));
+        return derot_slow(v, s, trig, phi0, step, K, kk0);
     }
 };
 
@@ -86,10 +92,24 @@ __device__ __forceinline__ float2 coarse_comp(int delta, int cp, int N, int cnt)
     return expj_f32(ph);
 }
 
-// LSB-first packing of the slicer decisions of one vector into bytes q in [B0, B1)
-template <int NB>
+// LSB-first packing of the slicer decisions of one vector into bytes q in [B0, B1).  One generic routine (nbits is
+// 1, 2, 3, 4, 6 or 8: a shift, then an exact multiply-shift division by 3 where needed) instead of eight
+// constant-divisor instantiations: the per-vector loop has to stay inside the instruction cache.
+struct BitDiv {
+    int sh, by3, nbits;
+    __device__ __forceinline__ explicit BitDiv(int nb) : nbits(nb) {
+        sh = __ffs(nb) - 1;
+        by3 = (nb >> sh) == 3;
+    }
+    // rel / nbits for 0 <= rel < 98304
+    __device__ __forceinline__ int div(int rel) const {
+        const int pre = rel >> sh;
+        return by3 ? (int)(((unsigned)pre * 43691u) >> 17) : pre;
+    }
+};
+
 __device__ __forceinline__ void pack_bytes(const uint8_t* sym, uint8_t* vb, int B0, int B1, int bit_base, unsigned carry,
-                                           int tid, int nthreads) {
+                                           int tid, int nthreads, const BitDiv bd) {
     for (int q = B0 + tid; q < B1; q += nthreads) {
         unsigned byte = 0;
 #pragma unroll
@@ -97,7 +117,10 @@ __device__ __forceinline__ void pack_bytes(const uint8_t* sym, uint8_t* vb, int 
             const int rel = 8 * q + i - bit_base;
             unsigned bit;
             if (rel < 0) bit = (carry >> i) & 1u;
-            else bit = ((unsigned)sym[rel / NB] >> (rel % NB)) & 1u;
+            else {
+                const int c = bd.div(rel);
+                bit = ((unsigned)sym[c] >> (rel - c * bd.nbits)) & 1u;
+            }
             byte |= bit << i;
         }
         vb[q - B0] = (uint8_t)byte;
@@ -136,6 +159,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     for (int i = tid; i < p.M; i += BT) s_cst[i] = p.cst[i];
     float2* S = (P::NP == 2) ? bufB : bufA;                 // shifted spectrum of the current vector
     const int bits_this = ncar * nbits;
+    const BitDiv bd(nbits);
 
     for (int f = blockIdx.x; f < F; f += gridDim.x) {
         int g = f, m = 0, vi = 0, cnt = 1, delta = 0, bit_base = 0;
@@ -257,38 +281,64 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
             } else {
                 const float2 car = s_car[par];
                 double er = 0.0, ei = 0.0;
-                for (int c = tid; c < ncar; c += BT) {
-                    const float2 d0 = dfe[c];
-                    const int i = LDG(p.sinkmap + c);
-                    const float2 eqv = cmul_x(cmul_x(H[i], cc), S[i + zl + delta]);
-                    const float2 r = cmul_x(cmul_x(eqv, car), d0);
+                // two carriers per pass with every load ahead of the first store: the two slicer chains are
+                // independent, which the compiler cannot see through the shared-memory stores of a one-carrier loop
+                for (int c = tid; c < ncar; c += 2 * BT) {
+                    const int c2 = c + BT;
+                    const bool two = c2 < ncar;
+                    const int cb = two ? c2 : c;
+                    const float2 d0a = dfe[c], d0b = dfe[cb];
+                    const int ia = LDG(p.sinkmap + c), ib = LDG(p.sinkmap + cb);
+                    const float2 Ha = H[ia], Hb = H[ib];
+                    const float2 Sa = S[ia + zl + delta], Sb = S[ib + zl + delta];
+                    const float2 eqa = cmul_x(cmul_x(Ha, cc), Sa), eqb = cmul_x(cmul_x(Hb, cc), Sb);
+                    const float2 ra = cmul_x(cmul_x(eqa, car), d0a), rb = cmul_x(cmul_x(eqb, car), d0b);
                     // slicer: first minimum of |r - const[k]|^2
-                    int b = 0;
-                    float best;
+                    int ba = 0, bb = 0;
+                    float besta, bestb;
                     {
                         const float2 c0 = s_cst[0];
-                        const float dx = fsub_rn(r.x, c0.x), dy = fsub_rn(r.y, c0.y);
-                        best = fadd_rn(fmul_rn(dx, dx), fmul_rn(dy, dy));
+                        const float dxa = fsub_rn(ra.x, c0.x), dya = fsub_rn(ra.y, c0.y);
+                        const float dxb = fsub_rn(rb.x, c0.x), dyb = fsub_rn(rb.y, c0.y);
+                        besta = fadd_rn(fmul_rn(dxa, dxa), fmul_rn(dya, dya));
+                        bestb = fadd_rn(fmul_rn(dxb, dxb), fmul_rn(dyb, dyb));
                     }
                     for (int k = 1; k < p.M; ++k) {
                         const float2 ck = s_cst[k];
-                        const float dx = fsub_rn(r.x, ck.x), dy = fsub_rn(r.y, ck.y);
-                        const float dd = fadd_rn(fmul_rn(dx, dx), fmul_rn(dy, dy));
-                        if (dd < best) { best = dd; b = k; }
+                        const float dxa = fsub_rn(ra.x, ck.x), dya = fsub_rn(ra.y, ck.y);
+                        const float dxb = fsub_rn(rb.x, ck.x), dyb = fsub_rn(rb.y, ck.y);
+                        const float dda = fadd_rn(fmul_rn(dxa, dxa), fmul_rn(dya, dya));
+                        const float ddb = fadd_rn(fmul_rn(dxb, dxb), fmul_rn(dyb, dyb));
+                        if (dda < besta) { besta = dda; ba = k; }
+                        if (ddb < bestb) { bestb = ddb; bb = k; }
                     }
-                    const float2 cl = s_cst[b];
-                    const float2 e = cmulc_x(r, cl);
-                    er += (double)e.x;
-                    ei += (double)e.y;
-                    if (norm_x(r) > 0.001f) {
-                        const float2 q = cdiv_x(cl, r);
-                        dfe[c] = make_float2(fadd_rn(d0.x, fmul_rn(0.05f, fsub_rn(q.x, d0.x))),
-                                             fadd_rn(d0.y, fmul_rn(0.05f, fsub_rn(q.y, d0.y))));
+                    const float2 cla = s_cst[ba], clb = s_cst[bb];
+                    const float2 ea = cmulc_x(ra, cla), eb = cmulc_x(rb, clb);
+                    er += (double)ea.x;
+                    ei += (double)ea.y;
+                    if (norm_x(ra) > 0.001f) {
+                        const float2 q = cdiv_x(cla, ra);
+                        dfe[c] = make_float2(fadd_rn(d0a.x, fmul_rn(0.05f, fsub_rn(q.x, d0a.x))),
+                                             fadd_rn(d0a.y, fmul_rn(0.05f, fsub_rn(q.y, d0a.y))));
                     }
-                    sym[c] = (uint8_t)b;
+                    sym[c] = (uint8_t)ba;
                     if (TAPS && tap) {
-                        if (p.sym_idx) p.sym_idx[vglob * ncar + c] = (uint8_t)b;
-                        if (p.derot_syms) p.derot_syms[vglob * ncar + c] = r;
+                        if (p.sym_idx) p.sym_idx[vglob * ncar + c] = (uint8_t)ba;
+                        if (p.derot_syms) p.derot_syms[vglob * ncar + c] = ra;
+                    }
+                    if (two) {
+                        er += (double)eb.x;
+                        ei += (double)eb.y;
+                        if (norm_x(rb) > 0.001f) {
+                            const float2 q = cdiv_x(clb, rb);
+                            dfe[c2] = make_float2(fadd_rn(d0b.x, fmul_rn(0.05f, fsub_rn(q.x, d0b.x))),
+                                                  fadd_rn(d0b.y, fmul_rn(0.05f, fsub_rn(q.y, d0b.y))));
+                        }
+                        sym[c2] = (uint8_t)bb;
+                        if (TAPS && tap) {
+                            if (p.sym_idx) p.sym_idx[vglob * ncar + c2] = (uint8_t)bb;
+                            if (p.derot_syms) p.derot_syms[vglob * ncar + c2] = rb;
+                        }
                     }
                 }
 #pragma unroll
@@ -315,16 +365,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 if (tid == 32) s_cc[par ^ 1] = coarse_comp(delta, p.cp, N, cnt_next);
                 // LSB-first byte packing; bits left over from the previous vector sit in s_carry
                 const unsigned carry = s_carry;
-                switch (nbits) {
-                    case 1: pack_bytes<1>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
-                    case 2: pack_bytes<2>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
-                    case 3: pack_bytes<3>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
-                    case 4: pack_bytes<4>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
-                    case 5: pack_bytes<5>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
-                    case 6: pack_bytes<6>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
-                    case 7: pack_bytes<7>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
-                    default: pack_bytes<8>(sym, vb, B0, B1, bit_base, carry, tid, BT); break;
-                }
+                pack_bytes(sym, vb, B0, B1, bit_base, carry, tid, BT, bd);
                 __syncthreads();
                 if (tid == 0) {
                     if (vi == 1) {
@@ -336,7 +377,8 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                     unsigned nc = 0;
                     for (int i = 0; i < nrb; ++i) {
                         const int rel = 8 * B1 + i - bit_base;
-                        nc |= (((unsigned)sym[rel / nbits] >> (rel % nbits)) & 1u) << i;
+                        const int c = bd.div(rel);
+                        nc |= (((unsigned)sym[c] >> (rel - c * nbits)) & 1u) << i;
                     }
                     s_carry = nc;
                 }

@@ -59,28 +59,69 @@ struct FiltParams {
     const float2* H;
 };
 
+// 16-byte (or 8-byte) asynchronous global -> shared copy; bytes beyond src_bytes are zero-filled
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+struct SmemRawIn {
+    const float2* p;
+    HDM float2 operator()(int i, int) const { return p[i]; }
+};
+
+// The two shared buffers of a block alternate roles: while the last inverse pass of block b streams its results
+// out of one of them, the input of block b+1 is already landing in the other (cp.async, zero-filled outside the
+// stream), so no pass waits on a global load.
 template <int NOS, int G>
-__global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 2) chan_filter_kernel(const FiltParams p) {
+__global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), G == 1 ? 4 : 2) chan_filter_kernel(const FiltParams p) {
     using P = FftPlan<NOS>;
     constexpr int E = P::E;
     constexpr int T = NOS / E;
-    constexpr int SB = fft_smem_elems<NOS>();
+    constexpr int SB = (fft_smem_elems<NOS>() + 1) & ~1;      // even: both buffers stay 16-byte aligned
     constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
     static_assert(P::NP == 3 && R2 == E && R1 == E, "overlap-save plan must end with full-width radices");
-    extern __shared__ float2 smem[];
+    extern __shared__ __align__(16) float2 smem[];
     const int g = threadIdx.x / T;
     const int tid = threadIdx.x - g * T;
-    float2* bufA = smem + (size_t)g * 2 * SB;
-    float2* bufB = bufA + SB;
+    float2* raw = smem + (size_t)g * 2 * SB;                  // holds the raw input of the current block
+    float2* oth = raw + SB;
+    const bool al16 = (((uintptr_t)p.x) & 15) == 0 && ((p.V | p.hist) & 1) == 0;
+    auto prefetch = [&](float2* dst, int64_t blk) {
+        if (blk < p.nblk) {
+            const int64_t in0 = blk * p.V - p.hist;
+            if (al16) {
+#pragma unroll
+                for (int i = 0; i < E / 2; ++i) {
+                    const int idx = 2 * (tid + i * T);
+                    const int64_t gi = in0 + idx;              // even, so a pair never straddles sample 0
+                    int bytes = 0;
+                    if (gi >= 0 && gi < p.n) bytes = (gi + 1 < p.n) ? 16 : 8;
+                    cp_async16(dst + idx, p.x + (bytes ? gi : 0), bytes);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < E; ++i) {
+                    const int idx = tid + i * T;
+                    const int64_t gi = in0 + idx;
+                    const bool in = gi >= 0 && gi < p.n;
+                    cp_async8(dst + idx, p.x + (in ? gi : 0), in ? 8 : 0);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    prefetch(raw, (int64_t)blockIdx.x * G + g);
     for (int64_t base = (int64_t)blockIdx.x * G; base < p.nblk; base += (int64_t)gridDim.x * G) {
         const int64_t blk = base + g;
         const bool active = blk < p.nblk;
-        const int64_t in0 = blk * p.V - p.hist;
         float2 regs[E];
-        auto ld = [&](int idx, int) -> float2 {
-            int64_t gi = in0 + idx;
-            return (gi >= 0 && gi < p.n) ? LDG(p.x + gi) : make_float2(0.f, 0.f);
-        };
         auto mulH = [&](int idx, float2 v, int slot) { regs[slot] = cmul(v, LDG(p.H + idx)); };
         auto fromRegs = [&](int, int slot) -> float2 { return regs[slot]; };
         auto st = [&](int idx, float2 v, int) {
@@ -89,24 +130,30 @@ __global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 2) chan_filter_ke
                 if (o < p.n) p.y[o] = v;
             }
         };
-        if (active) fft_pass<NOS, R0, 1, -1>(tid, p.tw, ld, SmemOut{bufA});
+        cp_async_wait_all();
         __syncthreads();
-        if (active) fft_pass<NOS, R1, R0, -1>(tid, p.tw, SmemIn{bufA}, SmemOut{bufB});
+        if (active) fft_pass<NOS, R0, 1, -1>(tid, p.tw, SmemRawIn{raw}, SmemOut{oth});
         __syncthreads();
-        if (active) fft_pass<NOS, R2, R0 * R1, -1>(tid, p.tw, SmemIn{bufB}, mulH);
+        if (active) fft_pass<NOS, R1, R0, -1>(tid, p.tw, SmemIn{oth}, SmemOut{raw});
+        __syncthreads();
+        if (active) fft_pass<NOS, R2, R0 * R1, -1>(tid, p.tw, SmemIn{raw}, mulH);
         // inverse, radix order reversed: R2, R1, R0
-        if (active) fft_pass<NOS, R2, 1, 1>(tid, p.tw, fromRegs, SmemOut{bufA});
+        if (active) fft_pass<NOS, R2, 1, 1>(tid, p.tw, fromRegs, SmemOut{oth});
         __syncthreads();
-        if (active) fft_pass<NOS, R1, R2, 1>(tid, p.tw, SmemIn{bufA}, SmemOut{bufB});
+        if (active) fft_pass<NOS, R1, R2, 1>(tid, p.tw, SmemIn{oth}, SmemOut{raw});
         __syncthreads();
-        if (active) fft_pass<NOS, R0, R2 * R1, 1>(tid, p.tw, SmemIn{bufB}, st);
+        prefetch(oth, blk + (int64_t)gridDim.x * G);
+        if (active) fft_pass<NOS, R0, R2 * R1, 1>(tid, p.tw, SmemIn{raw}, st);
+        float2* t = raw; raw = oth; oth = t;
     }
+    cp_async_wait_all();
 }
 
 template <int NOS, int G>
 static int launch_filter_n(ofdm_handle* h, const FiltParams& p, cudaStream_t st) {
     constexpr int T = NOS / FftPlan<NOS>::E;
-    size_t smem = ((size_t)G * 2 * fft_smem_elems<NOS>()) * sizeof(float2);
+    constexpr int SB = (fft_smem_elems<NOS>() + 1) & ~1;
+    size_t smem = ((size_t)G * 2 * SB) * sizeof(float2);
     static bool attr_done = false;
     if (!attr_done) {
         OFDM_CUDA_CHECK(cudaFuncSetAttribute(chan_filter_kernel<NOS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -115,7 +162,7 @@ static int launch_filter_n(ofdm_handle* h, const FiltParams& p, cudaStream_t st)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int64_t want = (p.nblk + G - 1) / G;
-    int64_t cap = (int64_t)sms * 8;
+    int64_t cap = (int64_t)sms * 16;
     int grid = (int)(want < cap ? want : cap);
     chan_filter_kernel<NOS, G><<<grid, G * T, smem, st>>>(p);
     OFDM_LAUNCH_CHECK();
@@ -127,7 +174,7 @@ int launch_chan_filter(ofdm_handle* h, const float2* x, int64_t n, float2* y, cu
     FiltParams p;
     p.x = x; p.y = y; p.n = n; p.hist = h->ntaps - 1; p.V = h->NOS - p.hist;
     p.nblk = (n + p.V - 1) / p.V; p.tw = h->d_tw_os; p.H = h->d_Hos;
-    if (h->NOS == 2048) return launch_filter_n<2048, 2>(h, p, st);
+    if (h->NOS == 2048) return launch_filter_n<2048, 1>(h, p, st);   // one block per CTA: 4 independent CTAs per SM
     if (h->NOS == 4096) return launch_filter_n<4096, 1>(h, p, st);
     ofdm_set_error("chan_filter: unsupported overlap-save size %d", h->NOS);
     return OFDM_E_INVAL;
