@@ -26,7 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-KERNELS_PER_STEP = 15   # make_packets, tx, chan_filter, stream_init, sync_stream, seg_scan, trig_gather, plan_init,
+KERNELS_PER_STEP = 16   # make_packets, tx, chan_filter, stream_init, metric_chunk, detect_seg, seg_scan, trig_gather, plan_init,
                         # plan_local, plan_offset, demod, next, liveness_fast, liveness (general walk, idle), crc
 
 
@@ -218,7 +218,7 @@ def run_b200(args):
         "tx_kernel": lambda: L_.ofdm_tx_modulate_batch(eng.h, eng._p(plan.pkts), eng._p(plan.d_pkt_off), F, 0, None,
                                                        plan.total_syms, plan.uniform_syms, eng._p(xs), st),
         "chan_filter_kernel": lambda: L_.ofdm_rx_chan_filter(eng.h, eng._p(xc), n, eng._p(y), st),
-        "sync_stream_kernel(+scan,gather)": lambda: L_.ofdm_rx_sync(eng.h, eng._p(y), n, C.byref(io), st),
+        "metric_chunk_kernel+detect_seg_kernel(+scan,gather)": lambda: L_.ofdm_rx_sync(eng.h, eng._p(y), n, C.byref(io), st),
         "plan_kernel": lambda: L_.ofdm_rx_plan(eng.h, n, C.byref(io), st),
         "demod_kernel": lambda: L_.ofdm_rx_demod(eng.h, eng._p(y), n, C.byref(io), st),
         "liveness+crc": lambda: L_.ofdm_rx_finish(eng.h, C.byref(io), st),

@@ -11,7 +11,7 @@ int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, voi
     (void)h;
     if (n < 0) n = 0;
     if (max_frames < 1) max_frames = 1;
-    int64_t seg_len = (n + 148 * 24 - 1) / (148 * 24);
+    int64_t seg_len = (n + 148 * 40 - 1) / (148 * 40);     // two full waves of the detector kernel (20 warps per SM)
     if (seg_len < 65536) seg_len = 65536;
     seg_len = (seg_len + 31) / 32 * 32;
     ws->seg_len = seg_len;
@@ -80,7 +80,7 @@ struct SmemRawIn {
 // out of one of them, the input of block b+1 is already landing in the other (cp.async, zero-filled outside the
 // stream), so no pass waits on a global load.
 template <int NOS, int G>
-__global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), G == 1 ? 4 : 2) chan_filter_kernel(const FiltParams p) {
+__global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 512 / (G * (NOS / FftPlan<NOS>::E))) chan_filter_kernel(const FiltParams p) {
     using P = FftPlan<NOS>;
     constexpr int E = P::E;
     constexpr int T = NOS / E;

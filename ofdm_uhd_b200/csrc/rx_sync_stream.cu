@@ -1,19 +1,26 @@
-// K_RX2 fused: the whole of upstream ofdm_sync_pn (Schmidl-Cox metric + peak_detector_fb) as ONE streaming
-// kernel -- the filtered stream is read once and only trigger indices are written (no timing-metric array).
+// K_RX2: the whole of upstream ofdm_sync_pn (Schmidl-Cox metric + peak_detector_fb) as two streaming kernels.
 // Reference wiring: ofdm_receiver.py~:97-101; math: SURVEY.md A.6-A.7; same arithmetic (operation order,
 // float64 accumulation, float32 rounding points) as sync_metric_kernel + peak_detect_kernel in rx_front.cu,
-// which remain the stage-level entry points (ofdm_rx_sync_metric / ofdm_rx_peak_detect).
+// which remain the stage-level entry points (ofdm_rx_sync_metric / ofdm_rx_peak_detect) and serve N >= 1024.
 //
-// One warp walks one contiguous segment, 32*K samples per step with K consecutive samples per lane, where
-// 32*K = N/2: a step is exactly one van Herk block, so
+// Both kernels run one warp per CTA (segment index and loop bounds are then CTA-uniform, so the compiler can
+// prove every shuffle convergent) and walk a contiguous piece of the stream, 32*K samples per step with K
+// consecutive samples per lane, where 32*K = N/2: a step is exactly one van Herk block, so
 //   * y[n - N/2] is the same lane's sample of the previous step (kept in registers, never re-read),
 //   * a window sum = [same lane's later elements + later lanes of the previous step] + [earlier lanes + own
 //     elements of this step]: two warp scans per sum, no shared memory, no subtraction,
 //   * the cp-wide average of the metric is a float64 prefix difference through a per-warp ring in shared memory,
 //   * the detector (IIR average scan, threshold ballot, run / arg-max state machine) consumes the K metric values
 //     straight from registers.
-// A segment starts OFDM_PEAK_WARM samples early (+2 priming steps for the sums) and runs past its end until an
-// open run closes; a run belongs to the segment it starts in.
+// The window sums and the detector have very different shapes -- the sums need ~170 registers and no history
+// beyond one block, the detector ~90 registers but a 24 576-sample warm-up of its IIR average -- so as two kernels
+// each runs at its own occupancy, the expensive half skips the warm-up overlap entirely, and the 4 B/sample
+// hand-over is noise next to the instruction-issue / XU-pipe limit both halves sit on (a fused single kernel
+// measured 5.3 ms on the 640 M-sample bench capture, the pair 4.2 ms).
+//   metric_chunk_kernel  one warp per chunk of MC_STEPS blocks (+1 priming block): y -> M = |P|^2 / R^2
+//   detect_seg_kernel    one warp per detector segment: M -> cp-average - 1 -> peak_detector_fb -> triggers;
+//                        a segment starts OFDM_PEAK_WARM samples early and runs past its end until an open run
+//                        closes; a run belongs to the segment it starts in.
 #include "internal.h"
 #include "common.cuh"
 #include <limits.h>
@@ -30,9 +37,6 @@ struct StreamParams {
     int64_t* first_nan;
     uint32_t* status;
 };
-
-constexpr int SS_WARPS = 1;       // one warp per CTA: segment index and loop bounds are CTA-uniform, so the
-                                   // compiler can prove the shuffles convergent (no WARPSYNC around each of them)
 
 // Warp scans of doubles.  A conditional add after a shuffle compiles to DADD + two FSEL; multiplying the shuffled
 // value by a per-lane 1.0 / 0.0 mask inside one DFMA is exact (x*1 = x, x*0 = 0 for finite x) and a single instruction.
@@ -53,32 +57,22 @@ struct StepHist {
     double bwd[3];                                   // sum of the products of the later lanes
 };
 
+constexpr int MC_STEPS = 32;
+
 template <int K>
-struct StreamCtx {
+struct MetricCtx {
     static constexpr int SZ = 32 * K;
-    const StreamParams& p;
-    double* ring;
+    const float2* y;
+    float* mt;
+    int64_t n;
     int lane;
-    int64_t seg, s0, s1;
-    bool vec_ok, cp_aligned;
-    int prime, cpq;
-    double tap, a1, a2, p32, plane;
-    double pw[5];                                    // IIR scan weights, 0 where the source lane does not exist
-    double mu[5], md[5];                             // 1.0 where lane - 2^k / lane + 2^k exists, else 0.0
-    // running state
-    double carry2 = 0.0;                             // prefix of the metric up to the previous step
-    double carry = 0.0;                              // detector average after the last consumed sample
-    int state = 0, count = 0;
-    float peak = -INFINITY;
-    int64_t ind = 0, run_start = 0;
+    bool vec_ok, st_ok;
+    double mu[5], md[5];
 
-    __device__ __forceinline__ StreamCtx(const StreamParams& p_) : p(p_) {}
-
-    // samples [i0 + lane*K, +K) of the stream, zero past its end
     __device__ __forceinline__ void load(float2 (&dst)[K], const int64_t i0) const {
         const int64_t b0 = i0 + (int64_t)lane * K;
-        if (i0 + SZ <= p.n && vec_ok) {                          // warp-uniform
-            const float4* q = (const float4*)(p.y + b0);
+        if (i0 >= 0 && i0 + SZ <= n && vec_ok) {                 // warp-uniform
+            const float4* q = (const float4*)(y + b0);
 #pragma unroll
             for (int i = 0; i < K / 2; ++i) {
                 const float4 t = __ldg(q + i);
@@ -87,28 +81,33 @@ struct StreamCtx {
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < K; ++i) dst[i] = (b0 + i < p.n) ? p.y[b0 + i] : make_float2(0.f, 0.f);
+            for (int i = 0; i < K; ++i) dst[i] = (b0 + i >= 0 && b0 + i < n) ? y[b0 + i] : make_float2(0.f, 0.f);
         }
     }
-
-    // cur.y holds this step's samples on entry; prev.y is refilled with the next step's as soon as the products
-    // are formed (the two histories swap roles every step), so the loads fly during the rest of the step
-    __device__ __forceinline__ void step(StepHist<K>& prev, StepHist<K>& cur, const int64_t i0, const int stepno) {
-        const int64_t b0 = i0 + (int64_t)lane * K;
-        const bool full = i0 + SZ <= p.n;                        // warp-uniform
-        int nvalid = K;                                          // samples of this lane inside the stream
-        if (!full) {
-            const int64_t r = p.n - b0;
-            nvalid = r < 0 ? 0 : (r > K ? K : (int)r);
-        }
-        // products of this step
+    __device__ __forceinline__ void products(const StepHist<K>& prev, StepHist<K>& cur) const {
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             const float2 c = cmulc_x(cur.y[i], prev.y[i]);      // y[n] * conj(y[n - N/2])
             cur.x[0][i] = c.x; cur.x[1][i] = c.y; cur.x[2][i] = norm_x(cur.y[i]);
         }
-        if (i0 + SZ < p.n) load(prev.y, i0 + SZ);
-        // three moving sums of width N/2 = SZ (van Herk: previous step's tail + this step's head), no subtraction
+    }
+    // priming block: only what the next block needs of it (products and the sums of the later lanes)
+    __device__ __forceinline__ void prime(const StepHist<K>& prev, StepHist<K>& cur) const {
+        products(prev, cur);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double run = 0.0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) run += (double)cur.x[a][i];
+            double bi = run;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
+            cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
+        }
+    }
+    __device__ __forceinline__ void step(StepHist<K>& prev, StepHist<K>& cur, const int64_t i0, const bool more) {
+        products(prev, cur);
+        if (more) load(prev.y, i0 + SZ);                         // next block's samples into the dead buffer
         float PR[3][K];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -124,7 +123,6 @@ struct StreamCtx {
             }
             const double fwd = shfl_up_d(fi, 1) * mu[0];
             cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
-            // previous step's part of each window: elements i+1.. of this lane, then the later lanes
             double tail[K];
             double sfx = prev.bwd[a];
             tail[K - 1] = sfx;
@@ -133,20 +131,112 @@ struct StreamCtx {
 #pragma unroll
             for (int i = 0; i < K; ++i) PR[a][i] = (float)(tail[i] + (pre[i] + fwd));
         }
-        // normalised metric and its cp-wide average (float64 prefix difference)
-        const bool zero_first = prime && stepno == 0;            // mid-stream start: sums miss the previous block
-        double mloc[K];
-        double mrun = 0.0;
+        float q[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             const float num = fadd_rn(fmul_rn(PR[0][i], PR[0][i]), fmul_rn(PR[1][i], PR[1][i]));
             const float den = fmul_rn(PR[2][i], PR[2][i]);
-            float q = fdiv_rn(num, den);
-            asm volatile("" : "+f"(q));                          // keep the division out of a branch
-            q = zero_first ? 0.f : q;                            // keeps the prefix finite
-            mrun += (double)q;
-            mloc[i] = mrun;
+            q[i] = fdiv_rn(num, den);
         }
+        const int64_t b0 = i0 + (int64_t)lane * K;
+        if (i0 + SZ <= n && st_ok) {
+#pragma unroll
+            for (int i = 0; i < K; i += 4) *(float4*)(mt + b0 + i) = make_float4(q[i], q[i + 1], q[i + 2], q[i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+                if (b0 + i < n) mt[b0 + i] = q[i];
+        }
+    }
+};
+
+template <int K>
+__global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __restrict__ y, float* __restrict__ mt, const int64_t n) {
+    constexpr int SZ = 32 * K;
+    static_assert(K % 4 == 0 || K == 2, "K");
+    MetricCtx<K> c;
+    c.y = y; c.mt = mt; c.n = n; c.lane = threadIdx.x;
+    c.vec_ok = (((uintptr_t)y) & 15) == 0;
+    c.st_ok = (((uintptr_t)mt) & 15) == 0 && (K % 4) == 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        c.mu[k] = (c.lane >= (1 << k)) ? 1.0 : 0.0;
+        c.md[k] = (c.lane + (1 << k) < 32) ? 1.0 : 0.0;
+    }
+    const int64_t i_begin = (int64_t)blockIdx.x * MC_STEPS * SZ;
+    if (i_begin >= n) return;
+    const int64_t i_end = (i_begin + (int64_t)MC_STEPS * SZ < n) ? i_begin + (int64_t)MC_STEPS * SZ : n;
+    StepHist<K> A, B;
+    if (i_begin == 0) {                              // zero history in front of the stream
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            A.y[i] = make_float2(0.f, 0.f);
+            A.x[0][i] = A.x[1][i] = A.x[2][i] = 0.f;
+        }
+        A.bwd[0] = A.bwd[1] = A.bwd[2] = 0.0;
+    } else {                                         // the block in front of the chunk, from the two blocks before it
+        c.load(B.y, i_begin - 2 * SZ);
+        c.load(A.y, i_begin - SZ);
+        c.prime(B, A);
+    }
+    c.load(B.y, i_begin);
+    for (int64_t i0 = i_begin; i0 < i_end;) {
+        c.step(A, B, i0, i0 + SZ < i_end);
+        i0 += SZ;
+        if (i0 >= i_end) break;
+        c.step(B, A, i0, i0 + SZ < i_end);
+        i0 += SZ;
+    }
+}
+
+template <int K>
+struct DetectCtx {
+    static constexpr int SZ = 32 * K;
+    const StreamParams& p;
+    const float* mt;
+    double* ring;
+    int lane;
+    int64_t seg, s0, s1;
+    bool vec_ok, cp_aligned;
+    int prime, cpq;
+    double tap, a1, a2, p32, plane;
+    double pw[5], mu[5];
+    double carry2 = 0.0;                             // prefix of the metric up to the previous step
+    double carry = 0.0;                              // detector average after the last consumed sample
+    int state = 0, count = 0;
+    float peak = -INFINITY;
+    int64_t ind = 0, run_start = 0;
+
+    __device__ __forceinline__ DetectCtx(const StreamParams& p_) : p(p_) {}
+
+    __device__ __forceinline__ void load(float (&dst)[K], const int64_t i0) const {
+        const int64_t b0 = i0 + (int64_t)lane * K;
+        if (i0 + SZ <= p.n && vec_ok) {
+#pragma unroll
+            for (int i = 0; i < K; i += 4) {
+                const float4 t = __ldg((const float4*)(mt + b0 + i));
+                dst[i] = t.x; dst[i + 1] = t.y; dst[i + 2] = t.z; dst[i + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) dst[i] = (b0 + i < p.n) ? mt[b0 + i] : 0.f;
+        }
+    }
+
+    // q holds this step's metric on entry and the next step's on return
+    __device__ __forceinline__ void step(float (&q)[K], const int64_t i0, const int stepno) {
+        const int64_t b0 = i0 + (int64_t)lane * K;
+        const bool full = i0 + SZ <= p.n;                        // warp-uniform
+        int nvalid = K;
+        if (!full) {
+            const int64_t r = p.n - b0;
+            nvalid = r < 0 ? 0 : (r > K ? K : (int)r);
+        }
+        double mloc[K];
+        double mrun = 0.0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) { mrun += (double)q[i]; mloc[i] = mrun; }
+        if (i0 + SZ < p.n) load(q, i0 + SZ);
         double mi = mrun;
 #pragma unroll
         for (int k = 0; k < 5; ++k) mi = fma(shfl_up_d(mi, 1 << k), mu[k], mi);
@@ -162,7 +252,6 @@ struct StreamCtx {
         __syncwarp();
         float v[K];
         if (cp_aligned) {
-            // n - cp sits cp/K lanes back: K consecutive ring slots, in this step's half or the previous one
             const int ql = lane - cpq;
             const double* src = ring + (ql >= 0 ? rb + ql * K : (rb ^ SZ) + (32 + ql) * K);
 #pragma unroll
@@ -174,14 +263,13 @@ struct StreamCtx {
         } else {
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-                const int e = lane * K + i - p.cp;               // position of n - cp relative to this step
+                const int e = lane * K + i - p.cp;
                 const double prevS = ring[e >= 0 ? rb + e : (rb ^ SZ) + SZ + e];
                 v[i] = fadd_rn((float)((mloc[i] - prevS) * tap), -1.0f);
             }
         }
         __syncwarp();
-        if (stepno < prime) return;                              // priming: sums not yet valid, detector idle
-        // first NaN of the metric (poisons the detector for the rest of the stream, C.1)
+        if (stepno < prime) return;                              // priming: the cp window reaches before the start
         if (v[K - 1] != v[K - 1]) {                              // a NaN poisons the prefix: the lane's last value shows it
             int first = K - 1;
 #pragma unroll
@@ -189,7 +277,6 @@ struct StreamCtx {
                 if (v[i] != v[i]) first = i;
             if (first < nvalid) atomicMin((unsigned long long*)p.first_nan, (unsigned long long)(b0 + first));
         }
-        // ---- peak_detector_fb: IIR average as an affine scan over lanes, threshold bits, run state machine ----
         double vd[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) vd[i] = a1 * (double)v[i];
@@ -213,7 +300,6 @@ struct StreamCtx {
         if (!full) mk &= (nvalid >= K) ? FULLM : ((1u << nvalid) - 1u);
         const unsigned any = __ballot_sync(0xffffffffu, mk != 0);
         if (state == 0 && any == 0) return;
-        // lane summaries for the bulk path: a lane fully inside a run only contributes its maximum
         float lmax = v[0];
         int larg = 0;
 #pragma unroll
@@ -252,30 +338,29 @@ struct StreamCtx {
                 }
             }
         }
-        state = (int)__reduce_or_sync(0xffffffffu, (unsigned)state);   // warp-uniform by construction; says so to the compiler
+        state = (int)__reduce_or_sync(0xffffffffu, (unsigned)state);
     }
 };
 
 template <int K>
-__global__ void __launch_bounds__(SS_WARPS * 32, 12) sync_stream_kernel(const StreamParams p) {
-    constexpr int SZ = 32 * K;                       // samples per step = N/2
-    extern __shared__ __align__(16) double s_ring[]; // [SS_WARPS][2*SZ] prefix sums of the metric
-    StreamCtx<K> c(p);
+__global__ void __launch_bounds__(32, 20) detect_seg_kernel(const StreamParams p, const float* __restrict__ mt) {
+    constexpr int SZ = 32 * K;
+    extern __shared__ __align__(16) double s_ring[];
+    DetectCtx<K> c(p);
+    c.mt = mt;
     c.lane = threadIdx.x;
     c.ring = s_ring;
     c.seg = (int64_t)blockIdx.x;
     if (c.seg >= p.n_seg) return;
     c.s0 = c.seg * p.seg_len;
     c.s1 = (c.s0 + p.seg_len < p.n) ? c.s0 + p.seg_len : p.n;
-    int64_t w0 = c.s0 - OFDM_PEAK_WARM - 2 * SZ;
+    int64_t w0 = c.s0 - OFDM_PEAK_WARM - SZ;
     if (w0 < 0) w0 = 0;
     w0 -= w0 % SZ;
     c.tap = (double)p.tapf;
-    c.vec_ok = (((uintptr_t)p.y) & 15) == 0;
+    c.vec_ok = (((uintptr_t)mt) & 15) == 0 && (K % 4) == 0;
     c.cp_aligned = (p.cp % K) == 0;
     c.cpq = p.cp / K;
-
-    // detector constants
     c.a1 = (double)0.001f;
     c.a2 = 1.0 - c.a1;
     double a2k = 1.0;
@@ -288,36 +373,19 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 12) sync_stream_kernel(const St
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         c.mu[k] = (c.lane >= (1 << k)) ? 1.0 : 0.0;
-        c.md[k] = (c.lane + (1 << k) < 32) ? 1.0 : 0.0;
         c.pw[k] *= c.mu[k];
     }
     c.plane = 1.0;
     for (int k = 0; k < c.lane; ++k) c.plane *= a2k;
-
-    StepHist<K> A, B;
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        A.y[i] = make_float2(0.f, 0.f);
-        A.x[0][i] = A.x[1][i] = A.x[2][i] = 0.f;
-    }
-    A.bwd[0] = A.bwd[1] = A.bwd[2] = 0.0;
-    if (w0 > 0) {                                    // mid-stream start: the delayed samples exist
-#pragma unroll
-        for (int i = 0; i < K; ++i) A.y[i] = p.y[w0 - SZ + c.lane * K + i];
-    }
     for (int i = c.lane; i < 2 * SZ; i += 32) c.ring[i] = 0.0;
     __syncwarp();
-    c.prime = (w0 > 0) ? 2 : 0;                      // steps whose sums still miss history
-
+    c.prime = (w0 > 0) ? 1 : 0;                      // the first step's cp window reaches in front of w0
+    float q[K];
     int step = 0;
-    if (w0 < p.n) c.load(B.y, w0);
-    for (int64_t i0 = w0; i0 < p.n;) {
+    if (w0 < p.n) c.load(q, w0);
+    for (int64_t i0 = w0; i0 < p.n; i0 += SZ, ++step) {
         if (i0 >= c.s1 && c.state == 0) break;
-        c.step(A, B, i0, step);
-        i0 += SZ; ++step;
-        if (i0 >= p.n || (i0 >= c.s1 && c.state == 0)) break;
-        c.step(B, A, i0, step);
-        i0 += SZ; ++step;
+        c.step(q, i0, step);
     }
     if (c.lane == 0) p.seg_count[c.seg] = c.count < p.seg_cap ? c.count : p.seg_cap;
 }
@@ -325,25 +393,23 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 12) sync_stream_kernel(const St
 __global__ void stream_init_kernel(int64_t* first_nan) { *first_nan = LLONG_MAX; }
 
 template <int K>
-static int launch_stream_k(const StreamParams& p, cudaStream_t st) {
-    const size_t smem = sizeof(double) * SS_WARPS * 2 * 32 * K;
-    static bool attr_done = false;
-    if (!attr_done) {
-        OFDM_CUDA_CHECK(cudaFuncSetAttribute(sync_stream_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
-    sync_stream_kernel<K><<<(unsigned)((p.n_seg + SS_WARPS - 1) / SS_WARPS), SS_WARPS * 32, smem, st>>>(p);
+static int launch_split_k(const StreamParams& p, float* mt, cudaStream_t st) {
+    constexpr int SZ = 32 * K;
+    const int64_t chunks = (p.n + (int64_t)MC_STEPS * SZ - 1) / ((int64_t)MC_STEPS * SZ);
+    metric_chunk_kernel<K><<<(unsigned)chunks, 32, 0, st>>>(p.y, mt, p.n);
+    OFDM_LAUNCH_CHECK();
+    detect_seg_kernel<K><<<(unsigned)p.n_seg, 32, sizeof(double) * 2 * SZ, st>>>(p, mt);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
 
-// returns 1 if the fused kernel does not apply (the caller then runs the two-kernel path): layouts outside
-// 32*K = N/2, cp > N/2, or -- unless force -- streams too short to give every SM a few warps (one warp per
-// >= 65 536-sample segment), where the tile-parallel metric kernel is the faster choice
+// returns 1 if the streaming kernels do not apply (the caller then runs the tile-parallel path): layouts outside
+// 32*K = N/2 with K in {2, 4, 8}, cp > N/2, or -- unless force -- streams too short to give every SM a few
+// warps (one warp per >= 65 536-sample detector segment)
 int launch_sync_stream(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, int force,
                        cudaStream_t st) {
     const int K = h->N / 64;                                     // 32*K = N/2
-    if (!(K == 2 || K == 4 || K == 8) || h->cp > 32 * K || ws->n_seg == 0) return 1;
+    if (!(K == 2 || K == 4 || K == 8) || h->cp > 32 * K || ws->n_seg == 0 || !ws->mf) return 1;
     if (!force && ws->n_seg < 148 * 8) return 1;
     StreamParams p;
     p.y = y; p.n = n; p.cp = h->cp; p.tapf = (float)(1.0 / (double)h->cp);
@@ -352,8 +418,8 @@ int launch_sync_stream(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* i
     stream_init_kernel<<<1, 1, 0, st>>>(p.first_nan);
     OFDM_LAUNCH_CHECK();
     switch (K) {
-        case 2: return launch_stream_k<2>(p, st);
-        case 4: return launch_stream_k<4>(p, st);
-        default: return launch_stream_k<8>(p, st);
+        case 2: return launch_split_k<2>(p, ws->mf, st);
+        case 4: return launch_split_k<4>(p, ws->mf, st);
+        default: return launch_split_k<8>(p, ws->mf, st);
     }
 }
