@@ -55,8 +55,9 @@ __device__ __noinline__ float2 derot_slow(float2 v, int64_t s, const int64_t* tr
     return cmul_x(v, phasor_f64(ph));
 }
 
+template <bool SMEM>
 struct DemodLoad {
-    const float2* y;
+    const float2* y;               // SMEM: the vector's samples staged in shared memory, else the stream
     int64_t st, t_next;
     const int64_t* trig;
     const double* phi0;
@@ -66,7 +67,7 @@ struct DemodLoad {
     const float2* Wt;
     __device__ __forceinline__ float2 operator()(int idx, int slot) const {
         const int64_t s = st + idx;
-        const float2 v = LDG(y + s);
+        const float2 v = SMEM ? y[idx] : LDG(y + s);
         if (s < t_next) return cmul_x(v, cmul(ph0, Wt[slot]));
         return derot_slow(v, s, trig, phi0, step, K, kk0);
     }
@@ -160,12 +161,26 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     float2* S = (P::NP == 2) ? bufB : bufA;                 // shifted spectrum of the current vector
     const int bits_this = ncar * nbits;
     const BitDiv bd(nbits);
+    // Three-pass plans leave bufB idle while a vector is sliced: the next vector's samples are copied into it
+    // asynchronously meanwhile, so the first FFT pass never waits on HBM.
+    constexpr bool PF = (P::NP == 3);
+    auto prefetch = [&](int64_t st2) {
+#pragma unroll
+        for (int i = 0; i < N / BT; ++i) {
+            const int idx = tid + i * BT;
+            cp_async8(bufB + idx, p.y + st2 + idx, 8);
+        }
+        cp_async_commit();
+    };
 
     for (int f = blockIdx.x; f < F; f += gridDim.x) {
         int g = f, m = 0, vi = 0, cnt = 1, delta = 0, bit_base = 0;
         int status = 3, nvec = INT_MAX / 2, len = 0;
+        int last_vi = INT_MAX;                              // data vector that completes the packet, once the header is in
         int kk_w = INT_MIN;                                 // trigger segment the table s_W belongs to
+        if (PF) cp_async_wait_all();                        // a copy left in flight by the previous session
         __syncthreads();
+        if (PF) prefetch(p.trig_idx[first_ok + f] - N + 1);
         while (g < F) {
             const int kg = first_ok + g;
             const int64_t t = p.trig_idx[kg];
@@ -195,8 +210,12 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 kk_w = kk;
                 __syncthreads();
             }
-            DemodLoad ld{p.y, st, t_next, p.trig_idx, p.phi0, p.step, K, kk < 0 ? 0 : kk, phasor_f64(ph_base), s_W};
+            DemodLoad<PF> ld{PF ? bufB : p.y, st, t_next, p.trig_idx, p.phi0, p.step, K, kk < 0 ? 0 : kk, phasor_f64(ph_base), s_W};
             if (kk < 0) ld.t_next = (K > 0) ? p.trig_idx[0] : LLONG_MAX;
+            if (PF) {
+                cp_async_wait_all();
+                __syncthreads();
+            }
             if (tid < T) fft_pass<N, R0, 1, -1>(tid, p.tw, ld, SmemOut{bufA});
             __syncthreads();
             if constexpr (P::NP == 2) {
@@ -207,6 +226,11 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 if (tid < T) fft_pass<N, R2, R0 * R1, -1>(tid, p.tw, SmemIn{bufB}, ShiftStore<N>{S});
             }
             __syncthreads();
+            if (PF && vi < last_vi) {                       // bufB is free: fetch the vector that follows
+                int g2 = g, m2 = m + 1;
+                if (m2 > p.frame_ndata[g]) { ++g2; m2 = 0; }
+                if (g2 < F) prefetch(p.trig_idx[first_ok + g2] - N + 1 + (int64_t)m2 * L);
+            }
             // ---- ofdm_frame_acquisition: correlate + calculate_equalizer on a flagged vector ----
             if (flag) {
                 double acc[2 * OFDM_MAX_SHIFT];
@@ -386,6 +410,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 const bool hdr_ok = s_hdr_ok != 0;
                 len = s_len;
                 if (vi == 1 && !hdr_ok) { status = 1; nvec = 2; len = 0; break; }
+                if (vi == 1) last_vi = (8 * (4 + len) + bits_this - 1) / bits_this;
                 for (int q = B0 + tid; q < B1; q += BT) {
                     const int pq = q - 4;
                     if (pq >= 0 && pq < len && pq < p.pkt_stride) p.pkt_bytes[(size_t)f * p.pkt_stride + pq] = vb[q - B0];
@@ -404,6 +429,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
             p.sess_nvec[f] = nvec;
         }
     }
+    if (PF) cp_async_wait_all();
 }
 
 template <int N, bool TAPS>
