@@ -374,6 +374,57 @@ class OfdmEngine:
     def demodulate(self, x, **kw) -> RxBatch:
         return self.collect(self.demodulate_async(x, **kw))
 
+    # ---- split collect: lets a caller keep several receive calls in flight (one stream + buffer set each) ----
+    def collect_begin(self, bufs, want_payload: bool = True):
+        """Queue, on the current stream, the device->host copies of one receive call's results into the buffer
+        set's pinned staging arrays and return a ticket for :meth:`collect_end`.  n_frames is not known on the
+        host yet, so every per-frame array travels at its allocated (max_frames) size."""
+        torch = self.torch
+        stream = torch.cuda.current_stream(self.dev)
+        mf = int(bufs["io"].max_frames)
+        hd = self._pinned(bufs, "head", bufs["n_trig"], 3)
+        hd[0:1].copy_(bufs["n_trig"], non_blocking=True)
+        hd[1:2].copy_(bufs["n_frames"], non_blocking=True)
+        hd[2:3].copy_(bufs["status"], non_blocking=True)
+        hc = self._pinned(bufs, "counters", bufs["counters"], 8)
+        hc.copy_(bufs["counters"], non_blocking=True)
+        host = {}
+        nbytes = 12 + 64
+        for k in ("frame_live", "frame_status", "pkt_len", "pkt_ok"):
+            t = self._pinned(bufs, k, bufs[k], mf)
+            t[:mf].copy_(bufs[k][:mf], non_blocking=True)
+            host[k] = t
+            nbytes += mf * t.element_size()
+        pb = None
+        if want_payload:
+            pb = self._pinned(bufs, "pkt_bytes", bufs["pkt_bytes"], mf * self.pkt_stride)
+            pb[:mf * self.pkt_stride].copy_(bufs["pkt_bytes"][:mf * self.pkt_stride], non_blocking=True)
+            nbytes += mf * self.pkt_stride
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return {"event": ev, "head": hd, "counters": hc, "host": host, "rows": pb, "max_frames": mf, "bytes": nbytes}
+
+    def collect_end(self, ticket) -> RxBatch:
+        """Wait for the copies of :meth:`collect_begin` and assemble the batch (arrays are views of the pinned
+        staging buffers: the next collect on the same buffer set overwrites them)."""
+        ticket["event"].synchronize()
+        hd = ticket["head"]
+        nt, nf, st = int(hd[0]), int(hd[1]), int(hd[2])
+        if st:
+            raise RuntimeError("receive: capacity overflow (status bits 0x%x): raise max_frames" % st)
+        h = ticket["host"]
+        live, fstat = h["frame_live"][:nf].numpy(), h["frame_status"][:nf].numpy()
+        plen, pok = h["pkt_len"][:nf].numpy(), h["pkt_ok"][:nf].numpy()
+        sel = np.flatnonzero((live == 1) & (fstat == 2))
+        rows = None
+        copied = 0
+        if ticket["rows"] is not None:
+            rows = ticket["rows"][:nf * self.pkt_stride].numpy().reshape(nf, self.pkt_stride)
+            copied = ticket["max_frames"] * self.pkt_stride
+        z = np.zeros(0)
+        return RxBatch(nt, nf, st, z, z, z, z, live, fstat, plen, pok, ticket["counters"].numpy().copy(), [], sel, rows,
+                       copied, ticket["bytes"] - copied)
+
 
 class SenseEngine:
     """stream_to_vector -> fft_vcc(N, True, blackmanharris) -> complex_to_mag_squared -> bin_statistics_f."""
