@@ -39,17 +39,33 @@ def peaks():
 
 
 def ncu_traffic(kernel_label, n_samples):
-    """dram__bytes_read+write of one launch of the named kernel from the committed ncu capture (bytes)."""
+    """dram__bytes_read+write of one launch of the named kernel(s) from the committed ncu capture (bytes)."""
     p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     try:
         with open(p) as f:
             k = json.load(f)["kernels"]
+        tot = 0.0
         for name, v in k.items():
-            if kernel_label.startswith(name):
-                return v["traffic_bytes"] * (n_samples / 640e6)
+            if name in kernel_label:
+                tot += v["traffic_bytes"] * (n_samples / 640e6)
+        return tot or None
     except Exception:
-        pass
-    return None
+        return None
+
+
+def issue_floor(n_samples, sm_mhz):
+    """Instruction-issue floor of one step: warp instructions of the five stream kernels (ncu smsp__inst_executed.sum
+    of the committed capture, scaled to this launch's samples) over 148 SMs x 4 schedulers x 1 instruction per clock."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            k = json.load(f)["kernels"]
+        inst = sum(v["inst_executed"] for v in k.values()) * (n_samples / 640e6)
+        peak = 148 * 4 * float(sm_mhz) * 1e6
+        return {"warp_inst_per_step": inst, "peak_warp_inst_per_s": peak, "floor_ms": inst / peak * 1e3,
+                "source": "profiles/r01_traffic.json (ncu smsp__inst_executed.sum per kernel)"}
+    except Exception:
+        return None
 
 
 def make_payloads(n_frames, size, seed):
@@ -341,6 +357,10 @@ def run_b200(args):
             "clocks": clocks,
             "parity": {"frames": frames_all, "messages": msgs_all, "crc_ok": ok_all, "sent": F * world},
         }
+        fl = issue_floor(n_sig, (clocks or {}).get("sm_max_mhz") or 1965.0)
+        if fl:
+            fl["frac"] = fl["floor_ms"] / ms_per_step      # share of the step explained by pure instruction issue
+            line["issue_roofline"] = fl
         line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))
     if world > 1:
