@@ -162,6 +162,11 @@ int ofdm_sense_fft(ofdm_sense_handle* s, const float* x_iq, int64_t n_frames, in
  * free_bits: uint8[N], hex: char[N/4] (no terminator) */
 int ofdm_sense_decide(ofdm_sense_handle* s, const float* maxhold, int32_t n_avg, double threshold,
                       double* avg_inorder, uint8_t* free_bits, char* hex, void* stream);
+/* sense_loop hop decision (secondary_tx.py:268-295) on the outputs of ofdm_sense_decide: out[0] = occupied bins in
+ * thrshold_inorder[required_index-16 : required_index+16] (Python slice semantics), out[1] = centre bin (+8) of the
+ * quietest 17-bin window over bins 200 .. N-218 (-1 if none sums below 50), out[2] = window length.  out: int32[3] */
+int ofdm_sense_hop(ofdm_sense_handle* s, const double* avg_inorder, const uint8_t* free_bits, int32_t required_index,
+                   int32_t* out, void* stream);
 
 #ifdef __cplusplus
 }

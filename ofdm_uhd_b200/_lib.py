@@ -19,7 +19,7 @@ EXPORTS = [
     "ofdm_rx_workspace_bytes", "ofdm_rx_chan_filter", "ofdm_rx_sync_metric", "ofdm_rx_peak_detect", "ofdm_rx_sync",
     "ofdm_rx_plan",
     "ofdm_rx_demod", "ofdm_rx_finish", "ofdm_rx_liveness", "ofdm_rx_demodulate", "ofdm_rx_workspace_ptr", "ofdm_channel",
-    "ofdm_sense_create", "ofdm_sense_destroy", "ofdm_sense", "ofdm_sense_fft", "ofdm_sense_decide",
+    "ofdm_sense_create", "ofdm_sense_destroy", "ofdm_sense", "ofdm_sense_fft", "ofdm_sense_decide", "ofdm_sense_hop",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.ofdm_sense.argtypes = [vp, vp, i64, C.c_int, i32, i32, vp, vp]
     L.ofdm_sense_fft.argtypes = [vp, vp, i64, C.c_int, vp, vp]
     L.ofdm_sense_decide.argtypes = [vp, vp, i32, f64, vp, vp, vp, vp]
+    L.ofdm_sense_hop.argtypes = [vp, vp, vp, i32, vp, vp]
     return L
 
 

@@ -466,3 +466,13 @@ extern "C" int ofdm_sense_decide(ofdm_sense_handle* s, const float* maxhold, int
     if (n_avg < 1) return OFDM_E_INVAL;
     return launch_sense_decide(s, maxhold, n_avg, threshold, avg_inorder, free_bits, hex, (cudaStream_t)stream);
 }
+
+extern "C" int ofdm_sense_hop(ofdm_sense_handle* s, const double* avg_inorder, const uint8_t* free_bits,
+                              int32_t required_index, int32_t* out, void* stream) {
+    NEED(s);
+    if (!avg_inorder || !free_bits || !out) {
+        ofdm_set_error("ofdm_sense_hop: null argument");
+        return OFDM_E_INVAL;
+    }
+    return launch_sense_hop(s, avg_inorder, free_bits, required_index, out, (cudaStream_t)stream);
+}

@@ -97,3 +97,5 @@ int launch_sense(ofdm_sense_handle* s, const float2* x, int64_t n_frames, int sh
                  int32_t dwell_delay, float* maxhold, float2* spectra, cudaStream_t st);
 int launch_sense_decide(ofdm_sense_handle* s, const float* maxhold, int32_t n_avg, double threshold,
                         double* avg_inorder, uint8_t* free_bits, char* hex, cudaStream_t st);
+int launch_sense_hop(ofdm_sense_handle* s, const double* avg_inorder, const uint8_t* free_bits, int32_t required_index,
+                     int32_t* out, cudaStream_t st);

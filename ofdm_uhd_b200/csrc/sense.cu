@@ -2,6 +2,7 @@
 // complex_to_mag_squared -> bin_statistics_f  (secondary_tx.py:163-202, sensing_and_tramsmitting.py:185-234,
 // predictive_sense.py:72-123, usrp_fft_save.py:58-62) and the sense_loop decision (secondary_tx.py:237-266,306-331).
 #include "internal.h"
+#include <limits.h>
 #include "fft.cuh"
 
 struct SenseParams {
@@ -153,6 +154,58 @@ int launch_sense_decide(ofdm_sense_handle* s, const float* maxhold, int32_t n_av
                         double* avg_inorder, uint8_t* free_bits, char* hex, cudaStream_t st) {
     int nq = s->N / 4;
     sense_decide_kernel<<<(nq + 127) / 128, 128, 0, st>>>(maxhold, s->N, n_avg, threshold, avg_inorder, free_bits, hex);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
+// sense_loop hop decision (secondary_tx.py:268-295): occupied bins in thrshold_inorder[ri-16 : ri+16] (Python slice
+// semantics: negative bounds wrap once, then clamp) and the centre (+8) of the quietest 17-bin window over
+// i in [200, N-217), each window summed left to right in double like the reference's inner loop, first strict
+// minimum below 50 wins.  out = {busy, index or -1, window length}.
+__global__ void __launch_bounds__(1024) sense_hop_kernel(const double* __restrict__ avg_inorder,
+                                                         const uint8_t* __restrict__ free_bits, int N, int ri,
+                                                         int32_t* __restrict__ out) {
+    __shared__ double s_p[32];
+    __shared__ int s_i[32];
+    __shared__ int s_busy;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_busy = 0;
+    __syncthreads();
+    int start = ri - 16, stop = ri + 16;
+    if (start < 0) { start += N; if (start < 0) start = 0; }
+    if (stop < 0) { stop += N; if (stop < 0) stop = 0; }
+    if (start > N) start = N;
+    if (stop > N) stop = N;
+    int busy = 0;
+    for (int i = start + tid; i < stop; i += 1024) busy += (free_bits[i] == 0);
+    if (busy) atomicAdd(&s_busy, busy);
+    double best = 50.0;
+    int bi = INT_MAX;
+    for (int i = 200 + tid; i < N - 217; i += 1024) {
+        double power = 0.0;
+        for (int j = 0; j < 17; ++j) power = power + avg_inorder[i + j];
+        if (power < best) { best = power; bi = i; }          // i ascends within a thread: first minimum kept
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { s_p[w] = best; s_i[w] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < 32; ++k)
+            if (s_p[k] < best || (s_p[k] == best && s_i[k] < bi)) { best = s_p[k]; bi = s_i[k]; }
+        out[0] = s_busy;
+        out[1] = (bi == INT_MAX) ? -1 : bi + 8;
+        out[2] = stop > start ? stop - start : 0;
+    }
+}
+
+int launch_sense_hop(ofdm_sense_handle* s, const double* avg_inorder, const uint8_t* free_bits, int32_t required_index,
+                     int32_t* out, cudaStream_t st) {
+    sense_hop_kernel<<<1, 1024, 0, st>>>(avg_inorder, free_bits, s->N, required_index, out);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }

@@ -473,8 +473,8 @@ class SenseEngine:
                                           C.c_void_p(out.data_ptr()), self._stream()), "sense_fft")
         return out
 
-    def decide(self, maxhold, threshold: float = 0.001):
-        """Mean of the dwell vectors, threshold, frequency-order swap, hex map (secondary_tx.py:237-266)."""
+    def decide_device(self, maxhold, threshold: float = 0.001):
+        """:meth:`decide` without the host copies: (avg_inorder float64[N], free uint8[N], hex uint8[N/4]) cuda tensors."""
         torch = self.torch
         n_avg = int(maxhold.shape[0])
         avg = torch.empty(self.N, dtype=torch.float64, device=self.dev)
@@ -483,4 +483,19 @@ class SenseEngine:
         _lib.check(self.L_.ofdm_sense_decide(self.s, C.c_void_p(maxhold.data_ptr()), n_avg, float(threshold),
                                              C.c_void_p(avg.data_ptr()), C.c_void_p(free.data_ptr()),
                                              C.c_void_p(hx.data_ptr()), self._stream()), "sense_decide")
+        return avg, free, hx
+
+    def decide(self, maxhold, threshold: float = 0.001):
+        """Mean of the dwell vectors, threshold, frequency-order swap, hex map (secondary_tx.py:237-266)."""
+        avg, free, hx = self.decide_device(maxhold, threshold)
         return avg.cpu().numpy(), free.cpu().numpy(), bytes(hx.cpu().numpy()).decode("ascii")
+
+    def hop(self, avg_inorder, free_bits, required_index: int):
+        """Busy-bin count around the operating frequency and the quietest 17-bin band (secondary_tx.py:268-295),
+        on the device tensors of :meth:`decide_device`.  Returns (busy, index or -1, window length)."""
+        torch = self.torch
+        out = torch.empty(3, dtype=torch.int32, device=self.dev)
+        _lib.check(self.L_.ofdm_sense_hop(self.s, C.c_void_p(avg_inorder.data_ptr()), C.c_void_p(free_bits.data_ptr()),
+                                          int(required_index), C.c_void_p(out.data_ptr()), self._stream()), "sense_hop")
+        busy, index, wlen = [int(v) for v in out.cpu().tolist()]
+        return busy, index, wlen

@@ -98,3 +98,26 @@ def best_band(avg_inorder, lo=200, span=17):
         if power < power_temp:
             power_temp, index = power, i + 8
     return index
+
+
+def sensed_frequency(center_freq, samp_rate, size, index):
+    """sensed_freq[index] of secondary_tx.py:250-262: the bin frequencies are built by repeated addition of
+    ``usr/size`` from ``center - res*((size/2)-1)`` (integer size/2), so the same sequence of float adds is kept."""
+    res = samp_rate / size
+    p = center_freq - res * ((size // 2) - 1)
+    for _ in range(int(index)):
+        p = p + res
+    return p
+
+
+def hop_decision(tb, avg_inorder_dev, free_dev, frequency, center_freq, ref_freq=8925 * 10 ** 5, busy_limit=9):
+    """The second half of ``sense_loop`` (secondary_tx.py:268-300) on the device tensors of
+    ``SenseEngine.decide_device``: the busy count of the 32-bin window around ``frequency`` and, when at least
+    ``busy_limit`` of them are occupied ('Primary Transmission detected'), the new operating frequency = centre of
+    the quietest 17-bin band rounded up to 100 kHz.  Returns (busy, new_frequency or None)."""
+    size = tb.fft_size
+    required_index = int(math.ceil((frequency - ref_freq) * size / tb.samp_rate))
+    busy, index, _ = tb.engine.hop(avg_inorder_dev, free_dev, required_index)
+    if busy < busy_limit or index < 0:
+        return busy, None
+    return busy, int(1e5 * math.ceil(sensed_frequency(center_freq, tb.samp_rate, size, index) / 1e5))

@@ -159,3 +159,58 @@ def test_log_option_dumps_stage_taps(tmp_path, monkeypatch):
     assert eq.shape[0] == len(ref.flags)
     sink = np.fromfile("ofdm_frame_sink_c.dat", dtype=np.complex64).reshape(-1, 200)
     assert sink.shape[0] == len(ref.derot) and np.linalg.norm(sink[:, :198] - np.array(ref.derot)) / np.linalg.norm(np.array(ref.derot)) < 1e-4
+
+
+def test_rendezvous_over_the_modem():
+    """The 920 MHz rendezvous of secondary_tx.py:54-73 / secondary_rx.py:51-85 carried by the GPU modem in loopback:
+    synchronisation packets announce a frequency, the receiver state machine follows it."""
+    from ofdm_uhd_b200 import transmit_path, receive_path, channel_model, rendezvous as rv
+    opts = options(modulation="qpsk")
+    tuned = []
+    state = rv.secondary_receiver(set_center_freq=tuned.append)
+    tx = transmit_path.transmit_path(opts, pad_seed=3)
+    rx = receive_path.receive_path(state.rx_callback, opts)
+    chan = channel_model.channel_model(tx.ofdm_tx._engine, noise_voltage=0.003, frequency_offset=0.1, seed=9,
+                                       lead_in=1200, tail=2600)
+    tx.connect(chan)
+    chan.connect(rx)
+    assert rv.synchronization(tx.send_pkt, 903700000) == 100
+    tx.send_pkt(eof=True)
+    rx.wait(timeout=60)
+    assert tuned == [903700000] and state.sync == 0 and state.n_right >= 95 and state.n_rcvd >= state.n_right
+
+
+def test_collect_begin_end_equals_collect():
+    """The split (asynchronous) collect returns what collect() returns, also with two receive calls in flight on
+    two streams and two buffer sets."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    from helpers import payloads, loopback_capture
+    lay = o.Layout(512, 200, 128, "qpsk")
+    rng = np.random.default_rng(8)
+    caps = [loopback_capture(lay, payloads(rng, 12), 25, cfo, seed=40 + i)[1] for i, cfo in enumerate((0.1, -0.3))]
+    eng = OfdmEngine(512, 200, 128, "qpsk")
+    refs = []
+    for c in caps:
+        r = eng.demodulate(torch.from_numpy(c).cuda())
+        r.payload_rows = r.payload_rows.copy()             # views of pinned staging: the next collect reuses it
+        refs.append(r)
+    lanes = []
+    for c in caps:
+        eng._ws_key = None
+        lanes.append((torch.cuda.Stream(), torch.from_numpy(c).cuda(), eng.rx_alloc(len(c))))
+    torch.cuda.synchronize()
+    tickets = []
+    for st, x, bufs in lanes:
+        with torch.cuda.stream(st):
+            eng.demodulate_async(x, bufs)
+            tickets.append(eng.collect_begin(bufs))
+    for t, ref in zip(tickets, refs):
+        r = eng.collect_end(t)
+        assert r.n_frames == ref.n_frames and np.array_equal(r.pkt_ok, ref.pkt_ok) and np.array_equal(r.pkt_len, ref.pkt_len)
+        assert np.array_equal(r.frame_live, ref.frame_live) and np.array_equal(r.counters, ref.counters)
+        assert np.array_equal(r.msg_frames, ref.msg_frames)
+        for f in r.msg_frames:
+            ln = int(r.pkt_len[f])
+            assert r.payload_rows[f, :ln].tobytes() == ref.payload_rows[f, :ln].tobytes()
+    eng.close()

@@ -66,3 +66,38 @@ def test_wideband_capture_bands_detected():
             inside[lo:hi] = True
         assert inside[busy].mean() > 0.9 and (free[inside] == 0).mean() > 0.7
     se.close()
+
+
+@pytest.mark.parametrize("N", [512, 1024, 2048])
+def test_hop_decision_on_device(N):
+    """ofdm_sense_hop (secondary_tx.py:268-295) against the host transcription in sensing.py: busy count of the
+    32-bin window with Python slice semantics (also for windows that run off either end) and the quietest
+    17-bin band, exact (same left-to-right double sums, first strict minimum)."""
+    import math
+    from types import SimpleNamespace
+    import torch
+    from ofdm_uhd_b200 import sensing
+    rng = np.random.default_rng(N)
+    tb = sensing.sensor(SimpleNamespace(fft_size=N, decim=4, tune_delay=0.0, dwell_delay=1e-3))
+    for trial in range(6):
+        avg = rng.random(N) * (10.0 if trial == 3 else 1e-3)          # trial 3: no window sums below 50
+        if trial == 4:
+            avg[300:330] = avg[700:730] = 0.0                         # tie between two all-zero windows: first wins
+        free = (rng.random(N) > 0.4).astype(np.uint8)
+        d_avg, d_free = torch.from_numpy(avg).cuda(), torch.from_numpy(free).cuda()
+        for ri in (-40, -3, 5, 16, N // 2, N - 10, N + 40):
+            busy, index, wlen = tb.engine.hop(d_avg, d_free, ri)
+            win = list(free)[ri - 16:ri + 16]
+            assert wlen == len(win) and busy == sum(1 for v in win if v == 0)
+            assert index == sensing.best_band(avg)
+        freq = 905 * 10 ** 6
+        ri = int(math.ceil((freq - 8925 * 10 ** 5) * N / tb.samp_rate))
+        busy, newf = sensing.hop_decision(tb, d_avg, d_free, freq, 905e6)
+        assert busy == sensing.busy_count(list(free), freq, tb.samp_rate, N)
+        idx = sensing.best_band(avg)
+        if busy >= 9 and idx >= 0:
+            assert newf == int(1e5 * math.ceil(sensing.sensed_frequency(905e6, tb.samp_rate, N, idx) / 1e5))
+            assert abs(newf - (905e6 + (idx - N / 2 + 1) * tb.samp_rate / N)) <= 1e5
+        else:
+            assert newf is None
+    tb.engine.close()

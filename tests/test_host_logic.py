@@ -94,3 +94,40 @@ def test_sharding_helpers():
         cover += list(range(lo, hi))
     assert cover == list(range(10))
     assert sharding.as_dict(range(8))["crc_ok"] == 2
+
+
+def test_rendezvous_protocol_state_machines():
+    """secondary_tx.py:54-73,345-381 / secondary_rx.py:51-85 without a radio: the receiver follows the announced
+    frequency, stores packets 21..70 of the source, and falls back to 920 MHz after 10 unmarked packets."""
+    import io
+    import struct
+    from ofdm_uhd_b200 import rendezvous as rv
+    sent = []
+    send = lambda payload, eof=False, cmap="FE7F": sent.append(payload)
+    assert rv.next_tx_frequency(1, 905000000) == rv.SYNC_FREQ and rv.next_tx_frequency(0, 905000000) == 905000000
+    assert rv.synchronization(send, 903700000) == 100
+    assert len(sent) == 100 and struct.unpack('!HHL', sent[0]) == (150, 11111, 903700000)
+    assert struct.unpack('!H', sent[-1][:2])[0] == 249
+    tuned = []
+    sink = io.BytesIO()
+    rx = rv.secondary_receiver(set_center_freq=tuned.append, sink=sink)
+    rx.rx_callback(False, sent[0])                       # bad CRC: counted, not followed
+    assert rx.sync == 1 and rx.n_rcvd == 1 and rx.n_right == 0 and not tuned
+    for p in sent[1:]:
+        rx.rx_callback(True, p)
+    assert tuned == [903700000] and rx.sync == 0 and rx.n_right == 99
+    source = bytes(range(256)) * 40
+    sent.clear()
+    n = rv.run_transmitter(send, source, 204)
+    npk = len(source) // 204
+    assert struct.unpack('!H', sent[20][4:6])[0] == npk
+    assert len(sent) == 21 + -(-len(source) // 200) + 20 and n == sum(len(p) for p in sent[:-20])
+    for p in sent:
+        rx.rx_callback(True, p)
+    assert rx.no_packets == npk + 20
+    assert sink.getvalue() == source[:50 * 200]          # packets 21..70 only (the reference's pktno window)
+    for _ in range(9):
+        rx.rx_callback(True, b"\x00\x01\x00\x00junk")
+    assert rx.freq == 903700000
+    rx.rx_callback(True, b"xy")                          # short payload counts as unmarked
+    assert rx.sync == 1 and rx.freq == rv.SYNC_FREQ and tuned[-1] == rv.SYNC_FREQ
