@@ -122,6 +122,11 @@ int ofdm_rx_peak_detect(ofdm_handle* h, const float* y_iq, const float* mf, int6
  * Uses the fused streaming kernel when 32*K = N/2 (N = 128, 256, 512) and cp <= N/2, else the two stages above
  * (ofdm_rx_demodulate also falls back to them for streams too short to fill the GPU with one warp per segment). */
 int ofdm_rx_sync(ofdm_handle* h, const float* y_iq, int64_t n, ofdm_rx_io* io, void* stream);
+/* upstream ofdm_sync_fixed(fft_length, cp_length, nsymbols, freq_offset) -- the reference's SYNC == "fixed" test mode
+ * (ofdm_receiver.py~:108-119): a trigger at the last sample of the first symbol of every nsymbols-symbol packet
+ * (index N+cp-1 + k*nsymbols*(N+cp)), every angle = pi*freq_offset, and the NCO already turning at that rate before the
+ * first trigger.  Replaces ofdm_rx_sync in the stage sequence; fills io->n_trig / trig_idx / trig_ang. */
+int ofdm_rx_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_offset, ofdm_rx_io* io, void* stream);
 /* gr.frequency_modulator_fc + digital.ofdm_sampler (ofdm_receiver.py~:123-125,133-136) as a frame table */
 int ofdm_rx_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, void* stream);
 /* multiply_cc (derotation) + fft_vcc(forward) + ofdm_frame_acquisition + ofdm_frame_sink
@@ -135,6 +140,10 @@ int ofdm_rx_finish(ofdm_handle* h, ofdm_rx_io* io, void* stream);
  * consumes sess_nvec[f] vectors of a stream in which frame f's preamble vector sits at position vbase[f]?
  * n_frames: device int32[1]; vbase: device int64[>= F]; sess_nvec: device int32[F]; scratch: device int32[2*max_frames+2];
  * live: device uint8[max_frames].  force_general != 0 skips the short-exception-list fast path. */
+/* the whole receive chain in the "fixed" test mode: chan_filt is gr.multiply_const_cc(1.0) there, so the capture is
+ * sampled directly: ofdm_rx_sync_fixed -> ofdm_rx_plan -> ofdm_rx_demod -> ofdm_rx_finish */
+int ofdm_rx_demodulate_fixed(ofdm_handle* h, const float* x_iq, int64_t n, int32_t nsymbols, float freq_offset,
+                             ofdm_rx_io* io, void* stream);
 int ofdm_rx_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_t* sess_nvec, int32_t max_frames,
                      int32_t* scratch, uint8_t* live, int force_general, void* stream);
 /* all of the above in order, no host synchronisation */

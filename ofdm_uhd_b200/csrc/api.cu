@@ -347,6 +347,7 @@ extern "C" int ofdm_rx_peak_detect(ofdm_handle* h, const float* y, const float* 
     RxWorkspace ws;
     int rc = get_ws(h, n, io, &ws);
     if (rc) return rc;
+    OFDM_CUDA_CHECK(cudaMemsetAsync(ws.nco_init, 0, sizeof(double), (cudaStream_t)stream));
     return launch_peak_detect(h, (const float2*)y, mf, n, first_nan, io, &ws, (cudaStream_t)stream);
 }
 
@@ -389,6 +390,7 @@ extern "C" int ofdm_rx_liveness(const int32_t* n_frames, const int64_t* vbase, c
 static int rx_sync(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, int force_fused,
                    cudaStream_t st) {
     OFDM_CUDA_CHECK(cudaMemsetAsync(io->status, 0, sizeof(uint32_t), st));
+    OFDM_CUDA_CHECK(cudaMemsetAsync(ws->nco_init, 0, sizeof(double), st));     // sample_and_hold starts at 0
     int rc = launch_sync_stream(h, y, n, io, ws, force_fused, st);
     if (rc == 0) return launch_trig_compact(h, y, n, io, ws, st);
     if (rc < 0) return rc;
@@ -414,6 +416,29 @@ extern "C" int ofdm_rx_demodulate(ofdm_handle* h, const float* x, int64_t n, ofd
     if ((rc = rx_sync(h, ws.y, n, io, &ws, 0, st))) return rc;
     if ((rc = launch_plan(h, n, io, &ws, st))) return rc;
     if ((rc = launch_demod(h, ws.y, n, io, &ws, st))) return rc;
+    return launch_finish(h, io, &ws, st);
+}
+
+extern "C" int ofdm_rx_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_offset, ofdm_rx_io* io,
+                                  void* stream) {
+    NEED(h);
+    RxWorkspace ws;
+    int rc = get_ws(h, n, io, &ws);
+    if (rc) return rc;
+    return launch_sync_fixed(h, n, nsymbols, freq_offset, io, &ws, (cudaStream_t)stream);
+}
+
+extern "C" int ofdm_rx_demodulate_fixed(ofdm_handle* h, const float* x, int64_t n, int32_t nsymbols, float freq_offset,
+                                        ofdm_rx_io* io, void* stream) {
+    NEED(h);
+    RxWorkspace ws;
+    int rc = get_ws(h, n, io, &ws);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // chan_filt = gr.multiply_const_cc(1.0): the capture itself is what the sampler reads
+    if ((rc = launch_sync_fixed(h, n, nsymbols, freq_offset, io, &ws, st))) return rc;
+    if ((rc = launch_plan(h, n, io, &ws, st))) return rc;
+    if ((rc = launch_demod(h, (const float2*)x, n, io, &ws, st))) return rc;
     return launch_finish(h, io, &ws, st);
 }
 

@@ -49,6 +49,18 @@ void ofdm_set_error(const char* fmt, ...);
         }                                                                                   \
     } while (0)
 #define OFDM_LAUNCH_CHECK() OFDM_CUDA_CHECK(cudaGetLastError())
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember the largest size set on each device
+// (one process may hold handles on several GPUs).  Pass a template-id in parentheses.
+#define OFDM_MAX_DEVICES 64
+#define OFDM_SET_MAX_SMEM(func, bytes, device)                                                                   \
+    do {                                                                                                          \
+        static size_t done__[OFDM_MAX_DEVICES] = {0};                                                             \
+        const int d__ = ((device) >= 0 && (device) < OFDM_MAX_DEVICES) ? (device) : 0;                            \
+        if ((size_t)(bytes) > done__[d__]) {                                                                      \
+            OFDM_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            done__[d__] = (size_t)(bytes);                                                                        \
+        }                                                                                                         \
+    } while (0)
 
 // workspace carve-out (rx.cu)
 struct RxWorkspace {
@@ -60,6 +72,7 @@ struct RxWorkspace {
     double* phi0;          // [max_frames] NCO phase just before each trigger takes effect
     double* step;          // [max_frames] NCO phase step per sample after each trigger
     int32_t* first_ok;     // [1] index of the first trigger the sampler can see
+    double* nco_init;      // [1] NCO phase step per sample before the first trigger (0 behind ofdm_sync_pn)
     int32_t* plan_hdr;     // [4] scratch of the two-launch plan
     double* plan_blk_d;    // [1024]
     int64_t* plan_blk_i;   // [1024]
@@ -87,6 +100,8 @@ int launch_trig_compact(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* 
 int launch_sync_stream(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, int force,
                        cudaStream_t st);
 int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_offset, ofdm_rx_io* io, RxWorkspace* ws,
+                      cudaStream_t st);
 int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
 int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
 int launch_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_t* sess_nvec, int32_t max_frames,

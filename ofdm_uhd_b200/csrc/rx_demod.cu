@@ -12,6 +12,7 @@ struct DemodParams {
     const int64_t* trig_idx;
     const double* phi0;
     const double* step;
+    const double* nco_init;
     const int32_t* n_trig;
     const int32_t* first_ok;
     const int32_t* n_frames;
@@ -196,10 +197,13 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 while (kk >= 0 && p.trig_idx[kk] > st) --kk;
             }
             const int64_t t_next = (kk + 1 < K) ? p.trig_idx[kk + 1] : LLONG_MAX;
-            double stp = 0.0, ph_base = 0.0;
+            double stp, ph_base;
             if (kk >= 0) {
                 stp = p.step[kk];
                 ph_base = p.phi0[kk] + stp * (double)(st + tid - p.trig_idx[kk] + 1);
+            } else {                                        // before the first trigger (0 behind ofdm_sync_pn)
+                stp = *p.nco_init;
+                ph_base = stp * (double)(st + tid + 1);
             }
             if (kk != kk_w) {                               // block-uniform
                 __syncthreads();
@@ -439,11 +443,7 @@ static int launch_demod_nt(ofdm_handle* h, const DemodParams& p, int max_frames,
     constexpr int NW = BT / 32;
     size_t smem = sizeof(double) * 8 * NW + sizeof(float2) * (2 * (size_t)fft_smem_elems<N>() + 2 * (size_t)p.occ + p.M) +
                   ((p.ncar + 15) & ~15) + (size_t)(p.ncar * p.nbits / 8 + 16);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        OFDM_CUDA_CHECK(cudaFuncSetAttribute(demod_kernel<N, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    OFDM_SET_MAX_SMEM((demod_kernel<N, TAPS>), smem, h->device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int grid = sms * 32;
@@ -462,7 +462,7 @@ static int launch_demod_n(ofdm_handle* h, const DemodParams& p, int max_frames, 
 
 int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
     DemodParams p;
-    p.y = y; p.n = n; p.trig_idx = io->trig_idx; p.phi0 = ws->phi0; p.step = ws->step; p.n_trig = io->n_trig;
+    p.y = y; p.n = n; p.trig_idx = io->trig_idx; p.phi0 = ws->phi0; p.step = ws->step; p.nco_init = ws->nco_init; p.n_trig = io->n_trig;
     p.first_ok = ws->first_ok; p.n_frames = io->n_frames; p.frame_ndata = io->frame_ndata; p.vbase = ws->vbase;
     p.tw = h->d_tw; p.cst = h->d_const; p.sinkmap = h->d_sinkmap; p.ks = h->d_ks; p.kd = h->d_kd;
     p.occ = h->occ; p.cp = h->cp; p.zl = h->zl; p.ncar = h->ncar; p.nbits = h->nbits; p.M = h->M; p.L = h->L;
@@ -733,11 +733,7 @@ int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t 
     if (grid > 148 * 32) grid = 148 * 32;
     const size_t row_smem = (size_t)32 * (io->pkt_stride / 4 + 1) * sizeof(uint32_t);
     const int staged = (io->pkt_stride & 3) == 0 && row_smem <= (size_t)CRC_SMEM_MAX && ((((uintptr_t)io->pkt_bytes) & 3) == 0);
-    static size_t attr_smem = 0;
-    if (staged && row_smem > attr_smem) {
-        OFDM_CUDA_CHECK(cudaFuncSetAttribute(crc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
-        attr_smem = row_smem;
-    }
+    if (staged) OFDM_SET_MAX_SMEM(crc_kernel, row_smem, h->device);
     crc_kernel<<<grid, 32, staged ? row_smem : 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len,
                                                         io->pkt_bytes, io->pkt_stride, io->pkt_ok, h->d_mask, h->d_crctab,
                                                         io->counters, staged);

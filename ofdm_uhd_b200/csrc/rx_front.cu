@@ -24,6 +24,7 @@ int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, voi
     ws->first_nan = (int64_t*)take(sizeof(int64_t));
     ws->first_ok = (int32_t*)take(sizeof(int32_t));
     ws->live_overflow = (int32_t*)take(sizeof(int32_t));
+    ws->nco_init = (double*)take(sizeof(double));
     ws->plan_hdr = (int32_t*)take(4 * sizeof(int32_t));
     ws->plan_blk_d = (double*)take(sizeof(double) * 1024);
     ws->plan_blk_i = (int64_t*)take(sizeof(int64_t) * 1024);
@@ -142,11 +143,7 @@ static int launch_filter_n(ofdm_handle* h, const FiltParams& p, cudaStream_t st)
     constexpr int T = NOS / FftPlan<NOS>::E;
     constexpr int SB = (fft_smem_elems<NOS>() + 1) & ~1;
     size_t smem = ((size_t)G * 2 * SB) * sizeof(float2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        OFDM_CUDA_CHECK(cudaFuncSetAttribute(chan_filter_kernel<NOS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    OFDM_SET_MAX_SMEM((chan_filter_kernel<NOS, G>), smem, h->device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int64_t want = (p.nblk + G - 1) / G;
@@ -373,11 +370,7 @@ static int launch_metric_kg(ofdm_handle* h, const float2* y, int64_t n, float* m
     const int T = SM_THREADS * K - need;
     if (T < 256) { ofdm_set_error("sync_metric: cp_length too large for the tile"); return OFDM_E_INVAL; }
     size_t smem = sizeof(double) * (size_t)(SM_THREADS * K + SM_THREADS + 8);
-    static bool attr_done = false;
-    if (!attr_done) {
-        OFDM_CUDA_CHECK(cudaFuncSetAttribute(sync_metric_kernel<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    OFDM_SET_MAX_SMEM((sync_metric_kernel<K, G>), smem, h->device);
     sync_metric_kernel<K, G><<<(unsigned)((n + T - 1) / T), SM_THREADS, smem, st>>>(y, n, h->cp, tapf, mf, first_nan);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
@@ -650,6 +643,7 @@ struct PlanParams {
     int32_t* frame_ndata;
     int64_t* vbase;
     int64_t* counters;
+    const double* nco_init;// [1] phase step per sample before the first trigger
     int32_t* hdr;          // [4] scratch: K, first_ok, frames before the first call that cannot run
     double* blk_d;         // [nblk] CTA totals of the phase increments
     long long* blk_i;      // [nblk] CTA totals of the vector counts
@@ -792,7 +786,11 @@ __global__ void __launch_bounds__(1024) plan_offset_kernel(const PlanParams p, i
     long long tot_i;
     const double ex_d = plan_block_scan<double>(tid < nblk ? p.blk_d[tid] : 0.0, s_wd, tot_d);
     const long long ex_i = plan_block_scan<long long>(tid < nblk ? p.blk_i[tid] : 0, s_wi, tot_i);
-    if (tid == blockIdx.x) { s_off_d = ex_d; s_off_i = ex_i; }
+    if (tid == blockIdx.x) {
+        // phase accumulated over samples 0 .. t0-1 (non-zero only behind ofdm_sync_fixed)
+        s_off_d = ex_d + (K > 0 ? *p.nco_init * (double)p.trig_idx[0] : 0.0);
+        s_off_i = ex_i;
+    }
     __syncthreads();
     const int k = blockIdx.x * 1024 + tid;
     if (k < K) {
@@ -823,7 +821,7 @@ int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cuda
     p.trig_idx = io->trig_idx;
     p.trig_ang = io->trig_ang; p.phi0 = ws->phi0; p.step = ws->step; p.first_ok = ws->first_ok; p.n_frames = io->n_frames;
     p.frame_start = io->frame_start; p.frame_ndata = io->frame_ndata; p.vbase = ws->vbase; p.counters = io->counters;
-    p.hdr = ws->plan_hdr; p.blk_d = ws->plan_blk_d; p.blk_i = (long long*)ws->plan_blk_i;
+    p.nco_init = ws->nco_init; p.hdr = ws->plan_hdr; p.blk_d = ws->plan_blk_d; p.blk_i = (long long*)ws->plan_blk_i;
     const int nblk = (io->max_frames + 1023) / 1024;
     if (nblk > 1024) {
         ofdm_set_error("plan: max_frames %d exceeds 1048576", io->max_frames);
@@ -835,6 +833,45 @@ int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cuda
     plan_local_kernel<<<nblk, 1024, 0, st>>>(p);
     OFDM_LAUNCH_CHECK();
     plan_offset_kernel<<<nblk, 1024, 0, st>>>(p, nblk);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// upstream ofdm_sync_fixed (ofdm_receiver.py~:108-119, "for testing only"): a trigger at the last sample of the
+// first symbol of every nsymbols-symbol packet and a constant frequency-offset stream pi*freq_offset.
+// ---------------------------------------------------------------------------------------------
+__global__ void sync_fixed_kernel(int64_t n, int L, int64_t period, float ang, double init_step, int max_frames,
+                                  int32_t* __restrict__ n_trig, int64_t* __restrict__ trig_idx,
+                                  float* __restrict__ trig_ang, double* __restrict__ nco_init,
+                                  int64_t* __restrict__ first_nan, uint32_t* __restrict__ status) {
+    const int64_t count = (n > L - 1) ? (n - L) / period + 1 : 0;          // indices L-1 + k*period < n
+    const int64_t kept = count < max_frames ? count : max_frames;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < kept; k += (int64_t)gridDim.x * blockDim.x) {
+        trig_idx[k] = (int64_t)(L - 1) + k * period;
+        trig_ang[k] = ang;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *n_trig = (int32_t)kept;
+        *nco_init = init_step;
+        *first_nan = LLONG_MAX;
+        *status = count > max_frames ? OFDM_ST_TRIG_OVERFLOW : 0u;
+    }
+}
+
+int launch_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_offset, ofdm_rx_io* io, RxWorkspace* ws,
+                      cudaStream_t st) {
+    if (nsymbols < 1) {
+        ofdm_set_error("sync_fixed: nsymbols %d < 1", nsymbols);
+        return OFDM_E_INVAL;
+    }
+    const float ang = (float)(3.14159265358979323846 * (double)freq_offset);
+    const double init_step = (-2.0 / (double)h->N) * (double)ang;
+    int grid = (io->max_frames + 255) / 256;
+    if (grid > 148 * 4) grid = 148 * 4;
+    if (grid < 1) grid = 1;
+    sync_fixed_kernel<<<grid, 256, 0, st>>>(n, h->L, (int64_t)nsymbols * h->L, ang, init_step, io->max_frames, io->n_trig,
+                                            io->trig_idx, io->trig_ang, ws->nco_init, ws->first_nan, io->status);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }

@@ -95,11 +95,7 @@ template <int N, int G>
 static int launch_sense_n(ofdm_sense_handle* s, const SenseParams& p, cudaStream_t st) {
     constexpr int T = N / FftPlan<N>::E;
     size_t smem = ((size_t)G * 2 * fft_smem_elems<N>()) * sizeof(float2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        OFDM_CUDA_CHECK(cudaFuncSetAttribute(sense_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    OFDM_SET_MAX_SMEM((sense_kernel<N, G>), smem, s->device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
     int64_t want = (p.n_dwell + G - 1) / G;

@@ -212,11 +212,7 @@ template <int N, int G>
 static int launch_tx_n(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
     constexpr int T = N / FftPlan<N>::E;
     size_t smem = (256 + (size_t)G * 2 * fft_smem_elems<N>()) * sizeof(float2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        OFDM_CUDA_CHECK(cudaFuncSetAttribute(tx_kernel<N, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    OFDM_SET_MAX_SMEM((tx_kernel<N, G>), smem, h->device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int64_t want = (p.total_syms + G - 1) / G;

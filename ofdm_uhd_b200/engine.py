@@ -280,13 +280,21 @@ class OfdmEngine:
         self._ws, self._ws_key = b, key
         return b
 
-    def demodulate_async(self, x, bufs=None, **kw):
-        """Run the whole receive chain on the current stream; returns the buffer dict (no sync)."""
+    def demodulate_async(self, x, bufs=None, sync: str = "pn", nsymbols: int = 18, freq_offset: float = 0.0, **kw):
+        """Run the whole receive chain on the current stream; returns the buffer dict (no sync).
+        ``sync="fixed"`` is the reference's test mode (ofdm_receiver.py~:108-119): no channel filter, a trigger
+        every ``nsymbols`` symbols, constant frequency offset ``freq_offset`` (subcarrier spacings)."""
         n = int(x.numel())
         if bufs is None:
             bufs = self.rx_alloc(n, **kw)
-        _lib.check(self.L_.ofdm_rx_demodulate(self.h, self._p(x), n, C.byref(bufs["io"]), self._stream()),
-                   "rx_demodulate")
+        if sync == "pn":
+            _lib.check(self.L_.ofdm_rx_demodulate(self.h, self._p(x), n, C.byref(bufs["io"]), self._stream()),
+                       "rx_demodulate")
+        elif sync == "fixed":
+            _lib.check(self.L_.ofdm_rx_demodulate_fixed(self.h, self._p(x), n, int(nsymbols), float(freq_offset),
+                                                        C.byref(bufs["io"]), self._stream()), "rx_demodulate_fixed")
+        else:
+            raise ValueError("sync %r: only 'pn' and 'fixed' exist (ml / pnac are not wired in the reference)" % (sync,))
         return bufs
 
     def ws_view(self, bufs, which: int, n: int):
@@ -373,6 +381,9 @@ class OfdmEngine:
 
     def demodulate(self, x, **kw) -> RxBatch:
         return self.collect(self.demodulate_async(x, **kw))
+
+    def demodulate_fixed(self, x, nsymbols: int = 18, freq_offset: float = 0.0, **kw) -> RxBatch:
+        return self.collect(self.demodulate_async(x, sync="fixed", nsymbols=nsymbols, freq_offset=freq_offset, **kw))
 
     # ---- split collect: lets a caller keep several receive calls in flight (one stream + buffer set each) ----
     def collect_begin(self, bufs, want_payload: bool = True):

@@ -277,6 +277,13 @@ class ofdm_demod:
                                   device=device, max_pkt_bytes=max_pkt_bytes, carrier_map=carrier_map)
         self.ofdm_recv = self.ofdm_demod = self._engine
         self._log = bool(getattr(options, "log", False))
+        # SYNC of ofdm_receiver.py~:89-119 is a source-level switch there ("pn" live, "fixed" for testing only);
+        # here it is read from the options object, with the reference's hard-coded fixed-mode parameters as defaults
+        self._sync = getattr(options, "sync", "pn")
+        self._sync_nsymbols = int(getattr(options, "sync_nsymbols", 18))
+        self._sync_freq_offset = float(getattr(options, "sync_freq_offset", 0.0))
+        if self._sync not in ("pn", "fixed"):
+            raise ValueError("sync %r: only 'pn' and 'fixed' exist (ml / pnac are not wired in the reference)" % (self._sync,))
         if options.verbose:
             self._print_verbage()
         self._watcher = _queue_watcher_thread(self._rcvd_pktq, callback)
@@ -292,7 +299,9 @@ class ofdm_demod:
         if samples.device.type != "cuda":
             samples = samples.to(self._engine.dev)
         samples = samples.contiguous()
-        if self._log:
+        if self._sync == "fixed":
+            res = self._engine.demodulate_fixed(samples, self._sync_nsymbols, self._sync_freq_offset, max_frames=max_frames)
+        elif self._log:
             res = self._feed_logged(samples, max_frames)
         else:
             res = self._engine.demodulate(samples, max_frames=max_frames)

@@ -641,6 +641,7 @@ class Plan:
     vec_flag: np.ndarray      # 1 = preamble vector
     frame_trig: np.ndarray    # index into trig of each frame the sampler emits
     n_data: np.ndarray        # data vectors emitted after each frame's preamble vector
+    init_step: float = 0.0    # NCO phase step per sample before the first trigger (0 for sync_pn: held angle starts at 0)
 
 
 def sampler_sim(trig: np.ndarray, n: int, N: int, L: int, timeout_max: int = 1000):
@@ -677,28 +678,35 @@ def sampler_sim(trig: np.ndarray, n: int, N: int, L: int, timeout_max: int = 100
             np.array(ftrig, dtype=np.int64), np.array(ndata, dtype=np.int64))
 
 
-def plan_frames(trig: np.ndarray, ang: np.ndarray, n: int, N: int, L: int, timeout: int = 1000) -> Plan:
+def plan_frames(trig: np.ndarray, ang: np.ndarray, n: int, N: int, L: int, timeout: int = 1000,
+                init_ang: float = 0.0) -> Plan:
+    """``init_ang``: the frequency-offset input of the NCO before the first trigger -- 0 behind ofdm_sync_pn
+    (sample_and_hold starts at 0), pi*freq_offset behind ofdm_sync_fixed (a constant stream)."""
     trig = np.asarray(trig, dtype=np.int64)
     ang = np.asarray(ang, dtype=F32)
     T = len(trig)
     step = (-2.0 / N) * ang.astype(np.float64)
+    init_step = (-2.0 / N) * float(F32(init_ang))
     phi0 = np.zeros(T, dtype=np.float64)
+    if T:
+        phi0[0] = init_step * float(trig[0])          # samples 0 .. t0-1 each advanced the phase by init_step
     for k in range(1, T):
         phi0[k] = phi0[k - 1] + step[k - 1] * float(trig[k] - trig[k - 1])
     vs, vf, ft, nd = sampler_sim(trig, n, N, L, timeout)
-    return Plan(trig, ang, phi0, vs, vf, ft, nd)
+    return Plan(trig, ang, phi0, vs, vf, ft, nd, init_step)
 
 
 def nco_phase_at(plan: Plan, idx: np.ndarray, N: int) -> np.ndarray:
     """float64 NCO phase phi[n] for sample indices ``idx`` (A.8, closed form)."""
     idx = np.asarray(idx, dtype=np.int64)
+    before = plan.init_step * (idx + 1).astype(np.float64)
     if len(plan.trig) == 0:
-        return np.zeros(idx.shape, dtype=np.float64)
+        return before
     k = np.searchsorted(plan.trig, idx, side="right") - 1
     step = (-2.0 / N) * plan.ang.astype(np.float64)
     kk = np.maximum(k, 0)
     ph = plan.phi0[kk] + step[kk] * (idx - plan.trig[kk] + 1).astype(np.float64)
-    return np.where(k >= 0, ph, 0.0)
+    return np.where(k >= 0, ph, before)
 
 
 def derotate(y: np.ndarray, idx: np.ndarray, plan: Plan, N: int) -> np.ndarray:
@@ -943,18 +951,39 @@ class RxResult:
     vec_start: Optional[np.ndarray] = None
 
 
-def rx_demodulate(x: np.ndarray, lay: Layout, keep: bool = False) -> RxResult:
+def sync_fixed(n: int, N: int, cp: int, nsymbols: int, freq_offset: float):
+    """upstream ofdm_sync_fixed(fft_length, cp_length, nsymbols, freq_offset) (ofdm_receiver.py~:108-119; recalled):
+    a repeating trigger vector with a 1 at the last sample of the first symbol of every nsymbols-symbol packet,
+    and a constant frequency-offset stream pi*freq_offset.  Returns (trigger indices, float32 angles)."""
+    L = N + cp
+    period = int(nsymbols) * L
+    trig = np.arange(L - 1, n, period, dtype=np.int64) if n > 0 else np.zeros(0, np.int64)
+    ang = np.full(len(trig), F32(math.pi * freq_offset), dtype=F32)
+    return trig, ang
+
+
+def rx_demodulate(x: np.ndarray, lay: Layout, keep: bool = False, sync: str = "pn", nsymbols: int = 18,
+                  freq_offset: float = 0.0) -> RxResult:
     """chan_filt -> sync_pn -> NCO -> sampler -> FFT -> frame_acq -> frame_sink -> unmake_packet
-    (ofdm_receiver.py~:131-142, ofdm.py:245-247,300-305), whole-stream semantics."""
+    (ofdm_receiver.py~:131-142, ofdm.py:245-247,300-305), whole-stream semantics.  ``sync="fixed"`` is the
+    reference's test mode (ofdm_receiver.py~:108-119): no channel filter, triggers and frequency offset given."""
     N, cp, L = lay.fft_length, lay.cp_length, lay.sym_len
     x = np.asarray(x, dtype=C64)
     n = len(x)
-    taps = chan_filter_taps(lay)
-    y = chan_filter(x, taps)
-    mf, Pr, Pi = sync_pn_metric(y, N, cp)
-    trig = peak_detect(mf)
-    ang = np.arctan2(Pi[trig].astype(np.float64), Pr[trig].astype(np.float64)).astype(F32)
-    plan = plan_frames(trig, ang, n, N, L)
+    if sync == "fixed":
+        y = x                                          # gr.multiply_const_cc(1.0)
+        mf = np.zeros(0, dtype=F32)
+        trig, ang = sync_fixed(n, N, cp, nsymbols, freq_offset)
+        plan = plan_frames(trig, ang, n, N, L, init_ang=math.pi * freq_offset)
+    elif sync == "pn":
+        taps = chan_filter_taps(lay)
+        y = chan_filter(x, taps)
+        mf, Pr, Pi = sync_pn_metric(y, N, cp)
+        trig = peak_detect(mf)
+        ang = np.arctan2(Pi[trig].astype(np.float64), Pr[trig].astype(np.float64)).astype(F32)
+        plan = plan_frames(trig, ang, n, N, L)
+    else:
+        raise ValueError("sync %r: only 'pn' and 'fixed' are restated (ml / pnac are not wired in the reference)" % sync)
     acq = FrameAcquisition(lay)
     sink = FrameSink(lay)
     eqs, flags, vstart = [], [], []

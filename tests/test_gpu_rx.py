@@ -337,3 +337,40 @@ def test_liveness_walk_fast_and_general(F, p_exc):
         got = live.cpu().numpy()
         assert np.array_equal(got[:F], live_ref), (force, int(np.flatnonzero(got[:F] != live_ref)[0]))
         assert not got[F:].any()
+
+
+@pytest.mark.parametrize("mod,nsym,fo", [("bpsk", 18, 0.0), ("qpsk", 10, 0.3), ("qam64", 4, -0.45)])
+def test_fixed_sync_mode_equals_oracle(mod, nsym, fo):
+    """The reference's SYNC == "fixed" test mode (ofdm_receiver.py~:108-119): no channel filter, a trigger at the end
+    of the first symbol of every nsym-symbol packet, constant frequency offset.  Frames sit back to back from sample
+    0; the GPU chain (ofdm_rx_demodulate_fixed) must deliver what the oracle's fixed-mode receiver delivers."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    lay = o.Layout(512, 200, 128, mod)
+    rng = np.random.default_rng(nsym)
+    pay = payloads(rng, 14)
+    pkts = [o.make_packet(p, 1, 1, False) for p in pay]
+    x = o.tx_modulate(pkts, lay, 0.25, seed=2)
+    assert len(x) == 14 * nsym * 640                       # 402-byte payloads: 18 / 10 / 4 symbols per frame
+    tail = np.zeros(3 * 640, dtype=np.complex64)
+    xc = o.channel(np.concatenate([x, tail]), 30.0, fo, 512, seed=6, sig_power=float(np.mean(np.abs(x) ** 2)))
+    ref = o.rx_demodulate(xc, lay, sync="fixed", nsymbols=nsym, freq_offset=fo)
+    assert sum(1 for ok, _ in ref.packets if ok) >= 13
+    eng = OfdmEngine(512, 200, 128, mod)
+    got = eng.demodulate_fixed(torch.from_numpy(xc).cuda(), nsym, fo)
+    assert np.array_equal(got.trig_idx, ref.trig) and np.array_equal(got.trig_ang, ref.ang)
+    assert got.packets == ref.packets
+    # the same call through the stage entry points
+    bufs = eng.rx_alloc(len(xc))
+    L_, st = eng.L_, eng._stream()
+    d = torch.from_numpy(xc).cuda()
+    from ofdm_uhd_b200 import _lib
+    _lib.check(L_.ofdm_rx_sync_fixed(eng.h, len(xc), nsym, fo, C.byref(bufs["io"]), st))
+    _lib.check(L_.ofdm_rx_plan(eng.h, len(xc), C.byref(bufs["io"]), st))
+    _lib.check(L_.ofdm_rx_demod(eng.h, eng._p(d), len(xc), C.byref(bufs["io"]), st))
+    _lib.check(L_.ofdm_rx_finish(eng.h, C.byref(bufs["io"]), st))
+    assert eng.collect(bufs).packets == ref.packets
+    # and a pn run afterwards on the same buffers starts its NCO at rest again
+    _, xc2 = loopback_capture(lay, pay[:6], 30, 0.2, seed=3)
+    assert eng.demodulate(torch.from_numpy(xc2).cuda()).packets == o.rx_demodulate(xc2, lay).packets
+    eng.close()
