@@ -1,6 +1,7 @@
 // Receive front end: channel filter, ofdm_sync_pn (Schmidl-Cox metric + peak detector + angle latch),
 // and the sampler / NCO plan.  Reference wiring: ofdm_receiver.py~:69-76,97-101,123-125,131-136.
 #include "internal.h"
+#include <stdlib.h>
 #include "fft.cuh"
 #include <limits.h>
 
@@ -11,7 +12,7 @@ int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, voi
     (void)h;
     if (n < 0) n = 0;
     if (max_frames < 1) max_frames = 1;
-    int64_t seg_len = (n + 148 * 40 - 1) / (148 * 40);     // two full waves of the detector kernel (20 warps per SM)
+    int64_t seg_len = (n + 148 * 32 - 1) / (148 * 32);     // one full wave of the detector kernel (32 one-warp CTAs per SM)
     if (seg_len < 65536) seg_len = 65536;
     seg_len = (seg_len + 31) / 32 * 32;
     ws->seg_len = seg_len;

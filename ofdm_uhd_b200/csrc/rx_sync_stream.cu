@@ -13,10 +13,10 @@
 //   * the detector (IIR average scan, threshold ballot, run / arg-max state machine) consumes the K metric values
 //     straight from registers.
 // The window sums and the detector have very different shapes -- the sums need ~170 registers and no history
-// beyond one block, the detector ~90 registers but a 24 576-sample warm-up of its IIR average -- so as two kernels
+// beyond one block, the detector ~60 registers but a 24 576-sample warm-up of its IIR average -- so as two kernels
 // each runs at its own occupancy, the expensive half skips the warm-up overlap entirely, and the 4 B/sample
 // hand-over is noise next to the instruction-issue / XU-pipe limit both halves sit on (a fused single kernel
-// measured 5.3 ms on the 640 M-sample bench capture, the pair 4.2 ms).
+// measured 5.3 ms on the 640 M-sample bench capture, the pair 3.4 ms).
 //   metric_chunk_kernel  one warp per chunk of MC_STEPS blocks (+1 priming block): y -> M = |P|^2 / R^2
 //   detect_seg_kernel    one warp per detector segment: M -> cp-average - 1 -> peak_detector_fb -> triggers;
 //                        a segment starts OFDM_PEAK_WARM samples early and runs past its end until an open run
@@ -49,6 +49,18 @@ __device__ __forceinline__ double shfl_down_d(double x, int d) {
                             __shfl_down_sync(0xffffffffu, __double2loint(x), d));
 }
 
+// 256-bit global accesses (sm_100): a lane owns K consecutive samples, i.e. lanes sit 8K bytes apart, and the L1 data
+// pipe -- which the shuffles share -- is charged per 128-byte line touched by an instruction, so a 64-byte run per
+// lane costs half as many wavefronts as two LDG.256 than as four LDG.128.
+__device__ __forceinline__ void ldg256(const void* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 // one step's worth of per-lane history (ping-ponged between two instances so nothing is copied per step)
 template <int K>
 struct StepHist {
@@ -72,12 +84,22 @@ struct MetricCtx {
     __device__ __forceinline__ void load(float2 (&dst)[K], const int64_t i0) const {
         const int64_t b0 = i0 + (int64_t)lane * K;
         if (i0 >= 0 && i0 + SZ <= n && vec_ok) {                 // warp-uniform
-            const float4* q = (const float4*)(y + b0);
+            if constexpr (K % 4 == 0) {
 #pragma unroll
-            for (int i = 0; i < K / 2; ++i) {
-                const float4 t = __ldg(q + i);
-                dst[2 * i] = make_float2(t.x, t.y);
-                dst[2 * i + 1] = make_float2(t.z, t.w);
+                for (int i = 0; i < K; i += 4) {
+                    float t[8];
+                    ldg256(y + b0 + i, t);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[i + j] = make_float2(t[2 * j], t[2 * j + 1]);
+                }
+            } else {
+                const float4* q = (const float4*)(y + b0);
+#pragma unroll
+                for (int i = 0; i < K / 2; ++i) {
+                    const float4 t = __ldg(q + i);
+                    dst[2 * i] = make_float2(t.x, t.y);
+                    dst[2 * i + 1] = make_float2(t.z, t.w);
+                }
             }
         } else {
 #pragma unroll
@@ -140,8 +162,12 @@ struct MetricCtx {
         }
         const int64_t b0 = i0 + (int64_t)lane * K;
         if (i0 + SZ <= n && st_ok) {
+            if constexpr (K == 8) {
+                stg256(mt + b0, q);
+            } else {
 #pragma unroll
-            for (int i = 0; i < K; i += 4) *(float4*)(mt + b0 + i) = make_float4(q[i], q[i + 1], q[i + 2], q[i + 3]);
+                for (int i = 0; i < K; i += 4) *(float4*)(mt + b0 + i) = make_float4(q[i], q[i + 1], q[i + 2], q[i + 3]);
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < K; ++i)
@@ -156,8 +182,8 @@ __global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __re
     static_assert(K % 4 == 0 || K == 2, "K");
     MetricCtx<K> c;
     c.y = y; c.mt = mt; c.n = n; c.lane = threadIdx.x;
-    c.vec_ok = (((uintptr_t)y) & 15) == 0;
-    c.st_ok = (((uintptr_t)mt) & 15) == 0 && (K % 4) == 0;
+    c.vec_ok = (((uintptr_t)y) & 31) == 0;
+    c.st_ok = (((uintptr_t)mt) & 31) == 0 && (K % 4) == 0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         c.mu[k] = (c.lane >= (1 << k)) ? 1.0 : 0.0;
@@ -212,10 +238,14 @@ struct DetectCtx {
     __device__ __forceinline__ void load(float (&dst)[K], const int64_t i0) const {
         const int64_t b0 = i0 + (int64_t)lane * K;
         if (i0 + SZ <= p.n && vec_ok) {
+            if constexpr (K == 8) {
+                ldg256(mt + b0, dst);
+            } else {
 #pragma unroll
-            for (int i = 0; i < K; i += 4) {
-                const float4 t = __ldg((const float4*)(mt + b0 + i));
-                dst[i] = t.x; dst[i + 1] = t.y; dst[i + 2] = t.z; dst[i + 3] = t.w;
+                for (int i = 0; i < K; i += 4) {
+                    const float4 t = __ldg((const float4*)(mt + b0 + i));
+                    dst[i] = t.x; dst[i + 1] = t.y; dst[i + 2] = t.z; dst[i + 3] = t.w;
+                }
             }
         } else {
 #pragma unroll
@@ -242,29 +272,30 @@ struct DetectCtx {
         for (int k = 0; k < 5; ++k) mi = fma(shfl_up_d(mi, 1 << k), mu[k], mi);
         const double mex = fma(shfl_up_d(mi, 1), mu[0], carry2);
         carry2 += __shfl_sync(0xffffffffu, mi, 31);
+        // ring layout [half][i][lane]: element i of lane l sits at i*32 + l, so every store and every load below is
+        // stride-1 across the warp (a lane-major layout has lanes 64 B apart: 4-way bank conflicts on both sides,
+        // which made the shared-memory pipe -- shared with the shuffles -- this kernel's bottleneck)
         const int rb = (stepno & 1) * SZ;                        // ring half of this step
-        double* mine = ring + rb + lane * K;
 #pragma unroll
-        for (int i = 0; i < K; i += 2) {
-            mloc[i] += mex; mloc[i + 1] += mex;
-            *(double2*)(mine + i) = make_double2(mloc[i], mloc[i + 1]);
+        for (int i = 0; i < K; ++i) {
+            mloc[i] += mex;
+            ring[rb + i * 32 + lane] = mloc[i];
         }
         __syncwarp();
         float v[K];
         if (cp_aligned) {
+            // n - cp sits cp/K lanes back, same element index: in this step's half or the previous one
             const int ql = lane - cpq;
-            const double* src = ring + (ql >= 0 ? rb + ql * K : (rb ^ SZ) + (32 + ql) * K);
+            const double* src = ring + (ql >= 0 ? rb + ql : (rb ^ SZ) + 32 + ql);
 #pragma unroll
-            for (int i = 0; i < K; i += 2) {
-                const double2 pv = *(const double2*)(src + i);
-                v[i] = fadd_rn((float)((mloc[i] - pv.x) * tap), -1.0f);
-                v[i + 1] = fadd_rn((float)((mloc[i + 1] - pv.y) * tap), -1.0f);
-            }
+            for (int i = 0; i < K; ++i) v[i] = fadd_rn((float)((mloc[i] - src[i * 32]) * tap), -1.0f);
         } else {
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-                const int e = lane * K + i - p.cp;
-                const double prevS = ring[e >= 0 ? rb + e : (rb ^ SZ) + SZ + e];
+                int e = lane * K + i - p.cp;                     // position of n - cp relative to this step
+                int hb = rb;
+                if (e < 0) { e += SZ; hb = rb ^ SZ; }
+                const double prevS = ring[hb + (e % K) * 32 + e / K];
                 v[i] = fadd_rn((float)((mloc[i] - prevS) * tap), -1.0f);
             }
         }
@@ -343,7 +374,7 @@ struct DetectCtx {
 };
 
 template <int K>
-__global__ void __launch_bounds__(32, 20) detect_seg_kernel(const StreamParams p, const float* __restrict__ mt) {
+__global__ void __launch_bounds__(32, 32) detect_seg_kernel(const StreamParams p, const float* __restrict__ mt) {
     constexpr int SZ = 32 * K;
     extern __shared__ __align__(16) double s_ring[];
     DetectCtx<K> c(p);
@@ -358,7 +389,7 @@ __global__ void __launch_bounds__(32, 20) detect_seg_kernel(const StreamParams p
     if (w0 < 0) w0 = 0;
     w0 -= w0 % SZ;
     c.tap = (double)p.tapf;
-    c.vec_ok = (((uintptr_t)mt) & 15) == 0 && (K % 4) == 0;
+    c.vec_ok = (((uintptr_t)mt) & 31) == 0 && (K % 4) == 0;
     c.cp_aligned = (p.cp % K) == 0;
     c.cpq = p.cp / K;
     c.a1 = (double)0.001f;
