@@ -2,6 +2,7 @@
 // Host-side table construction restates ofdm.py:71-101 (preamble / constellation wiring),
 // ofdm_receiver.py~:69-76 (firdes.low_pass design inputs) and SURVEY.md A.3/A.5/A.13.
 #include "internal.h"
+#include <algorithm>
 #include <ctype.h>
 #include <math.h>
 #include <stdarg.h>
@@ -216,6 +217,44 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
 
     std::vector<float2> cst(M);
     for (int i = 0; i < M; ++i) cst[i] = make_float2(cfg->host_constellation[2 * i], cfg->host_constellation[2 * i + 1]);
+    // A constellation whose points form a full L x L grid of (nearly) uniform levels -- qam.constellation for
+    // m >= 64 -- lets the frame sink's slicer look at the 3 x 3 cells around the received point instead of all M
+    // points; the result is provably the brute-force one (rx_demod.cu: slice_point).
+    std::vector<uint8_t> grid;
+    h->grid_L = 0;
+    if (M >= 64) {
+        std::vector<float> xs, ys;
+        for (int i = 0; i < M; ++i) { xs.push_back(cst[i].x); ys.push_back(cst[i].y); }
+        std::sort(xs.begin(), xs.end()); xs.erase(std::unique(xs.begin(), xs.end()), xs.end());
+        std::sort(ys.begin(), ys.end()); ys.erase(std::unique(ys.begin(), ys.end()), ys.end());
+        const int Lg = (int)xs.size();
+        bool ok = Lg >= 8 && (int)ys.size() == Lg && Lg * Lg == M;
+        double dx = 0, dy = 0;
+        if (ok) {
+            dx = ((double)xs[Lg - 1] - xs[0]) / (Lg - 1);
+            dy = ((double)ys[Lg - 1] - ys[0]) / (Lg - 1);
+            ok = dx > 0 && dy > 0;
+            for (int i = 0; ok && i < Lg; ++i)
+                ok = fabs(xs[i] - (xs[0] + i * dx)) < 1e-4 * dx && fabs(ys[i] - (ys[0] + i * dy)) < 1e-4 * dy;
+            // the candidate-search argument below assumes |coordinates| <= 1 (levels normalised by the largest)
+            ok = ok && fabs(xs[0]) <= 1.0001 && fabs(xs[Lg - 1]) <= 1.0001 && fabs(ys[0]) <= 1.0001 && fabs(ys[Lg - 1]) <= 1.0001;
+        }
+        if (ok) {
+            grid.assign((size_t)M, 255);
+            std::vector<int> seen((size_t)M, 0);
+            for (int i = 0; ok && i < M; ++i) {
+                const int ix = (int)(std::lower_bound(xs.begin(), xs.end(), cst[i].x) - xs.begin());
+                const int iy = (int)(std::lower_bound(ys.begin(), ys.end(), cst[i].y) - ys.begin());
+                if (seen[(size_t)iy * Lg + ix]++) ok = false;
+                grid[(size_t)iy * Lg + ix] = (uint8_t)i;
+            }
+        }
+        if (ok) {
+            h->grid_L = Lg;
+            h->grid_x0 = xs[0]; h->grid_y0 = ys[0];
+            h->grid_inv_dx = (float)(1.0 / dx); h->grid_inv_dy = (float)(1.0 / dy);
+        }
+    }
     std::vector<uint8_t> mask(4096);
     whitening_mask(mask.data());
     std::vector<uint32_t> crct(256);
@@ -233,6 +272,7 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
     rc |= upload(&h->d_pre_time, pre);
     rc |= upload(&h->d_mask, mask);
     rc |= upload(&h->d_crctab, crct);
+    if (h->grid_L) rc |= upload(&h->d_grid, grid);
     if (rc) { ofdm_destroy(h); return nullptr; }
     return h;
 }
@@ -242,7 +282,7 @@ extern "C" void ofdm_destroy(ofdm_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_const); cudaFree(h->d_bin2car); cudaFree(h->d_sinkmap); cudaFree(h->d_ks); cudaFree(h->d_kd);
     cudaFree(h->d_tw); cudaFree(h->d_tw_os); cudaFree(h->d_Hos); cudaFree(h->d_pre_time); cudaFree(h->d_mask);
-    cudaFree(h->d_crctab);
+    cudaFree(h->d_crctab); cudaFree(h->d_grid);
     delete h;
 }
 

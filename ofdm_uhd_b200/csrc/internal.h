@@ -30,6 +30,10 @@ struct ofdm_handle {
     uint8_t* d_mask;       // [4096] whitening mask
     uint32_t* d_crctab;    // [256]
     float h_taps[OFDM_MAX_TAPS];
+    // square-grid constellations (qam64 / qam256): levels per axis (0 = brute-force slicer only), cell -> index table
+    int grid_L;
+    float grid_x0, grid_y0, grid_inv_dx, grid_inv_dy;
+    uint8_t* d_grid;       // [grid_L * grid_L], row = y level
 };
 
 struct ofdm_sense_handle {

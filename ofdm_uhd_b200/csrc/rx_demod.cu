@@ -24,6 +24,9 @@ struct DemodParams {
     const float* ks;
     const float* kd;
     int occ, cp, zl, ncar, nbits, M, L, max_frames, pkt_stride;
+    int grid_L;
+    float grid_x0, grid_y0, grid_inv_dx, grid_inv_dy;
+    const uint8_t* grid;
     uint8_t* frame_status;
     int32_t* pkt_len;
     int32_t* sess_nvec;
@@ -129,6 +132,60 @@ __device__ __forceinline__ void pack_bytes(const uint8_t* sym, uint8_t* vb, int 
     }
 }
 
+// ofdm_frame_sink's slicer: the first minimum of |r - const[k]|^2 over k in index order, every distance in
+// individually rounded float32 arithmetic (A.11).
+//   Brute force over all M points -- or, for a square-grid constellation (grid_L > 0, |coordinates| <= 1) and a
+// received point with |re|, |im| <= 16, over the 3 x 3 cells around the nearest cell: a point outside that
+// neighbourhood is at least 1.5 cells away along one axis where some neighbourhood point is at most 0.5, so its
+// exact squared distance is larger by >= 2 cell^2 (>= 0.035 for qam256) while the float32 rounding of either
+// distance is below 2e-4 in that range; the minimum over the neighbourhood with ties broken towards the smaller
+// index is therefore exactly what the scan over all M points returns.
+struct Slicer {
+    const float2* cst;
+    const uint8_t* grid;
+    int M, L;
+    float x0, y0, inv_dx, inv_dy;
+    __device__ __forceinline__ int operator()(const float2 r) const {
+        if (L > 0 && fabsf(r.x) <= 16.f && fabsf(r.y) <= 16.f) {
+            int ix = __float2int_rn((r.x - x0) * inv_dx), iy = __float2int_rn((r.y - y0) * inv_dy);
+            ix = min(max(ix, 0), L - 1);
+            iy = min(max(iy, 0), L - 1);
+            float best = INFINITY;
+            int b = INT_MAX;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = iy + dy;
+                if (yy < 0 || yy >= L) continue;
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int xx = ix + dx;
+                    if (xx < 0 || xx >= L) continue;
+                    const int k = grid[yy * L + xx];
+                    const float2 ck = cst[k];
+                    const float ex = fsub_rn(r.x, ck.x), ey = fsub_rn(r.y, ck.y);
+                    const float dd = fadd_rn(fmul_rn(ex, ex), fmul_rn(ey, ey));
+                    if (dd < best || (dd == best && k < b)) { best = dd; b = k; }
+                }
+            }
+            return b;
+        }
+        int b = 0;
+        float best;
+        {
+            const float2 c0 = cst[0];
+            const float ex = fsub_rn(r.x, c0.x), ey = fsub_rn(r.y, c0.y);
+            best = fadd_rn(fmul_rn(ex, ex), fmul_rn(ey, ey));
+        }
+        for (int k = 1; k < M; ++k) {
+            const float2 ck = cst[k];
+            const float ex = fsub_rn(r.x, ck.x), ey = fsub_rn(r.y, ck.y);
+            const float dd = fadd_rn(fmul_rn(ex, ex), fmul_rn(ey, ey));
+            if (dd < best) { best = dd; b = k; }
+        }
+        return b;
+    }
+};
+
 template <int N, bool TAPS>
 __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E), (FftPlan<N>::E == 8 && !TAPS) ? 16 : 1) demod_kernel(const DemodParams p) {
     using P = FftPlan<N>;
@@ -147,6 +204,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     float2* s_cst = dfe + p.occ;                            // [M]
     uint8_t* sym = (uint8_t*)(s_cst + p.M);                 // [ncar]
     uint8_t* vb = sym + ((p.ncar + 15) & ~15);              // bytes of the current vector
+    uint8_t* s_grid = vb + ((p.ncar * p.nbits / 8 + 16 + 15) & ~15);   // [grid_L^2] cell -> constellation index
     __shared__ int s_delta, s_hdr_ok, s_len;
     __shared__ float2 s_cc[2], s_car[2], s_W[E];
     __shared__ float s_phase, s_freq;
@@ -159,6 +217,8 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     const int first_ok = *p.first_ok;
     const int occ = p.occ, ncar = p.ncar, nbits = p.nbits, zl = p.zl, L = p.L;
     for (int i = tid; i < p.M; i += BT) s_cst[i] = p.cst[i];
+    for (int i = tid; i < p.grid_L * p.grid_L; i += BT) s_grid[i] = p.grid[i];
+    const Slicer slicer{s_cst, s_grid, p.M, p.grid_L, p.grid_x0, p.grid_y0, p.grid_inv_dx, p.grid_inv_dy};
     float2* S = (P::NP == 2) ? bufB : bufA;                 // shifted spectrum of the current vector
     const int bits_this = ncar * nbits;
     const BitDiv bd(nbits);
@@ -321,24 +381,30 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                     const float2 Sa = S[ia + zl + delta], Sb = S[ib + zl + delta];
                     const float2 eqa = cmul_x(cmul_x(Ha, cc), Sa), eqb = cmul_x(cmul_x(Hb, cc), Sb);
                     const float2 ra = cmul_x(cmul_x(eqa, car), d0a), rb = cmul_x(cmul_x(eqb, car), d0b);
-                    // slicer: first minimum of |r - const[k]|^2
-                    int ba = 0, bb = 0;
-                    float besta, bestb;
-                    {
-                        const float2 c0 = s_cst[0];
-                        const float dxa = fsub_rn(ra.x, c0.x), dya = fsub_rn(ra.y, c0.y);
-                        const float dxb = fsub_rn(rb.x, c0.x), dyb = fsub_rn(rb.y, c0.y);
-                        besta = fadd_rn(fmul_rn(dxa, dxa), fmul_rn(dya, dya));
-                        bestb = fadd_rn(fmul_rn(dxb, dxb), fmul_rn(dyb, dyb));
-                    }
-                    for (int k = 1; k < p.M; ++k) {
-                        const float2 ck = s_cst[k];
-                        const float dxa = fsub_rn(ra.x, ck.x), dya = fsub_rn(ra.y, ck.y);
-                        const float dxb = fsub_rn(rb.x, ck.x), dyb = fsub_rn(rb.y, ck.y);
-                        const float dda = fadd_rn(fmul_rn(dxa, dxa), fmul_rn(dya, dya));
-                        const float ddb = fadd_rn(fmul_rn(dxb, dxb), fmul_rn(dyb, dyb));
-                        if (dda < besta) { besta = dda; ba = k; }
-                        if (ddb < bestb) { bestb = ddb; bb = k; }
+                    int ba, bb;
+                    if (p.grid_L > 0) {
+                        ba = slicer(ra);
+                        bb = slicer(rb);
+                    } else {
+                        // small constellations: both scans fused so the two chains interleave
+                        ba = 0; bb = 0;
+                        float besta, bestb;
+                        {
+                            const float2 c0 = s_cst[0];
+                            const float dxa = fsub_rn(ra.x, c0.x), dya = fsub_rn(ra.y, c0.y);
+                            const float dxb = fsub_rn(rb.x, c0.x), dyb = fsub_rn(rb.y, c0.y);
+                            besta = fadd_rn(fmul_rn(dxa, dxa), fmul_rn(dya, dya));
+                            bestb = fadd_rn(fmul_rn(dxb, dxb), fmul_rn(dyb, dyb));
+                        }
+                        for (int k = 1; k < p.M; ++k) {
+                            const float2 ck = s_cst[k];
+                            const float dxa = fsub_rn(ra.x, ck.x), dya = fsub_rn(ra.y, ck.y);
+                            const float dxb = fsub_rn(rb.x, ck.x), dyb = fsub_rn(rb.y, ck.y);
+                            const float dda = fadd_rn(fmul_rn(dxa, dxa), fmul_rn(dya, dya));
+                            const float ddb = fadd_rn(fmul_rn(dxb, dxb), fmul_rn(dyb, dyb));
+                            if (dda < besta) { besta = dda; ba = k; }
+                            if (ddb < bestb) { bestb = ddb; bb = k; }
+                        }
                     }
                     const float2 cla = s_cst[ba], clb = s_cst[bb];
                     const float2 ea = cmulc_x(ra, cla), eb = cmulc_x(rb, clb);
@@ -442,7 +508,7 @@ static int launch_demod_nt(ofdm_handle* h, const DemodParams& p, int max_frames,
     constexpr int BT = T < 64 ? 64 : T;
     constexpr int NW = BT / 32;
     size_t smem = sizeof(double) * 8 * NW + sizeof(float2) * (2 * (size_t)fft_smem_elems<N>() + 2 * (size_t)p.occ + p.M) +
-                  ((p.ncar + 15) & ~15) + (size_t)(p.ncar * p.nbits / 8 + 16);
+                  ((p.ncar + 15) & ~15) + (size_t)((p.ncar * p.nbits / 8 + 16 + 15) & ~15) + (size_t)p.grid_L * p.grid_L;
     OFDM_SET_MAX_SMEM((demod_kernel<N, TAPS>), smem, h->device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -466,6 +532,8 @@ int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxW
     p.first_ok = ws->first_ok; p.n_frames = io->n_frames; p.frame_ndata = io->frame_ndata; p.vbase = ws->vbase;
     p.tw = h->d_tw; p.cst = h->d_const; p.sinkmap = h->d_sinkmap; p.ks = h->d_ks; p.kd = h->d_kd;
     p.occ = h->occ; p.cp = h->cp; p.zl = h->zl; p.ncar = h->ncar; p.nbits = h->nbits; p.M = h->M; p.L = h->L;
+    p.grid_L = h->grid_L; p.grid_x0 = h->grid_x0; p.grid_y0 = h->grid_y0; p.grid_inv_dx = h->grid_inv_dx;
+    p.grid_inv_dy = h->grid_inv_dy; p.grid = h->d_grid;
     p.max_frames = io->max_frames; p.pkt_stride = io->pkt_stride;
     p.frame_status = io->frame_status; p.pkt_len = io->pkt_len; p.sess_nvec = ws->sess_nvec; p.pkt_bytes = io->pkt_bytes;
     p.eq_syms = (float2*)io->eq_syms; p.sym_idx = io->sym_idx; p.derot_syms = (float2*)io->derot_syms;

@@ -375,3 +375,35 @@ def test_fixed_sync_mode_equals_oracle(mod, nsym, fo):
     _, xc2 = loopback_capture(lay, pay[:6], 30, 0.2, seed=3)
     assert eng.demodulate(torch.from_numpy(xc2).cuda()).packets == o.rx_demodulate(xc2, lay).packets
     eng.close()
+
+
+@pytest.mark.parametrize("N,occ,cp,mod,snr", [(512, 200, 128, "qam64", 14), (512, 200, 128, "qam256", 18),
+                                                (1024, 400, 256, "qam256", 40)])
+def test_grid_slicer_equals_brute_force(N, occ, cp, mod, snr):
+    """The 3 x 3-cell slicer used for square-grid constellations must return, for every carrier, exactly the first
+    minimum of the float32 distances over ALL points (ofdm_frame_sink's scan).  Checked on the GPU's own derotated
+    symbols at an SNR low enough to scatter them over every cell, beyond the hull, and onto decision boundaries."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    lay = o.Layout(N, occ, cp, mod)
+    rng = np.random.default_rng(int(snr))
+    _, xc = loopback_capture(lay, payloads(rng, 12), snr, 0.2, seed=77)
+    eng = OfdmEngine(N, occ, cp, mod)
+    nv = 12 * 8
+    bufs = eng.rx_alloc(len(xc), taps=True, max_vectors=nv)
+    eng.demodulate_async(torch.from_numpy(xc).cuda(), bufs)
+    torch.cuda.synchronize()
+    r = bufs["derot_syms"][:nv * lay.ncar].cpu().numpy().reshape(nv, lay.ncar)
+    sym = bufs["sym_idx"][:nv * lay.ncar].cpu().numpy().reshape(nv, lay.ncar)
+    used = np.abs(r).sum(axis=1) > 0                       # vectors some session demapped
+    assert used.sum() >= 10
+    c = o.constellation_for(mod).astype(np.complex64)
+    rr, ri = r[used].real.astype(np.float32), r[used].imag.astype(np.float32)
+    dx = rr[..., None] - c.real.astype(np.float32)
+    dy = ri[..., None] - c.imag.astype(np.float32)
+    dd = (dx * dx).astype(np.float32) + (dy * dy).astype(np.float32)
+    ref = np.argmin(dd, axis=-1)                           # first minimum in index order
+    assert np.array_equal(sym[used], ref.astype(np.uint8))
+    spread = np.unique(ref).size
+    assert spread >= (40 if mod == "qam64" else 100)       # the noise really exercised the table
+    eng.close()
