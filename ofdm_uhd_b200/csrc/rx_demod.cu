@@ -187,7 +187,8 @@ struct Slicer {
 };
 
 template <int N, bool TAPS>
-__global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E), (FftPlan<N>::E == 8 && !TAPS) ? 16 : 1) demod_kernel(const DemodParams p) {
+__global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E),
+                                  TAPS ? 1 : (FftPlan<N>::E == 8 ? 1024 : 512) / ((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E))) demod_kernel(const DemodParams p) {
     using P = FftPlan<N>;
     constexpr int E = P::E;
     constexpr int T = N / E;

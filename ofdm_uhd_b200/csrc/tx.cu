@@ -146,7 +146,7 @@ struct TxStore {
 };
 
 template <int N, int G>
-__global__ void __launch_bounds__(G * (N / FftPlan<N>::E), FftPlan<N>::E == 8 ? 4 : 1) tx_kernel(const TxParams p) {
+__global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ? 1024 : 512) / (G * (N / FftPlan<N>::E))) tx_kernel(const TxParams p) {
     constexpr int T = N / FftPlan<N>::E;
     constexpr int SB = fft_smem_elems<N>();
     extern __shared__ float2 smem[];
@@ -216,7 +216,7 @@ static int launch_tx_n(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int64_t want = (p.total_syms + G - 1) / G;
-    int64_t cap = (int64_t)sms * 16;
+    int64_t cap = (int64_t)sms * (64 / G);
     int grid = (int)(want < cap ? want : cap);
     tx_kernel<N, G><<<grid, G * T, smem, st>>>(p);
     OFDM_LAUNCH_CHECK();
@@ -236,7 +236,7 @@ int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32
         case 64:   return launch_tx_n<64, 8>(h, p, st);
         case 128:  return launch_tx_n<128, 8>(h, p, st);
         case 256:  return launch_tx_n<256, 8>(h, p, st);
-        case 512:  return launch_tx_n<512, 4>(h, p, st);
+        case 512:  return launch_tx_n<512, 2>(h, p, st);
         case 1024: return launch_tx_n<1024, 4>(h, p, st);
         case 2048: return launch_tx_n<2048, 2>(h, p, st);
         case 4096: return launch_tx_n<4096, 1>(h, p, st);
