@@ -115,6 +115,22 @@ struct BitDiv {
 
 __device__ __forceinline__ void pack_bytes(const uint8_t* sym, uint8_t* vb, int B0, int B1, int bit_base, unsigned carry,
                                            int tid, int nthreads, const BitDiv bd) {
+    if (!bd.by3) {
+        // nbits divides 8 (bpsk, qpsk, qam16, qam256): a symbol never straddles a byte, and bit_base is a multiple of
+        // nbits, so a byte is 8/nbits whole symbols (or the previous vector's leftover bits in their place)
+        const int nb = bd.nbits;
+        const unsigned smask = (1u << nb) - 1u;
+        for (int q = B0 + tid; q < B1; q += nthreads) {
+            unsigned byte = 0;
+            int rel = 8 * q - bit_base;
+            for (int sh = 0; sh < 8; sh += nb, rel += nb) {
+                const unsigned v = (rel < 0) ? ((carry >> sh) & smask) : (unsigned)sym[rel >> bd.sh];
+                byte |= v << sh;
+            }
+            vb[q - B0] = (uint8_t)byte;
+        }
+        return;
+    }
     for (int q = B0 + tid; q < B1; q += nthreads) {
         unsigned byte = 0;
 #pragma unroll
