@@ -12,7 +12,7 @@ int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, voi
     (void)h;
     if (n < 0) n = 0;
     if (max_frames < 1) max_frames = 1;
-    int64_t seg_len = (n + 148 * 32 - 1) / (148 * 32);     // one full wave of the detector kernel (32 one-warp CTAs per SM)
+    int64_t seg_len = (n + 148 * 24 - 1) / (148 * 24);     // one full wave of the detector kernel (24 one-warp CTAs per SM)
     if (seg_len < 65536) seg_len = 65536;
     seg_len = (seg_len + 31) / 32 * 32;
     ws->seg_len = seg_len;

@@ -215,6 +215,139 @@ __global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same metric for N/2 = m * 256 (N = 1024, 2048, 4096): a window still is [tail of the previous W-block] +
+// [head of this one], but a step (256 samples, 8 per lane) is only one of the m sub-steps of a block, so
+//   head(o) = C_j + in-step prefix,   C_j = sum of this block's sub-steps before j      (warp-uniform, float64)
+//   tail(o) = in-step suffix of the PREVIOUS block's sub-step j + D_j,  D_j = sum of that block's sub-steps after j
+// with the previous block's products recomputed from y[n-W] and y[n-2W] (three stream reads per sample instead of
+// one -- HBM has the room -- rather than W-wide per-lane history).  A warp walks MW_BLOCKS blocks after collecting
+// the m sub-step totals of the block in front of its chunk.
+// ---------------------------------------------------------------------------------------------
+constexpr int MW_MAX_SUB = 8;
+
+template <int K>
+__global__ void __launch_bounds__(32, 12) metric_wide_kernel(const float2* __restrict__ y, float* __restrict__ mt,
+                                                             const int64_t n, const int m, const int chunk_blocks) {
+    constexpr int SZ = 32 * K;
+    __shared__ double s_T[3][MW_MAX_SUB];            // sub-step totals of the block being walked
+    __shared__ double s_D[3][MW_MAX_SUB];            // previous block: sum of the sub-steps after j
+    MetricCtx<K> c;
+    c.y = y; c.mt = mt; c.n = n; c.lane = threadIdx.x;
+    c.vec_ok = (((uintptr_t)y) & 31) == 0;
+    c.st_ok = (((uintptr_t)mt) & 31) == 0 && (K % 4) == 0;
+    const int lane = c.lane;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        c.mu[k] = (lane >= (1 << k)) ? 1.0 : 0.0;
+        c.md[k] = (lane + (1 << k) < 32) ? 1.0 : 0.0;
+    }
+    const int64_t W = (int64_t)m * SZ;
+    const int64_t blk0 = (int64_t)blockIdx.x * chunk_blocks;
+    if (blk0 * W >= n) return;
+    // totals of the block in front of the chunk (zero history in front of the stream)
+    if (blk0 == 0) {
+        if (lane < 3 * MW_MAX_SUB) (&s_D[0][0])[lane] = 0.0;
+    } else {
+        for (int j = 0; j < m; ++j) {
+            const int64_t i0 = (blk0 - 1) * W + (int64_t)j * SZ;
+            float2 ya[K], yb[K];
+            c.load(ya, i0);
+            c.load(yb, i0 - W);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                double run = 0.0;
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    const float2 cc = cmulc_x(ya[i], yb[i]);
+                    const float xv = (a == 0) ? cc.x : (a == 1) ? cc.y : norm_x(ya[i]);
+                    run += (double)xv;
+                }
+                double fi = run;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) fi = fma(shfl_up_d(fi, 1 << k), c.mu[k], fi);
+                if (lane == 31) s_T[a][j] = fi;
+            }
+        }
+        __syncwarp();
+        if (lane < 3) {
+            double d = 0.0;
+            for (int j = m - 1; j >= 0; --j) { s_D[lane][j] = d; d += s_T[lane][j]; }
+        }
+    }
+    __syncwarp();
+    for (int64_t blk = blk0; blk < blk0 + chunk_blocks && blk * W < n; ++blk) {
+        double C[3] = {0.0, 0.0, 0.0};
+        for (int j = 0; j < m; ++j) {
+            const int64_t i0 = blk * W + (int64_t)j * SZ;
+            if (i0 >= n) break;
+            float2 yc[K], yp[K], ypp[K];
+            c.load(yc, i0);
+            c.load(yp, i0 - W);
+            c.load(ypp, i0 - 2 * W);
+            float PR[3][K];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                double pre[K], xq[K];
+                double run = 0.0, runp = 0.0;
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    const float2 cc = cmulc_x(yc[i], yp[i]);
+                    const float2 cq = cmulc_x(yp[i], ypp[i]);
+                    const float xv = (a == 0) ? cc.x : (a == 1) ? cc.y : norm_x(yc[i]);
+                    const float xw = (a == 0) ? cq.x : (a == 1) ? cq.y : norm_x(yp[i]);
+                    run += (double)xv; pre[i] = run;
+                    xq[i] = (double)xw; runp += xq[i];
+                }
+                double fi = run, bi = runp;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    fi = fma(shfl_up_d(fi, 1 << k), c.mu[k], fi);
+                    bi = fma(shfl_down_d(bi, 1 << k), c.md[k], bi);
+                }
+                const double tot = __shfl_sync(0xffffffffu, fi, 31);
+                const double head0 = fma(shfl_up_d(fi, 1), c.mu[0], C[a]);           // earlier lanes + earlier sub-steps
+                double sfx = fma(shfl_down_d(bi, 1), c.md[0], s_D[a][j]);           // later lanes + later sub-steps
+                double tail[K];
+                tail[K - 1] = sfx;
+#pragma unroll
+                for (int i = K - 2; i >= 0; --i) { sfx += xq[i + 1]; tail[i] = sfx; }
+#pragma unroll
+                for (int i = 0; i < K; ++i) PR[a][i] = (float)(tail[i] + (pre[i] + head0));
+                C[a] += tot;
+                if (lane == 0) s_T[a][j] = tot;
+            }
+            float q[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const float num = fadd_rn(fmul_rn(PR[0][i], PR[0][i]), fmul_rn(PR[1][i], PR[1][i]));
+                const float den = fmul_rn(PR[2][i], PR[2][i]);
+                q[i] = fdiv_rn(num, den);
+            }
+            const int64_t b0 = i0 + (int64_t)lane * K;
+            if (i0 + SZ <= n && c.st_ok) {
+                if constexpr (K == 8) {
+                    stg256(mt + b0, q);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < K; i += 4) *(float4*)(mt + b0 + i) = make_float4(q[i], q[i + 1], q[i + 2], q[i + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+                    if (b0 + i < n) mt[b0 + i] = q[i];
+            }
+        }
+        // this block's totals become the next block's "sub-steps after j" sums
+        __syncwarp();
+        if (lane < 3) {
+            double d = 0.0;
+            for (int j = m - 1; j >= 0; --j) { const double t = s_T[lane][j]; s_D[lane][j] = d; d += t; }
+        }
+        __syncwarp();
+    }
+}
+
 template <int K>
 struct DetectCtx {
     static constexpr int SZ = 32 * K;
@@ -224,7 +357,7 @@ struct DetectCtx {
     int lane;
     int64_t seg, s0, s1;
     bool vec_ok, cp_aligned;
-    int prime, cpq;
+    int prime, cpq, ring_mask;                       // ring_mask = steps in the ring - 1 (power of two)
     double tap, a1, a2, p32, plane;
     double pw[5], mu[5];
     double carry2 = 0.0;                             // prefix of the metric up to the previous step
@@ -275,7 +408,7 @@ struct DetectCtx {
         // ring layout [half][i][lane]: element i of lane l sits at i*32 + l, so every store and every load below is
         // stride-1 across the warp (a lane-major layout has lanes 64 B apart: 4-way bank conflicts on both sides,
         // which made the shared-memory pipe -- shared with the shuffles -- this kernel's bottleneck)
-        const int rb = (stepno & 1) * SZ;                        // ring half of this step
+        const int rb = (stepno & ring_mask) * SZ;                // ring slot of this step
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             mloc[i] += mex;
@@ -284,18 +417,19 @@ struct DetectCtx {
         __syncwarp();
         float v[K];
         if (cp_aligned) {
-            // n - cp sits cp/K lanes back, same element index: in this step's half or the previous one
+            // n - cp sits cp/K lanes back, same element index: in this step's slot or sb steps earlier
             const int ql = lane - cpq;
-            const double* src = ring + (ql >= 0 ? rb + ql : (rb ^ SZ) + 32 + ql);
+            const int sb = (ql < 0) ? ((31 - ql) >> 5) : 0;
+            const double* src = ring + ((stepno - sb) & ring_mask) * SZ + ql + 32 * sb;
 #pragma unroll
             for (int i = 0; i < K; ++i) v[i] = fadd_rn((float)((mloc[i] - src[i * 32]) * tap), -1.0f);
         } else {
 #pragma unroll
             for (int i = 0; i < K; ++i) {
                 int e = lane * K + i - p.cp;                     // position of n - cp relative to this step
-                int hb = rb;
-                if (e < 0) { e += SZ; hb = rb ^ SZ; }
-                const double prevS = ring[hb + (e % K) * 32 + e / K];
+                const int sb = (e < 0) ? ((SZ - 1 - e) / SZ) : 0;
+                e += sb * SZ;
+                const double prevS = ring[((stepno - sb) & ring_mask) * SZ + (e % K) * 32 + e / K];
                 v[i] = fadd_rn((float)((mloc[i] - prevS) * tap), -1.0f);
             }
         }
@@ -374,7 +508,7 @@ struct DetectCtx {
 };
 
 template <int K>
-__global__ void __launch_bounds__(32, 32) detect_seg_kernel(const StreamParams p, const float* __restrict__ mt) {
+__global__ void __launch_bounds__(32, 24) detect_seg_kernel(const StreamParams p, const float* __restrict__ mt, const int ring_steps) {
     constexpr int SZ = 32 * K;
     extern __shared__ __align__(16) double s_ring[];
     DetectCtx<K> c(p);
@@ -385,9 +519,11 @@ __global__ void __launch_bounds__(32, 32) detect_seg_kernel(const StreamParams p
     if (c.seg >= p.n_seg) return;
     c.s0 = c.seg * p.seg_len;
     c.s1 = (c.s0 + p.seg_len < p.n) ? c.s0 + p.seg_len : p.n;
-    int64_t w0 = c.s0 - OFDM_PEAK_WARM - SZ;
+    const int back = (p.cp + SZ - 1) / SZ;           // steps the cp window reaches back
+    int64_t w0 = c.s0 - OFDM_PEAK_WARM - (int64_t)back * SZ;
     if (w0 < 0) w0 = 0;
     w0 -= w0 % SZ;
+    c.ring_mask = ring_steps - 1;
     c.tap = (double)p.tapf;
     c.vec_ok = (((uintptr_t)mt) & 31) == 0 && (K % 4) == 0;
     c.cp_aligned = (p.cp % K) == 0;
@@ -408,9 +544,9 @@ __global__ void __launch_bounds__(32, 32) detect_seg_kernel(const StreamParams p
     }
     c.plane = 1.0;
     for (int k = 0; k < c.lane; ++k) c.plane *= a2k;
-    for (int i = c.lane; i < 2 * SZ; i += 32) c.ring[i] = 0.0;
+    for (int i = c.lane; i < ring_steps * SZ; i += 32) c.ring[i] = 0.0;
     __syncwarp();
-    c.prime = (w0 > 0) ? 1 : 0;                      // the first step's cp window reaches in front of w0
+    c.prime = (w0 > 0) ? back : 0;                   // steps whose cp window reaches in front of w0
     float q[K];
     int step = 0;
     if (w0 < p.n) c.load(q, w0);
@@ -424,23 +560,33 @@ __global__ void __launch_bounds__(32, 32) detect_seg_kernel(const StreamParams p
 __global__ void stream_init_kernel(int64_t* first_nan) { *first_nan = LLONG_MAX; }
 
 template <int K>
-static int launch_split_k(const StreamParams& p, float* mt, cudaStream_t st) {
+static int launch_split_k(const StreamParams& p, float* mt, int m, cudaStream_t st) {
     constexpr int SZ = 32 * K;
-    const int64_t chunks = (p.n + (int64_t)MC_STEPS * SZ - 1) / ((int64_t)MC_STEPS * SZ);
-    metric_chunk_kernel<K><<<(unsigned)chunks, 32, 0, st>>>(p.y, mt, p.n);
+    if (m == 1) {
+        const int64_t chunks = (p.n + (int64_t)MC_STEPS * SZ - 1) / ((int64_t)MC_STEPS * SZ);
+        metric_chunk_kernel<K><<<(unsigned)chunks, 32, 0, st>>>(p.y, mt, p.n);
+    } else {
+        const int chunk_blocks = (2 * MC_STEPS + m - 1) / m;             // ~64 sub-steps per warp: priming costs ~m light ones
+        const int64_t W = (int64_t)m * SZ;
+        const int64_t chunks = (p.n + W * chunk_blocks - 1) / (W * chunk_blocks);
+        metric_wide_kernel<K><<<(unsigned)chunks, 32, 0, st>>>(p.y, mt, p.n, m, chunk_blocks);
+    }
     OFDM_LAUNCH_CHECK();
-    detect_seg_kernel<K><<<(unsigned)p.n_seg, 32, sizeof(double) * 2 * SZ, st>>>(p, mt);
+    int ring_steps = 2;
+    while (ring_steps < (p.cp + SZ - 1) / SZ + 1) ring_steps *= 2;
+    detect_seg_kernel<K><<<(unsigned)p.n_seg, 32, sizeof(double) * ring_steps * SZ, st>>>(p, mt, ring_steps);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
 
-// returns 1 if the streaming kernels do not apply (the caller then runs the tile-parallel path): layouts outside
-// 32*K = N/2 with K in {2, 4, 8}, cp > N/2, or -- unless force -- streams too short to give every SM a few
+// returns 1 if the streaming kernels do not apply (the caller then runs the tile-parallel path): N = 64, cp > N/2, or -- unless force -- streams too short to give every SM a few
 // warps (one warp per >= 65 536-sample detector segment)
 int launch_sync_stream(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, int force,
                        cudaStream_t st) {
-    const int K = h->N / 64;                                     // 32*K = N/2
-    if (!(K == 2 || K == 4 || K == 8) || h->cp > 32 * K || ws->n_seg == 0 || !ws->mf) return 1;
+    // a step is 32*K samples: N/2 for N <= 512, else 256 with m = N/512 sub-steps per N/2-wide block
+    const int K = h->N >= 512 ? 8 : h->N / 64;
+    const int m = h->N >= 512 ? h->N / 512 : 1;
+    if (!(K == 2 || K == 4 || K == 8) || m > MW_MAX_SUB || h->cp > h->N / 2 || ws->n_seg == 0 || !ws->mf) return 1;
     if (!force && ws->n_seg < 148 * 8) return 1;
     StreamParams p;
     p.y = y; p.n = n; p.cp = h->cp; p.tapf = (float)(1.0 / (double)h->cp);
@@ -449,8 +595,8 @@ int launch_sync_stream(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* i
     stream_init_kernel<<<1, 1, 0, st>>>(p.first_nan);
     OFDM_LAUNCH_CHECK();
     switch (K) {
-        case 2: return launch_split_k<2>(p, ws->mf, st);
-        case 4: return launch_split_k<4>(p, ws->mf, st);
-        default: return launch_split_k<8>(p, ws->mf, st);
+        case 2: return launch_split_k<2>(p, ws->mf, 1, st);
+        case 4: return launch_split_k<4>(p, ws->mf, 1, st);
+        default: return launch_split_k<8>(p, ws->mf, m, st);
     }
 }
