@@ -407,3 +407,36 @@ def test_grid_slicer_equals_brute_force(N, occ, cp, mod, snr):
     spread = np.unique(ref).size
     assert spread >= (40 if mod == "qam64" else 100)       # the noise really exercised the table
     eng.close()
+
+
+@pytest.mark.parametrize("N,occ,cp", [(512, 200, 128), (1024, 400, 256), (4096, 3200, 512), (128, 56, 32)])
+def test_streaming_sync_edge_lengths(N, occ, cp):
+    """ofdm_rx_sync forces the streaming kernels (one warp per chunk / segment) whatever the length: streams shorter
+    than a step, a block, a chunk, with ragged tails and with a zero gap (NaN poisoning) must give the oracle's
+    triggers exactly."""
+    import torch
+    from ofdm_uhd_b200 import _lib
+    from ofdm_uhd_b200.engine import OfdmEngine
+    lay = o.Layout(N, occ, cp, "qpsk")
+    rng = np.random.default_rng(N)
+    _, xc = loopback_capture(lay, payloads(rng, 6), 30, 0.1, seed=N + 9)
+    y = o.chan_filter(xc, o.chan_filter_taps(lay))
+    eng = OfdmEngine(N, occ, cp, "qpsk")
+    W = N // 2
+    lengths = [1, 7, 255, 256, 257, W - 1, W, W + 1, 2 * W + 3, 5 * W - 1, 16385, len(y) - 3, len(y)]
+    for n in sorted(set(v for v in lengths if 0 < v <= len(y))):
+        yy = y[:n].copy()
+        if n > 6 * W:
+            yy[3 * W + 5: 4 * W + 90] = 0                     # an exactly-zero window: 0/0 = NaN from there on (C.1)
+        mf, Pr, Pi = o.sync_pn_metric(yy, N, cp)
+        trig = o.peak_detect(mf)
+        nan = np.flatnonzero(np.isnan(mf))
+        if len(nan):
+            trig = trig[trig < nan[0]]
+        bufs = eng.rx_alloc(n)
+        _lib.check(eng.L_.ofdm_rx_sync(eng.h, eng._p(torch.from_numpy(yy).cuda()), n, C.byref(bufs["io"]), eng._stream()))
+        _lib.check(eng.L_.ofdm_rx_plan(eng.h, n, C.byref(bufs["io"]), eng._stream()))
+        torch.cuda.synchronize()
+        nt = int(bufs["n_trig"].item())
+        assert np.array_equal(bufs["trig_idx"][:nt].cpu().numpy(), trig), (n,)
+    eng.close()
