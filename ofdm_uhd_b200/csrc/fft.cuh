@@ -83,8 +83,11 @@ template <int R, int S> struct DftReg {
 //   in(j + r*N/R), r<R  ->  twiddle by w^{r*(j mod Ns)*N/(Ns*R)}  ->  DFT_R  ->  out((j/Ns)*Ns*R + j mod Ns + r*Ns)
 // Functors also receive the compile-time register slot q*R + r of the point, so a caller can keep
 // first-pass inputs / last-pass outputs in a register array (slot <-> index tid + q*T + r*N/R).
-template <int N, int R, int NS, int S, class In, class Out>
+// BAR: __syncthreads() between the loads and the stores of the pass, for passes that read and write the SAME buffer
+// (allowed only when a thread's E points form one butterfly, E == R, so that every load precedes every store).
+template <int N, int R, int NS, int S, class In, class Out, bool BAR = false>
 HD void fft_pass(int tid, const float2* __restrict__ tw, In in, Out out) {
+    static_assert(!BAR || FftPlan<N>::E == R, "in-place pass needs one butterfly per thread");
     constexpr int E = FftPlan<N>::E;
     constexpr int T = N / E;
 #pragma unroll
@@ -93,6 +96,9 @@ HD void fft_pass(int tid, const float2* __restrict__ tw, In in, Out out) {
         float2 v[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = in(j + r * (N / R), q * R + r);
+#if defined(__CUDA_ARCH__)
+        if (BAR) __syncthreads();
+#endif
         const int k = j & (NS - 1);
         if (NS > 1) {
             // twiddles w^r, r < R: only the power-of-two exponents are loaded (3-4 loads instead of R-1, which

@@ -214,8 +214,11 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
     extern __shared__ double smem_d[];
     double* red = smem_d;                                   // [8*NW]
+    // N = 4096: two FFT buffers + H + dfe would be 125 KB, one CTA per SM; with a single buffer (in-place passes, a
+    // barrier between their loads and stores, no prefetch) two CTAs fit
+    constexpr bool ONEBUF = (N == 4096);
     float2* bufA = (float2*)(red + 8 * NW);
-    float2* bufB = bufA + SB;
+    float2* bufB = ONEBUF ? bufA : bufA + SB;
     float2* H = bufB + SB;                                  // [occ]
     float2* dfe = H + p.occ;                                // [ncar]
     float2* s_cst = dfe + p.occ;                            // [M]
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     const BitDiv bd(nbits);
     // Three-pass plans leave bufB idle while a vector is sliced: the next vector's samples are copied into it
     // asynchronously meanwhile, so the first FFT pass never waits on HBM.
-    constexpr bool PF = (P::NP == 3);
+    constexpr bool PF = (P::NP == 3) && !ONEBUF;
     auto prefetch = [&](int64_t st2) {
 #pragma unroll
         for (int i = 0; i < N / BT; ++i) {
@@ -302,9 +305,9 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
             if constexpr (P::NP == 2) {
                 if (tid < T) fft_pass<N, R1, R0, -1>(tid, p.tw, SmemIn{bufA}, ShiftStore<N>{S});
             } else {
-                if (tid < T) fft_pass<N, R1, R0, -1>(tid, p.tw, SmemIn{bufA}, SmemOut{bufB});
+                if (tid < T) fft_pass<N, R1, R0, -1, SmemIn, SmemOut, ONEBUF>(tid, p.tw, SmemIn{bufA}, SmemOut{bufB});
                 __syncthreads();
-                if (tid < T) fft_pass<N, R2, R0 * R1, -1>(tid, p.tw, SmemIn{bufB}, ShiftStore<N>{S});
+                if (tid < T) fft_pass<N, R2, R0 * R1, -1, SmemIn, ShiftStore<N>, ONEBUF>(tid, p.tw, SmemIn{bufB}, ShiftStore<N>{S});
             }
             __syncthreads();
             if (PF && vi < last_vi) {                       // bufB is free: fetch the vector that follows
@@ -524,7 +527,7 @@ static int launch_demod_nt(ofdm_handle* h, const DemodParams& p, int max_frames,
     constexpr int T = N / FftPlan<N>::E;
     constexpr int BT = T < 64 ? 64 : T;
     constexpr int NW = BT / 32;
-    size_t smem = sizeof(double) * 8 * NW + sizeof(float2) * (2 * (size_t)fft_smem_elems<N>() + 2 * (size_t)p.occ + p.M) +
+    size_t smem = sizeof(double) * 8 * NW + sizeof(float2) * ((N == 4096 ? 1 : 2) * (size_t)fft_smem_elems<N>() + 2 * (size_t)p.occ + p.M) +
                   ((p.ncar + 15) & ~15) + (size_t)((p.ncar * p.nbits / 8 + 16 + 15) & ~15) + (size_t)p.grid_L * p.grid_L;
     OFDM_SET_MAX_SMEM((demod_kernel<N, TAPS>), smem, h->device);
     int sms = 148;
