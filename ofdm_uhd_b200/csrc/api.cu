@@ -257,8 +257,18 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
     }
     std::vector<uint8_t> mask(4096);
     whitening_mask(mask.data());
-    std::vector<uint32_t> crct(256);
+    // CRC table, then x^(8*128*j) mod P (j < 32) and x^(8*r) mod P (r < 128): the shift factors with which the
+    // warp-per-packet CRC kernel combines the partial CRCs of 128-byte slices
+    std::vector<uint32_t> crct(256 + 32 + 128);
     crc_table(crct.data());
+    {
+        uint32_t s = 1u;                                            // the polynomial 1 = x^0
+        for (int r = 0; r <= 128 * 31; ++r) {
+            if (r < 128) crct[256 + 32 + r] = s;
+            if ((r & 127) == 0) crct[256 + (r >> 7)] = s;
+            s = crct[s >> 24] ^ (s << 8);                           // times x^8 mod P (one zero byte)
+        }
+    }
 
     int rc = 0;
     rc |= upload(&h->d_const, cst);

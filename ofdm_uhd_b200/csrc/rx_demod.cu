@@ -797,6 +797,85 @@ __global__ void __launch_bounds__(32) crc_kernel(const int32_t* __restrict__ n_f
     }
 }
 
+// unmake_packet for long packets: one warp per packet.  CRC-32 is linear over GF(2): lane l runs the table CRC over
+// its 128-byte slice (lane 0 from the all-ones preset, the others from 0) and the slice CRCs are combined after
+// multiplying each by x^(8 * bytes after the slice) mod P, the factor taken from two host tables (x^(1024 j), x^(8 r)).
+__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+#pragma unroll 4
+    for (int i = 31; i >= 0; --i) {
+        r = (r << 1) ^ ((r & 0x80000000u) ? 0x04C11DB7u : 0u);
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(128) crc_warp_kernel(const int32_t* __restrict__ n_frames, const uint8_t* __restrict__ live,
+                                                       const uint8_t* __restrict__ status, const int32_t* __restrict__ pkt_len,
+                                                       uint8_t* __restrict__ pkt_bytes, int stride, uint8_t* __restrict__ pkt_ok,
+                                                       const uint8_t* __restrict__ mask, const uint32_t* __restrict__ crctab,
+                                                       int64_t* __restrict__ counters) {
+    __shared__ uint32_t s_crc[256 + 32 + 128];
+    __shared__ uint32_t s_mask[1024];
+    for (int i = threadIdx.x; i < 256 + 32 + 128; i += blockDim.x) s_crc[i] = crctab[i];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_mask[i] = ((const uint32_t*)mask)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int F = *n_frames;
+    const int wpb = blockDim.x >> 5;
+    for (int f = blockIdx.x * wpb + (threadIdx.x >> 5); f < F; f += gridDim.x * wpb) {
+        const bool mine = live[f] && status[f] == 2;
+        uint8_t ok = 0;
+        int len = 0;
+        if (mine) {
+            len = pkt_len[f];
+            const int nst = len < stride ? len : stride;           // bytes present in the slot
+            const int Lc = len - 4;                                 // bytes under the CRC
+            uint32_t* row = (uint32_t*)(pkt_bytes + (size_t)f * stride);
+            const int b0 = lane * 128;
+            uint32_t crc = (lane == 0) ? 0xFFFFFFFFu : 0u;
+            uint32_t tail = 0;                                      // this lane's share of the 4 CRC bytes
+#pragma unroll 4
+            for (int w = 0; w < 32; ++w) {
+                const int b = b0 + 4 * w;
+                if (b >= nst) break;
+                const uint32_t keep = (b + 4 <= nst) ? 0xFFFFFFFFu : ((1u << (8 * (nst - b))) - 1u);
+                const uint32_t v = row[b >> 2] ^ (s_mask[(b >> 2) & 1023] & keep);     // bytes past nst are left alone
+                row[b >> 2] = v;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t byte = (v >> (8 * k)) & 0xFFu;
+                    const int i = b + k;
+                    if (i < Lc) crc = s_crc[(byte ^ (crc >> 24)) & 0xFFu] ^ (crc << 8);
+                    else if (Lc >= 0 && i < len && i < nst) tail |= byte << (8 * (3 - (i - Lc)));
+                }
+            }
+            // bytes of the CRC'd region that follow this lane's slice
+            int after = Lc - (b0 + 128);
+            if (after < 0) after = 0;
+            if (b0 >= Lc) crc = 0;                                  // no slice (lane 0 always has one when Lc > 0)
+            else crc = crc_mulmod(crc_mulmod(crc, s_crc[256 + (after >> 7)]), s_crc[256 + 32 + (after & 127)]);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                crc ^= __shfl_xor_sync(0xffffffffu, crc, d);
+                tail |= __shfl_xor_sync(0xffffffffu, tail, d);
+            }
+            if (Lc <= 0) crc = 0xFFFFFFFFu;                         // empty payload: the preset itself
+            ok = (len >= 4 && len <= stride && (~crc) == tail) ? 1 : 0;
+        }
+        if (lane == 0) {
+            pkt_ok[f] = ok;
+            if (mine) {
+                atomicAdd((unsigned long long*)&counters[1], 1ull);
+                if (ok) {
+                    atomicAdd((unsigned long long*)&counters[2], 1ull);
+                    atomicAdd((unsigned long long*)&counters[3], (unsigned long long)(len - 4));
+                }
+            }
+        }
+    }
+}
+
 int launch_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_t* sess_nvec, int32_t max_frames,
                     int32_t* next, int32_t* exitf, int32_t* overflow, uint8_t* live, int force_general, cudaStream_t st) {
     // exitf doubles as the flag bytes of next_kernel (the general walk overwrites it only after the fast path is done)
@@ -817,6 +896,14 @@ int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t 
     int rc = launch_liveness(io->n_frames, ws->vbase, ws->sess_nvec, io->max_frames, ws->next_frame, ws->exit_frame,
                              ws->live_overflow, io->frame_live, 0, st);
     if (rc) return rc;
+    if (io->pkt_stride >= 1024 && (io->pkt_stride & 3) == 0 && ((((uintptr_t)io->pkt_bytes) & 3) == 0)) {
+        int wgrid = (io->max_frames + 3) / 4;                       // long packets: a warp each
+        if (wgrid > 148 * 16) wgrid = 148 * 16;
+        crc_warp_kernel<<<wgrid, 128, 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len, io->pkt_bytes,
+                                               io->pkt_stride, io->pkt_ok, h->d_mask, h->d_crctab, io->counters);
+        OFDM_LAUNCH_CHECK();
+        return OFDM_OK;
+    }
     int grid = (io->max_frames + 31) / 32;
     if (grid > 148 * 32) grid = 148 * 32;
     const size_t row_smem = (size_t)32 * (io->pkt_stride / 4 + 1) * sizeof(uint32_t);

@@ -440,3 +440,32 @@ def test_streaming_sync_edge_lengths(N, occ, cp):
         nt = int(bufs["n_trig"].item())
         assert np.array_equal(bufs["trig_idx"][:nt].cpu().numpy(), trig), (n,)
     eng.close()
+
+
+def test_ragged_and_long_packets_dewhiten_crc():
+    """unmake_packet on the device for every slice shape of the warp-per-packet CRC (payloads of 0 .. 4091 bytes, one
+    with a corrupted byte) and, with small slots, of the staged thread-per-packet CRC: verdicts and bytes must equal
+    the oracle's."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    lay = o.Layout(512, 200, 128, "qam16")
+    rng = np.random.default_rng(99)
+    sizes = [0, 1, 3, 4, 123, 124, 125, 252, 1000, 2047, 4090, 4091, 402, 402]
+    pay = [bytes(rng.integers(0, 256, s, dtype=np.uint8)) for s in sizes]
+    pkts = [o.make_packet(p, 1, 1, False) for p in pay]
+    bad = bytearray(pkts[8]); bad[300] ^= 0x10; pkts[8] = bytes(bad)              # CRC must fail for the 1000-byte one
+    x = o.tx_modulate(pkts, lay, 0.25, seed=4)
+    lead = np.zeros(2 * lay.sym_len, dtype=np.complex64)
+    xc = o.channel(np.concatenate([lead, x, lead]), 45.0, 0.05, 512, seed=8, sig_power=float(np.mean(np.abs(x) ** 2)))
+    ref = o.rx_demodulate(xc, lay)
+    assert len(ref.packets) >= 13 and sum(1 for ok, _ in ref.packets if not ok) >= 1
+    for mpb in (4096, 1016, 420):
+        eng = OfdmEngine(512, 200, 128, "qam16", max_pkt_bytes=mpb)
+        got = eng.demodulate(torch.from_numpy(xc).cuda())
+        assert len(got.packets) == len(ref.packets)
+        for (gok, gp), (rok, rp) in zip(got.packets, ref.packets):
+            if len(rp) + 4 <= eng.pkt_stride:
+                assert (gok, gp) == (rok, rp)
+            else:
+                assert not gok                                                   # does not fit the slot: reported bad
+        eng.close()
