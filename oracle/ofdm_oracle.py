@@ -10,9 +10,13 @@ output.txt:1-3) that are not vendored in the reference tree, and neither
 GNU Radio nor Python 2 exists in this environment.  This file restates the
 published algorithm of those blocks as wired by the reference's own Python
 (ofdm.py:62-118,202-261; ofdm_receiver.py~:69-142; ofdm_packet_utils.py:84-191;
-secondary_tx.py:163-331), following SURVEY.md Appendix A.  The only in-tree
-data that pin tables exactly (whitening mask, known symbols, docstring
-examples) are checked in tests/test_oracle_tables.py.
+secondary_tx.py:163-331), following SURVEY.md Appendix A.  What the tree does
+pin is checked in tests/test_tables.py: the tables (whitening mask, known
+symbols, constellations, docstring examples) and -- the only recorded OUTPUTS of
+the path -- the console logs of the authors' sensing runs (output.txt,
+output_with_detection.txt: bin frequency / 10-dwell average / free flag /
+carrier-map hex of 32 sweeps), which the sensing decision stage reproduces
+exactly.  The modem stages remain unpinned.
 
 Precision policy: every inter-block stream is float32 /
 complex64; FIR / sliding sums, correlation sums, the slicer error sum and the

@@ -101,3 +101,23 @@ def test_hop_decision_on_device(N):
         else:
             assert newf is None
     tb.engine.close()
+
+
+def test_decide_kernel_equals_reference_console_logs():
+    """ofdm_sense_decide on the averages the reference itself printed (tests/golden/reference_sense_logs.npz): flags and
+    carrier-map hex strings must be the ones in the logs; ofdm_sense_hop's busy count must equal the count of 0 flags
+    in the printed window."""
+    import os
+    import torch
+    from ofdm_uhd_b200.engine import SenseEngine
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sense_logs.npz"))
+    se = SenseEngine(256)
+    for s in range(len(d["hex"])):
+        dwell = np.zeros((1, 256), dtype=np.float32)
+        dwell[0, (np.arange(256) + 128) % 256] = d["avg"][s].astype(np.float32)
+        avg, free, hx = se.decide(torch.from_numpy(dwell).cuda(), 1e-4)
+        assert hx == str(d["hex"][s]) and np.array_equal(free, d["flag"][s])
+        a_d, f_d, _ = se.decide_device(torch.from_numpy(dwell).cuda(), 1e-4)
+        busy, _, wlen = se.hop(a_d, f_d, 128)
+        assert wlen == 32 and busy == int((d["flag"][s][112:144] == 0).sum())
+    se.close()

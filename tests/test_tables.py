@@ -94,3 +94,27 @@ def test_blackmanharris_window():
     assert w.dtype == np.float32 and abs(float(w.max()) - 1.0) < 1e-3 and float(w.min()) < 1e-4
     # the (i+0.5)/(N-1) argument of GNU Radio 3.x makes it asymmetric by one sample (A.13)
     assert np.allclose(w[:-1], w[:-1][::-1], atol=1e-6) and int(np.argmax(w)) in (510, 511, 512)
+
+
+def test_sense_decision_equals_reference_console_logs():
+    """tests/golden/reference_sense_logs.npz holds what the reference's own sense_loop printed on the authors' radio
+    (output.txt, output_with_detection.txt: 32 sweeps x 256 bins of frequency / 10-dwell average / free flag, and the
+    carrier map hex_conv() made of them).  The oracle's decision half and the host mirror must reproduce every flag,
+    every hex string and every printed bin frequency."""
+    import os
+    from ofdm_uhd_b200 import sensing
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sense_logs.npz"))
+    avg, flag, hexes = d["avg"], d["flag"], d["hex"]
+    assert avg.shape == (32, 256) and float(np.min(np.abs(avg - 1e-4))) > 1e-7        # nothing sits on the threshold
+    for s in range(len(hexes)):
+        dwell = np.zeros((1, 256), dtype=np.float32)
+        dwell[0, (np.arange(256) + 128) % 256] = avg[s].astype(np.float32)           # frequency order -> FFT order
+        a, free, hx = o.sense_decide(dwell, 1e-4)                                     # threshold of that script variant
+        assert np.array_equal(free, flag[s]) and hx == str(hexes[s])
+        assert sensing.hex_conv(list(flag[s])) == str(hexes[s]) and o.hex_conv(list(flag[s])) == str(hexes[s])
+    # Python 2 printed the bin frequencies with str(float) = 12 significant digits
+    for i in range(256):
+        t = "%.12g" % sensing.sensed_frequency(900e6, 100e6 / 16, 256, i)
+        if "." not in t and "e" not in t:
+            t += ".0"
+        assert t == str(d["freq_txt"][0][i])
