@@ -277,8 +277,7 @@ def run_b200(args):
         else:
             ln.x = torch.zeros(n, dtype=torch.complex64, device=dev)
             ln.xc = torch.empty(n, dtype=torch.complex64, device=dev)
-            eng._ws_key = None                                     # a second, independent buffer set
-            ln.bufs = eng.rx_alloc(n, max_frames=F + 1024)
+            ln.bufs = eng.rx_alloc(n, max_frames=F + 1024, fresh=True)     # a second, independent buffer set
             ln.plan = eng.tx_plan(pay_off, pad_for_usrp=False)
         ln.xs = ln.x[lead:lead + n_sig]
         ln.d_pay = torch.empty_like(d_pay)

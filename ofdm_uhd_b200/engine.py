@@ -234,13 +234,15 @@ class OfdmEngine:
         return out
 
     # ------------------------------------------------------------------ receive
-    def rx_alloc(self, n: int, max_frames: Optional[int] = None, taps: bool = False, max_vectors: int = 0):
-        """Allocate (and cache) the output arrays + workspace of one receive call."""
+    def rx_alloc(self, n: int, max_frames: Optional[int] = None, taps: bool = False, max_vectors: int = 0,
+                 fresh: bool = False):
+        """Allocate (and cache) the output arrays + workspace of one receive call.  ``fresh=True`` always allocates an
+        independent buffer set (for callers that keep several receive calls in flight, one stream each)."""
         torch = self.torch
         if max_frames is None:
             max_frames = max(64, int(n // self.L) + 64)
         key = (int(n), int(max_frames), bool(taps), int(max_vectors))
-        if self._ws_key == key:
+        if self._ws_key == key and not fresh:
             return self._ws
         dev = self.dev
         need = int(self.L_.ofdm_rx_workspace_bytes(self.h, int(n), int(max_frames)))
@@ -277,7 +279,8 @@ class OfdmEngine:
         io.max_vectors = int(max_vectors) if taps else 0
         b["io"] = io
         b["n"] = int(n)
-        self._ws, self._ws_key = b, key
+        if not fresh:
+            self._ws, self._ws_key = b, key
         return b
 
     def demodulate_async(self, x, bufs=None, sync: str = "pn", nsymbols: int = 18, freq_offset: float = 0.0, **kw):

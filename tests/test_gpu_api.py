@@ -197,8 +197,7 @@ def test_collect_begin_end_equals_collect():
         refs.append(r)
     lanes = []
     for c in caps:
-        eng._ws_key = None
-        lanes.append((torch.cuda.Stream(), torch.from_numpy(c).cuda(), eng.rx_alloc(len(c))))
+        lanes.append((torch.cuda.Stream(), torch.from_numpy(c).cuda(), eng.rx_alloc(len(c), fresh=True)))
     torch.cuda.synchronize()
     tickets = []
     for st, x, bufs in lanes:
