@@ -121,3 +121,34 @@ def test_decide_kernel_equals_reference_console_logs():
         busy, _, wlen = se.hop(a_d, f_d, 128)
         assert wlen == 32 and busy == int((d["flag"][s][112:144] == 0).sum())
     se.close()
+
+
+def test_full_size_capture_properties():
+    """BASELINE configs[3] at its full size: 100 M samples = 97 656 frames of 1024, Blackman-Harris, dwell 12.
+    Size-independent properties: scaling the capture by 2 scales every max-hold power by exactly 4 (powers of two are
+    exact in float32), a capture made of two identical halves gives two identical halves of dwell vectors, and the
+    decision over any 10 dwells is the oracle's on those same dwell vectors."""
+    import torch
+    from ofdm_uhd_b200.engine import SenseEngine
+    N, dwell = 1024, 12
+    nfr = 100_000_000 // N
+    per_half = (nfr // 2) // dwell * dwell
+    g = torch.Generator(device="cuda").manual_seed(5)
+    half = torch.randn(per_half * N, 2, device="cuda", generator=g) * 1.5e-3
+    t = torch.arange(per_half * N, device="cuda", dtype=torch.float32)
+    half[:, 0] += 0.01 * torch.cos(2 * np.pi * 0.21 * t)
+    half[:, 1] += 0.01 * torch.sin(2 * np.pi * 0.21 * t)
+    x = torch.view_as_complex(torch.cat([half, half]).contiguous())
+    se = SenseEngine(N)
+    mh = se.maxhold(x, 0, dwell)
+    nd = mh.shape[0]
+    assert nd == 2 * per_half // dwell and nd >= 8100
+    assert torch.equal(mh[:nd // 2], mh[nd // 2:])
+    mh2 = se.maxhold(x * 2, 0, dwell)
+    assert torch.equal(mh2, mh * 4)
+    for g0 in (0, nd // 3, nd - 10):
+        avg, free, hx = se.decide(mh[g0:g0 + 10], 1e-3)
+        a2, f2, h2 = o.sense_decide(mh[g0:g0 + 10].cpu().numpy(), 1e-3)
+        assert hx == h2 and np.array_equal(free, f2) and np.array_equal(avg, a2)
+        assert (free == 0).sum() >= 1 and free[(N // 2 + int(0.21 * N)) % N] == 0       # the tone is seen as occupied
+    se.close()
