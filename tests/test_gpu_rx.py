@@ -529,3 +529,39 @@ def test_full_size_loopback_properties():
     assert abs(np.median(d) - 6400) <= 2 and (np.abs(d - 6400) <= 64).mean() > 0.99   # one trigger per frame (the
     # Schmidl-Cox plateau lets the arg-max wander inside the cyclic prefix at 20 dB)
     eng.close()
+
+
+def test_cfg5_stream_properties():
+    """One stream of BASELINE configs[4] (fft 4096 / occ 3200 / cp 512, QAM256, maximum 4091-byte payloads, 3 symbols
+    per frame) long enough for the streaming sync kernels: the wide (N/2 = 8 x 256) metric kernel, the multi-step
+    detector ring, the single-buffer N = 4096 demodulator, the 3 x 3-cell slicer and the warp-per-packet CRC all sit
+    on this path.  CRC-good payloads must be the ones sent; a second run must be identical."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    F, psize = 6000, 4091
+    eng = OfdmEngine(4096, 3200, 512, "qam256", 0.25, pad_seed=2)
+    rng = np.random.default_rng(31)
+    body = rng.integers(0, 256, size=(F, psize), dtype=np.uint8)
+    body[:, 0], body[:, 1] = np.arange(F) >> 8, np.arange(F) & 0xFF
+    plan = eng.tx_plan(np.arange(F + 1, dtype=np.int64) * psize)
+    assert plan.uniform_syms == 3 and plan.n_samples == F * 3 * 4608
+    lead = 2 * eng.L
+    n = plan.n_samples + 2 * lead
+    x = torch.zeros(n, dtype=torch.complex64, device="cuda")
+    xs = x[lead:lead + plan.n_samples]
+    eng.tx_run(plan, torch.from_numpy(body.reshape(-1)).cuda(), out=xs)
+    p_sig = float((xs[:1 << 22].abs() ** 2).mean())
+    xc = eng.channel(x, cfo=0.37, sigma=(p_sig / 10 ** 4.2 / 2) ** 0.5, seed=77)          # 42 dB
+    bufs = eng.rx_alloc(n, max_frames=F + 256)
+    r1 = eng.collect(eng.demodulate_async(xc, bufs), want_packets=False, want_payload=True)
+    sel, ok = r1.msg_frames, r1.pkt_ok.copy()
+    good = sel[ok[sel] == 1]
+    assert len(sel) >= F - 10 and len(good) >= 0.9 * F
+    got = r1.payload_rows[good, :psize].copy()
+    num = (got[:, 0].astype(np.int64) << 8) | got[:, 1]
+    assert np.all(np.diff(num) > 0) and np.array_equal(got, body[num])
+    trig1 = bufs["trig_idx"][:r1.n_trig].clone()
+    r2 = eng.collect(eng.demodulate_async(xc, bufs), want_packets=False, want_payload=True)
+    assert torch.equal(bufs["trig_idx"][:r2.n_trig], trig1) and np.array_equal(r2.pkt_ok, ok)
+    assert np.array_equal(r2.payload_rows[good, :psize], got)
+    eng.close()
