@@ -293,12 +293,18 @@ def run_b200(args):
             eng.demodulate_async(ln.xc, ln.bufs)
             ln.ticket = eng.collect_begin(ln.bufs, want_payload=True)
 
+    trace = [] if os.environ.get("OFDM_E2E_TRACE") else None
+
     def e2e_run(k_steps):
         last = None
         for k in range(k_steps):
+            t_a = time.perf_counter()
             e2e_launch(lanes[k % 2])
+            t_b = time.perf_counter()
             if k > 0:
                 last = eng.collect_end(lanes[(k - 1) % 2].ticket)
+            if trace is not None:
+                trace.append((t_b - t_a, time.perf_counter() - t_b))
         return eng.collect_end(lanes[(k_steps - 1) % 2].ticket)
 
     e2e_run(2)
@@ -308,6 +314,9 @@ def run_b200(args):
     r2 = e2e_run(e2e_steps)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if trace is not None:
+        sys.stderr.write("rank %d e2e %.2f ms/step; per step (enqueue ms, wait ms): %s\n" % (
+            rank, e2e_s * 1e3, " ".join("(%.2f,%.2f)" % (a * 1e3, b * 1e3) for a, b in trace[-e2e_steps:])))
     d2h = int(r2.payload_bytes_copied + r2.meta_bytes_copied)
     e2e_ok = int(r2.counters[2])
 
