@@ -255,21 +255,35 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
-__device__ __forceinline__ float2 channel_sample(float2 v, int64_t i, double w, double phase0, float sigma, uint64_t seed) {
+// e^{j(phase0 + w i)}: the phase is reduced in float64 (i runs to 10^9), the sine / cosine taken in float32
+__device__ __forceinline__ float2 channel_phasor(int64_t i, double w, double phase0) {
     double r = (phase0 + w * (double)i) * 0.15915494309189533577;        // turns
     r -= rint(r);
     float s, c;
     sincospif(2.0f * (float)r, &s, &c);
-    float2 o = make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+    return make_float2(c, s);
+}
+
+// complex Gaussian of standard deviation sigma per component, a pure function of (seed, sample index): Box-Muller on
+// two 23-bit uniforms cut from one 64-bit hash (mantissa stuffing instead of int -> float conversions: the XU pipe is
+// this kernel's bottleneck), fast intrinsics -- it is only noise
+__device__ __forceinline__ float2 channel_noise(int64_t i, float sigma, uint64_t seed) {
+    const uint64_t hsh = mix64(seed ^ (uint64_t)i * 0xD6E8FEB86659FD93ull);
+    const float u1 = __uint_as_float(0x3F800000u | (uint32_t)(hsh >> 41)) - 0.99999994f;      // (0, 1]
+    const float u2 = __uint_as_float(0x3F800000u | ((uint32_t)hsh & 0x7FFFFFu)) - 1.0f;      // [0, 1)
+    const float rad = sigma * sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.283185307f * u2, &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}
+
+__device__ __forceinline__ float2 channel_sample(float2 v, int64_t i, double w, double phase0, float sigma, uint64_t seed) {
+    const float2 ph = channel_phasor(i, w, phase0);
+    float2 o = make_float2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
     if (sigma > 0.f) {
-        const uint64_t hsh = mix64(seed ^ (uint64_t)i * 0xD6E8FEB86659FD93ull);
-        const float u1 = ((float)(uint32_t)(hsh >> 40) + 0.5f) * (1.0f / 16777216.0f);
-        const float u2 = ((float)(uint32_t)((hsh >> 8) & 0xFFFFFF) + 0.5f) * (1.0f / 16777216.0f);
-        const float rad = sigma * sqrtf(-2.0f * __logf(u1));             // Box-Muller, fast intrinsics: noise only
-        float sn, cs;
-        __sincosf(6.283185307f * u2, &sn, &cs);
-        o.x += rad * cs;
-        o.y += rad * sn;
+        const float2 g = channel_noise(i, sigma, seed);
+        o.x += g.x;
+        o.y += g.y;
     }
     return o;
 }
@@ -280,11 +294,21 @@ __global__ void __launch_bounds__(256) channel_kernel(const float2* __restrict__
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec) {
+        // two samples per thread and pass: the second phasor is the first one turned by e^{jw}
+        double sw, cw;
+        sincos(w, &sw, &cw);
+        const float2 step = make_float2((float)cw, (float)sw);
         const int64_t n2 = n >> 1;
         for (int64_t k = t; k < n2; k += stride) {
             const float4 q = __ldg((const float4*)x + k);
-            const float2 a = channel_sample(make_float2(q.x, q.y), 2 * k, w, phase0, sigma, seed);
-            const float2 b = channel_sample(make_float2(q.z, q.w), 2 * k + 1, w, phase0, sigma, seed);
+            const float2 p0 = channel_phasor(2 * k, w, phase0);
+            const float2 p1 = make_float2(p0.x * step.x - p0.y * step.y, p0.x * step.y + p0.y * step.x);
+            float2 a = make_float2(q.x * p0.x - q.y * p0.y, q.x * p0.y + q.y * p0.x);
+            float2 b = make_float2(q.z * p1.x - q.w * p1.y, q.z * p1.y + q.w * p1.x);
+            if (sigma > 0.f) {
+                const float2 ga = channel_noise(2 * k, sigma, seed), gb = channel_noise(2 * k + 1, sigma, seed);
+                a.x += ga.x; a.y += ga.y; b.x += gb.x; b.y += gb.y;
+            }
             ((float4*)y)[k] = make_float4(a.x, a.y, b.x, b.y);
         }
         if ((n & 1) && t == 0) y[n - 1] = channel_sample(x[n - 1], n - 1, w, phase0, sigma, seed);
