@@ -399,7 +399,10 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                     const int ia = LDG(p.sinkmap + c), ib = LDG(p.sinkmap + cb);
                     const float2 Ha = H[ia], Hb = H[ib];
                     const float2 Sa = S[ia + zl + delta], Sb = S[ib + zl + delta];
-                    const float2 eqa = cmul_x(cmul_x(Ha, cc), Sa), eqb = cmul_x(cmul_x(Hb, cc), Sb);
+                    // no coarse offset: comp = (1, -0) and H * comp is H itself (up to the sign of an exact zero, which no
+                    // comparison downstream can see), so the multiply is skipped
+                    const float2 Hca = (delta == 0) ? Ha : cmul_x(Ha, cc), Hcb = (delta == 0) ? Hb : cmul_x(Hb, cc);
+                    const float2 eqa = cmul_x(Hca, Sa), eqb = cmul_x(Hcb, Sb);
                     const float2 ra = cmul_x(cmul_x(eqa, car), d0a), rb = cmul_x(cmul_x(eqb, car), d0b);
                     int ba, bb;
                     if (p.grid_L > 0) {
