@@ -288,8 +288,51 @@ class ofdm_demod:
             self._print_verbage()
         self._watcher = _queue_watcher_thread(self._rcvd_pktq, callback)
         self.last = None
+        # continuous-stream mode (feed_stream): tail of the stream seen so far, its absolute position, and the
+        # absolute start of the last frame handed to the callback
+        self._carry = None
+        self._carry_abs = 0
+        self._last_abs_start = None
 
-    def feed(self, samples, max_frames=None):
+    def stream_carry_samples(self):
+        """Samples of the past that feed_stream() keeps in front of every new buffer: the detector's IIR warm-up
+        (24 576 samples), the channel-filter delay, and the longest frame the header can announce (4095 + 9 bytes),
+        so that a frame cut by a buffer boundary is demodulated whole by the next call."""
+        eng = self._engine
+        longest = 1 + -(-8 * (4095 + 9) // (eng.ncar * eng.nbits))
+        return 24576 + eng.ntaps + (longest + 1) * eng.L
+
+    def feed_stream(self, samples, max_frames=None):
+        """feed() for a source delivered in consecutive buffers (a file read in pieces, a radio): the receiver runs
+        on [carried tail | new samples] and only frames that start after the last delivered one reach the callback,
+        so every frame is delivered once, in order, wherever the buffer boundaries fall.  (The reference's flowgraph
+        is continuous; feed() by itself treats each buffer as a separate stream.)"""
+        import torch
+        if not isinstance(samples, torch.Tensor):
+            samples = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.complex64))
+        if samples.device.type != "cuda":
+            samples = samples.to(self._engine.dev)
+        buf = samples.contiguous() if self._carry is None else torch.cat([self._carry, samples.contiguous()])
+        abs0 = self._carry_abs
+        res = self.feed(buf, max_frames=max_frames, _deliver=False)
+        L = self._engine.L
+        # a frame still open at the end of the buffer (the sink ran out of vectors) is left to the next call
+        delivered = []
+        for k, f in enumerate(res.msg_frames):
+            start = abs0 + int(res.frame_start[f])
+            if self._last_abs_start is not None and start <= self._last_abs_start + L:
+                continue
+            self._last_abs_start = start
+            delivered.append(res.packets[k])
+        for ok, payload in delivered:
+            self._rcvd_pktq.insert_tail(_rx_message(ok, payload))
+        keep = min(self.stream_carry_samples(), buf.numel())
+        self._carry = buf[buf.numel() - keep:].clone()
+        self._carry_abs = abs0 + buf.numel() - keep
+        res.stream_delivered = delivered
+        return res
+
+    def feed(self, samples, max_frames=None, _deliver=True):
         """Run the receiver on one buffer of complex64 samples (cuda tensor, or host array copied to the
         device) and queue every packet the frame sink produced for the watcher thread.  Each call is a
         self-contained stream (filter history, detector average and NCO phase start from zero)."""
@@ -306,8 +349,9 @@ class ofdm_demod:
         else:
             res = self._engine.demodulate(samples, max_frames=max_frames)
         self.last = res
-        for ok, payload in res.packets:
-            self._rcvd_pktq.insert_tail(message(0, 0, 0, payload) if False else _rx_message(ok, payload))
+        if _deliver:
+            for ok, payload in res.packets:
+                self._rcvd_pktq.insert_tail(_rx_message(ok, payload))
         return res
 
     def _feed_logged(self, samples, max_frames):

@@ -25,6 +25,10 @@ class receive_path:
         """Run the receiver on one buffer of complex64 baseband samples."""
         return self.ofdm_rx.feed(samples, max_frames=max_frames)
 
+    def feed_stream(self, samples, max_frames=None):
+        """feed() for consecutive buffers of one continuous stream (see ofdm_demod.feed_stream)."""
+        return self.ofdm_rx.feed_stream(samples, max_frames=max_frames)
+
     def wait(self, timeout=None):
         self.ofdm_rx.wait(timeout)
 

@@ -213,3 +213,29 @@ def test_collect_begin_end_equals_collect():
             ln = int(r.pkt_len[f])
             assert r.payload_rows[f, :ln].tobytes() == ref.payload_rows[f, :ln].tobytes()
     eng.close()
+
+
+@pytest.mark.parametrize("chunk", [50_000, 131_072, 400_001])
+def test_feed_stream_equals_whole_stream(chunk):
+    """ofdm_demod.feed_stream on consecutive buffers of one capture delivers what feed() delivers on the whole capture:
+    every packet once, in order, wherever the buffer boundaries cut the frames."""
+    from helpers import payloads, loopback_capture
+    from ofdm_uhd_b200 import receive_path
+    lay = o.Layout(512, 200, 128, "qpsk")
+    rng = np.random.default_rng(3)
+    pay = payloads(rng, 150)
+    _, xc = loopback_capture(lay, pay, 28, 0.12, seed=15)
+    opts = options(modulation="qpsk")
+    whole, parts = [], []
+    rx1 = receive_path.receive_path(lambda ok, p: whole.append((ok, p)), opts)
+    rx1.feed(xc)
+    rx1.wait(timeout=60)
+    rx2 = receive_path.receive_path(lambda ok, p: parts.append((ok, p)), opts)
+    for a in range(0, len(xc), chunk):
+        rx2.feed_stream(xc[a:a + chunk])
+    rx2.wait(timeout=60)
+    assert len(whole) >= 145
+    good_w = [p for ok, p in whole if ok]
+    good_p = [p for ok, p in parts if ok]
+    assert good_p == good_w                                  # same good packets, same order, none twice
+    assert len(parts) == len(whole)
