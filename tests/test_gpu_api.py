@@ -261,3 +261,20 @@ def test_benchmark_loopback_example_script(tmp_path):
     assert n_right >= pktno - 2 and out.read_bytes() == got
     # the first frame after the CFO step may be lost (C.2): it is one of the 20 filler packets, so the file is whole
     assert got == data
+
+
+def test_secondary_user_example_script():
+    """examples/secondary_loopback.py: sense -> hop decision -> 920 MHz rendezvous -> file on the new frequency, the loop
+    of secondary_tx.py / secondary_rx.py, with every numeric stage on the GPU."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("sec_loop", os.path.join(root, "examples", "secondary_loopback.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    new_freq, tuned, data, got, state = mod.main(seed=3, verbose=False)
+    assert tuned == [new_freq] and new_freq % 100000 == 0 and abs(new_freq - 905e6) > 1e6     # away from the primary
+    # the receiver stores packets 21..70 (the reference's pktno window, secondary_rx.py:58-75): the 40 file packets, then
+    # the first ten of the transmitter's trailing filler packets -- as the reference pair would
+    assert got[:len(data)] == data and got[len(data):] == b"This is also Garbage data" * 10
+    assert state.n_right >= state.n_rcvd - 3
