@@ -2,6 +2,7 @@
 // Host-side table construction restates ofdm.py:71-101 (preamble / constellation wiring),
 // ofdm_receiver.py~:69-76 (firdes.low_pass design inputs) and SURVEY.md A.3/A.5/A.13.
 #include "internal.h"
+#include "fft.cuh"
 #include <algorithm>
 #include <ctype.h>
 #include <math.h>
@@ -121,9 +122,10 @@ template <class T> static int upload(T** dptr, const std::vector<T>& v) {
     return 0;
 }
 
+// per-pass, thread-ordered twiddle sections (fft.cuh: fft_fill_twiddles)
 static std::vector<float2> twiddles(int N) {
-    std::vector<float2> tw(N);
-    for (int i = 0; i < N; ++i) tw[i] = make_float2((float)cos(2 * M_PI * i / N), (float)(-sin(2 * M_PI * i / N)));
+    std::vector<float2> tw((size_t)fft_twiddle_elems(N), make_float2(0.f, 0.f));
+    fft_fill_twiddles_n(N, tw.data());
     return tw;
 }
 

@@ -25,6 +25,49 @@ template <> struct FftPlan<1024> { static constexpr int E = 16, NP = 3; static c
 template <> struct FftPlan<2048> { static constexpr int E = 16, NP = 3; static constexpr int R[4] = {8, 16, 16, 1}; };
 template <> struct FftPlan<4096> { static constexpr int E = 16, NP = 3; static constexpr int R[4] = {16, 16, 16, 1}; };
 
+// ---- twiddle table, one section per pass, laid out for the threads that read it -------------------------------
+// A pass of radix R after NS = 2^s points of earlier radices needs, per thread and butterfly, the log2(R) power-of-two
+// twiddles w^(r * (j mod NS) * N/(NS*R)), r = 1, 2, 4[, 8].  Read from the plain table exp(-2*pi*i*k/N) those loads are
+// strided by r (or hit NS distinct lines) and cost up to 16 L1 wavefronts each -- on kernels whose limit is the
+// L1/shared-memory data pipe.  Here section s holds them as [butterfly q][li][thread]: every load is 32 consecutive
+// float2.  Section s starts at s * N/2 (a section has at most N/4 * 4 / 2 entries); passes of the forward and of the
+// reversed radix order never share an NS with different radices, so one table serves both.
+HD constexpr int fft_ilog2(int v) { return v <= 1 ? 0 : 1 + fft_ilog2(v >> 1); }
+HD constexpr int fft_twiddle_elems(int N) { return 12 * (N / 2); }
+
+template <int N> inline void fft_fill_twiddles(float2* t) {           // t: fft_twiddle_elems(N) entries, zero-initialised
+    using P = FftPlan<N>;
+    constexpr int E = P::E, T = N / E;
+    auto fill = [&](int R, int NS) {
+        if (NS <= 1 || R <= 1) return;
+        const int s = fft_ilog2(NS), LG = fft_ilog2(R);
+        for (int q = 0; q < E / R; ++q)
+            for (int li = 0; li < LG; ++li)
+                for (int tid = 0; tid < T; ++tid) {
+                    const int k = (tid + q * T) & (NS - 1);
+                    const long idx = (long)(1 << li) * k * (N / (NS * R));
+                    const double a = 2.0 * 3.14159265358979323846 * (double)idx / (double)N;
+                    t[(size_t)s * (N / 2) + (size_t)(q * LG + li) * T + tid] = make_float2((float)cos(a), (float)(-sin(a)));
+                }
+    };
+    int NS = 1;
+    for (int p = 0; p < P::NP; ++p) { fill(P::R[p], NS); NS *= P::R[p]; }
+    NS = 1;
+    for (int p = P::NP - 1; p >= 0; --p) { fill(P::R[p], NS); NS *= P::R[p]; }
+}
+inline bool fft_fill_twiddles_n(int N, float2* t) {
+    switch (N) {
+        case 64: fft_fill_twiddles<64>(t); return true;
+        case 128: fft_fill_twiddles<128>(t); return true;
+        case 256: fft_fill_twiddles<256>(t); return true;
+        case 512: fft_fill_twiddles<512>(t); return true;
+        case 1024: fft_fill_twiddles<1024>(t); return true;
+        case 2048: fft_fill_twiddles<2048>(t); return true;
+        case 4096: fft_fill_twiddles<4096>(t); return true;
+    }
+    return false;
+}
+
 template <int N> HD constexpr int fft_threads() { return N / FftPlan<N>::E; }
 template <int N> HD constexpr int fft_smem_elems() { return FFT_PAD(N) + 1; }   // float2 elements per buffer
 
@@ -101,13 +144,15 @@ HD void fft_pass(int tid, const float2* __restrict__ tw, In in, Out out) {
 #endif
         const int k = j & (NS - 1);
         if (NS > 1) {
-            // twiddles w^r, r < R: only the power-of-two exponents are loaded (3-4 loads instead of R-1, which
-            // were the long-scoreboard stalls of every FFT kernel); the others are products of two loaded ones
+            // twiddles w^r, r < R: only the power-of-two exponents are loaded (3-4 coalesced loads from this pass's
+            // section of the table); the others are products of two loaded ones
             float2 w[R];
+            constexpr int LG = fft_ilog2(R);
+            const float2* twp = tw + fft_ilog2(NS) * (N / 2) + q * LG * T + tid;    // this pass, this butterfly, this thread
 #pragma unroll
-            for (int r = 1; r < R; r <<= 1) {
-                w[r] = LDG(tw + r * k * (N / (NS * R)));
-                if (S > 0) w[r].y = -w[r].y;
+            for (int li = 0; li < LG; ++li) {
+                w[1 << li] = LDG(twp + li * T);
+                if (S > 0) w[1 << li].y = -w[1 << li].y;
             }
 #pragma unroll
             for (int r = 3; r < R; ++r)

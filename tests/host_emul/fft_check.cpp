@@ -11,11 +11,9 @@
 template <int N, int S> double check() {
     using P = FftPlan<N>;
     constexpr int T = N / P::E;
-    std::vector<float2> tw(N), x(N), out(N), A(fft_smem_elems<N>()), B(fft_smem_elems<N>());
-    for (int i = 0; i < N; ++i) {
-        tw[i] = make_float2((float)cos(2 * M_PI * i / N), (float)-sin(2 * M_PI * i / N));
-        x[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
-    }
+    std::vector<float2> tw(fft_twiddle_elems(N), make_float2(0.f, 0.f)), x(N), out(N), A(fft_smem_elems<N>()), B(fft_smem_elems<N>());
+    fft_fill_twiddles<N>(tw.data());
+    for (int i = 0; i < N; ++i) x[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
     auto ld = [&](int i, int) { return x[i]; };
     auto st = [&](int i, float2 v, int) { out[i] = v; };
     constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
