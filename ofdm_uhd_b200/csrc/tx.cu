@@ -112,22 +112,33 @@ struct TxParams {
     float s1, amp;
 };
 
+// The carrier map and the bytes of the symbol are staged in shared memory before the first pass: from global memory
+// the map lookup and the packet byte it leads to are two dependent loads per carrier (a quarter of this kernel's
+// stall samples were long-scoreboard waits on them).
 template <int N>
 struct TxLoad {
     const TxParams& p;
-    const uint8_t* pkt;
+    const uint8_t* s_bytes;      // packet bytes from byte0 on (this symbol's share)
+    int byte0;
     int pkt_bits;
     int64_t frame_id;
     int dsym;                    // data symbol number inside the frame
     const float2* s_cst;
+    const int16_t* s_b2c;
     __device__ __forceinline__ float2 operator()(int idx, int) const {
         const int v = (idx + N / 2) & (N - 1);          // ifftshift: IFFT input idx holds vector bin v
-        const int c = LDG(p.bin2car + v);
+        const int c = s_b2c[v];
         if (c < 0) return make_float2(0.f, 0.f);
         const int bit0 = (dsym * p.ncar + c) * p.nbits;          // < 8 * 4112: 32-bit math
         uint32_t val;
-        if (bit0 + p.nbits <= pkt_bits) val = extract_bits32(pkt, bit0, p.nbits);
-        else val = pad_index(p.seed, (uint64_t)frame_id, (uint32_t)dsym, (uint32_t)c, (uint32_t)p.M);
+        if (bit0 + p.nbits <= pkt_bits) {
+            const int b = (bit0 >> 3) - byte0, sh = bit0 & 7;
+            uint32_t w = s_bytes[b];
+            if (sh + p.nbits > 8) w |= ((uint32_t)s_bytes[b + 1]) << 8;
+            val = (w >> sh) & ((1u << p.nbits) - 1u);
+        } else {
+            val = pad_index(p.seed, (uint64_t)frame_id, (uint32_t)dsym, (uint32_t)c, (uint32_t)p.M);
+        }
         return s_cst[val];
     }
 };
@@ -152,12 +163,18 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
     extern __shared__ float2 smem[];
     float2* s_cst = smem;                                  // [M]
     float2* bufs = smem + 256;                             // G * 2 * SB
+    int16_t* s_b2c = (int16_t*)(bufs + (size_t)G * 2 * SB);     // [N]
+    const int sym_bytes = (p.ncar * p.nbits + 7) / 8 + 2;       // bytes one symbol can touch (+ straddle)
+    const int sb_stride = (sym_bytes + 15) & ~15;
+    uint8_t* s_sym = (uint8_t*)(s_b2c + N);                     // [G][sb_stride]
     const int g = threadIdx.x / T;
     const int tid = threadIdx.x - g * T;
     for (int i = threadIdx.x; i < p.M; i += blockDim.x) s_cst[i] = p.cst[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_b2c[i] = p.bin2car[i];
     __syncthreads();
     float2* bufA = bufs + (size_t)g * 2 * SB;
     float2* bufB = bufA + SB;
+    uint8_t* my_bytes = s_sym + (size_t)g * sb_stride;
     const int L = N + p.cp;
     auto bar = [] { __syncthreads(); };
     const unsigned total = (unsigned)p.total_syms;               // launcher guarantees < 2^31
@@ -191,7 +208,16 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
         }
         const int64_t o0 = active ? LDG(p.pkt_off + f) : 0;
         const int64_t o1 = active ? LDG(p.pkt_off + f + 1) : 0;
-        TxLoad<N> ld{p, p.pkts + o0, (int)(o1 - o0) * 8, p.first_frame + f, m - 1, s_cst};
+        const int pkt_len = (int)(o1 - o0);
+        const int byte0 = data ? ((m - 1) * p.ncar * p.nbits) >> 3 : 0;
+        if (data) {                                              // (the barriers after the previous first pass cover my_bytes)
+            int nb = pkt_len - byte0;
+            if (nb > sym_bytes) nb = sym_bytes;
+            const uint8_t* src = p.pkts + o0 + byte0;
+            for (int i = tid; i < nb; i += T) my_bytes[i] = LDG(src + i);
+        }
+        bar();
+        TxLoad<N> ld{p, my_bytes, byte0, pkt_len * 8, p.first_frame + f, m - 1, s_cst, s_b2c};
         TxStore<N> st{dst, p.cp, p.s1, p.amp};
         using P = FftPlan<N>;
         constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
@@ -211,7 +237,9 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
 template <int N, int G>
 static int launch_tx_n(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
     constexpr int T = N / FftPlan<N>::E;
-    size_t smem = (256 + (size_t)G * 2 * fft_smem_elems<N>()) * sizeof(float2);
+    const int sym_bytes = (p.ncar * p.nbits + 7) / 8 + 2;
+    size_t smem = (256 + (size_t)G * 2 * fft_smem_elems<N>()) * sizeof(float2) + (size_t)N * sizeof(int16_t) +
+                  (size_t)G * ((sym_bytes + 15) & ~15);
     OFDM_SET_MAX_SMEM((tx_kernel<N, G>), smem, h->device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
