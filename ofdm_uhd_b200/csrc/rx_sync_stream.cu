@@ -133,10 +133,35 @@ struct MetricCtx {
         float PR[3][K];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            double pre[K];
-            double run = 0.0;
+            double pre[K], tail[K];
+            double run;
+            if constexpr (K == 8) {
+                // in-lane prefix and suffix sums as depth-3 trees instead of 7-deep chains: a warp issues in order, so
+                // the chains' latency, not the FP64 rate, paced this kernel
+                double xd[8], pd[8];
 #pragma unroll
-            for (int i = 0; i < K; ++i) { run += (double)cur.x[a][i]; pre[i] = run; }
+                for (int i = 0; i < 8; ++i) { xd[i] = (double)cur.x[a][i]; pd[i] = (double)prev.x[a][i]; }
+                const double s01 = xd[0] + xd[1], s23 = xd[2] + xd[3], s45 = xd[4] + xd[5], s67 = xd[6] + xd[7];
+                const double s0123 = s01 + s23, s4567 = s45 + s67;
+                pre[0] = xd[0]; pre[1] = s01; pre[2] = s01 + xd[2]; pre[3] = s0123;
+                pre[4] = s0123 + xd[4]; pre[5] = s0123 + s45; pre[6] = pre[5] + xd[6]; pre[7] = s0123 + s4567;
+                run = pre[7];
+                const double q67 = pd[6] + pd[7], q45 = pd[4] + pd[5], q23 = pd[2] + pd[3];
+                const double q4567 = q45 + q67;
+                const double b = prev.bwd[a];
+                // tail[i] = (later lanes) + sum of this lane's elements after i
+                tail[7] = b; tail[6] = b + pd[7]; tail[5] = b + q67; tail[4] = b + (pd[5] + q67);
+                tail[3] = b + q4567; tail[2] = b + (pd[3] + q4567); tail[1] = b + (q23 + q4567);
+                tail[0] = b + (pd[1] + (q23 + q4567));
+            } else {
+                run = 0.0;
+#pragma unroll
+                for (int i = 0; i < K; ++i) { run += (double)cur.x[a][i]; pre[i] = run; }
+                double sfx = prev.bwd[a];
+                tail[K - 1] = sfx;
+#pragma unroll
+                for (int i = K - 2; i >= 0; --i) { sfx += (double)prev.x[a][i + 1]; tail[i] = sfx; }
+            }
             double fi = run, bi = run;                           // inclusive scans: earlier lanes, later lanes
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
@@ -145,11 +170,6 @@ struct MetricCtx {
             }
             const double fwd = shfl_up_d(fi, 1) * mu[0];
             cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
-            double tail[K];
-            double sfx = prev.bwd[a];
-            tail[K - 1] = sfx;
-#pragma unroll
-            for (int i = K - 2; i >= 0; --i) { sfx += (double)prev.x[a][i + 1]; tail[i] = sfx; }
 #pragma unroll
             for (int i = 0; i < K; ++i) PR[a][i] = (float)(tail[i] + (pre[i] + fwd));
         }
