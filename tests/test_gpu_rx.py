@@ -565,3 +565,35 @@ def test_cfg5_stream_properties():
     assert torch.equal(bufs["trig_idx"][:r2.n_trig], trig1) and np.array_equal(r2.pkt_ok, ok)
     assert np.array_equal(r2.payload_rows[good, :psize], got)
     eng.close()
+
+
+@pytest.mark.parametrize("N,occ,cp", [(512, 200, 128), (4096, 3200, 512)])
+def test_degenerate_inputs_terminate_and_deliver_nothing(N, occ, cp):
+    """All-zero, astronomically large, denormal-small, NaN- and Inf-contaminated captures: both sync paths (tile and
+    forced streaming) must come back with no trigger, no frame and no message -- the reference's detector is poisoned
+    by a NaN metric for the rest of the stream (C.1), and noise alone never crosses its threshold."""
+    import torch
+    from ofdm_uhd_b200 import _lib
+    from ofdm_uhd_b200.engine import OfdmEngine
+    eng = OfdmEngine(N, occ, cp, "qpsk")
+    n = 300000
+    rng = np.random.default_rng(1)
+    base = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.01).astype(np.complex64)
+    nan_in, inf_in = base.copy(), base.copy()
+    nan_in[100000] = np.nan
+    inf_in[150000] = np.inf
+    cases = {"zeros": np.zeros(n, np.complex64), "huge": (base * 1e20).astype(np.complex64),
+             "tiny": (base * 1e-28).astype(np.complex64), "noise": base, "nan": nan_in, "inf": inf_in}
+    for name, x in cases.items():
+        d = torch.from_numpy(x).cuda()
+        r = eng.demodulate(d)
+        assert (r.n_trig, r.n_frames, len(r.packets)) == (0, 0, 0), name
+        bufs = eng.rx_alloc(n)
+        io, st = C.byref(bufs["io"]), eng._stream()
+        _lib.check(eng.L_.ofdm_rx_sync(eng.h, eng._p(d), n, io, st))            # streaming kernels, forced
+        _lib.check(eng.L_.ofdm_rx_plan(eng.h, n, io, st))
+        _lib.check(eng.L_.ofdm_rx_demod(eng.h, eng._p(d), n, io, st))
+        _lib.check(eng.L_.ofdm_rx_finish(eng.h, io, st))
+        r = eng.collect(bufs)
+        assert (r.n_trig, r.n_frames, len(r.packets)) == (0, 0, 0), name
+    eng.close()
