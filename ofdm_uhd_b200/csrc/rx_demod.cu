@@ -310,10 +310,20 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 if (tid < T) fft_pass<N, R2, R0 * R1, -1, SmemIn, ShiftStore<N>, ONEBUF>(tid, p.tw, SmemIn{bufB}, ShiftStore<N>{S});
             }
             __syncthreads();
-            if (PF && vi < last_vi) {                       // bufB is free: fetch the vector that follows
+            if ((PF || ONEBUF) && vi < last_vi) {           // fetch the vector that follows
                 int g2 = g, m2 = m + 1;
                 if (m2 > p.frame_ndata[g]) { ++g2; m2 = 0; }
-                if (g2 < F) prefetch(p.trig_idx[first_ok + g2] - N + 1 + (int64_t)m2 * L);
+                if (g2 < F) {
+                    const int64_t st2 = p.trig_idx[first_ok + g2] - N + 1 + (int64_t)m2 * L;
+                    if (PF) {
+                        prefetch(st2);                      // bufB is free: asynchronous copy into it
+                    } else {
+                        // single-buffer layout: no landing zone in shared memory, so at least pull the vector's lines
+                        // into L2 while this one is sliced (one 128-byte line per thread)
+                        for (int i = tid * 16; i < N; i += BT * 16)
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(p.y + st2 + i));
+                    }
+                }
             }
             // ---- ofdm_frame_acquisition: correlate + calculate_equalizer on a flagged vector ----
             if (flag) {
