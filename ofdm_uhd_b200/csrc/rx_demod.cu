@@ -310,7 +310,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 if (tid < T) fft_pass<N, R2, R0 * R1, -1, SmemIn, ShiftStore<N>, ONEBUF>(tid, p.tw, SmemIn{bufB}, ShiftStore<N>{S});
             }
             __syncthreads();
-            if ((PF || ONEBUF) && vi < last_vi) {           // fetch the vector that follows
+            if (vi < last_vi) {                             // fetch the vector that follows
                 int g2 = g, m2 = m + 1;
                 if (m2 > p.frame_ndata[g]) { ++g2; m2 = 0; }
                 if (g2 < F) {
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                     if (PF) {
                         prefetch(st2);                      // bufB is free: asynchronous copy into it
                     } else {
-                        // single-buffer layout: no landing zone in shared memory, so at least pull the vector's lines
+                        // two-pass plans and the single-buffer layout have no landing zone in shared memory: at least pull the vector's lines
                         // into L2 while this one is sliced (one 128-byte line per thread)
                         for (int i = tid * 16; i < N; i += BT * 16)
                             asm volatile("prefetch.global.L2 [%0];" :: "l"(p.y + st2 + i));
