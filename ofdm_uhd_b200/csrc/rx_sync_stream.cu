@@ -61,6 +61,23 @@ __device__ __forceinline__ void stg256(void* p, const float (&v)[8]) {
                  :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 
+// In-lane inclusive prefix and "elements after i" suffix sums of 8 doubles as depth-3 trees instead of 7-deep chains:
+// a warp issues in order, so the chains' latency, not the FP64 rate, paced the metric kernels.
+__device__ __forceinline__ void prefix8_tree(const double (&x)[8], double (&pre)[8]) {
+    const double s01 = x[0] + x[1], s23 = x[2] + x[3], s45 = x[4] + x[5], s67 = x[6] + x[7];
+    const double s0123 = s01 + s23, s4567 = s45 + s67;
+    pre[0] = x[0]; pre[1] = s01; pre[2] = s01 + x[2]; pre[3] = s0123;
+    pre[4] = s0123 + x[4]; pre[5] = s0123 + s45; pre[6] = pre[5] + x[6]; pre[7] = s0123 + s4567;
+}
+// tail[i] = b + sum of x[i+1 .. 7]   (b: what follows this lane)
+__device__ __forceinline__ void suffix8_tree(const double (&x)[8], const double b, double (&tail)[8]) {
+    const double q67 = x[6] + x[7], q45 = x[4] + x[5], q23 = x[2] + x[3];
+    const double q4567 = q45 + q67;
+    tail[7] = b; tail[6] = b + x[7]; tail[5] = b + q67; tail[4] = b + (x[5] + q67);
+    tail[3] = b + q4567; tail[2] = b + (x[3] + q4567); tail[1] = b + (q23 + q4567);
+    tail[0] = b + (x[1] + (q23 + q4567));
+}
+
 // one step's worth of per-lane history (ping-ponged between two instances so nothing is copied per step)
 template <int K>
 struct StepHist {
@@ -136,23 +153,12 @@ struct MetricCtx {
             double pre[K], tail[K];
             double run;
             if constexpr (K == 8) {
-                // in-lane prefix and suffix sums as depth-3 trees instead of 7-deep chains: a warp issues in order, so
-                // the chains' latency, not the FP64 rate, paced this kernel
                 double xd[8], pd[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { xd[i] = (double)cur.x[a][i]; pd[i] = (double)prev.x[a][i]; }
-                const double s01 = xd[0] + xd[1], s23 = xd[2] + xd[3], s45 = xd[4] + xd[5], s67 = xd[6] + xd[7];
-                const double s0123 = s01 + s23, s4567 = s45 + s67;
-                pre[0] = xd[0]; pre[1] = s01; pre[2] = s01 + xd[2]; pre[3] = s0123;
-                pre[4] = s0123 + xd[4]; pre[5] = s0123 + s45; pre[6] = pre[5] + xd[6]; pre[7] = s0123 + s4567;
+                prefix8_tree(xd, pre);
                 run = pre[7];
-                const double q67 = pd[6] + pd[7], q45 = pd[4] + pd[5], q23 = pd[2] + pd[3];
-                const double q4567 = q45 + q67;
-                const double b = prev.bwd[a];
-                // tail[i] = (later lanes) + sum of this lane's elements after i
-                tail[7] = b; tail[6] = b + pd[7]; tail[5] = b + q67; tail[4] = b + (pd[5] + q67);
-                tail[3] = b + q4567; tail[2] = b + (pd[3] + q4567); tail[1] = b + (q23 + q4567);
-                tail[0] = b + (pd[1] + (q23 + q4567));
+                suffix8_tree(pd, prev.bwd[a], tail);
             } else {
                 run = 0.0;
 #pragma unroll
@@ -308,16 +314,23 @@ __global__ void __launch_bounds__(32, 12) metric_wide_kernel(const float2* __res
             float PR[3][K];
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                double pre[K], xq[K];
-                double run = 0.0, runp = 0.0;
+                double pre[K], xq[K], xc[K];
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
                     const float2 cc = cmulc_x(yc[i], yp[i]);
                     const float2 cq = cmulc_x(yp[i], ypp[i]);
-                    const float xv = (a == 0) ? cc.x : (a == 1) ? cc.y : norm_x(yc[i]);
-                    const float xw = (a == 0) ? cq.x : (a == 1) ? cq.y : norm_x(yp[i]);
-                    run += (double)xv; pre[i] = run;
-                    xq[i] = (double)xw; runp += xq[i];
+                    xc[i] = (double)((a == 0) ? cc.x : (a == 1) ? cc.y : norm_x(yc[i]));
+                    xq[i] = (double)((a == 0) ? cq.x : (a == 1) ? cq.y : norm_x(yp[i]));
+                }
+                double run, runp;
+                if constexpr (K == 8) {
+                    prefix8_tree(xc, pre);
+                    run = pre[7];
+                    runp = ((xq[0] + xq[1]) + (xq[2] + xq[3])) + ((xq[4] + xq[5]) + (xq[6] + xq[7]));
+                } else {
+                    run = 0.0; runp = 0.0;
+#pragma unroll
+                    for (int i = 0; i < K; ++i) { run += xc[i]; pre[i] = run; runp += xq[i]; }
                 }
                 double fi = run, bi = runp;
 #pragma unroll
@@ -329,9 +342,13 @@ __global__ void __launch_bounds__(32, 12) metric_wide_kernel(const float2* __res
                 const double head0 = fma(shfl_up_d(fi, 1), c.mu[0], C[a]);           // earlier lanes + earlier sub-steps
                 double sfx = fma(shfl_down_d(bi, 1), c.md[0], s_D[a][j]);           // later lanes + later sub-steps
                 double tail[K];
-                tail[K - 1] = sfx;
+                if constexpr (K == 8) {
+                    suffix8_tree(xq, sfx, tail);
+                } else {
+                    tail[K - 1] = sfx;
 #pragma unroll
-                for (int i = K - 2; i >= 0; --i) { sfx += xq[i + 1]; tail[i] = sfx; }
+                    for (int i = K - 2; i >= 0; --i) { sfx += xq[i + 1]; tail[i] = sfx; }
+                }
 #pragma unroll
                 for (int i = 0; i < K; ++i) PR[a][i] = (float)(tail[i] + (pre[i] + head0));
                 C[a] += tot;
