@@ -278,3 +278,29 @@ def test_secondary_user_example_script():
     # the first ten of the transmitter's trailing filler packets -- as the reference pair would
     assert got[:len(data)] == data and got[len(data):] == b"This is also Garbage data" * 10
     assert state.n_right >= state.n_rcvd - 3
+
+
+def test_usrp_path_shims_loopback_and_retune():
+    """The scripts' own structure -- tb.txpath = usrp_transmit_path(options), tb.rxpath = usrp_receive_path(cb, options),
+    tb.txpath.send_pkt(payload, eof, carrier_map), tb.rxpath.u.u.set_center_freq(freq, 0) -- over the loop-back medium:
+    packets arrive while both ends are on the same frequency and stop arriving after the receiver retunes."""
+    from ofdm_uhd_b200 import usrp_transmit_path, usrp_receive_path, loopback_air
+    loopback_air.AIR.reset(noise_voltage=0.003, frequency_offset=0.1, seed=5)
+    opts = options(modulation="qpsk", tx_freq=905e6, rx_freq=905e6)
+    got = []
+    rxpath = usrp_receive_path.usrp_receive_path(lambda ok, p: got.append((ok, p)), opts)
+    txpath = usrp_transmit_path.usrp_transmit_path(opts, pad_seed=1)
+    pay = [struct.pack("!HH", i, 0) + bytes([i]) * 100 for i in range(12)]
+    for p in pay:
+        txpath.send_pkt(p, False, "FE7F")
+    txpath.send_pkt(eof=True)
+    rxpath.wait(timeout=60)
+    good = [p for ok, p in got if ok]
+    assert len(good) >= 11 and all(p in pay for p in good)
+    rxpath.u.u.set_center_freq(920e6, 0)                     # secondary_rx.py:85
+    n0 = len(got)
+    for p in pay:
+        txpath.send_pkt(p, False, "FE7F")
+    txpath.flush()
+    rxpath.wait(timeout=10)
+    assert len(got) == n0 and rxpath.u.history == [905e6, 920e6]

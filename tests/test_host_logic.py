@@ -131,3 +131,30 @@ def test_rendezvous_protocol_state_machines():
     assert rx.freq == 903700000
     rx.rx_callback(True, b"xy")                          # short payload counts as unmarked
     assert rx.sync == 1 and rx.freq == rv.SYNC_FREQ and tuned[-1] == rv.SYNC_FREQ
+
+
+def test_usrp_path_shims_options_and_missing_frequency():
+    """usrp_transmit_path / usrp_receive_path keep the reference's option surface (-f sets both frequencies,
+    usrp_transmit_path.py:28-38) and its SystemExit when no frequency is given (:54-56, usrp_receive_path.py:53-55)."""
+    sys.path.insert(0, os.path.join(ROOT, "ofdm_uhd_b200"))
+    try:
+        import importlib
+        utx = importlib.import_module("usrp_transmit_path")
+        urx = importlib.import_module("usrp_receive_path")
+        ofdm = importlib.import_module("ofdm")
+    finally:
+        sys.path.pop(0)
+    parser = optparse.OptionParser(conflict_handler="resolve")
+    expert = parser.add_option_group("Expert")
+    utx.add_options(parser, expert)
+    urx.add_options(parser, expert)
+    ofdm.ofdm_mod.add_options(parser, expert)
+    ofdm.ofdm_demod.add_options(parser, expert)
+    opts, args = parser.parse_args(["-f", "905e6", "-m", "qpsk", "--tx-amplitude", "0.3"])
+    assert opts.tx_freq == 905e6 and opts.rx_freq == 905e6 and opts.modulation == "qpsk" and opts.tx_amplitude == 0.3
+    opts2, _ = parser.parse_args([])
+    assert opts2.tx_freq is None
+    with pytest.raises(SystemExit):
+        utx.usrp_transmit_path(opts2)
+    with pytest.raises(SystemExit):
+        urx.usrp_receive_path(lambda ok, p: None, opts2)
