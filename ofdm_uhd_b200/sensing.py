@@ -121,3 +121,22 @@ def hop_decision(tb, avg_inorder_dev, free_dev, frequency, center_freq, ref_freq
     if busy < busy_limit or index < 0:
         return busy, None
     return busy, int(1e5 * math.ceil(sensed_frequency(center_freq, tb.samp_rate, size, index) / 1e5))
+
+
+def fft_save(capture, path="fft_data", fft_size=512, device=None, append=False):
+    """usrp_fft_save.fft (usrp_fft_save.py:44-62) without the radio: stream_to_vector(512) ->
+    fft_vcc(512, True, blackmanharris(512), shift=True) -> file_sink: the windowed, shifted spectra of consecutive
+    ``fft_size``-sample frames written as raw interleaved float32 (the layout utils/read_complex_binary.m:39-46 reads).
+    ``capture``: complex64 cuda tensor or NumPy array.  Returns the number of frames written."""
+    import torch
+    eng = SenseEngine(int(fft_size), device=device)
+    try:
+        x = capture if isinstance(capture, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(capture, dtype=np.complex64))
+        if x.device.type != "cuda":
+            x = x.to(eng.dev)
+        sp = eng.spectra(x.contiguous(), shift=True)
+        with open(path, "ab" if append else "wb") as f:
+            f.write(sp.cpu().numpy().astype(np.complex64).tobytes())
+        return int(sp.shape[0])
+    finally:
+        eng.close()

@@ -152,3 +152,16 @@ def test_full_size_capture_properties():
         assert hx == h2 and np.array_equal(free, f2) and np.array_equal(avg, a2)
         assert (free == 0).sum() >= 1 and free[(N // 2 + int(0.21 * N)) % N] == 0       # the tone is seen as occupied
     se.close()
+
+
+def test_fft_save_file_format(tmp_path):
+    """sensing.fft_save = usrp_fft_save.py's flowgraph: the file holds fftshift(fft(blackmanharris(512) * frame)) of every
+    512-sample frame as raw interleaved float32 (what utils/read_complex_binary.m reads back)."""
+    from ofdm_uhd_b200 import sensing
+    x = capture(512, 9, 3)
+    path = tmp_path / "fft_data"
+    n = sensing.fft_save(x[:9 * 512 - 100], str(path))                 # the incomplete last frame is dropped
+    assert n == 8
+    got = np.fromfile(str(path), dtype=np.complex64).reshape(n, 512)
+    assert rel_l2(got, o.sense_fft(x[:8 * 512], 512, True)) < 1e-4
+    assert sensing.fft_save(x[:512], str(path), append=True) == 1 and path.stat().st_size == 9 * 512 * 8
