@@ -79,13 +79,13 @@ template <int R, int K, int S> HD float2 tw_const(float2 o) {
     constexpr int Q = (16 / R) * K;                   // position on the 16-point circle
     if (Q == 0) return o;
     if (Q == 4) return S < 0 ? make_float2(o.y, -o.x) : make_float2(-o.y, o.x);
-    if (Q == 2) return make_float2(C8 * (o.x - S * o.y), C8 * (S * o.x + o.y));
-    if (Q == 6) return make_float2(C8 * (-o.x - S * o.y), C8 * (S * o.x - o.y));
+    if (Q == 2) return cmul_const(o, C8, S * C8);
+    if (Q == 6) return cmul_const(o, -C8, S * C8);
     float c = (Q == 1 || Q == 7) ? C16a : C16b;
     float s = (Q == 1 || Q == 7) ? C16b : C16a;
     if (Q == 5 || Q == 7) c = -c;
     // (x + jy)(c + jSs)
-    return make_float2(o.x * c - S * o.y * s, S * o.x * s + o.y * c);
+    return cmul_const(o, c, S * s);
 }
 
 template <int R, int S> struct DftReg;

@@ -7,6 +7,7 @@
 
 #define OFDM_MAX_TAPS 512
 #define OFDM_SAMPLER_TIMEOUT 1000       // digital_swig.py:4719-4720
+#define OFDM_SAMPLER_MAXDATA (OFDM_SAMPLER_TIMEOUT + 1)   // `if (d_timeout-- == 0)`: the FRAME state emits timeout + 1 data vectors
 #define OFDM_ACQ_MAX_SYMBOLS 1000       // upstream MAX_NUM_SYMBOLS
 #define OFDM_MAX_SHIFT 4                // digital_swig.py:4320 (max_fft_shift_len)
 #define OFDM_PEAK_WARM 24576            // samples of IIR warm-up before a detector segment

@@ -737,17 +737,17 @@ __global__ void __launch_bounds__(1024) plan_local_kernel(const PlanParams p) {
                 const int64_t tp = p.trig_idx[k - 1];
                 int64_t mm = ceil_div64(t - tp - 1, L);
                 if (mm < 1) mm = 1;
-                if (mm <= OFDM_SAMPLER_TIMEOUT) {
+                if (mm <= OFDM_SAMPLER_MAXDATA) {
                     ok = tp + 1 + mm * L < n;
                 } else {
-                    const int64_t q0 = tp + 1 + (int64_t)OFDM_SAMPLER_TIMEOUT * L;   // pos + N of the first NO_SIG call
+                    const int64_t q0 = tp + 1 + (int64_t)OFDM_SAMPLER_MAXDATA * L;   // pos + N of the first NO_SIG call
                     const int64_t c = (t - q0) / (L + 1);
                     ok = q0 + c * (L + 1) + L < n;
                 }
             }
             if (!ok) atomicMin(&p.hdr[2], k - first_ok);     // later ones fail too (pos only grows)
             // (4) data vectors of the frame
-            int64_t J = OFDM_SAMPLER_TIMEOUT;
+            int64_t J = OFDM_SAMPLER_MAXDATA;
             if (k + 1 < K) {
                 int64_t mm = ceil_div64(tn - t - 1, L);
                 if (mm < 1) mm = 1;

@@ -23,7 +23,9 @@ __device__ __forceinline__ void frame_one_packet(const uint8_t* src, int plen, u
         const uint8_t b = (uint8_t)(crc >> (24 - 8 * i));
         dst[4 + o] = whitening ? (uint8_t)(b ^ mask[o]) : b;
     }
-    for (; 4 + o < total; ++o) dst[4 + o] = whitening ? (uint8_t)(0x55 ^ mask[o & 4095]) : (uint8_t)0x55;
+    // the body never exceeds the 4096-byte mask: the host side rejects such payloads where the reference's
+    // make_packet raises (ofdm_packet_utils.py:117-135); nothing wraps around the table here
+    for (; 4 + o < total && o < 4096; ++o) dst[4 + o] = whitening ? (uint8_t)(0x55 ^ mask[o]) : (uint8_t)0x55;
 }
 
 __device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* src, int nbytes, int lane) {

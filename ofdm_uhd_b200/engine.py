@@ -131,17 +131,26 @@ class OfdmEngine:
         return int(self.L_.ofdm_frame_symbols(self.h, int(pkt_len)))
 
     # ------------------------------------------------------------------ transmit
+    @staticmethod
+    def _packet_lengths(plen: np.ndarray, pad_for_usrp: bool) -> np.ndarray:
+        """Framed length of every packet; ValueError where the reference's make_packet raises one
+        (ofdm_packet_utils.py:117-135): the whitened body payload || crc32 || 0x55 [|| padding] must fit the
+        4096-byte PN table, i.e. len(payload) <= 4091 (4087 with pad_for_usrp)."""
+        klen = plen + 9
+        if pad_for_usrp:
+            klen = (klen + 15) // 16 * 16
+        if len(klen) and int(klen.max()) - 4 > 4096:
+            raise ValueError("len(payload) must be in [0, %d]: payload || crc32 || 0x55%s exceeds the 4096-byte "
+                             "whitening table" % (4087 if pad_for_usrp else 4091, " || padding" if pad_for_usrp else ""))
+        return klen
+
     def tx_plan(self, payload_off: np.ndarray, pad_for_usrp: bool = False) -> TxPlan:
         """Everything about a batch that does not depend on the payload bytes."""
         torch = self.torch
         payload_off = np.ascontiguousarray(payload_off, dtype=np.int64)
         plen = np.diff(payload_off)
         F = len(plen)
-        if F and int(plen.max()) > 4092:
-            raise ValueError("len(payload) must be in [0, 4092]")
-        klen = plen + 9
-        if pad_for_usrp:
-            klen = (klen + 15) // 16 * 16
+        klen = self._packet_lengths(plen, pad_for_usrp)
         pkt_off = np.zeros(F + 1, dtype=np.int64)
         np.cumsum(klen, out=pkt_off[1:])
         per = self.ncar * self.nbits
@@ -182,11 +191,7 @@ class OfdmEngine:
         torch = self.torch
         payload_off = np.ascontiguousarray(payload_off, dtype=np.int64)
         plen = np.diff(payload_off)
-        if len(plen) and int(plen.max()) + 4 > 4095 + 1:
-            raise ValueError("len(payload) must be in [0, 4092]")
-        klen = plen + 9
-        if pad_for_usrp:
-            klen = (klen + 15) // 16 * 16
+        klen = self._packet_lengths(plen, pad_for_usrp)
         pkt_off = np.zeros(len(plen) + 1, dtype=np.int64)
         np.cumsum(klen, out=pkt_off[1:])
         pkts = torch.empty(int(pkt_off[-1]), dtype=torch.uint8, device=self.dev)

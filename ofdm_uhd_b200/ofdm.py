@@ -13,6 +13,7 @@ from __future__ import annotations
 import math
 import queue
 import threading
+import traceback
 
 import numpy as np
 
@@ -432,6 +433,7 @@ class _queue_watcher_thread(threading.Thread):
         self.callback = callback
         self.keep_running = True
         self._pending = 0
+        self.errors = 0
         self._cv = threading.Condition()
         _insert = rcvd_pktq.insert_tail
 
@@ -452,6 +454,11 @@ class _queue_watcher_thread(threading.Thread):
                     ok, payload = ofdm_packet_utils.unmake_packet(msg.to_string())
                 if self.callback:
                     self.callback(ok, payload)
+            except Exception:
+                # a failing user callback must not end the thread: later packets would never be delivered and
+                # wait() would block for ever on _pending
+                self.errors += 1
+                traceback.print_exc()
             finally:
                 with self._cv:
                     self._pending -= 1

@@ -19,18 +19,55 @@ class OcCfg(C.Structure):
                 ("constellation", C.POINTER(C.c_float)), ("amp", C.c_float), ("pad_seed", C.c_uint64)]
 
 
+STAMP = LIB + ".stamp"
+
+
+def _cpu_stamp() -> str:
+    """The library is built -march=native: a copy built on another CPU model (this container vs the GPU box) must be
+    rebuilt, not loaded.  Stamp = hash of the host's CPU flags + the Makefile."""
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = line
+                    break
+    except OSError:
+        pass
+    with open(os.path.join(HERE, "Makefile")) as f:
+        mk = f.read()
+    return hashlib.sha256((flags + mk).encode()).hexdigest()[:16]
+
+
 def build():
-    subprocess.run(["make", "-s", "-C", HERE], check=True)
+    subprocess.run(["make", "-s", "-C", HERE, "clean", "all"], check=True)
+    with open(STAMP, "w") as f:
+        f.write(_cpu_stamp())
+
+
+def _fresh() -> bool:
+    if not os.path.exists(LIB):
+        return False
+    if os.path.getmtime(os.path.join(HERE, "ofdm_oracle_c.c")) > os.path.getmtime(LIB):
+        return False
+    try:
+        with open(STAMP) as f:
+            return f.read().strip() == _cpu_stamp()
+    except OSError:
+        return False
 
 
 def available() -> bool:
-    return os.path.exists(LIB)
+    """True when the C port can be used here (built for this CPU, or gcc + make are present to build it)."""
+    import shutil
+    return _fresh() or (shutil.which("gcc") is not None and shutil.which("make") is not None)
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not available():
+        if not _fresh():
             build()
         L = C.CDLL(LIB)
         L.oc_tx.restype = C.c_int64
@@ -98,6 +135,6 @@ def time_loopback(mod="qpsk", frames=0, snr=20.0, threads=None):
     return {"value": float(samples / secs / 1e6), "unit": "Msamples/s", "cores": int(threads), "kind": "port",
             "ms": float(secs * 1e3),
             "sample": "%d threads x %d frames (%d samples in all) of the bench workload through the C port of the oracle "
-                      "(oracle/ofdm_oracle_c.c, gcc -O2, one independent stream per thread); %d/%d packets ok; "
+                      "(oracle/ofdm_oracle_c.c, gcc -O3 -march=native -ffp-contract=off, one independent stream per thread); %d/%d packets ok; "
                       "t_mod %.0f ms + t_demod %.0f ms" % (threads, frames, int(samples), int(nok), threads * frames,
                                                             out[4] * 1e3, out[5] * 1e3)}

@@ -672,9 +672,9 @@ def sampler_sim(trig: np.ndarray, n: int, N: int, L: int, timeout_max: int = 100
             starts.append(pos + L)
             flags.append(0)
             ndata[-1] += 1
+            if timeout == 0:                 # upstream `if (d_timeout-- == 0)`: post-decrement, so a frame carries
+                state = 0                    # up to timeout_max + 1 data vectors
             timeout -= 1
-            if timeout == 0:
-                state = 0
             pos += L
         else:
             pos += L + 1

@@ -443,7 +443,7 @@ int64_t oc_rx(const oc_cfg* c, const float* xin, int64_t n, int64_t* trig_out, f
             if (lo < nt && trig[lo] <= pos + L + N) {
                 vs = trig[lo] - N + 1; flag = 1; timeout = 1000; sstate = 2; pos = vs;
             } else if (sstate == 2) {
-                vs = pos + L; timeout--; if (timeout == 0) sstate = 0; pos += L;
+                vs = pos + L; if (timeout-- == 0) sstate = 0; pos += L;   /* post-decrement: up to 1001 data vectors */
             } else { pos += L + 1; continue; }
             ++nvec;
             /* derotate + FFT + shift */

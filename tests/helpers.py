@@ -32,6 +32,7 @@ def plan_closed_form(trig, n, N, L, timeout=1000):
     Returns (first_ok, frame_start[], n_data[])."""
     trig = [int(t) for t in trig]
     K = len(trig)
+    timeout = timeout + 1          # `if (d_timeout-- == 0)`: the FRAME state emits timeout + 1 data vectors
     first_ok = K
     for k in range(K):
         if trig[k] >= N:

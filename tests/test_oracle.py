@@ -76,6 +76,22 @@ def test_plan_closed_form_equals_sampler_calls():
         assert np.array_equal(ndc, nd), (case, trig, n, nd, ndc)
 
 
+def test_sampler_emits_timeout_plus_one_data_vectors():
+    # upstream `if (d_timeout-- == 0) d_state = STATE_NO_SIG` is a post-decrement: a lone trigger followed by more
+    # than 1001 symbols of signal-free stream yields exactly 1001 data vectors
+    N, L = 64, 80
+    trig = np.array([100], dtype=np.int64)
+    vs, vf, ft, nd = o.sampler_sim(trig, 100 + 1200 * L, N, L)
+    assert list(nd) == [1001] and len(vs) == 1002 and vf[0] == 1 and not vf[1:].any()
+    first_ok, st, ndc = plan_closed_form(trig, 100 + 1200 * L, N, L)
+    assert list(ndc) == [1001] and list(st) == [100 - N + 1]
+    # a second trigger caught by the first NO_SIG call: 1001 data vectors, then the new frame
+    trig = np.array([100, 100 + 1001 * L + 7], dtype=np.int64)
+    vs, vf, ft, nd = o.sampler_sim(trig, 100 + 1300 * L, N, L)
+    first_ok, st, ndc = plan_closed_form(trig, 100 + 1300 * L, N, L)
+    assert nd[0] == 1001 and np.array_equal(ndc, nd) and np.array_equal(st, trig[ft] - N + 1)
+
+
 CASES = [(512, 200, 128, "bpsk", 40, 0.0), (512, 200, 128, "qpsk", 20, 0.3), (512, 200, 128, "8psk", 30, 0.2),
          (512, 200, 128, "qam16", 25, -0.4), (1024, 400, 256, "qam64", 30, 1.3), (1024, 800, 256, "qam64", 30, 0.3),
          (4096, 3200, 512, "qam256", 38, 0.3)]

@@ -7,6 +7,9 @@ template <int OP> __global__ void k(float* out, float a, double b) {
     float f0 = a + threadIdx.x, f1 = a * 2 + threadIdx.x, f2 = a * 3, f3 = a * 5;
     double d0 = b + threadIdx.x, d1 = b * 2, d2 = b * 3, d3 = b * 5;
     unsigned u0 = threadIdx.x, u1 = 7;
+    unsigned long long q0 = 0x3f8000003f800000ull + threadIdx.x, q1 = 0x3f8000013f800001ull, q2 = 0x3f8000023f800002ull,
+                       q3 = 0x3f8000033f800003ull, qa = 0x3f8000103f800010ull;
+#pragma unroll 8
     for (int i = 0; i < ITER; ++i) {
         if (OP == 0) { f0 = __fmaf_rn(f0, a, f1); f1 = __fmaf_rn(f1, a, f2); f2 = __fmaf_rn(f2, a, f3); f3 = __fmaf_rn(f3, a, f0); }
         if (OP == 1) { d0 = __dadd_rn(d0, d1); d1 = __dadd_rn(d1, d2); d2 = __dadd_rn(d2, d3); d3 = __dadd_rn(d3, d0); }
@@ -21,9 +24,26 @@ template <int OP> __global__ void k(float* out, float a, double b) {
                        f0 += 1.f; f1 += 1.f; f2 += 1.f; f3 += 1.f; }
         if (OP == 5) { u0 = __shfl_up_sync(0xffffffffu, u0, 1); u1 = __shfl_up_sync(0xffffffffu, u1, 2);
                        u0 += u1; u1 ^= u0; }
+        if (OP == 8) {   // packed fp32: 4 independent FFMA2 chains (two fp32 FMAs per lane each)
+            asm volatile("fma.rn.f32x2 %0, %0, %4, %1;\n\tfma.rn.f32x2 %1, %1, %4, %2;\n\tfma.rn.f32x2 %2, %2, %4, %3;\n\tfma.rn.f32x2 %3, %3, %4, %0;"
+                         : "+l"(q0), "+l"(q1), "+l"(q2), "+l"(q3) : "l"(qa)); }
+        if (OP == 9) {   // FADD2
+            asm volatile("add.rn.f32x2 %0, %0, %1;\n\tadd.rn.f32x2 %1, %1, %2;\n\tadd.rn.f32x2 %2, %2, %3;\n\tadd.rn.f32x2 %3, %3, %0;"
+                         : "+l"(q0), "+l"(q1), "+l"(q2), "+l"(q3)); }
+        if (OP == 10) {  // 2 FFMA2 + 2 scalar FFMA interleaved
+            asm volatile("fma.rn.f32x2 %0, %0, %2, %1;\n\tfma.rn.f32x2 %1, %1, %2, %0;" : "+l"(q0), "+l"(q1) : "l"(qa));
+            f0 = __fmaf_rn(f0, a, f1); f1 = __fmaf_rn(f1, a, f0); }
+        if (OP == 11) {  // FADD x4 (scalar)
+            f0 = __fadd_rn(f0, f1); f1 = __fadd_rn(f1, f2); f2 = __fadd_rn(f2, f3); f3 = __fadd_rn(f3, f0); }
+        if (OP == 12) {  // 2 FFMA2 + 2 integer (alu pipe) ops
+            asm volatile("fma.rn.f32x2 %0, %0, %2, %1;\n\tfma.rn.f32x2 %1, %1, %2, %0;" : "+l"(q0), "+l"(q1) : "l"(qa));
+            u0 = (u0 ^ u1) + 3u; u1 = (u1 & u0) + 5u; }
+        if (OP == 13) {  // 2 scalar FFMA + 2 integer ops
+            f0 = __fmaf_rn(f0, a, f1); f1 = __fmaf_rn(f1, a, f0);
+            u0 = (u0 ^ u1) + 3u; u1 = (u1 & u0) + 5u; }
         if (OP == 6) { d0 = fma(d0, d1, d2); d1 = fma(d1, d2, d3); d2 = fma(d2, d3, d0); d3 = fma(d3, d0, d1); }
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = f0 + f1 + f2 + f3 + (float)(d0 + d1 + d2 + d3) + u0 + u1;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = f0 + f1 + f2 + f3 + (float)(d0 + d1 + d2 + d3) + u0 + u1 + (float)(q0 ^ q1 ^ q2 ^ q3);
 }
 template <int OP> void run(const char* name, double ops_per_iter) {
     float* out; cudaMalloc(&out, 148 * 8 * 128 * 4);
@@ -48,5 +68,11 @@ int main() {
     run<4>("fdiv_rn x4 (+4 FADD)", 4);
     run<7>("F2F f32->f64 x4 (+4 FADD)", 4);
     run<5>("SHFL x2", 2);
+    run<11>("FADD x4", 4);
+    run<8>("FFMA2 x4", 4);
+    run<9>("FADD2 x4", 4);
+    run<10>("FFMA2 x2 + FFMA x2", 4);
+    run<12>("FFMA2 x2 + int x4 (count FFMA2)", 2);
+    run<13>("FFMA x2 + int x4 (count FFMA)", 2);
     return 0;
 }
