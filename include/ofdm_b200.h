@@ -47,6 +47,12 @@ typedef struct ofdm_cfg {
 
 const char* ofdm_last_error(void);
 int ofdm_version(void);
+/* Device self-test of the packed-fp32 (FFMA2 / FADD2 / FMUL2) arithmetic helpers the kernels are built on: n random
+ * operand sets (zeros, denormals, huge values included) through every helper of the decision paths -- the ones that
+ * replace the individually rounded float32 operations of ofdm_frame_acquisition / ofdm_frame_sink (ofdm.py:238-247,
+ * ofdm_receiver.py~:127-129) -- against their scalar definitions.  host_out2[0] = operand sets with any mismatch
+ * (must be 0), host_out2[1] = OR of the failing helpers' bits.  Synchronous; not part of the hot path. */
+int ofdm_selftest_packed_math(int32_t device, int64_t n, uint64_t seed, int64_t* host_out2);
 
 ofdm_handle* ofdm_create(const ofdm_cfg* cfg);
 void ofdm_destroy(ofdm_handle* h);
@@ -76,6 +82,17 @@ int32_t ofdm_frame_symbols(const ofdm_handle* h, int32_t pkt_len);
 int ofdm_tx_modulate_batch(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames,
                            int64_t first_frame, const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms,
                            float* out_iq, void* stream);
+
+/* The same transmit chain for the frames of several independent streams in one launch (the transmit side of
+ * ofdm_rx_demodulate_batch; the reference runs one benchmark_ofdm_tx.py flowgraph per stream): frames
+ * [stream_frame0[s], stream_frame0[s+1]) belong to stream s, whose first OFDM symbol is written at
+ * out[stream_out_off[s]] (complex samples) and whose later symbols follow it back to back; the frames of a stream are
+ * numbered from first_frame again and its pad carriers use pad_seed + s.  stream_frame0: DEVICE int64[S+1]
+ * (stream_frame0[0] = 0, stream_frame0[S] = n_frames), stream_out_off: DEVICE int64[S]. */
+int ofdm_tx_modulate_streams(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames,
+                             int64_t first_frame, const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms,
+                             const int64_t* stream_frame0, const int64_t* stream_out_off, int32_t n_streams,
+                             float* out_iq, void* stream);
 
 /* ---- receive -------------------------------------------------------------------------------- */
 typedef struct ofdm_rx_io {
@@ -148,6 +165,25 @@ int ofdm_rx_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_
                      int32_t* scratch, uint8_t* live, int force_general, void* stream);
 /* all of the above in order, no host synchronisation */
 int ofdm_rx_demodulate(ofdm_handle* h, const float* x_iq, int64_t n, ofdm_rx_io* io, void* stream);
+/* ---- many independent streams in one call ---------------------------------------------------------------
+ * The reference's unit of work is one flowgraph per stream (benchmark_ofdm_rx.py:42-87 builds one
+ * ofdm_receiver chain, ofdm_receiver.py~:131-142, per capture); BASELINE configs[2] runs 64 of them.  Here the S
+ * streams lie back to back in ONE sample buffer, stream s = samples [stream_off[s], stream_off[s+1]), and every
+ * kernel of the chain takes the stream index from its grid: each stream starts from zero history (filter, window
+ * sums, detector average, NCO phase, sink state) exactly as if it had been passed to ofdm_rx_demodulate alone, and
+ * no launch is repeated per stream.
+ *   stream_off : DEVICE int64[S+1], ascending, stream_off[0] >= 0 (offsets that are multiples of 4 samples keep
+ *                the 32-byte vector accesses)
+ *   io         : one ofdm_rx_io whose arrays hold S consecutive per-stream tables: every [max_frames] array becomes
+ *                [S][max_frames] (io->max_frames = capacity PER STREAM), pkt_bytes [S][max_frames][pkt_stride],
+ *                status / n_trig / n_frames [S], counters [S][8]; workspace >= ofdm_rx_workspace_bytes_batch().
+ *                The parity taps (eq_syms / sym_idx / derot_syms) must be NULL.
+ *   total_samples, max_stream_samples : stream_off[S] and the longest stream (host knowledge for grid sizing).
+ * Layouts without the streaming synchroniser (fft_length 64, cp_length > fft_length/2) return OFDM_E_INVAL. */
+size_t ofdm_rx_workspace_bytes_batch(const ofdm_handle* h, int32_t n_streams, int64_t total_samples,
+                                     int64_t max_stream_samples, int32_t max_frames_per_stream);
+int ofdm_rx_demodulate_batch(ofdm_handle* h, const float* x_iq, const int64_t* stream_off, int32_t n_streams,
+                             int64_t total_samples, int64_t max_stream_samples, ofdm_rx_io* io, void* stream);
 /* pointers into the workspace for parity tests: which = 0 filtered stream y (2n floats), 1 metric mf (n floats) */
 void* ofdm_rx_workspace_ptr(const ofdm_handle* h, const ofdm_rx_io* io, int64_t n, int which);
 

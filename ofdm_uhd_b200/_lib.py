@@ -14,11 +14,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libofdm_b200.so")
 
 EXPORTS = [
-    "ofdm_last_error", "ofdm_version", "ofdm_create", "ofdm_destroy", "ofdm_set_tx_amplitude", "ofdm_get_layout",
-    "ofdm_get_chan_taps", "ofdm_packet_len", "ofdm_make_packets", "ofdm_frame_symbols", "ofdm_tx_modulate_batch",
+    "ofdm_last_error", "ofdm_version", "ofdm_selftest_packed_math", "ofdm_create", "ofdm_destroy", "ofdm_set_tx_amplitude", "ofdm_get_layout",
+    "ofdm_get_chan_taps", "ofdm_packet_len", "ofdm_make_packets", "ofdm_frame_symbols", "ofdm_tx_modulate_batch", "ofdm_tx_modulate_streams",
     "ofdm_rx_workspace_bytes", "ofdm_rx_chan_filter", "ofdm_rx_sync_metric", "ofdm_rx_peak_detect", "ofdm_rx_sync",
     "ofdm_rx_plan",
-    "ofdm_rx_demod", "ofdm_rx_finish", "ofdm_rx_liveness", "ofdm_rx_sync_fixed", "ofdm_rx_demodulate_fixed", "ofdm_rx_demodulate", "ofdm_rx_workspace_ptr", "ofdm_channel",
+    "ofdm_rx_demod", "ofdm_rx_finish", "ofdm_rx_liveness", "ofdm_rx_sync_fixed", "ofdm_rx_demodulate_fixed", "ofdm_rx_demodulate", "ofdm_rx_workspace_bytes_batch", "ofdm_rx_demodulate_batch", "ofdm_rx_workspace_ptr", "ofdm_channel",
     "ofdm_sense_create", "ofdm_sense_destroy", "ofdm_sense", "ofdm_sense_fft", "ofdm_sense_decide", "ofdm_sense_hop",
 ]
 
@@ -52,6 +52,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     vp, i32, i64, u64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
     L.ofdm_last_error.restype = C.c_char_p
     L.ofdm_version.restype = C.c_int
+    L.ofdm_selftest_packed_math.argtypes = [i32, i64, u64, C.POINTER(i64)]
     L.ofdm_create.restype = vp
     L.ofdm_create.argtypes = [C.POINTER(OfdmCfg)]
     L.ofdm_destroy.argtypes = [vp]
@@ -65,6 +66,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.ofdm_frame_symbols.argtypes = [vp, i32]
     L.ofdm_frame_symbols.restype = i32
     L.ofdm_tx_modulate_batch.argtypes = [vp, vp, vp, i32, i64, vp, i64, i32, vp, vp]
+    L.ofdm_tx_modulate_streams.argtypes = [vp, vp, vp, i32, i64, vp, i64, i32, vp, vp, i32, vp, vp]
     L.ofdm_rx_workspace_bytes.argtypes = [vp, i64, i32]
     L.ofdm_rx_workspace_bytes.restype = C.c_size_t
     L.ofdm_rx_chan_filter.argtypes = [vp, vp, i64, vp, vp]
@@ -78,6 +80,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.ofdm_rx_sync_fixed.argtypes = [vp, i64, i32, f32, C.POINTER(RxIo), vp]
     L.ofdm_rx_demodulate_fixed.argtypes = [vp, vp, i64, i32, f32, C.POINTER(RxIo), vp]
     L.ofdm_rx_demodulate.argtypes = [vp, vp, i64, C.POINTER(RxIo), vp]
+    L.ofdm_rx_workspace_bytes_batch.argtypes = [vp, i32, i64, i64, i32]
+    L.ofdm_rx_workspace_bytes_batch.restype = C.c_size_t
+    L.ofdm_rx_demodulate_batch.argtypes = [vp, vp, vp, i32, i64, i64, C.POINTER(RxIo), vp]
     L.ofdm_rx_workspace_ptr.argtypes = [vp, C.POINTER(RxIo), i64, C.c_int]
     L.ofdm_rx_workspace_ptr.restype = vp
     L.ofdm_channel.argtypes = [vp, vp, i64, f32, f64, f32, u64, vp, vp]

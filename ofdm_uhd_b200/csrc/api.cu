@@ -145,6 +145,8 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
     ofdm_handle* h = new ofdm_handle();
     memset(h, 0, sizeof(*h));
     h->device = cfg->device;
+    h->sms = 148;
+    cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, cfg->device);
     h->N = N; h->occ = occ; h->cp = cp; h->L = N + cp; h->M = M; h->nbits = nbits;
     h->zl = (int)ceil((N - occ) / 2.0);
     h->amp = fmaxf(0.f, fminf(cfg->tx_amplitude, 1.f));
@@ -345,22 +347,45 @@ extern "C" int ofdm_tx_modulate_batch(ofdm_handle* h, const uint8_t* pkts, const
     NEED(h);
     if (n_frames <= 0) return OFDM_OK;
     if (uniform_syms <= 0 && !sym_off) { ofdm_set_error("tx: sym_off required for ragged frames"); return OFDM_E_INVAL; }
-    return launch_tx(h, pkts, pkt_off, n_frames, first_frame, sym_off, total_syms, uniform_syms, (float2*)out_iq,
-                     (cudaStream_t)stream);
+    return launch_tx(h, pkts, pkt_off, n_frames, first_frame, sym_off, total_syms, uniform_syms, nullptr, nullptr, 0,
+                     (float2*)out_iq, (cudaStream_t)stream);
+}
+
+extern "C" int ofdm_tx_modulate_streams(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames,
+                                        int64_t first_frame, const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms,
+                                        const int64_t* stream_frame0, const int64_t* stream_out_off, int32_t n_streams,
+                                        float* out_iq, void* stream) {
+    NEED(h);
+    if (n_frames <= 0) return OFDM_OK;
+    if (uniform_syms <= 0 && !sym_off) { ofdm_set_error("tx: sym_off required for ragged frames"); return OFDM_E_INVAL; }
+    if (n_streams < 1 || !stream_frame0 || !stream_out_off) { ofdm_set_error("tx streams: bad stream tables"); return OFDM_E_INVAL; }
+    return launch_tx(h, pkts, pkt_off, n_frames, first_frame, sym_off, total_syms, uniform_syms, stream_frame0, stream_out_off,
+                     n_streams, (float2*)out_iq, (cudaStream_t)stream);
 }
 
 extern "C" size_t ofdm_rx_workspace_bytes(const ofdm_handle* h, int64_t n, int32_t max_frames) {
     if (!h) return 0;
     size_t need = 0;
     RxWorkspace ws;
-    rx_workspace_layout(h, n, max_frames, nullptr, 0, &ws, &need);
+    rx_workspace_layout(h, single_stream(n), max_frames, nullptr, 0, &ws, &need);
     return need;
 }
 
-static int get_ws(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws) {
+extern "C" size_t ofdm_rx_workspace_bytes_batch(const ofdm_handle* h, int32_t n_streams, int64_t total_samples,
+                                                int64_t max_stream_samples, int32_t max_frames_per_stream) {
+    if (!h || n_streams < 1) return 0;
+    StreamSet ss;
+    ss.S = n_streams; ss.off = nullptr; ss.n_max = max_stream_samples; ss.n_total = total_samples;
+    size_t need = 0;
+    RxWorkspace ws;
+    rx_workspace_layout(h, ss, max_frames_per_stream, nullptr, 0, &ws, &need);
+    return need;
+}
+
+static int get_ws(ofdm_handle* h, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws) {
     if (!io || !io->workspace) { ofdm_set_error("rx: null io/workspace"); return OFDM_E_INVAL; }
     size_t need = 0;
-    int rc = rx_workspace_layout(h, n, io->max_frames, io->workspace, io->workspace_bytes, ws, &need);
+    int rc = rx_workspace_layout(h, ss, io->max_frames, io->workspace, io->workspace_bytes, ws, &need);
     if (rc) ofdm_set_error("rx: workspace too small (%zu < %zu)", io->workspace_bytes, need);
     return rc;
 }
@@ -369,7 +394,7 @@ extern "C" void* ofdm_rx_workspace_ptr(const ofdm_handle* h, const ofdm_rx_io* i
     if (!h || !io) return nullptr;
     RxWorkspace ws;
     size_t need = 0;
-    if (rx_workspace_layout(h, n, io->max_frames, io->workspace, io->workspace_bytes, &ws, &need)) return nullptr;
+    if (rx_workspace_layout(h, single_stream(n), io->max_frames, io->workspace, io->workspace_bytes, &ws, &need)) return nullptr;
     switch (which) {
         case 0: return ws.y;
         case 1: return ws.mf;
@@ -385,7 +410,7 @@ extern "C" void* ofdm_rx_workspace_ptr(const ofdm_handle* h, const ofdm_rx_io* i
 extern "C" int ofdm_rx_chan_filter(ofdm_handle* h, const float* x, int64_t n, float* y, void* stream) {
     NEED(h);
     if (n <= 0) return OFDM_OK;
-    return launch_chan_filter(h, (const float2*)x, n, (float2*)y, (cudaStream_t)stream);
+    return launch_chan_filter(h, (const float2*)x, single_stream(n), (float2*)y, (cudaStream_t)stream);
 }
 
 extern "C" int ofdm_rx_sync_metric(ofdm_handle* h, const float* y, int64_t n, float* mf, int64_t* first_nan, void* stream) {
@@ -397,7 +422,7 @@ extern "C" int ofdm_rx_peak_detect(ofdm_handle* h, const float* y, const float* 
                                    ofdm_rx_io* io, void* stream) {
     NEED(h);
     RxWorkspace ws;
-    int rc = get_ws(h, n, io, &ws);
+    int rc = get_ws(h, single_stream(n), io, &ws);
     if (rc) return rc;
     OFDM_CUDA_CHECK(cudaMemsetAsync(ws.nco_init, 0, sizeof(double), (cudaStream_t)stream));
     return launch_peak_detect(h, (const float2*)y, mf, n, first_nan, io, &ws, (cudaStream_t)stream);
@@ -406,25 +431,25 @@ extern "C" int ofdm_rx_peak_detect(ofdm_handle* h, const float* y, const float* 
 extern "C" int ofdm_rx_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, void* stream) {
     NEED(h);
     RxWorkspace ws;
-    int rc = get_ws(h, n, io, &ws);
+    int rc = get_ws(h, single_stream(n), io, &ws);
     if (rc) return rc;
-    return launch_plan(h, n, io, &ws, (cudaStream_t)stream);
+    return launch_plan(h, single_stream(n), io, &ws, (cudaStream_t)stream);
 }
 
 extern "C" int ofdm_rx_demod(ofdm_handle* h, const float* y, int64_t n, ofdm_rx_io* io, void* stream) {
     NEED(h);
     RxWorkspace ws;
-    int rc = get_ws(h, n, io, &ws);
+    int rc = get_ws(h, single_stream(n), io, &ws);
     if (rc) return rc;
-    return launch_demod(h, (const float2*)y, n, io, &ws, (cudaStream_t)stream);
+    return launch_demod(h, (const float2*)y, single_stream(n), io, &ws, (cudaStream_t)stream);
 }
 
 extern "C" int ofdm_rx_finish(ofdm_handle* h, ofdm_rx_io* io, void* stream) {
     NEED(h);
     RxWorkspace ws;
-    int rc = get_ws(h, 0, io, &ws);
+    int rc = get_ws(h, single_stream(0), io, &ws);
     if (rc) return rc;
-    return launch_finish(h, io, &ws, (cudaStream_t)stream);
+    return launch_finish(h, 1, io, &ws, (cudaStream_t)stream);
 }
 
 extern "C" int ofdm_rx_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_t* sess_nvec, int32_t max_frames,
@@ -433,49 +458,72 @@ extern "C" int ofdm_rx_liveness(const int32_t* n_frames, const int64_t* vbase, c
         ofdm_set_error("ofdm_rx_liveness: null argument or max_frames < 1");
         return OFDM_E_INVAL;
     }
-    return launch_liveness(n_frames, vbase, sess_nvec, max_frames, scratch, scratch + max_frames, scratch + 2 * max_frames,
-                           live, force_general, (cudaStream_t)stream);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return launch_liveness(sms, 1, n_frames, vbase, (int64_t)max_frames + 1, sess_nvec, max_frames, scratch, scratch + max_frames,
+                           scratch + 2 * max_frames, live, force_general, (cudaStream_t)stream);
 }
 
-// ofdm_sync_pn: the fused streaming kernel where the layout allows it (32*K = N/2, cp <= N/2), else the
-// metric kernel followed by the detector kernel
-static int rx_sync(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, int force_fused,
+// ofdm_sync_pn: the streaming kernel pair where the layout allows it (N >= 128, cp <= N/2), else -- single stream
+// only -- the tile-parallel metric kernel followed by the detector kernel
+static int rx_sync(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, int force_fused,
                    cudaStream_t st) {
-    OFDM_CUDA_CHECK(cudaMemsetAsync(io->status, 0, sizeof(uint32_t), st));
-    OFDM_CUDA_CHECK(cudaMemsetAsync(ws->nco_init, 0, sizeof(double), st));     // sample_and_hold starts at 0
-    int rc = launch_sync_stream(h, y, n, io, ws, force_fused, st);
-    if (rc == 0) return launch_trig_compact(h, y, n, io, ws, st);
+    OFDM_CUDA_CHECK(cudaMemsetAsync(io->status, 0, sizeof(uint32_t) * ss.S, st));
+    OFDM_CUDA_CHECK(cudaMemsetAsync(ws->nco_init, 0, sizeof(double) * ss.S, st));     // sample_and_hold starts at 0
+    int rc = launch_sync_stream(h, y, ss, io, ws, force_fused, st);
+    if (rc == 0) return launch_trig_compact(h, y, ss, io, ws, st);
     if (rc < 0) return rc;
-    if ((rc = launch_sync_metric(h, y, n, ws->mf, ws->first_nan, st))) return rc;
-    return launch_peak_detect(h, y, ws->mf, n, ws->first_nan, io, ws, st);
+    if (ss.S > 1 || ss.off) {
+        ofdm_set_error("rx batch: this layout (fft_length %d, cp_length %d) has no streaming synchroniser; feed its streams one by one", h->N, h->cp);
+        return OFDM_E_INVAL;
+    }
+    if ((rc = launch_sync_metric(h, y, ss.n_max, ws->mf, ws->first_nan, st))) return rc;
+    return launch_peak_detect(h, y, ws->mf, ss.n_max, ws->first_nan, io, ws, st);
 }
 
 extern "C" int ofdm_rx_sync(ofdm_handle* h, const float* y, int64_t n, ofdm_rx_io* io, void* stream) {
     NEED(h);
     RxWorkspace ws;
-    int rc = get_ws(h, n, io, &ws);
+    int rc = get_ws(h, single_stream(n), io, &ws);
     if (rc) return rc;
-    return rx_sync(h, (const float2*)y, n, io, &ws, 1, (cudaStream_t)stream);
+    return rx_sync(h, (const float2*)y, single_stream(n), io, &ws, 1, (cudaStream_t)stream);
+}
+
+static int rx_chain(ofdm_handle* h, const float2* x, const StreamSet& ss, ofdm_rx_io* io, cudaStream_t st) {
+    RxWorkspace ws;
+    int rc = get_ws(h, ss, io, &ws);
+    if (rc) return rc;
+    if ((rc = launch_chan_filter(h, x, ss, ws.y, st))) return rc;
+    if ((rc = rx_sync(h, ws.y, ss, io, &ws, 0, st))) return rc;
+    if ((rc = launch_plan(h, ss, io, &ws, st))) return rc;
+    if ((rc = launch_demod(h, ws.y, ss, io, &ws, st))) return rc;
+    return launch_finish(h, ss.S, io, &ws, st);
 }
 
 extern "C" int ofdm_rx_demodulate(ofdm_handle* h, const float* x, int64_t n, ofdm_rx_io* io, void* stream) {
     NEED(h);
-    RxWorkspace ws;
-    int rc = get_ws(h, n, io, &ws);
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = launch_chan_filter(h, (const float2*)x, n, ws.y, st))) return rc;
-    if ((rc = rx_sync(h, ws.y, n, io, &ws, 0, st))) return rc;
-    if ((rc = launch_plan(h, n, io, &ws, st))) return rc;
-    if ((rc = launch_demod(h, ws.y, n, io, &ws, st))) return rc;
-    return launch_finish(h, io, &ws, st);
+    return rx_chain(h, (const float2*)x, single_stream(n), io, (cudaStream_t)stream);
+}
+
+extern "C" int ofdm_rx_demodulate_batch(ofdm_handle* h, const float* x, const int64_t* stream_off, int32_t n_streams,
+                                        int64_t total_samples, int64_t max_stream_samples, ofdm_rx_io* io, void* stream) {
+    NEED(h);
+    if (n_streams < 1 || !stream_off || total_samples < 0 || max_stream_samples < 0 || max_stream_samples > total_samples) {
+        ofdm_set_error("ofdm_rx_demodulate_batch: bad stream set");
+        return OFDM_E_INVAL;
+    }
+    if (n_streams > 65535) { ofdm_set_error("ofdm_rx_demodulate_batch: more than 65535 streams in one call"); return OFDM_E_INVAL; }
+    StreamSet ss;
+    ss.S = n_streams; ss.off = stream_off; ss.n_max = max_stream_samples; ss.n_total = total_samples;
+    return rx_chain(h, (const float2*)x, ss, io, (cudaStream_t)stream);
 }
 
 extern "C" int ofdm_rx_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_offset, ofdm_rx_io* io,
                                   void* stream) {
     NEED(h);
     RxWorkspace ws;
-    int rc = get_ws(h, n, io, &ws);
+    int rc = get_ws(h, single_stream(n), io, &ws);
     if (rc) return rc;
     return launch_sync_fixed(h, n, nsymbols, freq_offset, io, &ws, (cudaStream_t)stream);
 }
@@ -484,14 +532,15 @@ extern "C" int ofdm_rx_demodulate_fixed(ofdm_handle* h, const float* x, int64_t 
                                         ofdm_rx_io* io, void* stream) {
     NEED(h);
     RxWorkspace ws;
-    int rc = get_ws(h, n, io, &ws);
+    const StreamSet ss = single_stream(n);
+    int rc = get_ws(h, ss, io, &ws);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     // chan_filt = gr.multiply_const_cc(1.0): the capture itself is what the sampler reads
     if ((rc = launch_sync_fixed(h, n, nsymbols, freq_offset, io, &ws, st))) return rc;
-    if ((rc = launch_plan(h, n, io, &ws, st))) return rc;
-    if ((rc = launch_demod(h, (const float2*)x, n, io, &ws, st))) return rc;
-    return launch_finish(h, io, &ws, st);
+    if ((rc = launch_plan(h, ss, io, &ws, st))) return rc;
+    if ((rc = launch_demod(h, (const float2*)x, ss, io, &ws, st))) return rc;
+    return launch_finish(h, 1, io, &ws, st);
 }
 
 extern "C" int ofdm_channel(ofdm_handle* h, const float* x, int64_t n, float cfo, double phase0, float sigma,
@@ -508,6 +557,8 @@ extern "C" ofdm_sense_handle* ofdm_sense_create(int32_t N, int32_t device) {
     ofdm_sense_handle* s = new ofdm_sense_handle();
     memset(s, 0, sizeof(*s));
     s->device = device;
+    s->sms = 148;
+    cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device);
     s->N = N;
     std::vector<float> w(N);
     for (int i = 0; i < N; ++i) {                       // gnuradio window.blackmanharris (A.13)

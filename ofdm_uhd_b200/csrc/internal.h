@@ -13,8 +13,27 @@
 #define OFDM_PEAK_WARM 24576            // samples of IIR warm-up before a detector segment
 #define OFDM_SEG_CAP_SHIFT 6            // detector segment slot list: seg_len >> 6 triggers
 
+// One receive call serves S independent streams laid back to back in one sample buffer (S = 1: the classic
+// single-stream call).  Stream s occupies samples [off[s], off[s+1]) of x / y / mf and starts from zero history
+// (filter, window sums, detector average, NCO phase) exactly like a call of its own; every per-stream table sits at
+// base + s * stride.  Kernels take the stream index from blockIdx.y.
+struct StreamSet {
+    int S;                   // number of streams
+    const int64_t* off;      // device [S+1]; nullptr for a single stream [0, n_max)
+    int64_t n_max;           // longest stream (host knowledge: grids and segment tables are sized by it)
+    int64_t n_total;         // samples in all (off[S])
+};
+static inline StreamSet single_stream(int64_t n) { StreamSet ss; ss.S = 1; ss.off = nullptr; ss.n_max = n; ss.n_total = n; return ss; }
+#ifdef __CUDACC__
+// span of stream s: first sample a, length n
+__device__ __forceinline__ void stream_span(const int64_t* off, int s, int64_t n_single, int64_t& a, int64_t& n) {
+    if (off) { a = off[s]; n = off[s + 1] - a; } else { a = 0; n = n_single; }
+}
+#endif
+
 struct ofdm_handle {
     int device;
+    int sms;                 // multiprocessors of the device (grid sizing)
     int N, occ, cp, L, zl, M, nbits, ncar, ntaps, NOS, pkt_stride;
     float amp;
     uint64_t pad_seed;
@@ -39,6 +58,7 @@ struct ofdm_handle {
 
 struct ofdm_sense_handle {
     int device;
+    int sms;
     int N;
     float* d_win;          // [N] Blackman-Harris
     float2* d_tw;          // [N]
@@ -67,50 +87,54 @@ void ofdm_set_error(const char* fmt, ...);
         }                                                                                                         \
     } while (0)
 
-// workspace carve-out (rx.cu)
+// workspace carve-out (rx_front.cu); "per stream" arrays hold S consecutive copies (stride = the size given)
 struct RxWorkspace {
-    float2* y;             // [n]
-    float* mf;             // [n]
-    int64_t* first_nan;    // [1]
-    int32_t* seg_count;    // [n_seg]
-    int64_t* seg_trig;     // [n_seg * seg_cap]
-    double* phi0;          // [max_frames] NCO phase just before each trigger takes effect
-    double* step;          // [max_frames] NCO phase step per sample after each trigger
-    int32_t* first_ok;     // [1] index of the first trigger the sampler can see
-    double* nco_init;      // [1] NCO phase step per sample before the first trigger (0 behind ofdm_sync_pn)
-    int32_t* plan_hdr;     // [4] scratch of the two-launch plan
-    double* plan_blk_d;    // [1024]
-    int64_t* plan_blk_i;   // [1024]
-    int32_t* live_overflow;// [1] set when the liveness fast path hands over to the general walk
-    int64_t* vbase;        // [max_frames] position of each frame's preamble vector in the vector stream
-    int32_t* sess_nvec;    // [max_frames] vectors consumed by a sink session started at this frame
-    int32_t* next_frame;   // [max_frames] scratch of the liveness walk
-    int32_t* exit_frame;   // [max_frames] scratch of the liveness walk
-    int32_t* seg_off;      // [n_seg+1] exclusive scan of seg_count
-    int64_t n_seg, seg_len, seg_cap;
+    float2* y;             // [n_total]
+    float* mf;             // [n_total]
+    int64_t* first_nan;    // per stream [1]
+    int32_t* seg_count;    // per stream [n_seg + 1]
+    int64_t* seg_trig;     // per stream [n_seg * seg_cap]
+    double* phi0;          // per stream [max_frames] NCO phase just before each trigger takes effect
+    double* step;          // per stream [max_frames] NCO phase step per sample after each trigger
+    int32_t* first_ok;     // per stream [1] index of the first trigger the sampler can see
+    double* nco_init;      // per stream [1] NCO phase step per sample before the first trigger (0 behind ofdm_sync_pn)
+    int32_t* plan_hdr;     // per stream [4] scratch of the two-launch plan
+    double* plan_blk_d;    // per stream [1024]
+    int64_t* plan_blk_i;   // per stream [1024]
+    int32_t* live_overflow;// per stream [1] set when the liveness fast path hands over to the general walk
+    int64_t* vbase;        // per stream [max_frames + 1] position of each frame's preamble vector in the vector stream
+    int32_t* sess_nvec;    // per stream [max_frames] vectors consumed by a sink session started at this frame
+    int32_t* next_frame;   // per stream [max_frames] scratch of the liveness walk
+    int32_t* exit_frame;   // per stream [max_frames] scratch of the liveness walk
+    int32_t* seg_off;      // per stream [n_seg + 1] exclusive scan of seg_count
+    int64_t n_seg, seg_len, seg_cap;      // n_seg: detector segments of the LONGEST stream (table stride)
+    int32_t max_frames;
 };
-int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, void* base, size_t bytes,
+int rx_workspace_layout(const ofdm_handle* h, const StreamSet& ss, int32_t max_frames, void* base, size_t bytes,
                         RxWorkspace* ws, size_t* need);
 
 // launchers
 int launch_make_packets(ofdm_handle* h, const uint8_t* payload, const int64_t* payload_off, int32_t n_pkts,
                         int whitening, uint8_t* pkts, const int64_t* pkt_off, cudaStream_t st);
 int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames, int64_t first_frame,
-              const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms, float2* out, cudaStream_t st);
-int launch_chan_filter(ofdm_handle* h, const float2* x, int64_t n, float2* y, cudaStream_t st);
+              const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms, const int64_t* stream_frame0,
+              const int64_t* stream_out_off, int32_t n_streams, float2* out, cudaStream_t st);
+int launch_chan_filter(ofdm_handle* h, const float2* x, const StreamSet& ss, float2* y, cudaStream_t st);
 int launch_sync_metric(ofdm_handle* h, const float2* y, int64_t n, float* mf, int64_t* first_nan, cudaStream_t st);
 int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t n, const int64_t* first_nan,
                        ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
-int launch_trig_compact(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
-int launch_sync_stream(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, int force,
+int launch_trig_compact(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_sync_stream(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, int force,
                        cudaStream_t st);
-int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_plan(ofdm_handle* h, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
 int launch_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_offset, ofdm_rx_io* io, RxWorkspace* ws,
                       cudaStream_t st);
-int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
-int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
-int launch_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_t* sess_nvec, int32_t max_frames,
-                    int32_t* next, int32_t* exitf, int32_t* overflow, uint8_t* live, int force_general, cudaStream_t st);
+int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_finish(ofdm_handle* h, int S, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+// per-stream strides: n_frames / overflow 1, vbase max_frames + 1, everything else max_frames
+int launch_liveness(int sms, int S, const int32_t* n_frames, const int64_t* vbase, int64_t vbase_stride, const int32_t* sess_nvec,
+                    int32_t max_frames, int32_t* next, int32_t* exitf, int32_t* overflow, uint8_t* live, int force_general,
+                    cudaStream_t st);
 int launch_channel(ofdm_handle* h, const float2* x, int64_t n, float cfo, double phase0, float sigma,
                    uint64_t seed, float2* y, cudaStream_t st);
 int launch_sense(ofdm_sense_handle* s, const float2* x, int64_t n_frames, int shift, int32_t tune_delay,

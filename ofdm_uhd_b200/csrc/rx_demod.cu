@@ -5,9 +5,11 @@
 #include "internal.h"
 #include "fft.cuh"
 #include <limits.h>
+#include <stdlib.h>
 
 struct DemodParams {
     const float2* y;
+    const int64_t* soff;           // stream offsets (nullptr: one stream of n samples); tables below are per stream
     int64_t n;
     const int64_t* trig_idx;
     const double* phi0;
@@ -178,8 +180,7 @@ struct Slicer {
                     if (xx < 0 || xx >= L) continue;
                     const int k = grid[yy * L + xx];
                     const float2 ck = cst[k];
-                    const float ex = fsub_rn(r.x, ck.x), ey = fsub_rn(r.y, ck.y);
-                    const float dd = fadd_rn(fmul_rn(ex, ex), fmul_rn(ey, ey));
+                    const float dd = norm_x(csub_x(r, ck));
                     if (dd < best || (dd == best && k < b)) { best = dd; b = k; }
                 }
             }
@@ -188,14 +189,10 @@ struct Slicer {
         int b = 0;
         float best;
         {
-            const float2 c0 = cst[0];
-            const float ex = fsub_rn(r.x, c0.x), ey = fsub_rn(r.y, c0.y);
-            best = fadd_rn(fmul_rn(ex, ex), fmul_rn(ey, ey));
+            best = norm_x(csub_x(r, cst[0]));
         }
         for (int k = 1; k < M; ++k) {
-            const float2 ck = cst[k];
-            const float ex = fsub_rn(r.x, ck.x), ey = fsub_rn(r.y, ck.y);
-            const float dd = fadd_rn(fmul_rn(ex, ex), fmul_rn(ey, ey));
+            const float dd = norm_x(csub_x(r, cst[k]));
             if (dd < best) { best = dd; b = k; }
         }
         return b;
@@ -204,7 +201,39 @@ struct Slicer {
 
 template <int N, bool TAPS>
 __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E),
-                                  TAPS ? 1 : (FftPlan<N>::E == 8 ? 1024 : 512) / ((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E))) demod_kernel(const DemodParams p) {
+                                  TAPS ? 1 : (FftPlan<N>::E == 8 ? 1024 : 512) / ((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E))) demod_kernel(const DemodParams p_all) {
+    // The tables of this CTA's stream (blockIdx.y): CTA-uniform offsets on top of the kernel parameters, held in a
+    // view of their own (v) -- a locally modified COPY of the parameter struct is not safe: nvcc kept reading the
+    // unshifted y pointer from the parameter space in the instantiations that load samples straight from global memory.
+    const DemodParams& p = p_all;
+    struct {
+        const float2* y;
+        const int64_t* trig_idx;
+        const double* phi0;
+        const double* step;
+        const double* nco_init;
+        const int32_t* n_trig;
+        const int32_t* first_ok;
+        const int32_t* n_frames;
+        const int32_t* frame_ndata;
+        const int64_t* vbase;
+        uint8_t* frame_status;
+        int32_t* pkt_len;
+        int32_t* sess_nvec;
+        uint8_t* pkt_bytes;
+    } v;
+    {
+        const int64_t sidx = p_all.soff ? (int64_t)blockIdx.y : 0;
+        const int64_t mf = p_all.max_frames;
+        const int64_t a = p_all.soff ? p_all.soff[sidx] : 0;
+        v.y = p_all.y + a;
+        v.trig_idx = p_all.trig_idx + sidx * mf; v.phi0 = p_all.phi0 + sidx * mf; v.step = p_all.step + sidx * mf;
+        v.nco_init = p_all.nco_init + sidx; v.n_trig = p_all.n_trig + sidx; v.first_ok = p_all.first_ok + sidx;
+        v.n_frames = p_all.n_frames + sidx; v.frame_ndata = p_all.frame_ndata + sidx * mf;
+        v.vbase = p_all.vbase + sidx * (mf + 1); v.frame_status = p_all.frame_status + sidx * mf;
+        v.pkt_len = p_all.pkt_len + sidx * mf; v.sess_nvec = p_all.sess_nvec + sidx * mf;
+        v.pkt_bytes = p_all.pkt_bytes + sidx * mf * (int64_t)p_all.pkt_stride;
+    }
     using P = FftPlan<N>;
     constexpr int E = P::E;
     constexpr int T = N / E;
@@ -231,10 +260,10 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     __shared__ unsigned s_carry;
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int F = *p.n_frames;
-    int K = *p.n_trig;
+    const int F = *v.n_frames;
+    int K = *v.n_trig;
     if (K > p.max_frames) K = p.max_frames;
-    const int first_ok = *p.first_ok;
+    const int first_ok = *v.first_ok;
     const int occ = p.occ, ncar = p.ncar, nbits = p.nbits, zl = p.zl, L = p.L;
     for (int i = tid; i < p.M; i += BT) s_cst[i] = p.cst[i];
     for (int i = tid; i < p.grid_L * p.grid_L; i += BT) s_grid[i] = p.grid[i];
@@ -249,7 +278,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
 #pragma unroll
         for (int i = 0; i < N / BT; ++i) {
             const int idx = tid + i * BT;
-            cp_async8(bufB + idx, p.y + st2 + idx, 8);
+            cp_async8(bufB + idx, v.y + st2 + idx, 8);
         }
         cp_async_commit();
     };
@@ -261,28 +290,28 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
         int kk_w = INT_MIN;                                 // trigger segment the table s_W belongs to
         if (PF) cp_async_wait_all();                        // a copy left in flight by the previous session
         __syncthreads();
-        if (PF) prefetch(p.trig_idx[first_ok + f] - N + 1);
+        if (PF) prefetch(v.trig_idx[first_ok + f] - N + 1);
         while (g < F) {
             const int kg = first_ok + g;
-            const int64_t t = p.trig_idx[kg];
+            const int64_t t = v.trig_idx[kg];
             const int64_t st = t - N + 1 + (int64_t)m * L;
             const bool flag = (m == 0);
-            const int64_t vglob = TAPS ? p.vbase[g] + m : 0;
+            const int64_t vglob = TAPS ? v.vbase[g] + m : 0;
             const bool tap = TAPS && (g == f) && vglob < p.max_vectors;
             const int par = vi & 1;
             // ---- sigmix + fft_demod ----
             int kk = kg;
             if (flag) {
                 kk = kg - 1;
-                while (kk >= 0 && p.trig_idx[kk] > st) --kk;
+                while (kk >= 0 && v.trig_idx[kk] > st) --kk;
             }
-            const int64_t t_next = (kk + 1 < K) ? p.trig_idx[kk + 1] : LLONG_MAX;
+            const int64_t t_next = (kk + 1 < K) ? v.trig_idx[kk + 1] : LLONG_MAX;
             double stp, ph_base;
             if (kk >= 0) {
-                stp = p.step[kk];
-                ph_base = p.phi0[kk] + stp * (double)(st + tid - p.trig_idx[kk] + 1);
+                stp = v.step[kk];
+                ph_base = v.phi0[kk] + stp * (double)(st + tid - v.trig_idx[kk] + 1);
             } else {                                        // before the first trigger (0 behind ofdm_sync_pn)
-                stp = *p.nco_init;
+                stp = *v.nco_init;
                 ph_base = stp * (double)(st + tid + 1);
             }
             if (kk != kk_w) {                               // block-uniform
@@ -294,8 +323,8 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 kk_w = kk;
                 __syncthreads();
             }
-            DemodLoad<PF> ld{PF ? bufB : p.y, st, t_next, p.trig_idx, p.phi0, p.step, K, kk < 0 ? 0 : kk, phasor_f64(ph_base), s_W};
-            if (kk < 0) ld.t_next = (K > 0) ? p.trig_idx[0] : LLONG_MAX;
+            DemodLoad<PF> ld{PF ? bufB : v.y, st, t_next, v.trig_idx, v.phi0, v.step, K, kk < 0 ? 0 : kk, phasor_f64(ph_base), s_W};
+            if (kk < 0) ld.t_next = (K > 0) ? v.trig_idx[0] : LLONG_MAX;
             if (PF) {
                 cp_async_wait_all();
                 __syncthreads();
@@ -312,16 +341,16 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
             __syncthreads();
             if (vi < last_vi) {                             // fetch the vector that follows
                 int g2 = g, m2 = m + 1;
-                if (m2 > p.frame_ndata[g]) { ++g2; m2 = 0; }
+                if (m2 > v.frame_ndata[g]) { ++g2; m2 = 0; }
                 if (g2 < F) {
-                    const int64_t st2 = p.trig_idx[first_ok + g2] - N + 1 + (int64_t)m2 * L;
+                    const int64_t st2 = v.trig_idx[first_ok + g2] - N + 1 + (int64_t)m2 * L;
                     if (PF) {
                         prefetch(st2);                      // bufB is free: asynchronous copy into it
                     } else {
                         // two-pass plans and the single-buffer layout have no landing zone in shared memory: at least pull the vector's lines
                         // into L2 while this one is sliced (one 128-byte line per thread)
                         for (int i = tid * 16; i < N; i += BT * 16)
-                            asm volatile("prefetch.global.L2 [%0];" :: "l"(p.y + st2 + i));
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(v.y + st2 + i));
                     }
                 }
             }
@@ -336,8 +365,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                     for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) {
                         const int pi = zl - OFDM_MAX_SHIFT + s + j;
                         const float2 a = S[pi], b = S[pi + 2];
-                        const float2 d = make_float2(fsub_rn(a.x, b.x), fsub_rn(a.y, b.y));
-                        acc[s] += (double)kdj * (double)norm_x(d);
+                        acc[s] += (double)kdj * (double)norm_x(csub_x(a, b));
                     }
                 }
 #pragma unroll
@@ -371,7 +399,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 __syncthreads();
                 for (int i = 2 * tid + 1; i + 1 < occ; i += 2 * BT) {
                     const float2 a = H[i + 1], b = H[i - 1];
-                    H[i] = make_float2(fmul_rn(fadd_rn(a.x, b.x), 0.5f), fmul_rn(fadd_rn(a.y, b.y), 0.5f));
+                    H[i] = cscale_x(cadd_x(a, b), 0.5f);
                 }
                 if (tid == 0 && (occ & 1) == 0) H[occ - 1] = H[occ - 2];
                 __syncthreads();
@@ -424,17 +452,13 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                         float besta, bestb;
                         {
                             const float2 c0 = s_cst[0];
-                            const float dxa = fsub_rn(ra.x, c0.x), dya = fsub_rn(ra.y, c0.y);
-                            const float dxb = fsub_rn(rb.x, c0.x), dyb = fsub_rn(rb.y, c0.y);
-                            besta = fadd_rn(fmul_rn(dxa, dxa), fmul_rn(dya, dya));
-                            bestb = fadd_rn(fmul_rn(dxb, dxb), fmul_rn(dyb, dyb));
+                            besta = norm_x(csub_x(ra, c0));
+                            bestb = norm_x(csub_x(rb, c0));
                         }
                         for (int k = 1; k < p.M; ++k) {
                             const float2 ck = s_cst[k];
-                            const float dxa = fsub_rn(ra.x, ck.x), dya = fsub_rn(ra.y, ck.y);
-                            const float dxb = fsub_rn(rb.x, ck.x), dyb = fsub_rn(rb.y, ck.y);
-                            const float dda = fadd_rn(fmul_rn(dxa, dxa), fmul_rn(dya, dya));
-                            const float ddb = fadd_rn(fmul_rn(dxb, dxb), fmul_rn(dyb, dyb));
+                            const float dda = norm_x(csub_x(ra, ck));
+                            const float ddb = norm_x(csub_x(rb, ck));
                             if (dda < besta) { besta = dda; ba = k; }
                             if (ddb < bestb) { bestb = ddb; bb = k; }
                         }
@@ -444,9 +468,8 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                     er += (double)ea.x;
                     ei += (double)ea.y;
                     if (norm_x(ra) > 0.001f) {
-                        const float2 q = cdiv_x(cla, ra);
-                        dfe[c] = make_float2(fadd_rn(d0a.x, fmul_rn(0.05f, fsub_rn(q.x, d0a.x))),
-                                             fadd_rn(d0a.y, fmul_rn(0.05f, fsub_rn(q.y, d0a.y))));
+                        const float2 dq = cscale_x(csub_x(cdiv_x(cla, ra), d0a), 0.05f);      // eq_gain * (q - dfe)
+                        dfe[c] = make_float2(fadd_rn(d0a.x, dq.x), fadd_rn(d0a.y, dq.y));
                     }
                     sym[c] = (uint8_t)ba;
                     if (TAPS && tap) {
@@ -457,9 +480,8 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                         er += (double)eb.x;
                         ei += (double)eb.y;
                         if (norm_x(rb) > 0.001f) {
-                            const float2 q = cdiv_x(clb, rb);
-                            dfe[c2] = make_float2(fadd_rn(d0b.x, fmul_rn(0.05f, fsub_rn(q.x, d0b.x))),
-                                                  fadd_rn(d0b.y, fmul_rn(0.05f, fsub_rn(q.y, d0b.y))));
+                            const float2 dq = cscale_x(csub_x(cdiv_x(clb, rb), d0b), 0.05f);
+                            dfe[c2] = make_float2(fadd_rn(d0b.x, dq.x), fadd_rn(d0b.y, dq.y));
                         }
                         sym[c2] = (uint8_t)bb;
                         if (TAPS && tap) {
@@ -516,7 +538,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 if (vi == 1) last_vi = (8 * (4 + len) + bits_this - 1) / bits_this;
                 for (int q = B0 + tid; q < B1; q += BT) {
                     const int pq = q - 4;
-                    if (pq >= 0 && pq < len && pq < p.pkt_stride) p.pkt_bytes[(size_t)f * p.pkt_stride + pq] = vb[q - B0];
+                    if (pq >= 0 && pq < len && pq < p.pkt_stride) v.pkt_bytes[(size_t)f * p.pkt_stride + pq] = vb[q - B0];
                 }
                 bit_base += bits_this;
                 if (B1 >= 4 + len) { status = 2; nvec = vi + 1; break; }
@@ -524,44 +546,43 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
             cnt = cnt_next;
             ++vi;
             ++m;
-            if (m > p.frame_ndata[g]) { ++g; m = 0; }
+            if (m > v.frame_ndata[g]) { ++g; m = 0; }
         }
         if (tid == 0) {
-            p.frame_status[f] = (uint8_t)status;
-            p.pkt_len[f] = status == 2 ? len : 0;
-            p.sess_nvec[f] = nvec;
+            v.frame_status[f] = (uint8_t)status;
+            v.pkt_len[f] = status == 2 ? len : 0;
+            v.sess_nvec[f] = nvec;
         }
     }
     if (PF) cp_async_wait_all();
 }
 
 template <int N, bool TAPS>
-static int launch_demod_nt(ofdm_handle* h, const DemodParams& p, int max_frames, cudaStream_t st) {
+static int launch_demod_nt(ofdm_handle* h, const DemodParams& p, int max_frames, int S, cudaStream_t st) {
     constexpr int T = N / FftPlan<N>::E;
     constexpr int BT = T < 64 ? 64 : T;
     constexpr int NW = BT / 32;
     size_t smem = sizeof(double) * 8 * NW + sizeof(float2) * ((N == 4096 ? 1 : 2) * (size_t)fft_smem_elems<N>() + 2 * (size_t)p.occ + p.M) +
                   ((p.ncar + 15) & ~15) + (size_t)((p.ncar * p.nbits / 8 + 16 + 15) & ~15) + (size_t)p.grid_L * p.grid_L;
     OFDM_SET_MAX_SMEM((demod_kernel<N, TAPS>), smem, h->device);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    int grid = sms * 32;
+    int grid = (h->sms * 32 + S - 1) / S;                  // resident CTAs are shared by the streams
     if (grid > max_frames) grid = max_frames;
     if (grid < 1) grid = 1;
-    demod_kernel<N, TAPS><<<grid, BT, smem, st>>>(p);
+    demod_kernel<N, TAPS><<<dim3(grid, S), BT, smem, st>>>(p);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
 
 template <int N>
-static int launch_demod_n(ofdm_handle* h, const DemodParams& p, int max_frames, cudaStream_t st) {
+static int launch_demod_n(ofdm_handle* h, const DemodParams& p, int max_frames, int S, cudaStream_t st) {
     const bool taps = p.eq_syms || p.sym_idx || p.derot_syms;
-    return taps ? launch_demod_nt<N, true>(h, p, max_frames, st) : launch_demod_nt<N, false>(h, p, max_frames, st);
+    if (taps && S > 1) { ofdm_set_error("demod: the parity taps (eq_syms / sym_idx / derot_syms) are single-stream only"); return OFDM_E_INVAL; }
+    return taps ? launch_demod_nt<N, true>(h, p, max_frames, S, st) : launch_demod_nt<N, false>(h, p, max_frames, S, st);
 }
 
-int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
     DemodParams p;
-    p.y = y; p.n = n; p.trig_idx = io->trig_idx; p.phi0 = ws->phi0; p.step = ws->step; p.nco_init = ws->nco_init; p.n_trig = io->n_trig;
+    p.y = y; p.soff = ss.off; p.n = ss.n_max; p.trig_idx = io->trig_idx; p.phi0 = ws->phi0; p.step = ws->step; p.nco_init = ws->nco_init; p.n_trig = io->n_trig;
     p.first_ok = ws->first_ok; p.n_frames = io->n_frames; p.frame_ndata = io->frame_ndata; p.vbase = ws->vbase;
     p.tw = h->d_tw; p.cst = h->d_const; p.sinkmap = h->d_sinkmap; p.ks = h->d_ks; p.kd = h->d_kd;
     p.occ = h->occ; p.cp = h->cp; p.zl = h->zl; p.ncar = h->ncar; p.nbits = h->nbits; p.M = h->M; p.L = h->L;
@@ -572,13 +593,13 @@ int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxW
     p.eq_syms = (float2*)io->eq_syms; p.sym_idx = io->sym_idx; p.derot_syms = (float2*)io->derot_syms;
     p.max_vectors = io->max_vectors;
     switch (h->N) {
-        case 64:   return launch_demod_n<64>(h, p, io->max_frames, st);
-        case 128:  return launch_demod_n<128>(h, p, io->max_frames, st);
-        case 256:  return launch_demod_n<256>(h, p, io->max_frames, st);
-        case 512:  return launch_demod_n<512>(h, p, io->max_frames, st);
-        case 1024: return launch_demod_n<1024>(h, p, io->max_frames, st);
-        case 2048: return launch_demod_n<2048>(h, p, io->max_frames, st);
-        case 4096: return launch_demod_n<4096>(h, p, io->max_frames, st);
+        case 64:   return launch_demod_n<64>(h, p, io->max_frames, ss.S, st);
+        case 128:  return launch_demod_n<128>(h, p, io->max_frames, ss.S, st);
+        case 256:  return launch_demod_n<256>(h, p, io->max_frames, ss.S, st);
+        case 512:  return launch_demod_n<512>(h, p, io->max_frames, ss.S, st);
+        case 1024: return launch_demod_n<1024>(h, p, io->max_frames, ss.S, st);
+        case 2048: return launch_demod_n<2048>(h, p, io->max_frames, ss.S, st);
+        case 4096: return launch_demod_n<4096>(h, p, io->max_frames, ss.S, st);
     }
     ofdm_set_error("demod: unsupported fft_length %d", h->N);
     return OFDM_E_INVAL;
@@ -598,8 +619,14 @@ int launch_demod(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxW
 constexpr int LIVE_CAP = 3072;
 
 __global__ void __launch_bounds__(256) next_kernel(const int32_t* __restrict__ n_frames, const int64_t* __restrict__ vbase,
-                                                   const int32_t* __restrict__ sess_nvec, int32_t* __restrict__ next,
-                                                   uint8_t* __restrict__ exc, uint8_t* __restrict__ live, int max_frames) {
+                                                   int64_t vbase_stride, const int32_t* __restrict__ sess_nvec,
+                                                   int32_t* __restrict__ next, uint8_t* __restrict__ exc,
+                                                   uint8_t* __restrict__ live, int max_frames) {
+    {
+        const int64_t s = blockIdx.y;                   // per-stream tables
+        n_frames += s; vbase += s * vbase_stride; sess_nvec += s * max_frames; next += s * max_frames;
+        exc += s * max_frames * 4; live += s * max_frames;   // exc aliases the int32 exit table: 4 bytes per frame
+    }
     const int F = *n_frames;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < max_frames; f += gridDim.x * blockDim.x) {
         if (f >= F) { live[f] = 0; continue; }
@@ -624,7 +651,11 @@ __global__ void __launch_bounds__(256) next_kernel(const int32_t* __restrict__ n
 __global__ void __launch_bounds__(1024) liveness_fast_kernel(const int32_t* __restrict__ n_frames,
                                                              const int32_t* __restrict__ next,
                                                              const uint8_t* __restrict__ exc, uint8_t* __restrict__ live,
-                                                             int32_t* __restrict__ overflow, int force_general) {
+                                                             int32_t* __restrict__ overflow, int force_general, int max_frames) {
+    {
+        const int64_t s = blockIdx.x;                   // one CTA per stream
+        n_frames += s; next += s * max_frames; exc += s * max_frames * 4; live += s * max_frames; overflow += s;
+    }
     __shared__ int s_e[LIVE_CAP], s_nx[LIVE_CAP];   // flagged frames in order, and their next(); reused as dead ranges
     __shared__ int s_w[32];
     __shared__ int s_total, s_ndead;
@@ -696,7 +727,11 @@ __global__ void __launch_bounds__(1024) liveness_fast_kernel(const int32_t* __re
 __global__ void __launch_bounds__(1024) liveness_kernel(const int32_t* __restrict__ n_frames,
                                                         const int32_t* __restrict__ run_flag,
                                                         const int32_t* __restrict__ next, int32_t* __restrict__ exitf,
-                                                        uint8_t* __restrict__ live) {
+                                                        uint8_t* __restrict__ live, int max_frames) {
+    {
+        const int64_t s = blockIdx.x;                   // one CTA per stream
+        n_frames += s; run_flag += s; next += s * max_frames; exitf += s * max_frames; live += s * max_frames;
+    }
     __shared__ int s_entry[1024];
     __shared__ int s_first_exit[1024];
     const int tid = threadIdx.x;
@@ -755,7 +790,12 @@ __global__ void __launch_bounds__(32) crc_kernel(const int32_t* __restrict__ n_f
                                                  const uint8_t* __restrict__ status, const int32_t* __restrict__ pkt_len,
                                                  uint8_t* __restrict__ pkt_bytes, int stride, uint8_t* __restrict__ pkt_ok,
                                                  const uint8_t* __restrict__ mask, const uint32_t* __restrict__ crctab,
-                                                 int64_t* __restrict__ counters, int staged_in) {
+                                                 int64_t* __restrict__ counters, int staged_in, int max_frames) {
+    {
+        const int64_t s = blockIdx.y;                   // per-stream tables
+        n_frames += s; live += s * max_frames; status += s * max_frames; pkt_len += s * max_frames;
+        pkt_bytes += s * max_frames * (int64_t)stride; pkt_ok += s * max_frames; counters += s * 8;
+    }
     __shared__ uint32_t s_crc[256];
     extern __shared__ uint32_t s_rows[];                          // [32][stride/4 + 1] when staged, else empty
     const int lane = threadIdx.x;
@@ -827,7 +867,12 @@ __global__ void __launch_bounds__(128) crc_warp_kernel(const int32_t* __restrict
                                                        const uint8_t* __restrict__ status, const int32_t* __restrict__ pkt_len,
                                                        uint8_t* __restrict__ pkt_bytes, int stride, uint8_t* __restrict__ pkt_ok,
                                                        const uint8_t* __restrict__ mask, const uint32_t* __restrict__ crctab,
-                                                       int64_t* __restrict__ counters) {
+                                                       int64_t* __restrict__ counters, int max_frames) {
+    {
+        const int64_t s = blockIdx.y;                   // per-stream tables
+        n_frames += s; live += s * max_frames; status += s * max_frames; pkt_len += s * max_frames;
+        pkt_bytes += s * max_frames * (int64_t)stride; pkt_ok += s * max_frames; counters += s * 8;
+    }
     __shared__ uint32_t s_crc[256 + 32 + 128];
     __shared__ uint32_t s_mask[1024];
     for (int i = threadIdx.x; i < 256 + 32 + 128; i += blockDim.x) s_crc[i] = crctab[i];
@@ -889,42 +934,47 @@ __global__ void __launch_bounds__(128) crc_warp_kernel(const int32_t* __restrict
     }
 }
 
-int launch_liveness(const int32_t* n_frames, const int64_t* vbase, const int32_t* sess_nvec, int32_t max_frames,
-                    int32_t* next, int32_t* exitf, int32_t* overflow, uint8_t* live, int force_general, cudaStream_t st) {
+int launch_liveness(int sms, int S, const int32_t* n_frames, const int64_t* vbase, int64_t vbase_stride, const int32_t* sess_nvec,
+                    int32_t max_frames, int32_t* next, int32_t* exitf, int32_t* overflow, uint8_t* live, int force_general,
+                    cudaStream_t st) {
     // exitf doubles as the flag bytes of next_kernel (the general walk overwrites it only after the fast path is done)
     uint8_t* exc = (uint8_t*)exitf;
     int ngrid = (max_frames + 255) / 256;
-    if (ngrid > 148 * 8) ngrid = 148 * 8;
+    const int cap = (sms * 8 + S - 1) / S;
+    if (ngrid > cap) ngrid = cap;
     if (ngrid < 1) ngrid = 1;
-    next_kernel<<<ngrid, 256, 0, st>>>(n_frames, vbase, sess_nvec, next, exc, live, max_frames);
+    next_kernel<<<dim3(ngrid, S), 256, 0, st>>>(n_frames, vbase, vbase_stride, sess_nvec, next, exc, live, max_frames);
     OFDM_LAUNCH_CHECK();
-    liveness_fast_kernel<<<1, 1024, 0, st>>>(n_frames, next, exc, live, overflow, force_general);
+    liveness_fast_kernel<<<S, 1024, 0, st>>>(n_frames, next, exc, live, overflow, force_general, max_frames);
     OFDM_LAUNCH_CHECK();
-    liveness_kernel<<<1, 1024, 0, st>>>(n_frames, overflow, next, exitf, live);
+    liveness_kernel<<<S, 1024, 0, st>>>(n_frames, overflow, next, exitf, live, max_frames);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
 
-int launch_finish(ofdm_handle* h, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
-    int rc = launch_liveness(io->n_frames, ws->vbase, ws->sess_nvec, io->max_frames, ws->next_frame, ws->exit_frame,
-                             ws->live_overflow, io->frame_live, 0, st);
+int launch_finish(ofdm_handle* h, int S, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+    int rc = launch_liveness(h->sms, S, io->n_frames, ws->vbase, (int64_t)io->max_frames + 1, ws->sess_nvec, io->max_frames,
+                             ws->next_frame, ws->exit_frame, ws->live_overflow, io->frame_live, 0, st);
     if (rc) return rc;
     if (io->pkt_stride >= 1024 && (io->pkt_stride & 3) == 0 && ((((uintptr_t)io->pkt_bytes) & 3) == 0)) {
         int wgrid = (io->max_frames + 3) / 4;                       // long packets: a warp each
-        if (wgrid > 148 * 16) wgrid = 148 * 16;
-        crc_warp_kernel<<<wgrid, 128, 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len, io->pkt_bytes,
-                                               io->pkt_stride, io->pkt_ok, h->d_mask, h->d_crctab, io->counters);
+        const int cap = (h->sms * 16 + S - 1) / S;
+        if (wgrid > cap) wgrid = cap;
+        crc_warp_kernel<<<dim3(wgrid, S), 128, 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len, io->pkt_bytes,
+                                                        io->pkt_stride, io->pkt_ok, h->d_mask, h->d_crctab, io->counters,
+                                                        io->max_frames);
         OFDM_LAUNCH_CHECK();
         return OFDM_OK;
     }
     int grid = (io->max_frames + 31) / 32;
-    if (grid > 148 * 32) grid = 148 * 32;
+    const int cap = (h->sms * 32 + S - 1) / S;
+    if (grid > cap) grid = cap;
     const size_t row_smem = (size_t)32 * (io->pkt_stride / 4 + 1) * sizeof(uint32_t);
     const int staged = (io->pkt_stride & 3) == 0 && row_smem <= (size_t)CRC_SMEM_MAX && ((((uintptr_t)io->pkt_bytes) & 3) == 0);
     if (staged) OFDM_SET_MAX_SMEM(crc_kernel, row_smem, h->device);
-    crc_kernel<<<grid, 32, staged ? row_smem : 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len,
-                                                        io->pkt_bytes, io->pkt_stride, io->pkt_ok, h->d_mask, h->d_crctab,
-                                                        io->counters, staged);
+    crc_kernel<<<dim3(grid, S), 32, staged ? row_smem : 0, st>>>(io->n_frames, io->frame_live, io->frame_status, io->pkt_len,
+                                                                 io->pkt_bytes, io->pkt_stride, io->pkt_ok, h->d_mask,
+                                                                 h->d_crctab, io->counters, staged, io->max_frames);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }

@@ -7,39 +7,42 @@
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, void* base, size_t bytes,
+int rx_workspace_layout(const ofdm_handle* h, const StreamSet& ss, int32_t max_frames, void* base, size_t bytes,
                         RxWorkspace* ws, size_t* need) {
-    (void)h;
-    if (n < 0) n = 0;
+    const int64_t n_total = ss.n_total < 0 ? 0 : ss.n_total, n_max = ss.n_max < 0 ? 0 : ss.n_max;
+    const size_t S = ss.S < 1 ? 1 : (size_t)ss.S;
     if (max_frames < 1) max_frames = 1;
-    int64_t seg_len = (n + 148 * 24 - 1) / (148 * 24);     // one full wave of the detector kernel (24 one-warp CTAs per SM)
+    const int sms = (h && h->sms > 0) ? h->sms : 148;
+    // one full wave of the detector kernel (24 one-warp CTAs per SM) over all streams together
+    int64_t seg_len = (n_total + (int64_t)sms * 24 - 1) / ((int64_t)sms * 24);
     if (seg_len < 65536) seg_len = 65536;
     seg_len = (seg_len + 31) / 32 * 32;
     ws->seg_len = seg_len;
-    ws->n_seg = n > 0 ? (n + seg_len - 1) / seg_len : 0;
+    ws->n_seg = n_max > 0 ? (n_max + seg_len - 1) / seg_len : 0;
     ws->seg_cap = seg_len >> OFDM_SEG_CAP_SHIFT;
+    ws->max_frames = max_frames;
     size_t off = 0;
     char* b = (char*)base;
     auto take = [&](size_t sz) { size_t o = off; off = align_up(off + sz, 256); return b ? (void*)(b + o) : nullptr; };
-    // fixed-size part first, so that the pointers do not depend on n
-    ws->first_nan = (int64_t*)take(sizeof(int64_t));
-    ws->first_ok = (int32_t*)take(sizeof(int32_t));
-    ws->live_overflow = (int32_t*)take(sizeof(int32_t));
-    ws->nco_init = (double*)take(sizeof(double));
-    ws->plan_hdr = (int32_t*)take(4 * sizeof(int32_t));
-    ws->plan_blk_d = (double*)take(sizeof(double) * 1024);
-    ws->plan_blk_i = (int64_t*)take(sizeof(int64_t) * 1024);
-    ws->phi0 = (double*)take(sizeof(double) * max_frames);
-    ws->step = (double*)take(sizeof(double) * max_frames);
-    ws->vbase = (int64_t*)take(sizeof(int64_t) * ((size_t)max_frames + 1));
-    ws->sess_nvec = (int32_t*)take(sizeof(int32_t) * max_frames);
-    ws->next_frame = (int32_t*)take(sizeof(int32_t) * max_frames);
-    ws->exit_frame = (int32_t*)take(sizeof(int32_t) * max_frames);
-    ws->seg_count = (int32_t*)take(sizeof(int32_t) * (size_t)(ws->n_seg + 1));
-    ws->seg_off = (int32_t*)take(sizeof(int32_t) * (size_t)(ws->n_seg + 1));
-    ws->seg_trig = (int64_t*)take(sizeof(int64_t) * (size_t)(ws->n_seg * ws->seg_cap));
-    ws->mf = (float*)take(sizeof(float) * (size_t)n);
-    ws->y = (float2*)take(sizeof(float2) * (size_t)n);
+    // fixed-size part first, so that the pointers do not depend on the stream lengths
+    ws->first_nan = (int64_t*)take(sizeof(int64_t) * S);
+    ws->first_ok = (int32_t*)take(sizeof(int32_t) * S);
+    ws->live_overflow = (int32_t*)take(sizeof(int32_t) * S);
+    ws->nco_init = (double*)take(sizeof(double) * S);
+    ws->plan_hdr = (int32_t*)take(4 * sizeof(int32_t) * S);
+    ws->plan_blk_d = (double*)take(sizeof(double) * 1024 * S);
+    ws->plan_blk_i = (int64_t*)take(sizeof(int64_t) * 1024 * S);
+    ws->phi0 = (double*)take(sizeof(double) * max_frames * S);
+    ws->step = (double*)take(sizeof(double) * max_frames * S);
+    ws->vbase = (int64_t*)take(sizeof(int64_t) * ((size_t)max_frames + 1) * S);
+    ws->sess_nvec = (int32_t*)take(sizeof(int32_t) * max_frames * S);
+    ws->next_frame = (int32_t*)take(sizeof(int32_t) * max_frames * S);
+    ws->exit_frame = (int32_t*)take(sizeof(int32_t) * max_frames * S);
+    ws->seg_count = (int32_t*)take(sizeof(int32_t) * (size_t)(ws->n_seg + 1) * S);
+    ws->seg_off = (int32_t*)take(sizeof(int32_t) * (size_t)(ws->n_seg + 1) * S);
+    ws->seg_trig = (int64_t*)take(sizeof(int64_t) * (size_t)(ws->n_seg * ws->seg_cap) * S);
+    ws->mf = (float*)take(sizeof(float) * (size_t)n_total);
+    ws->y = (float2*)take(sizeof(float2) * (size_t)n_total);
     *need = off;
     if (b && bytes < off) return OFDM_E_NOMEM;
     return OFDM_OK;
@@ -54,8 +57,8 @@ int rx_workspace_layout(const ofdm_handle* h, int64_t n, int32_t max_frames, voi
 struct FiltParams {
     const float2* x;
     float2* y;
+    const int64_t* soff;       // stream offsets (nullptr: one stream of n samples)
     int64_t n;
-    int64_t nblk;
     int V, hist;
     const float2* tw;
     const float2* H;
@@ -82,9 +85,14 @@ __global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 512 / (G * (NOS /
     const int tid = threadIdx.x - g * T;
     float2* raw = smem + (size_t)g * 2 * SB;                  // holds the raw input of the current block
     float2* oth = raw + SB;
-    const bool al16 = (((uintptr_t)p.x) & 15) == 0 && ((p.V | p.hist) & 1) == 0;
+    int64_t s_a, s_n;
+    stream_span(p.soff, blockIdx.y, p.n, s_a, s_n);           // this CTA's stream: zero history in front of it
+    const float2* __restrict__ px = p.x + s_a;
+    float2* __restrict__ py = p.y + s_a;
+    const int64_t nblk = (s_n + p.V - 1) / p.V;
+    const bool al16 = (((uintptr_t)px) & 15) == 0 && ((p.V | p.hist) & 1) == 0;
     auto prefetch = [&](float2* dst, int64_t blk) {
-        if (blk < p.nblk) {
+        if (blk < nblk) {
             const int64_t in0 = blk * p.V - p.hist;
             if (al16) {
 #pragma unroll
@@ -92,32 +100,32 @@ __global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 512 / (G * (NOS /
                     const int idx = 2 * (tid + i * T);
                     const int64_t gi = in0 + idx;              // even, so a pair never straddles sample 0
                     int bytes = 0;
-                    if (gi >= 0 && gi < p.n) bytes = (gi + 1 < p.n) ? 16 : 8;
-                    cp_async16(dst + idx, p.x + (bytes ? gi : 0), bytes);
+                    if (gi >= 0 && gi < s_n) bytes = (gi + 1 < s_n) ? 16 : 8;
+                    cp_async16(dst + idx, px + (bytes ? gi : 0), bytes);
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < E; ++i) {
                     const int idx = tid + i * T;
                     const int64_t gi = in0 + idx;
-                    const bool in = gi >= 0 && gi < p.n;
-                    cp_async8(dst + idx, p.x + (in ? gi : 0), in ? 8 : 0);
+                    const bool in = gi >= 0 && gi < s_n;
+                    cp_async8(dst + idx, px + (in ? gi : 0), in ? 8 : 0);
                 }
             }
         }
         cp_async_commit();
     };
     prefetch(raw, (int64_t)blockIdx.x * G + g);
-    for (int64_t base = (int64_t)blockIdx.x * G; base < p.nblk; base += (int64_t)gridDim.x * G) {
+    for (int64_t base = (int64_t)blockIdx.x * G; base < nblk; base += (int64_t)gridDim.x * G) {
         const int64_t blk = base + g;
-        const bool active = blk < p.nblk;
+        const bool active = blk < nblk;
         float2 regs[E];
         auto mulH = [&](int idx, float2 v, int slot) { regs[slot] = cmul(v, LDG(p.H + idx)); };
         auto fromRegs = [&](int, int slot) -> float2 { return regs[slot]; };
         auto st = [&](int idx, float2 v, int) {
             if (idx >= p.hist) {
                 int64_t o = blk * p.V + (idx - p.hist);
-                if (o < p.n) p.y[o] = v;
+                if (o < s_n) py[o] = v;
             }
         };
         cp_async_wait_all();
@@ -140,28 +148,29 @@ __global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 512 / (G * (NOS /
 }
 
 template <int NOS, int G>
-static int launch_filter_n(ofdm_handle* h, const FiltParams& p, cudaStream_t st) {
+static int launch_filter_n(ofdm_handle* h, const FiltParams& p, int64_t nblk_max, int S, cudaStream_t st) {
     constexpr int T = NOS / FftPlan<NOS>::E;
     constexpr int SB = (fft_smem_elems<NOS>() + 1) & ~1;
     size_t smem = ((size_t)G * 2 * SB) * sizeof(float2);
     OFDM_SET_MAX_SMEM((chan_filter_kernel<NOS, G>), smem, h->device);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    int64_t want = (p.nblk + G - 1) / G;
-    int64_t cap = (int64_t)sms * 16;
+    const int sms = h->sms;
+    int64_t want = (nblk_max + G - 1) / G;
+    int64_t cap = ((int64_t)sms * 16 + S - 1) / S;            // resident CTAs are shared by the streams
     int grid = (int)(want < cap ? want : cap);
-    chan_filter_kernel<NOS, G><<<grid, G * T, smem, st>>>(p);
+    if (grid < 1) grid = 1;
+    chan_filter_kernel<NOS, G><<<dim3(grid, S), G * T, smem, st>>>(p);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
 
-int launch_chan_filter(ofdm_handle* h, const float2* x, int64_t n, float2* y, cudaStream_t st) {
-    if (n <= 0) return OFDM_OK;
+int launch_chan_filter(ofdm_handle* h, const float2* x, const StreamSet& ss, float2* y, cudaStream_t st) {
+    if (ss.n_max <= 0) return OFDM_OK;
     FiltParams p;
-    p.x = x; p.y = y; p.n = n; p.hist = h->ntaps - 1; p.V = h->NOS - p.hist;
-    p.nblk = (n + p.V - 1) / p.V; p.tw = h->d_tw_os; p.H = h->d_Hos;
-    if (h->NOS == 2048) return launch_filter_n<2048, 1>(h, p, st);   // one block per CTA: 4 independent CTAs per SM
-    if (h->NOS == 4096) return launch_filter_n<4096, 1>(h, p, st);
+    p.x = x; p.y = y; p.soff = ss.off; p.n = ss.n_max; p.hist = h->ntaps - 1; p.V = h->NOS - p.hist;
+    p.tw = h->d_tw_os; p.H = h->d_Hos;
+    const int64_t nblk_max = (ss.n_max + p.V - 1) / p.V;
+    if (h->NOS == 2048) return launch_filter_n<2048, 1>(h, p, nblk_max, ss.S, st);   // one block per CTA: 4 independent CTAs per SM
+    if (h->NOS == 4096) return launch_filter_n<4096, 1>(h, p, nblk_max, ss.S, st);
     ofdm_set_error("chan_filter: unsupported overlap-save size %d", h->NOS);
     return OFDM_E_INVAL;
 }
@@ -514,12 +523,20 @@ __global__ void __launch_bounds__(128) peak_detect_kernel(const PeakParams p) {
 }
 
 // exclusive scan of the segment counts (one CTA), then gather + angle
-__global__ void __launch_bounds__(1024) seg_scan_kernel(const int32_t* __restrict__ seg_count, int64_t n_seg,
+__global__ void __launch_bounds__(1024) seg_scan_kernel(const int32_t* __restrict__ seg_count, int64_t seg_stride,
+                                                        const int64_t* __restrict__ soff, int64_t n_single, int64_t seg_len,
                                                         int32_t* __restrict__ seg_off, int32_t* __restrict__ n_trig,
                                                         int max_frames, uint32_t* status) {
     __shared__ int s_w[32];
     __shared__ int s_carry;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t s_a, s_n;
+    stream_span(soff, blockIdx.x, n_single, s_a, s_n);
+    const int64_t n_seg = s_n > 0 ? (s_n + seg_len - 1) / seg_len : 0;      // segments of THIS stream
+    seg_count += (int64_t)blockIdx.x * (seg_stride + 1);
+    seg_off += (int64_t)blockIdx.x * (seg_stride + 1);
+    n_trig += blockIdx.x;
+    status += blockIdx.x;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     for (int64_t base = 0; base < n_seg; base += 1024) {
@@ -559,15 +576,25 @@ __global__ void __launch_bounds__(1024) seg_scan_kernel(const int32_t* __restric
 
 // one warp per trigger slot: copy the index, recompute P = sum_{k<N/2} y[t-k] conj(y[t-k-N/2]) (float64
 // accumulation of float32 products, rounded to float32) and latch angle = atan2(Im P, Re P)
-__global__ void __launch_bounds__(256) trig_gather_kernel(const float2* __restrict__ y, int64_t n, int N,
+__global__ void __launch_bounds__(256) trig_gather_kernel(const float2* __restrict__ y, const int64_t* __restrict__ soff,
+                                                          int64_t n_single, int64_t seg_len, int N,
                                                           const int32_t* __restrict__ seg_count,
                                                           const int32_t* __restrict__ seg_off,
-                                                          const int64_t* __restrict__ seg_trig, int64_t n_seg, int seg_cap,
+                                                          const int64_t* __restrict__ seg_trig, int64_t seg_stride, int seg_cap,
                                                           int max_frames, int64_t* __restrict__ trig_idx,
                                                           float* __restrict__ trig_ang) {
     const int lane = threadIdx.x & 31;
     const int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t s_a, n;
+    stream_span(soff, blockIdx.y, n_single, s_a, n);
+    const int64_t n_seg = n > 0 ? (n + seg_len - 1) / seg_len : 0;
     if (seg >= n_seg) return;
+    y += s_a;
+    seg_count += (int64_t)blockIdx.y * (seg_stride + 1);
+    seg_off += (int64_t)blockIdx.y * (seg_stride + 1);
+    seg_trig += (int64_t)blockIdx.y * seg_stride * seg_cap;
+    trig_idx += (int64_t)blockIdx.y * max_frames;
+    trig_ang += (int64_t)blockIdx.y * max_frames;
     const int cnt = seg_count[seg];
     const int off = seg_off[seg];
     const int h = N / 2;
@@ -596,12 +623,13 @@ __global__ void __launch_bounds__(256) trig_gather_kernel(const float2* __restri
     }
 }
 
-int launch_trig_compact(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
-    seg_scan_kernel<<<1, 1024, 0, st>>>(ws->seg_count, ws->n_seg, ws->seg_off, io->n_trig, io->max_frames, io->status);
+int launch_trig_compact(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+    seg_scan_kernel<<<ss.S, 1024, 0, st>>>(ws->seg_count, ws->n_seg, ss.off, ss.n_max, ws->seg_len, ws->seg_off, io->n_trig,
+                                           io->max_frames, io->status);
     OFDM_LAUNCH_CHECK();
-    trig_gather_kernel<<<(unsigned)((ws->n_seg + 7) / 8), 256, 0, st>>>(y, n, h->N, ws->seg_count, ws->seg_off, ws->seg_trig,
-                                                                        ws->n_seg, (int)ws->seg_cap, io->max_frames,
-                                                                        io->trig_idx, io->trig_ang);
+    trig_gather_kernel<<<dim3((unsigned)((ws->n_seg + 7) / 8), ss.S), 256, 0, st>>>(
+        y, ss.off, ss.n_max, ws->seg_len, h->N, ws->seg_count, ws->seg_off, ws->seg_trig, ws->n_seg, (int)ws->seg_cap,
+        io->max_frames, io->trig_idx, io->trig_ang);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
@@ -621,7 +649,7 @@ int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t
     const int wpb = 4;
     peak_detect_kernel<<<(unsigned)((ws->n_seg + wpb - 1) / wpb), wpb * 32, 0, st>>>(p);
     OFDM_LAUNCH_CHECK();
-    return launch_trig_compact(h, y, n, io, ws, st);
+    return launch_trig_compact(h, y, single_stream(n), io, ws, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -631,6 +659,7 @@ int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t
 // ---------------------------------------------------------------------------------------------
 struct PlanParams {
     int64_t n;
+    const int64_t* soff;   // stream offsets (nullptr: one stream of n samples); every table below is per stream
     int N, L, max_frames;
     int32_t* n_trig;
     const int64_t* first_nan;
@@ -651,6 +680,22 @@ struct PlanParams {
 };
 
 __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// the tables of stream s (blockIdx.y), built field by field (not as a modified copy of the kernel parameter: see
+// demod_kernel in rx_demod.cu)
+__device__ __forceinline__ PlanParams plan_stream_view(const PlanParams& q, int s) {
+    PlanParams p;
+    int64_t a;
+    stream_span(q.soff, s, q.n, a, p.n);
+    const int64_t mf = q.max_frames;
+    p.soff = q.soff; p.N = q.N; p.L = q.L; p.max_frames = q.max_frames;
+    p.n_trig = q.n_trig + s; p.first_nan = q.first_nan + s; p.trig_idx = q.trig_idx + s * mf; p.trig_ang = q.trig_ang + s * mf;
+    p.phi0 = q.phi0 + s * mf; p.step = q.step + s * mf; p.first_ok = q.first_ok + s; p.n_frames = q.n_frames + s;
+    p.frame_start = q.frame_start + s * mf; p.frame_ndata = q.frame_ndata + s * mf; p.vbase = q.vbase + s * (mf + 1);
+    p.counters = q.counters + s * 8; p.nco_init = q.nco_init + s; p.hdr = q.hdr + s * 4; p.blk_d = q.blk_d + s * 1024;
+    p.blk_i = q.blk_i + s * 1024;
+    return p;
+}
 
 // exclusive block scan of one value per thread (1024 threads); total = sum over the block.  s_w: [33] scratch.
 template <typename T>
@@ -688,7 +733,8 @@ __device__ __forceinline__ T plan_block_scan(T v, T* s_w, T& total) {
 
 // P1 (grid-wide, one trigger per thread): per-trigger NCO step and phase increment, per-frame vector count, their
 // CTA-local exclusive prefixes and the CTA totals; hdr = {K after the NaN cut, first_ok, first trigger whose call cannot run}.
-__global__ void __launch_bounds__(1024) plan_local_kernel(const PlanParams p) {
+__global__ void __launch_bounds__(1024) plan_local_kernel(const PlanParams p_all) {
+    const PlanParams p = plan_stream_view(p_all, blockIdx.y);
     __shared__ double s_wd[33];
     __shared__ long long s_wi[33];
     __shared__ int s_K, s_first_ok;
@@ -773,7 +819,8 @@ __global__ void __launch_bounds__(1024) plan_local_kernel(const PlanParams p) {
 }
 
 // P2 (same grid): every CTA scans the CTA totals (at most 1024 of them), adds its own offset; CTA 0 publishes the scalars.
-__global__ void __launch_bounds__(1024) plan_offset_kernel(const PlanParams p, int nblk) {
+__global__ void __launch_bounds__(1024) plan_offset_kernel(const PlanParams p_all, int nblk) {
+    const PlanParams p = plan_stream_view(p_all, blockIdx.y);
     __shared__ double s_wd[33];
     __shared__ long long s_wi[33];
     __shared__ double s_off_d;
@@ -814,11 +861,14 @@ __global__ void __launch_bounds__(1024) plan_offset_kernel(const PlanParams p, i
     }
 }
 
-__global__ void plan_init_kernel(int32_t* hdr) { hdr[0] = 0; hdr[1] = 0; hdr[2] = INT_MAX; }
+__global__ void plan_init_kernel(int32_t* hdr, int S) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) { hdr[4 * s] = 0; hdr[4 * s + 1] = 0; hdr[4 * s + 2] = INT_MAX; }
+}
 
-int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+int launch_plan(ofdm_handle* h, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
     PlanParams p;
-    p.n = n; p.N = h->N; p.L = h->L; p.max_frames = io->max_frames; p.n_trig = io->n_trig; p.first_nan = ws->first_nan;
+    p.n = ss.n_max; p.soff = ss.off; p.N = h->N; p.L = h->L; p.max_frames = io->max_frames; p.n_trig = io->n_trig; p.first_nan = ws->first_nan;
     p.trig_idx = io->trig_idx;
     p.trig_ang = io->trig_ang; p.phi0 = ws->phi0; p.step = ws->step; p.first_ok = ws->first_ok; p.n_frames = io->n_frames;
     p.frame_start = io->frame_start; p.frame_ndata = io->frame_ndata; p.vbase = ws->vbase; p.counters = io->counters;
@@ -828,12 +878,12 @@ int launch_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, cuda
         ofdm_set_error("plan: max_frames %d exceeds 1048576", io->max_frames);
         return OFDM_E_INVAL;
     }
-    OFDM_CUDA_CHECK(cudaMemsetAsync(io->counters, 0, 8 * sizeof(int64_t), st));
-    plan_init_kernel<<<1, 1, 0, st>>>(p.hdr);
+    OFDM_CUDA_CHECK(cudaMemsetAsync(io->counters, 0, 8 * sizeof(int64_t) * ss.S, st));
+    plan_init_kernel<<<(ss.S + 255) / 256, 256, 0, st>>>(p.hdr, ss.S);
     OFDM_LAUNCH_CHECK();
-    plan_local_kernel<<<nblk, 1024, 0, st>>>(p);
+    plan_local_kernel<<<dim3(nblk, ss.S), 1024, 0, st>>>(p);
     OFDM_LAUNCH_CHECK();
-    plan_offset_kernel<<<nblk, 1024, 0, st>>>(p, nblk);
+    plan_offset_kernel<<<dim3(nblk, ss.S), 1024, 0, st>>>(p, nblk);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
@@ -869,7 +919,7 @@ int launch_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_of
     const float ang = (float)(3.14159265358979323846 * (double)freq_offset);
     const double init_step = (-2.0 / (double)h->N) * (double)ang;
     int grid = (io->max_frames + 255) / 256;
-    if (grid > 148 * 4) grid = 148 * 4;
+    if (grid > h->sms * 4) grid = h->sms * 4;
     if (grid < 1) grid = 1;
     sync_fixed_kernel<<<grid, 256, 0, st>>>(n, h->L, (int64_t)nsymbols * h->L, ang, init_step, io->max_frames, io->n_trig,
                                             io->trig_idx, io->trig_ang, ws->nco_init, ws->first_nan, io->status);

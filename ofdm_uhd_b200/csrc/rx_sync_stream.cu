@@ -27,6 +27,8 @@
 
 struct StreamParams {
     const float2* y;
+    const int64_t* soff;          // stream offsets (nullptr: one stream of n samples); tables below are per stream
+    int max_frames;
     int64_t n;
     int cp;
     float tapf;
@@ -203,9 +205,14 @@ struct MetricCtx {
 };
 
 template <int K>
-__global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __restrict__ y, float* __restrict__ mt, const int64_t n) {
+__global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __restrict__ y, float* __restrict__ mt, const int64_t n_single,
+                                                               const int64_t* __restrict__ soff) {
     constexpr int SZ = 32 * K;
     static_assert(K % 4 == 0 || K == 2, "K");
+    int64_t s_a, n;
+    stream_span(soff, blockIdx.y, n_single, s_a, n);        // zero history in front of every stream
+    y += s_a;
+    mt += s_a;
     MetricCtx<K> c;
     c.y = y; c.mt = mt; c.n = n; c.lane = threadIdx.x;
     c.vec_ok = (((uintptr_t)y) & 31) == 0;
@@ -254,10 +261,15 @@ constexpr int MW_MAX_SUB = 8;
 
 template <int K>
 __global__ void __launch_bounds__(32, 12) metric_wide_kernel(const float2* __restrict__ y, float* __restrict__ mt,
-                                                             const int64_t n, const int m, const int chunk_blocks) {
+                                                             const int64_t n_single, const int64_t* __restrict__ soff,
+                                                             const int m, const int chunk_blocks) {
     constexpr int SZ = 32 * K;
     __shared__ double s_T[3][MW_MAX_SUB];            // sub-step totals of the block being walked
     __shared__ double s_D[3][MW_MAX_SUB];            // previous block: sum of the sub-steps after j
+    int64_t s_a, n;
+    stream_span(soff, blockIdx.y, n_single, s_a, n);
+    y += s_a;
+    mt += s_a;
     MetricCtx<K> c;
     c.y = y; c.mt = mt; c.n = n; c.lane = threadIdx.x;
     c.vec_ok = (((uintptr_t)y) & 31) == 0;
@@ -545,9 +557,22 @@ struct DetectCtx {
 };
 
 template <int K>
-__global__ void __launch_bounds__(32, 24) detect_seg_kernel(const StreamParams p, const float* __restrict__ mt, const int ring_steps) {
+__global__ void __launch_bounds__(32, 24) detect_seg_kernel(const StreamParams p_all, const float* __restrict__ mt, const int ring_steps) {
     constexpr int SZ = 32 * K;
     extern __shared__ __align__(16) double s_ring[];
+    // the tables of this CTA's stream (blockIdx.y), built field by field (not as a modified copy of the kernel
+    // parameter: see demod_kernel in rx_demod.cu); the stream starts with a zero detector average
+    StreamParams p;
+    int64_t s_a;
+    stream_span(p_all.soff, blockIdx.y, p_all.n, s_a, p.n);
+    mt += s_a;
+    p.y = p_all.y; p.soff = p_all.soff; p.max_frames = p_all.max_frames; p.cp = p_all.cp; p.tapf = p_all.tapf;
+    p.seg_len = p_all.seg_len; p.seg_cap = p_all.seg_cap;
+    p.seg_count = p_all.seg_count + (int64_t)blockIdx.y * (p_all.n_seg + 1);
+    p.seg_trig = p_all.seg_trig + (int64_t)blockIdx.y * p_all.n_seg * p_all.seg_cap;
+    p.first_nan = p_all.first_nan + blockIdx.y;
+    p.status = p_all.status + blockIdx.y;
+    p.n_seg = p.n > 0 ? (p.n + p.seg_len - 1) / p.seg_len : 0;
     DetectCtx<K> c(p);
     c.mt = mt;
     c.lane = threadIdx.x;
@@ -594,46 +619,50 @@ __global__ void __launch_bounds__(32, 24) detect_seg_kernel(const StreamParams p
     if (c.lane == 0) p.seg_count[c.seg] = c.count < p.seg_cap ? c.count : p.seg_cap;
 }
 
-__global__ void stream_init_kernel(int64_t* first_nan) { *first_nan = LLONG_MAX; }
+__global__ void stream_init_kernel(int64_t* first_nan, int S) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) first_nan[s] = LLONG_MAX;
+}
 
 template <int K>
-static int launch_split_k(const StreamParams& p, float* mt, int m, cudaStream_t st) {
+static int launch_split_k(const StreamParams& p, float* mt, int m, int S, cudaStream_t st) {
     constexpr int SZ = 32 * K;
     if (m == 1) {
         const int64_t chunks = (p.n + (int64_t)MC_STEPS * SZ - 1) / ((int64_t)MC_STEPS * SZ);
-        metric_chunk_kernel<K><<<(unsigned)chunks, 32, 0, st>>>(p.y, mt, p.n);
+        metric_chunk_kernel<K><<<dim3((unsigned)chunks, S), 32, 0, st>>>(p.y, mt, p.n, p.soff);
     } else {
         const int chunk_blocks = (2 * MC_STEPS + m - 1) / m;             // ~64 sub-steps per warp: priming costs ~m light ones
         const int64_t W = (int64_t)m * SZ;
         const int64_t chunks = (p.n + W * chunk_blocks - 1) / (W * chunk_blocks);
-        metric_wide_kernel<K><<<(unsigned)chunks, 32, 0, st>>>(p.y, mt, p.n, m, chunk_blocks);
+        metric_wide_kernel<K><<<dim3((unsigned)chunks, S), 32, 0, st>>>(p.y, mt, p.n, p.soff, m, chunk_blocks);
     }
     OFDM_LAUNCH_CHECK();
     int ring_steps = 2;
     while (ring_steps < (p.cp + SZ - 1) / SZ + 1) ring_steps *= 2;
-    detect_seg_kernel<K><<<(unsigned)p.n_seg, 32, sizeof(double) * ring_steps * SZ, st>>>(p, mt, ring_steps);
+    detect_seg_kernel<K><<<dim3((unsigned)p.n_seg, S), 32, sizeof(double) * ring_steps * SZ, st>>>(p, mt, ring_steps);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
 
-// returns 1 if the streaming kernels do not apply (the caller then runs the tile-parallel path): N = 64, cp > N/2, or -- unless force -- streams too short to give every SM a few
-// warps (one warp per >= 65 536-sample detector segment)
-int launch_sync_stream(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, int force,
+// returns 1 if the streaming kernels do not apply (the caller then runs the tile-parallel stage kernels, single
+// stream only): N = 64 or cp > N/2.  `force` is kept for the stage-level entry point; every stream length takes the
+// streaming pair now (one warp per >= 65 536-sample detector segment: short streams simply use few warps).
+int launch_sync_stream(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, int force,
                        cudaStream_t st) {
+    (void)force;
     // a step is 32*K samples: N/2 for N <= 512, else 256 with m = N/512 sub-steps per N/2-wide block
     const int K = h->N >= 512 ? 8 : h->N / 64;
     const int m = h->N >= 512 ? h->N / 512 : 1;
     if (!(K == 2 || K == 4 || K == 8) || m > MW_MAX_SUB || h->cp > h->N / 2 || ws->n_seg == 0 || !ws->mf) return 1;
-    if (!force && ws->n_seg < 148 * 8) return 1;
     StreamParams p;
-    p.y = y; p.n = n; p.cp = h->cp; p.tapf = (float)(1.0 / (double)h->cp);
+    p.y = y; p.soff = ss.off; p.max_frames = io->max_frames; p.n = ss.n_max; p.cp = h->cp; p.tapf = (float)(1.0 / (double)h->cp);
     p.seg_len = ws->seg_len; p.n_seg = ws->n_seg; p.seg_cap = (int)ws->seg_cap;
     p.seg_count = ws->seg_count; p.seg_trig = ws->seg_trig; p.first_nan = ws->first_nan; p.status = io->status;
-    stream_init_kernel<<<1, 1, 0, st>>>(p.first_nan);
+    stream_init_kernel<<<(ss.S + 255) / 256, 256, 0, st>>>(p.first_nan, ss.S);
     OFDM_LAUNCH_CHECK();
     switch (K) {
-        case 2: return launch_split_k<2>(p, ws->mf, 1, st);
-        case 4: return launch_split_k<4>(p, ws->mf, 1, st);
-        default: return launch_split_k<8>(p, ws->mf, m, st);
+        case 2: return launch_split_k<2>(p, ws->mf, 1, ss.S, st);
+        case 4: return launch_split_k<4>(p, ws->mf, 1, ss.S, st);
+        default: return launch_split_k<8>(p, ws->mf, m, ss.S, st);
     }
 }

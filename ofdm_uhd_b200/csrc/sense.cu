@@ -96,8 +96,7 @@ static int launch_sense_n(ofdm_sense_handle* s, const SenseParams& p, cudaStream
     constexpr int T = N / FftPlan<N>::E;
     size_t smem = ((size_t)G * 2 * fft_smem_elems<N>()) * sizeof(float2);
     OFDM_SET_MAX_SMEM((sense_kernel<N, G>), smem, s->device);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    const int sms = s->sms;
     int64_t want = (p.n_dwell + G - 1) / G;
     int64_t cap = (int64_t)sms * 16;
     int grid = (int)(want < cap ? want : cap);

@@ -112,6 +112,12 @@ struct TxParams {
     const float2* pre_time;
     int cp, ncar, nbits, M;
     float s1, amp;
+    // several streams in one batch (n_streams > 0): frames [stream_frame0[s], stream_frame0[s+1]) belong to stream s,
+    // whose first symbol is written at out[stream_out_off[s]]; its frames are numbered from first_frame again and
+    // its pad symbols use seed + s
+    const int64_t* stream_frame0;
+    const int64_t* stream_out_off;
+    int n_streams;
 };
 
 // The carrier map and the bytes of the symbol are staged in shared memory before the first pass: from global memory
@@ -124,6 +130,7 @@ struct TxLoad {
     int byte0;
     int pkt_bits;
     int64_t frame_id;
+    uint64_t seed;
     int dsym;                    // data symbol number inside the frame
     const float2* s_cst;
     const int16_t* s_b2c;
@@ -139,7 +146,7 @@ struct TxLoad {
             if (sh + p.nbits > 8) w |= ((uint32_t)s_bytes[b + 1]) << 8;
             val = (w >> sh) & ((1u << p.nbits) - 1u);
         } else {
-            val = pad_index(p.seed, (uint64_t)frame_id, (uint32_t)dsym, (uint32_t)c, (uint32_t)p.M);
+            val = pad_index(seed, (uint64_t)frame_id, (uint32_t)dsym, (uint32_t)c, (uint32_t)p.M);
         }
         return s_cst[val];
     }
@@ -152,7 +159,7 @@ struct TxStore {
     float s1, amp;
     __device__ __forceinline__ void operator()(int n, float2 v, int) const {
         // float32 after each multiply_const, like the two upstream blocks
-        float2 o = make_float2(fmul_rn(fmul_rn(v.x, s1), amp), fmul_rn(fmul_rn(v.y, s1), amp));
+        const float2 o = cscale_x(cscale_x(v, s1), amp);
         dst[cp + n] = o;
         if (n >= N - cp) dst[n - (N - cp)] = o;
     }
@@ -200,12 +207,26 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
             }
         }
         float2* dst = p.out + (size_t)s * L;
+        int64_t frame_id = p.first_frame + f;
+        uint64_t seed = p.seed;
+        if (p.n_streams > 0 && active) {
+            int lo = 0, hi = p.n_streams;                 // last stream with stream_frame0[q] <= f
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (LDG(p.stream_frame0 + mid) <= (int64_t)f) lo = mid; else hi = mid;
+            }
+            const int64_t f0 = LDG(p.stream_frame0 + lo);
+            const int64_t sym0 = p.uniform_syms > 0 ? f0 * p.uniform_syms : LDG(p.sym_off + f0);
+            dst = p.out + LDG(p.stream_out_off + lo) + ((int64_t)s - sym0) * L;
+            frame_id = p.first_frame + ((int64_t)f - f0);
+            seed += (uint64_t)lo;
+        }
         const bool data = active && m > 0;
         if (active && m == 0) {
             // ofdm_insert_preamble: the pre-modulated known symbol
             for (int i = tid; i < L; i += T) {
                 float2 v = LDG(p.pre_time + i);
-                dst[i] = make_float2(fmul_rn(v.x, p.amp), fmul_rn(v.y, p.amp));
+                dst[i] = cscale_x(v, p.amp);
             }
         }
         const int64_t o0 = active ? LDG(p.pkt_off + f) : 0;
@@ -219,7 +240,7 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
             for (int i = tid; i < nb; i += T) my_bytes[i] = LDG(src + i);
         }
         bar();
-        TxLoad<N> ld{p, my_bytes, byte0, pkt_len * 8, p.first_frame + f, m - 1, s_cst, s_b2c};
+        TxLoad<N> ld{p, my_bytes, byte0, pkt_len * 8, frame_id, seed, m - 1, s_cst, s_b2c};
         TxStore<N> st{dst, p.cp, p.s1, p.amp};
         using P = FftPlan<N>;
         constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
@@ -243,8 +264,7 @@ static int launch_tx_n(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
     size_t smem = (256 + (size_t)G * 2 * fft_smem_elems<N>()) * sizeof(float2) + (size_t)N * sizeof(int16_t) +
                   (size_t)G * ((sym_bytes + 15) & ~15);
     OFDM_SET_MAX_SMEM((tx_kernel<N, G>), smem, h->device);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int sms = h->sms;
     int64_t want = (p.total_syms + G - 1) / G;
     int64_t cap = (int64_t)sms * (64 / G);
     int grid = (int)(want < cap ? want : cap);
@@ -254,8 +274,10 @@ static int launch_tx_n(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
 }
 
 int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames, int64_t first_frame,
-              const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms, float2* out, cudaStream_t st) {
+              const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms, const int64_t* stream_frame0,
+              const int64_t* stream_out_off, int32_t n_streams, float2* out, cudaStream_t st) {
     TxParams p;
+    p.stream_frame0 = stream_frame0; p.stream_out_off = stream_out_off; p.n_streams = n_streams;
     p.pkts = pkts; p.pkt_off = pkt_off; p.sym_off = sym_off; p.n_frames = n_frames; p.uniform_syms = uniform_syms;
     p.first_frame = first_frame; p.seed = h->pad_seed; p.out = out; p.cst = h->d_const; p.bin2car = h->d_bin2car;
     p.tw = h->d_tw; p.pre_time = h->d_pre_time; p.cp = h->cp; p.ncar = h->ncar; p.nbits = h->nbits; p.M = h->M;
@@ -350,7 +372,7 @@ __global__ void __launch_bounds__(256) channel_kernel(const float2* __restrict__
 int launch_channel(ofdm_handle* h, const float2* x, int64_t n, float cfo, double phase0, float sigma, uint64_t seed,
                    float2* y, cudaStream_t st) {
     int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > (int64_t)h->sms * 32) blocks = (int64_t)h->sms * 32;
     double w = 2.0 * M_PI * (double)cfo / (double)h->N;
     channel_kernel<<<(int)blocks, 256, 0, st>>>(x, n, w, phase0, sigma, seed, y);
     OFDM_LAUNCH_CHECK();

@@ -47,6 +47,11 @@ class TxPlan:
     uniform_syms: int
     n_samples: int
     pad_for_usrp: bool
+    # several streams in one batch (ofdm_tx_modulate_streams): frames [stream_frame0[s], stream_frame0[s+1]) go to
+    # out[stream_out_off[s]:]; None for the classic back-to-back batch
+    n_streams: int = 0
+    d_stream_frame0: object = None
+    d_stream_out_off: object = None
 
 
 @dataclass
@@ -144,8 +149,11 @@ class OfdmEngine:
                              "whitening table" % (4087 if pad_for_usrp else 4091, " || padding" if pad_for_usrp else ""))
         return klen
 
-    def tx_plan(self, payload_off: np.ndarray, pad_for_usrp: bool = False) -> TxPlan:
-        """Everything about a batch that does not depend on the payload bytes."""
+    def tx_plan(self, payload_off: np.ndarray, pad_for_usrp: bool = False, stream_frame0=None,
+                stream_out_off=None) -> TxPlan:
+        """Everything about a batch that does not depend on the payload bytes.  With ``stream_frame0`` (int64 [S+1],
+        frame index where each stream starts) and ``stream_out_off`` (int64 [S], sample offset of each stream's first
+        symbol in the output buffer) the batch is the transmit side of S independent streams."""
         torch = self.torch
         payload_off = np.ascontiguousarray(payload_off, dtype=np.int64)
         plen = np.diff(payload_off)
@@ -162,10 +170,21 @@ class OfdmEngine:
             sym_off = np.zeros(F + 1, dtype=np.int64)
             np.cumsum(nsym, out=sym_off[1:])
             d_sym_off = torch.from_numpy(sym_off).to(self.dev)
-        return TxPlan(F, payload_off, pkt_off, torch.from_numpy(payload_off).to(self.dev),
+        plan = TxPlan(F, payload_off, pkt_off, torch.from_numpy(payload_off).to(self.dev),
                       torch.from_numpy(pkt_off).to(self.dev), d_sym_off,
                       torch.empty(int(pkt_off[-1]), dtype=torch.uint8, device=self.dev), total, uniform,
                       total * self.L, bool(pad_for_usrp))
+        if stream_frame0 is not None:
+            sf = np.ascontiguousarray(stream_frame0, dtype=np.int64)
+            so = np.ascontiguousarray(stream_out_off, dtype=np.int64)
+            if len(sf) != len(so) + 1 or sf[0] != 0 or sf[-1] != F or (np.diff(sf) < 0).any():
+                raise ValueError("tx_plan: stream_frame0 must ascend from 0 to the number of frames, one entry per stream + 1")
+            sym0 = np.concatenate([[0], np.cumsum(nsym)])[sf]
+            plan.n_streams = len(so)
+            plan.d_stream_frame0 = torch.from_numpy(sf).to(self.dev)
+            plan.d_stream_out_off = torch.from_numpy(so).to(self.dev)
+            plan.n_samples = int((so + (sym0[1:] - sym0[:-1]) * self.L).max()) if len(so) else 0
+        return plan
 
     def tx_run(self, plan: TxPlan, payload, out=None, first_frame: int = 0, whitening: bool = True):
         """make_packets + K_TX for a prepared batch: two kernel launches, nothing else."""
@@ -180,9 +199,16 @@ class OfdmEngine:
         _lib.check(self.L_.ofdm_make_packets(self.h, self._p(payload), self._p(plan.d_payload_off), plan.n_frames,
                                              int(whitening), self._p(plan.pkts), self._p(plan.d_pkt_off), st),
                    "make_packets")
-        _lib.check(self.L_.ofdm_tx_modulate_batch(self.h, self._p(plan.pkts), self._p(plan.d_pkt_off), plan.n_frames,
-                                                  int(first_frame), self._p(plan.d_sym_off), plan.total_syms,
-                                                  plan.uniform_syms, self._p(out), st), "tx_modulate_batch")
+        if plan.n_streams:
+            _lib.check(self.L_.ofdm_tx_modulate_streams(self.h, self._p(plan.pkts), self._p(plan.d_pkt_off), plan.n_frames,
+                                                        int(first_frame), self._p(plan.d_sym_off), plan.total_syms,
+                                                        plan.uniform_syms, self._p(plan.d_stream_frame0),
+                                                        self._p(plan.d_stream_out_off), plan.n_streams, self._p(out), st),
+                       "tx_modulate_streams")
+        else:
+            _lib.check(self.L_.ofdm_tx_modulate_batch(self.h, self._p(plan.pkts), self._p(plan.d_pkt_off), plan.n_frames,
+                                                      int(first_frame), self._p(plan.d_sym_off), plan.total_syms,
+                                                      plan.uniform_syms, self._p(out), st), "tx_modulate_batch")
         return out[:plan.n_samples]
 
     def make_packets(self, payload, payload_off: np.ndarray, pad_for_usrp: bool = False, whitening: bool = True):
@@ -304,6 +330,85 @@ class OfdmEngine:
         else:
             raise ValueError("sync %r: only 'pn' and 'fixed' exist (ml / pnac are not wired in the reference)" % (sync,))
         return bufs
+
+    # ---- many independent streams in one call (ofdm_rx_demodulate_batch) ----
+    def rx_alloc_batch(self, stream_off, max_frames: int):
+        """Output arrays + workspace for S streams lying back to back in one sample buffer (stream s = samples
+        [stream_off[s], stream_off[s+1])).  Every per-frame array is [S, max_frames]; scalars are [S]."""
+        torch = self.torch
+        dev = self.dev
+        so = np.ascontiguousarray(stream_off, dtype=np.int64)
+        S = len(so) - 1
+        if S < 1 or (np.diff(so) < 0).any():
+            raise ValueError("rx_alloc_batch: stream_off must ascend and hold at least two entries")
+        n_total, n_max = int(so[-1]), int(np.diff(so).max())
+        mf = int(max_frames)
+        need = int(self.L_.ofdm_rx_workspace_bytes_batch(self.h, S, n_total, n_max, mf))
+        b = {"workspace": torch.empty(need, dtype=torch.uint8, device=dev)}
+        for k, dt, per in (("status", torch.int32, 1), ("n_trig", torch.int32, 1), ("n_frames", torch.int32, 1),
+                           ("trig_idx", torch.int64, mf), ("trig_ang", torch.float32, mf), ("frame_start", torch.int64, mf),
+                           ("frame_ndata", torch.int32, mf), ("frame_live", torch.uint8, mf), ("frame_status", torch.uint8, mf),
+                           ("pkt_len", torch.int32, mf), ("pkt_ok", torch.uint8, mf), ("pkt_bytes", torch.uint8, mf * self.pkt_stride),
+                           ("counters", torch.int64, 8)):
+            b[k] = torch.zeros(S * per, dtype=dt, device=dev)
+        io = _lib.RxIo()
+        io.max_frames = mf
+        io.pkt_stride = self.pkt_stride
+        io.workspace = b["workspace"].data_ptr()
+        io.workspace_bytes = need
+        for k in ("status", "n_trig", "trig_idx", "trig_ang", "n_frames", "frame_start", "frame_ndata", "frame_live",
+                  "frame_status", "pkt_len", "pkt_ok", "pkt_bytes", "counters"):
+            setattr(io, k, b[k].data_ptr())
+        io.eq_syms = io.sym_idx = io.derot_syms = None
+        io.max_vectors = 0
+        b.update(io=io, n=n_total, S=S, n_max=n_max, max_frames=mf, stream_off=so,
+                 d_stream_off=torch.from_numpy(so).to(dev))
+        return b
+
+    def demodulate_batch_async(self, x, bufs):
+        """The whole receive chain on S streams at once, on the current stream (no sync)."""
+        if int(x.numel()) < bufs["n"]:
+            raise ValueError("demodulate_batch: sample buffer shorter than stream_off[-1]")
+        _lib.check(self.L_.ofdm_rx_demodulate_batch(self.h, self._p(x), self._p(bufs["d_stream_off"]), bufs["S"], bufs["n"],
+                                                    bufs["n_max"], C.byref(bufs["io"]), self._stream()), "rx_demodulate_batch")
+        return bufs
+
+    def collect_batch(self, bufs, want_packets: bool = True) -> List[RxBatch]:
+        """Synchronise and return one RxBatch per stream (what S separate demodulate() calls would return)."""
+        torch = self.torch
+        S, mf = bufs["S"], bufs["max_frames"]
+        torch.cuda.current_stream(self.dev).synchronize()
+        host = {k: bufs[k].cpu().numpy() for k in ("status", "n_trig", "n_frames", "counters", "frame_live", "frame_status",
+                                                   "pkt_len", "pkt_ok")}
+        if int(host["status"].max(initial=0)):
+            raise RuntimeError("receive: capacity overflow in stream %d (status bits 0x%x): raise max_frames"
+                               % (int(np.argmax(host["status"] != 0)), int(host["status"].max())))
+        if want_packets:
+            for k in ("trig_idx", "trig_ang", "frame_start", "frame_ndata"):
+                host[k] = bufs[k].cpu().numpy()
+        out = []
+        z = np.zeros(0)
+        for s in range(S):
+            nt, nf = int(host["n_trig"][s]), int(host["n_frames"][s])
+            sl = slice(s * mf, s * mf + nf)
+            live, fstat, plen, pok = (host[k][sl] for k in ("frame_live", "frame_status", "pkt_len", "pkt_ok"))
+            sel = np.flatnonzero((live == 1) & (fstat == 2))
+            packets, rows = [], None
+            if want_packets:
+                rows = bufs["pkt_bytes"][s * mf * self.pkt_stride:(s * mf + nf) * self.pkt_stride].cpu().numpy()
+                rows = rows.reshape(nf, self.pkt_stride)
+                for f in sel:
+                    ln = int(plen[f])
+                    body = rows[f, :min(ln, self.pkt_stride)].tobytes()
+                    packets.append((bool(pok[f]), body[:-4] if ln >= 4 else b""))
+                tl = slice(s * mf, s * mf + nt)
+                extra = (host["trig_idx"][tl].copy(), host["trig_ang"][tl].copy(), host["frame_start"][sl].copy(),
+                         host["frame_ndata"][sl].copy())
+            else:
+                extra = (z, z, z, z)
+            out.append(RxBatch(nt, nf, 0, *extra, live.copy(), fstat.copy(), plen.copy(), pok.copy(),
+                               host["counters"][8 * s:8 * s + 8].copy(), packets, sel, rows))
+        return out
 
     def ws_view(self, bufs, which: int, n: int):
         """Tensor views of the workspace taps (0: filtered stream y, 1: timing metric mf)."""

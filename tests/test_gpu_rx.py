@@ -597,3 +597,35 @@ def test_degenerate_inputs_terminate_and_deliver_nothing(N, occ, cp):
         r = eng.collect(bufs)
         assert (r.n_trig, r.n_frames, len(r.packets)) == (0, 0, 0), name
     eng.close()
+
+
+def test_packed_math_selftest():
+    """Every packed-fp32 helper of the decision paths returns, bit for bit, what its scalar definition returns
+    (ptxas contracts packed multiply -> packed add pairs; common.cuh keeps them apart)."""
+    from ofdm_uhd_b200 import _lib
+    L_ = _lib.lib()
+    out = (C.c_int64 * 2)()
+    _lib.check(L_.ofdm_selftest_packed_math(0, 1 << 24, 12345, out), "selftest")
+    assert out[0] == 0, "packed helpers differ from their scalar definitions (mask 0x%x) in %d of %d cases" % (out[1], out[0], 1 << 24)
+
+
+def test_sampler_emits_1001_data_vectors():
+    """`if (d_timeout-- == 0)`: a lone trigger followed by more than 1001 symbols yields a frame of exactly
+    1001 data vectors -- plan kernel == oracle sampler, through the fixed synchroniser (one trigger per 1200 symbols)."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    N, occ, cp = 128, 56, 32
+    L = N + cp
+    n = 1300 * L
+    rng = np.random.default_rng(3)
+    xc = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.01).astype(np.complex64)
+    lay = o.Layout(N, occ, cp, "qpsk")
+    trig, ang = o.sync_fixed(n, N, cp, 1200, 0.0)
+    plan = o.plan_frames(trig, ang, n, N, L)
+    assert list(plan.n_data[:1]) == [1001]
+    eng = OfdmEngine(N, occ, cp, "qpsk")
+    got = eng.demodulate_fixed(torch.from_numpy(xc).cuda(), 1200, 0.0)
+    assert np.array_equal(got.trig_idx, trig)
+    assert np.array_equal(got.frame_ndata, plan.n_data) and got.frame_ndata[0] == 1001
+    assert np.array_equal(got.frame_start, trig[plan.frame_trig] - N + 1)
+    eng.close()
