@@ -184,6 +184,20 @@ size_t ofdm_rx_workspace_bytes_batch(const ofdm_handle* h, int32_t n_streams, in
                                      int64_t max_stream_samples, int32_t max_frames_per_stream);
 int ofdm_rx_demodulate_batch(ofdm_handle* h, const float* x_iq, const int64_t* stream_off, int32_t n_streams,
                              int64_t total_samples, int64_t max_stream_samples, ofdm_rx_io* io, void* stream);
+/* The hand-over of the delivered messages to the host (the reference pushes every message the frame sink completes
+ * into a gr.msg_queue popped by _queue_watcher_thread, ofdm.py:290-305): after ofdm_rx_finish / ofdm_rx_demodulate
+ * [_batch], pack the messages of all n_streams streams (frames with frame_live && frame_status == 2, in stream and
+ * arrival order) into one dense byte array, so that the device -> host copy is sized by what was delivered instead of
+ * max_frames * pkt_stride.  All pointers are DEVICE pointers:
+ *   out_bytes [out_capacity]               dewhitened payload || crc of message 0, 1, ... back to back
+ *   msg_off   [n_streams*max_frames + 1]   byte offset of each message in out_bytes (msg_off[n_msgs] = total bytes)
+ *   msg_frame [n_streams*max_frames]       frame slot s*max_frames + f the message came from
+ *   ok_bits   [(n_streams*max_frames+31)/32] uint32, bit m = CRC-32 verdict of message m
+ *   totals    [3]  n_msgs, bytes in all, messages whose bytes fitted out_capacity
+ *   scratch   [2 * ((n_streams*max_frames + 1023) / 1024)] int64 */
+int ofdm_rx_compact(ofdm_handle* h, const ofdm_rx_io* io, int32_t n_streams, uint8_t* out_bytes, int64_t out_capacity,
+                    int64_t* msg_off, int32_t* msg_frame, uint32_t* ok_bits, int64_t* totals, int64_t* scratch,
+                    void* stream);
 /* pointers into the workspace for parity tests: which = 0 filtered stream y (2n floats), 1 metric mf (n floats) */
 void* ofdm_rx_workspace_ptr(const ofdm_handle* h, const ofdm_rx_io* io, int64_t n, int which);
 

@@ -18,7 +18,7 @@ EXPORTS = [
     "ofdm_get_chan_taps", "ofdm_packet_len", "ofdm_make_packets", "ofdm_frame_symbols", "ofdm_tx_modulate_batch", "ofdm_tx_modulate_streams",
     "ofdm_rx_workspace_bytes", "ofdm_rx_chan_filter", "ofdm_rx_sync_metric", "ofdm_rx_peak_detect", "ofdm_rx_sync",
     "ofdm_rx_plan",
-    "ofdm_rx_demod", "ofdm_rx_finish", "ofdm_rx_liveness", "ofdm_rx_sync_fixed", "ofdm_rx_demodulate_fixed", "ofdm_rx_demodulate", "ofdm_rx_workspace_bytes_batch", "ofdm_rx_demodulate_batch", "ofdm_rx_workspace_ptr", "ofdm_channel",
+    "ofdm_rx_demod", "ofdm_rx_finish", "ofdm_rx_liveness", "ofdm_rx_sync_fixed", "ofdm_rx_demodulate_fixed", "ofdm_rx_demodulate", "ofdm_rx_workspace_bytes_batch", "ofdm_rx_demodulate_batch", "ofdm_rx_compact", "ofdm_rx_workspace_ptr", "ofdm_channel",
     "ofdm_sense_create", "ofdm_sense_destroy", "ofdm_sense", "ofdm_sense_fft", "ofdm_sense_decide", "ofdm_sense_hop",
 ]
 
@@ -83,6 +83,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.ofdm_rx_workspace_bytes_batch.argtypes = [vp, i32, i64, i64, i32]
     L.ofdm_rx_workspace_bytes_batch.restype = C.c_size_t
     L.ofdm_rx_demodulate_batch.argtypes = [vp, vp, vp, i32, i64, i64, C.POINTER(RxIo), vp]
+    L.ofdm_rx_compact.argtypes = [vp, C.POINTER(RxIo), i32, vp, i64, vp, vp, vp, vp, vp, vp]
     L.ofdm_rx_workspace_ptr.argtypes = [vp, C.POINTER(RxIo), i64, C.c_int]
     L.ofdm_rx_workspace_ptr.restype = vp
     L.ofdm_channel.argtypes = [vp, vp, i64, f32, f64, f32, u64, vp, vp]

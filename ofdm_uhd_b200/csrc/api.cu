@@ -543,6 +543,18 @@ extern "C" int ofdm_rx_demodulate_fixed(ofdm_handle* h, const float* x, int64_t 
     return launch_finish(h, 1, io, &ws, st);
 }
 
+extern "C" int ofdm_rx_compact(ofdm_handle* h, const ofdm_rx_io* io, int32_t n_streams, uint8_t* out_bytes,
+                               int64_t out_capacity, int64_t* msg_off, int32_t* msg_frame, uint32_t* ok_bits, int64_t* totals,
+                               int64_t* scratch, void* stream) {
+    NEED(h);
+    if (!io || n_streams < 1 || !out_bytes || !msg_off || !msg_frame || !ok_bits || !totals || !scratch || out_capacity < 0) {
+        ofdm_set_error("ofdm_rx_compact: null argument");
+        return OFDM_E_INVAL;
+    }
+    return launch_compact(h, io, n_streams, out_bytes, out_capacity, msg_off, msg_frame, ok_bits, totals, scratch,
+                          (cudaStream_t)stream);
+}
+
 extern "C" int ofdm_channel(ofdm_handle* h, const float* x, int64_t n, float cfo, double phase0, float sigma,
                             uint64_t seed, float* y, void* stream) {
     NEED(h);

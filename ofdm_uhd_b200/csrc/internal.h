@@ -135,6 +135,9 @@ int launch_finish(ofdm_handle* h, int S, ofdm_rx_io* io, RxWorkspace* ws, cudaSt
 int launch_liveness(int sms, int S, const int32_t* n_frames, const int64_t* vbase, int64_t vbase_stride, const int32_t* sess_nvec,
                     int32_t max_frames, int32_t* next, int32_t* exitf, int32_t* overflow, uint8_t* live, int force_general,
                     cudaStream_t st);
+int launch_compact(ofdm_handle* h, const ofdm_rx_io* io, int32_t n_streams, uint8_t* out_bytes, int64_t capacity,
+                   int64_t* msg_off, int32_t* msg_frame, uint32_t* ok_bits, int64_t* totals, int64_t* scratch,
+                   cudaStream_t st);
 int launch_channel(ofdm_handle* h, const float2* x, int64_t n, float cfo, double phase0, float sigma,
                    uint64_t seed, float2* y, cudaStream_t st);
 int launch_sense(ofdm_sense_handle* s, const float2* x, int64_t n_frames, int shift, int32_t tune_delay,

@@ -978,3 +978,173 @@ int launch_finish(ofdm_handle* h, int S, ofdm_rx_io* io, RxWorkspace* ws, cudaSt
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Hand-over of the delivered messages to the host (the reference pushes each message into a gr.msg_queue that
+// _queue_watcher_thread pops, ofdm.py:290-305): the messages of all streams, in stream / arrival order, packed into
+// one dense byte array with an offset table and a bit-packed CRC verdict -- so the device -> host copy is sized by
+// what was delivered, not by max_frames * pkt_stride.
+//   compact_count_kernel   per 1024-frame block: messages and bytes
+//   compact_scan_kernel    (one CTA) exclusive scan of the block totals, grand totals
+//   compact_copy_kernel    per block: in-block prefix, offsets / frame ids / verdict bits, one warp per message row
+// ---------------------------------------------------------------------------------------------
+struct CompactParams {
+    const int32_t* n_frames;     // [S]
+    const uint8_t* live;         // [S][max_frames]
+    const uint8_t* status;
+    const int32_t* pkt_len;
+    const uint8_t* pkt_ok;
+    const uint8_t* pkt_bytes;    // [S][max_frames][stride]
+    int S, max_frames, stride;
+    int64_t capacity;            // bytes in out_bytes
+    int64_t* blk_cnt;            // [nblk] then, after the scan, exclusive prefixes
+    int64_t* blk_bytes;          // [nblk]
+    uint8_t* out_bytes;
+    int64_t* msg_off;            // [n_msgs + 1]
+    int32_t* msg_frame;          // [n_msgs] global frame slot s * max_frames + f
+    uint32_t* ok_bits;           // [(S * max_frames + 31) / 32], bit m = CRC verdict of message m
+    int64_t* totals;             // [0] messages, [1] bytes (uncapped), [2] messages copied
+};
+
+__device__ __forceinline__ bool compact_flag(const CompactParams& p, int64_t g, int& len) {
+    const int s = (int)(g / p.max_frames), f = (int)(g - (int64_t)s * p.max_frames);
+    len = 0;
+    if (s >= p.S || f >= p.n_frames[s]) return false;
+    if (!(p.live[g] && p.status[g] == 2)) return false;
+    const int l = p.pkt_len[g];
+    len = l < p.stride ? l : p.stride;
+    if (len < 0) len = 0;
+    return true;
+}
+
+__global__ void __launch_bounds__(1024) compact_count_kernel(const CompactParams p) {
+    __shared__ long long s_c[32], s_b[32];
+    const int64_t g = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    int len;
+    const bool m = compact_flag(p, g, len);
+    long long c = m ? 1 : 0, b = len;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+    if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = c; s_b[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        c = s_c[threadIdx.x]; b = s_b[threadIdx.x];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+        if (threadIdx.x == 0) { p.blk_cnt[blockIdx.x] = c; p.blk_bytes[blockIdx.x] = b; }
+    }
+}
+
+__global__ void __launch_bounds__(1024) compact_scan_kernel(const CompactParams p, int nblk) {
+    __shared__ long long s_c[33], s_b[33];
+    __shared__ long long s_cc, s_cb;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_cc = 0; s_cb = 0; }
+    __syncthreads();
+    for (int base = 0; base < nblk; base += 1024) {
+        const int i = base + threadIdx.x;
+        const long long vc = i < nblk ? p.blk_cnt[i] : 0, vb = i < nblk ? p.blk_bytes[i] : 0;
+        long long ic = vc, ib = vb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long oc = __shfl_up_sync(0xffffffffu, ic, d), ob = __shfl_up_sync(0xffffffffu, ib, d);
+            if (lane >= d) { ic += oc; ib += ob; }
+        }
+        if (lane == 31) { s_c[w] = ic; s_b[w] = ib; }
+        __syncthreads();
+        if (w == 0) {
+            long long tc = s_c[lane], tb = s_b[lane];
+            const long long oc0 = tc, ob0 = tb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long oc = __shfl_up_sync(0xffffffffu, tc, d), ob = __shfl_up_sync(0xffffffffu, tb, d);
+                if (lane >= d) { tc += oc; tb += ob; }
+            }
+            s_c[lane] = tc - oc0; s_b[lane] = tb - ob0;
+            if (lane == 31) { s_c[32] = tc; s_b[32] = tb; }
+        }
+        __syncthreads();
+        if (i < nblk) { p.blk_cnt[i] = s_cc + s_c[w] + ic - vc; p.blk_bytes[i] = s_cb + s_b[w] + ib - vb; }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_cc += s_c[32]; s_cb += s_b[32]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { p.totals[0] = s_cc; p.totals[1] = s_cb; p.msg_off[s_cc] = s_cb; }
+}
+
+__global__ void __launch_bounds__(1024) compact_copy_kernel(const CompactParams p) {
+    __shared__ long long s_c[33], s_b[33];
+    __shared__ int s_len[1024];
+    __shared__ long long s_dst[1024];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    int len;
+    const bool m = compact_flag(p, g, len);
+    const long long vc = m ? 1 : 0, vb = len;
+    long long ic = vc, ib = vb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long oc = __shfl_up_sync(0xffffffffu, ic, d), ob = __shfl_up_sync(0xffffffffu, ib, d);
+        if (lane >= d) { ic += oc; ib += ob; }
+    }
+    if (lane == 31) { s_c[w] = ic; s_b[w] = ib; }
+    __syncthreads();
+    if (w == 0) {
+        long long tc = s_c[lane], tb = s_b[lane];
+        const long long oc0 = tc, ob0 = tb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long oc = __shfl_up_sync(0xffffffffu, tc, d), ob = __shfl_up_sync(0xffffffffu, tb, d);
+            if (lane >= d) { tc += oc; tb += ob; }
+        }
+        s_c[lane] = tc - oc0; s_b[lane] = tb - ob0;
+    }
+    __syncthreads();
+    const long long mi = p.blk_cnt[blockIdx.x] + s_c[w] + ic - vc;        // message number
+    const long long bo = p.blk_bytes[blockIdx.x] + s_b[w] + ib - vb;      // byte offset
+    s_len[threadIdx.x] = -1;
+    if (m) {
+        p.msg_off[mi] = bo;
+        p.msg_frame[mi] = (int32_t)g;
+        if (p.pkt_ok[g]) atomicOr(p.ok_bits + (mi >> 5), 1u << (mi & 31));
+        if (bo + len <= p.capacity) { s_len[threadIdx.x] = len; s_dst[threadIdx.x] = bo; atomicAdd((unsigned long long*)&p.totals[2], 1ull); }
+    }
+    __syncthreads();
+    // one warp per message row of this block
+    for (int r = w; r < 1024; r += 32) {
+        const int l = s_len[r];
+        if (l <= 0) continue;
+        const uint8_t* src = p.pkt_bytes + ((int64_t)blockIdx.x * 1024 + r) * p.stride;
+        uint8_t* dst = p.out_bytes + s_dst[r];
+        if (((((uintptr_t)src) | ((uintptr_t)dst)) & 3) == 0) {
+            const int nw = l >> 2;
+            for (int i = lane; i < nw; i += 32) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
+            for (int i = 4 * nw + lane; i < l; i += 32) dst[i] = src[i];
+        } else {
+            for (int i = lane; i < l; i += 32) dst[i] = src[i];
+        }
+    }
+}
+
+int launch_compact(ofdm_handle* h, const ofdm_rx_io* io, int32_t n_streams, uint8_t* out_bytes, int64_t capacity,
+                   int64_t* msg_off, int32_t* msg_frame, uint32_t* ok_bits, int64_t* totals, int64_t* scratch,
+                   cudaStream_t st) {
+    (void)h;
+    CompactParams p;
+    p.n_frames = io->n_frames; p.live = io->frame_live; p.status = io->frame_status; p.pkt_len = io->pkt_len;
+    p.pkt_ok = io->pkt_ok; p.pkt_bytes = io->pkt_bytes; p.S = n_streams; p.max_frames = io->max_frames; p.stride = io->pkt_stride;
+    p.capacity = capacity; p.out_bytes = out_bytes; p.msg_off = msg_off; p.msg_frame = msg_frame; p.ok_bits = ok_bits;
+    p.totals = totals;
+    const int64_t slots = (int64_t)n_streams * io->max_frames;
+    const int nblk = (int)((slots + 1023) / 1024);
+    p.blk_cnt = scratch; p.blk_bytes = scratch + nblk;
+    OFDM_CUDA_CHECK(cudaMemsetAsync(ok_bits, 0, sizeof(uint32_t) * (size_t)((slots + 31) / 32), st));
+    OFDM_CUDA_CHECK(cudaMemsetAsync(totals, 0, 3 * sizeof(int64_t), st));
+    compact_count_kernel<<<nblk, 1024, 0, st>>>(p);
+    OFDM_LAUNCH_CHECK();
+    compact_scan_kernel<<<1, 1024, 0, st>>>(p, nblk);
+    OFDM_LAUNCH_CHECK();
+    compact_copy_kernel<<<nblk, 1024, 0, st>>>(p);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}

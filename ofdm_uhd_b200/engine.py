@@ -550,6 +550,76 @@ class OfdmEngine:
                        copied, ticket["bytes"] - copied)
 
 
+    # ---- dense hand-over of the delivered messages (ofdm_rx_compact) ----
+    def deliver_begin(self, bufs, expect_msgs: Optional[int] = None, expect_bytes: Optional[int] = None):
+        """Queue, on the current stream, the device-side packing of every delivered message of one receive call
+        (single stream or batch) into a dense byte array and the device->host copies of the result; returns a ticket
+        for :meth:`deliver_end`.  The copies are sized by what the caller expects to come back (``expect_msgs``
+        messages, ``expect_bytes`` payload+crc bytes -- e.g. what it transmitted), not by max_frames * pkt_stride;
+        messages beyond that are reported by ``overflow`` in the result and can be fetched with :meth:`collect`."""
+        torch = self.torch
+        S = int(bufs.get("S", 1))
+        mf = int(bufs["io"].max_frames)
+        slots = S * mf
+        d = bufs.get("_dense")
+        if d is None:
+            dev = self.dev
+            d = {"bytes": torch.empty(slots * self.pkt_stride, dtype=torch.uint8, device=dev),
+                 "off": torch.empty(slots + 1, dtype=torch.int64, device=dev),
+                 "frame": torch.empty(slots, dtype=torch.int32, device=dev),
+                 "ok": torch.empty((slots + 31) // 32, dtype=torch.int32, device=dev),
+                 "totals": torch.empty(3, dtype=torch.int64, device=dev),
+                 "scratch": torch.empty(2 * ((slots + 1023) // 1024), dtype=torch.int64, device=dev)}
+            bufs["_dense"] = d
+        _lib.check(self.L_.ofdm_rx_compact(self.h, C.byref(bufs["io"]), S, self._p(d["bytes"]), d["bytes"].numel(),
+                                           self._p(d["off"]), self._p(d["frame"]), self._p(d["ok"]), self._p(d["totals"]),
+                                           self._p(d["scratch"]), self._stream()), "rx_compact")
+        nm = slots if expect_msgs is None else min(int(expect_msgs), slots)
+        nb = d["bytes"].numel() if expect_bytes is None else min(int(expect_bytes), d["bytes"].numel())
+        host = {}
+        nbytes = 0
+        for key, src, cnt in (("totals", d["totals"], 3), ("counters", bufs["counters"], 8 * S), ("status", bufs["status"], S),
+                              ("ok", d["ok"], (nm + 31) // 32), ("off", d["off"], nm + 1), ("frame", d["frame"], nm),
+                              ("bytes", d["bytes"], nb)):
+            t = self._pinned(bufs, "dense_" + key, src, cnt)
+            if cnt:
+                t[:cnt].copy_(src[:cnt], non_blocking=True)
+            host[key] = t[:cnt]
+            nbytes += cnt * t.element_size()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        return {"event": ev, "host": host, "nm": nm, "nb": nb, "d2h_bytes": nbytes, "S": S}
+
+    def deliver_end(self, ticket):
+        """Wait for :meth:`deliver_begin`; returns a dict: n_msgs, ok (bool [n]), off (int64 [n+1]), frame (int32 [n]),
+        data (uint8, dense payload||crc bytes), counters ([S, 8]), overflow (messages or bytes beyond the expected
+        sizes), d2h_bytes.  Arrays are views of pinned staging buffers reused by the next call on the buffer set."""
+        ticket["event"].synchronize()
+        h = ticket["host"]
+        if int(h["status"].numpy().max(initial=0)):
+            raise RuntimeError("receive: capacity overflow (status bits 0x%x): raise max_frames" % int(h["status"].numpy().max()))
+        n_all, b_all = int(h["totals"][0]), int(h["totals"][1])
+        n = min(n_all, ticket["nm"])
+        off = h["off"].numpy()[:n + 1]
+        while n > 0 and off[n] > ticket["nb"]:           # messages whose bytes were not copied
+            n -= 1
+        okw = h["ok"].numpy().view(np.uint32)
+        ok = ((okw[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool) if n else np.zeros(0, bool)
+        return {"n_msgs": n, "n_msgs_device": n_all, "ok": ok, "off": off[:n + 1], "frame": h["frame"].numpy()[:n],
+                "data": h["bytes"].numpy(), "counters": h["counters"].numpy().reshape(ticket["S"], 8).copy(),
+                "overflow": n_all - n, "d2h_bytes": ticket["d2h_bytes"], "bytes_device": b_all}
+
+    def deliver(self, bufs, **kw):
+        """(ok, payload) of every delivered message, in stream / arrival order, through the dense hand-over."""
+        r = self.deliver_end(self.deliver_begin(bufs, **kw))
+        data, off = r["data"], r["off"]
+        out = []
+        for m in range(r["n_msgs"]):
+            body = data[off[m]:off[m + 1]].tobytes()
+            out.append((bool(r["ok"][m]), body[:-4] if len(body) >= 4 else b""))
+        return out, r
+
+
 class SenseEngine:
     """stream_to_vector -> fft_vcc(N, True, blackmanharris) -> complex_to_mag_squared -> bin_statistics_f."""
 

@@ -226,6 +226,27 @@ class ofdm_mod:
         if eof:
             self.flush()
 
+    def send_pkts(self, payloads):
+        """Bulk twin of :meth:`send_pkt`: the whole list is framed on the device (make_packets_kernel: header, CRC-32,
+        whitening -- what ofdm_packet_utils.make_packet does per packet on the host) and modulated in one pass; packets
+        queued by earlier send_pkt calls go out first.  Raises ValueError where make_packet would."""
+        import torch
+        self.flush()
+        payloads = [p.encode("latin-1") if isinstance(p, str) else bytes(p) for p in payloads]
+        if not payloads:
+            return None
+        with self._lock:
+            off = np.zeros(len(payloads) + 1, dtype=np.int64)
+            np.cumsum([len(p) for p in payloads], out=off[1:])
+            plan = self._engine.tx_plan(off, pad_for_usrp=self._pad_for_usrp)
+            blob = b"".join(payloads)
+            host = torch.frombuffer(bytearray(blob), dtype=torch.uint8) if blob else torch.zeros(1, dtype=torch.uint8)
+            out = self._engine.tx_run(plan, host.to(self._engine.dev), first_frame=self._frames_sent)
+            self._frames_sent += len(payloads)
+        for s in self._sinks:
+            (s.feed if hasattr(s, "feed") else s)(out)
+        return out
+
     @staticmethod
     def add_options(normal, expert):
         """
@@ -288,6 +309,7 @@ class ofdm_demod:
         if options.verbose:
             self._print_verbage()
         self._watcher = _queue_watcher_thread(self._rcvd_pktq, callback)
+        self._batch_callback = None
         self.last = None
         # continuous-stream mode (feed_stream): tail of the stream seen so far, its absolute position, and the
         # absolute start of the last frame handed to the callback
@@ -333,6 +355,14 @@ class ofdm_demod:
         res.stream_delivered = delivered
         return res
 
+    def set_batch_callback(self, fn):
+        """Bulk twin of the per-packet callback: with ``fn`` set, every feed() hands ALL the packets it produced to
+        ``fn(ok, data, offsets)`` in one call -- ok: bool array [n], data: uint8 array of the payload || crc bytes back
+        to back, offsets: int64 [n + 1] (payload of packet k = data[offsets[k] : offsets[k+1] - 4]) -- straight from the
+        device's dense hand-over (ofdm_rx_compact) instead of one Python message per packet.  ``None`` restores the
+        per-packet path."""
+        self._batch_callback = fn
+
     def feed(self, samples, max_frames=None, _deliver=True):
         """Run the receiver on one buffer of complex64 samples (cuda tensor, or host array copied to the
         device) and queue every packet the frame sink produced for the watcher thread.  Each call is a
@@ -343,6 +373,13 @@ class ofdm_demod:
         if samples.device.type != "cuda":
             samples = samples.to(self._engine.dev)
         samples = samples.contiguous()
+        if self._batch_callback is not None and _deliver and self._sync == "pn" and not self._log:
+            bufs = self._engine.demodulate_async(samples, max_frames=max_frames)
+            r = self._engine.deliver_end(self._engine.deliver_begin(bufs))
+            n = r["n_msgs"]
+            self._batch_callback(r["ok"], r["data"][:int(r["off"][n])] if n else r["data"][:0], r["off"])
+            self.last = r
+            return r
         if self._sync == "fixed":
             res = self._engine.demodulate_fixed(samples, self._sync_nsymbols, self._sync_freq_offset, max_frames=max_frames)
         elif self._log:

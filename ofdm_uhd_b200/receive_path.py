@@ -29,6 +29,10 @@ class receive_path:
         """feed() for consecutive buffers of one continuous stream (see ofdm_demod.feed_stream)."""
         return self.ofdm_rx.feed_stream(samples, max_frames=max_frames)
 
+    def set_batch_callback(self, fn):
+        """rx_callback_batch(ok[], bytes, offsets): one call per feed() instead of one per packet (ofdm_demod.set_batch_callback)."""
+        self.ofdm_rx.set_batch_callback(fn)
+
     def wait(self, timeout=None):
         self.ofdm_rx.wait(timeout)
 

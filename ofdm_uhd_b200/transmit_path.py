@@ -77,6 +77,14 @@ class transmit_path:
             self.carrier_map_old = carrier_map_new
         return self.ofdm_tx.send_pkt(payload, eof)
 
+    def send_pkts(self, payloads, carrier_map_new="FE7F"):
+        """Bulk twin of send_pkt: the list is framed by make_packets_kernel and modulated in one pass."""
+        if carrier_map_new != self.carrier_map_old:
+            if self._honor_carrier_map:
+                self.ofdm_tx.reset_carrier_map(carrier_map_new)
+            self.carrier_map_old = carrier_map_new
+        return self.ofdm_tx.send_pkts(payloads)
+
     @staticmethod
     def add_options(normal, expert):
         groups = {"normal": normal, "expert": expert}

@@ -78,6 +78,7 @@ def lib():
         L.oc_frame_symbols.argtypes = [C.POINTER(OcCfg), C.c_int]
         L.oc_make_packet.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oc_loopback_mt.argtypes = [C.POINTER(OcCfg), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
+        L.oc_loopback_mt2.argtypes = [C.POINTER(OcCfg), C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -124,17 +125,24 @@ def rx(cfg, x, max_pkts=None):
     return pkts, trig[:nt], ang[:nt], counts
 
 
-def time_loopback(mod="qpsk", frames=0, snr=20.0, threads=None):
+def time_loopback(mod="qpsk", frames=0, snr=20.0, threads=None, cfos=None):
+    """Timed loopback of the bench workload on ``threads`` host threads, one independent stream each.  ``cfos``: the
+    bench capture's per-10 000-frame carrier offsets; thread t works on a piece of segment t (mod their number)."""
     L = lib()
     threads = threads or (os.cpu_count() or 1)
     cfg = make_cfg(512, 200, 128, mod)
     frames = frames or 4000                                 # per thread: ~5 s of work on every core
     out = np.zeros(6, dtype=np.float64)
-    L.oc_loopback_mt(C.byref(cfg), frames, 402, threads, snr, 0.2, out.ctypes.data)
+    if cfos is None or len(cfos) == 0:
+        cfos = [0.2]
+    cf = np.ascontiguousarray([float(cfos[t % len(cfos)]) for t in range(threads)], dtype=np.float64)
+    L.oc_loopback_mt2(C.byref(cfg), frames, 402, threads, snr, cf.ctypes.data, out.ctypes.data)
     samples, secs, npk, nok = out[0], out[1], out[2], out[3]
     return {"value": float(samples / secs / 1e6), "unit": "Msamples/s", "cores": int(threads), "kind": "port",
-            "ms": float(secs * 1e3),
-            "sample": "%d threads x %d frames (%d samples in all) of the bench workload through the C port of the oracle "
-                      "(oracle/ofdm_oracle_c.c, gcc -O3 -march=native -ffp-contract=off, one independent stream per thread); %d/%d packets ok; "
-                      "t_mod %.0f ms + t_demod %.0f ms" % (threads, frames, int(samples), int(nok), threads * frames,
-                                                            out[4] * 1e3, out[5] * 1e3)}
+            "ms": float(secs * 1e3), "flags": "gcc -O3 -march=native -ffp-contract=off, pthreads",
+            "sample": "%d threads x %d frames (%d samples in all) of the bench workload (each thread a piece of one "
+                      "10 000-frame CFO segment, offsets %s) through the C port of the oracle "
+                      "(oracle/ofdm_oracle_c.c, one independent stream per thread); %d/%d packets ok; "
+                      "t_mod %.0f ms + t_demod %.0f ms" % (threads, frames, int(samples),
+                                                            ",".join("%.3f" % v for v in cf[:4]) + ("..." if threads > 4 else ""),
+                                                            int(nok), threads * frames, out[4] * 1e3, out[5] * 1e3)}

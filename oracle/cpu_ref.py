@@ -39,11 +39,11 @@ def time_loopback_numpy(mod: str, frames: int, snr: float):
     return len(x), t_mod + t_dem, ok
 
 
-def time_loopback(mod: str = "qpsk", frames: int = 0, snr: float = 20.0, threads=None):
+def time_loopback(mod: str = "qpsk", frames: int = 0, snr: float = 20.0, threads=None, cfos=None):
     try:
         from . import c_port
         if c_port.available():
-            return c_port.time_loopback(mod, frames, snr, threads)
+            return c_port.time_loopback(mod, frames, snr, threads, cfos)
     except ImportError:
         pass
     frames = frames or 150

@@ -658,12 +658,23 @@ static void* job_run(void* arg) {
 
 /* out: [0] samples total, [1] seconds (max over threads of t_mod + t_demod), [2] packets, [3] crc ok,
  *      [4] max t_mod, [5] max t_demod */
+int oc_loopback_mt2(const oc_cfg* c, int frames_per_thread, int psize, int nthreads, double snr_db, const double* cfos, double* out);
 int oc_loopback_mt(const oc_cfg* c, int frames_per_thread, int psize, int nthreads, double snr_db, double cfo, double* out) {
+    double* cf_ = (double*)malloc(sizeof(double) * (nthreads > 0 ? nthreads : 1));
+    for (int t = 0; t < nthreads; ++t) cf_[t] = cfo;
+    int rc = oc_loopback_mt2(c, frames_per_thread, psize, nthreads, snr_db, cf_, out);
+    free(cf_);
+    return rc;
+}
+
+/* the same with one carrier-frequency offset per thread: every thread works on a piece of one 10 000-frame CFO segment of
+ * the bench capture (bench.py redraws the offset per segment), cfos[t] = that segment's offset */
+int oc_loopback_mt2(const oc_cfg* c, int frames_per_thread, int psize, int nthreads, double snr_db, const double* cfos, double* out) {
     init_tables();
     job* jobs = (job*)calloc(nthreads, sizeof(job));
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
     for (int t = 0; t < nthreads; ++t) {
-        jobs[t].cfg = c; jobs[t].frames = frames_per_thread; jobs[t].psize = psize; jobs[t].snr_db = snr_db; jobs[t].cfo = cfo;
+        jobs[t].cfg = c; jobs[t].frames = frames_per_thread; jobs[t].psize = psize; jobs[t].snr_db = snr_db; jobs[t].cfo = cfos[t];
         jobs[t].seed = 1234 + 7919 * (uint64_t)t;
         pthread_create(&th[t], NULL, job_run, &jobs[t]);
     }

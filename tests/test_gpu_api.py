@@ -304,3 +304,43 @@ def test_usrp_path_shims_loopback_and_retune():
     txpath.flush()
     rxpath.wait(timeout=10)
     assert len(got) == n0 and rxpath.u.history == [905e6, 920e6]
+
+
+def test_bulk_send_pkts_and_batch_callback_equal_per_packet_surface():
+    """transmit_path.send_pkts (make_packets_kernel on the device) produces the samples a loop of send_pkt calls
+    produces, and receive_path.set_batch_callback hands over, in one call, exactly the (ok, payload) sequence the
+    per-packet rx_callback sees."""
+    import torch
+    from ofdm_uhd_b200 import transmit_path, receive_path, channel_model
+    opts = options(modulation="qpsk")
+    rng = np.random.default_rng(12)
+    sent = [struct.pack("!HH", k, 0) + bytes(rng.integers(0, 256, int(rng.integers(0, 700)), dtype=np.uint8)) for k in range(40)]
+    outs = {}
+    for mode in ("loop", "bulk"):
+        tx = transmit_path.transmit_path(opts, pad_seed=3)
+        tx.connect(lambda smp, mode=mode: outs.setdefault(mode, smp.cpu().numpy()))
+        if mode == "loop":
+            for p in sent:
+                tx.send_pkt(p, False, "FE7F")
+            tx.send_pkt(eof=True)
+        else:
+            tx.send_pkts(sent)
+    assert np.array_equal(outs["loop"], outs["bulk"])
+    with pytest.raises(ValueError):
+        tx.send_pkts([b"x" * 4092])
+    # receive side
+    eng = tx.ofdm_tx._engine
+    chan = channel_model.channel_model(eng, noise_voltage=0.004, frequency_offset=0.15, seed=2, lead_in=1300, tail=2600)
+    cap = chan.process(torch.from_numpy(outs["bulk"]).cuda())
+    per_packet, bulk = [], []
+    rx = receive_path.receive_path(lambda ok, payload: per_packet.append((ok, payload)), opts)
+    rx.feed(cap)
+    rx.wait(timeout=60)
+    rx.set_batch_callback(lambda ok, data, off: bulk.extend((bool(ok[k]), data[off[k]:off[k + 1] - 4].tobytes()) for k in range(len(ok))))
+    rx.feed(cap)
+    assert bulk == per_packet and sum(1 for ok, _ in bulk if ok) >= 36
+    rx.set_batch_callback(None)
+    per_packet.clear()
+    rx.feed(cap)
+    rx.wait(timeout=60)
+    assert per_packet == bulk

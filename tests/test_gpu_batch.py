@@ -103,3 +103,39 @@ def test_tx_streams_equal_oracle(N, occ, cp, mod):
         mask[out_off[s]:out_off[s] + len(r)] = False
     assert not g[mask].any()                          # nothing written between the streams
     eng.close()
+
+
+@pytest.mark.parametrize("batch", [False, True])
+def test_dense_delivery_equals_collect(batch):
+    """ofdm_rx_compact: the dense hand-over (messages back to back + bit-packed verdicts) delivers exactly what
+    collect() assembles from the per-frame slots, for a single stream and for a batch, ragged payloads and a bad CRC
+    included; with an expected size too small the rest is reported as overflow."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    lay = o.Layout(512, 200, 128, "qam16")
+    eng = OfdmEngine(512, 200, 128, "qam16", max_pkt_bytes=1024)
+    rng = np.random.default_rng(8)
+    caps = []
+    for s in range(3 if batch else 1):
+        pay = [bytes(rng.integers(0, 256, int(k), dtype=np.uint8)) for k in rng.integers(0, 1000, size=7 + s)]
+        pk = [o.make_packet(p, 1, 1, False) for p in pay]
+        bad = bytearray(pk[3]); bad[9] ^= 0x40; pk[3] = bytes(bad)                       # CRC must fail for this one
+        x = o.tx_modulate(pk, lay, 0.25, seed=1)
+        xin = np.concatenate([np.zeros(700, np.complex64), x, np.zeros(3000, np.complex64)])
+        caps.append(o.channel(xin, 35.0, 0.1 * s, 512, seed=60 + s, sig_power=float(np.mean(np.abs(x) ** 2))))
+    if batch:
+        off = np.zeros(len(caps) + 1, dtype=np.int64)
+        np.cumsum([len(c) for c in caps], out=off[1:])
+        bufs = eng.rx_alloc_batch(off, max_frames=32)
+        eng.demodulate_batch_async(torch.from_numpy(np.concatenate(caps)).cuda(), bufs)
+        ref = [p for r in eng.collect_batch(bufs) for p in r.packets]
+    else:
+        bufs = eng.rx_alloc(len(caps[0]))
+        eng.demodulate_async(torch.from_numpy(caps[0]).cuda(), bufs)
+        ref = eng.collect(bufs).packets
+    got, info = eng.deliver(bufs)
+    assert got == ref and len(ref) >= 6 and not all(ok for ok, _ in ref) and info["overflow"] == 0
+    assert info["bytes_device"] == sum(len(p) + 4 for _, p in ref)
+    few, info2 = eng.deliver(bufs, expect_msgs=4, expect_bytes=1 << 20)
+    assert few == ref[:4] and info2["overflow"] == len(ref) - 4
+    eng.close()
