@@ -271,7 +271,10 @@ def oracle_prefix_parity(torch, eng, xc, lead, frame_samples, n_frames_total, mo
         t.join()
     secs = time.perf_counter() - t0
     equal = [got[i] == ref[i] for i in range(len(caps))]
-    return {"oracle_prefix_equal": bool(all(equal)), "oracle_windows_equal": equal, "oracle_windows": len(caps),
+    verdicts = all([ok for ok, _ in got[i]] == [ok for ok, _ in ref[i]] for i in range(len(caps)))
+    good = all(all(p == q for (ok, p), (_, q) in zip(got[i], ref[i]) if ok) for i in range(len(caps)))
+    return {"oracle_prefix_equal": bool(all(equal)), "oracle_windows_equal": equal, "oracle_crc_verdicts_equal": bool(verdicts),
+            "oracle_good_payloads_equal": bool(good), "oracle_windows": len(caps),
             "oracle_frames_per_window": frames_per_window,
             "oracle_window_first_frames": starts, "oracle_messages": int(sum(len(r) for r in ref)),
             "oracle_crc_ok": int(sum(1 for r in ref for ok, _ in r if ok)),

@@ -122,6 +122,8 @@ typedef struct ofdm_rx_io {
     uint8_t* sym_idx;          /* [max_vectors*ncar]  slicer decisions                   */
     float*   derot_syms;       /* [max_vectors*ncar*2] frame-sink derotated symbols      */
     int64_t  max_vectors;
+    float*   fft_out;          /* [max_vectors*N*2] fft_demod output, shifted (ofdm_receiver-fft_out_c.dat) */
+    float*   sampler_out;      /* [max_vectors*N*2] ofdm_sampler output vectors (ofdm_receiver-sampler_c.dat) */
 } ofdm_rx_io;
 
 size_t ofdm_rx_workspace_bytes(const ofdm_handle* h, int64_t n_samples, int32_t max_frames);

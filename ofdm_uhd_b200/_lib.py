@@ -37,7 +37,8 @@ class RxIo(C.Structure):
                 ("frame_start", C.c_void_p), ("frame_ndata", C.c_void_p), ("frame_live", C.c_void_p),
                 ("frame_status", C.c_void_p), ("pkt_len", C.c_void_p), ("pkt_ok", C.c_void_p),
                 ("pkt_bytes", C.c_void_p), ("counters", C.c_void_p), ("eq_syms", C.c_void_p),
-                ("sym_idx", C.c_void_p), ("derot_syms", C.c_void_p), ("max_vectors", C.c_int64)]
+                ("sym_idx", C.c_void_p), ("derot_syms", C.c_void_p), ("max_vectors", C.c_int64),
+                ("fft_out", C.c_void_p), ("sampler_out", C.c_void_p)]
 
 
 _lib: Optional[C.CDLL] = None

@@ -107,6 +107,8 @@ struct RxWorkspace {
     int32_t* next_frame;   // per stream [max_frames] scratch of the liveness walk
     int32_t* exit_frame;   // per stream [max_frames] scratch of the liveness walk
     int32_t* seg_off;      // per stream [n_seg + 1] exclusive scan of seg_count
+    float2* eq;            // per stream [eq_stride * occ] equalised vectors (acq_kernel -> sink_kernel)
+    int64_t eq_stride;     // vectors per stream: n_max / L + max_frames + 2 bounds what the sampler can emit
     int64_t n_seg, seg_len, seg_cap;      // n_seg: detector segments of the LONGEST stream (table stride)
     int32_t max_frames;
 };

@@ -1,5 +1,5 @@
-// Receive back end: derotation + forward FFT + ofdm_frame_acquisition + ofdm_frame_sink as one
-// CTA per frame-sink session, then the sink's liveness walk, dewhitening and CRC.
+// Receive back end: derotation + forward FFT + ofdm_frame_acquisition (one CTA per frame), ofdm_frame_sink (one warp
+// per sink session), then the sink's liveness walk, dewhitening and CRC, and the dense hand-over to the host.
 // Reference wiring: ofdm_receiver.py~:124-129 (sigmix, fft_demod, ofdm_frame_acq), ofdm.py:238-247
 // (ofdm_frame_sink), ofdm.py:300-305 + ofdm_packet_utils.py:169-191 (unmake_packet).
 #include "internal.h"
@@ -7,7 +7,18 @@
 #include <limits.h>
 #include <stdlib.h>
 
-struct DemodParams {
+// The receive back end is two kernels:
+//   acq_kernel<N>   multiply_cc (NCO derotation) + fft_vcc (forward, shifted) + ofdm_frame_acquisition for every vector
+//                   the sampler emits, one CTA per frame: the equalised occ-wide vectors land in the workspace (they are
+//                   a function of the vector stream alone: the acquisition block re-estimates at EVERY flagged vector,
+//                   whatever state the sink is in);
+//   sink_kernel     ofdm_frame_sink, one WARP per speculative session (one per frame): walks the equalised vectors from
+//                   its frame's preamble on -- across later frames if the header it finds says so -- with the PLL / DFE
+//                   slicer, the byte packing and the header parse done warp-synchronously (no block barriers, the
+//                   serial carrier-loop update computed redundantly by all lanes).
+// (One fused kernel did both until round 2: 8 block barriers and a one-thread PLL section per vector on 64-thread CTAs,
+// 20 % of its stall samples waiting on instruction fetch.)
+struct AcqParams {
     const float2* y;
     const int64_t* soff;           // stream offsets (nullptr: one stream of n samples); tables below are per stream
     int64_t n;
@@ -21,11 +32,26 @@ struct DemodParams {
     const int32_t* frame_ndata;
     const int64_t* vbase;
     const float2* tw;
-    const float2* cst;
-    const int16_t* sinkmap;
     const float* ks;
     const float* kd;
-    int occ, cp, zl, ncar, nbits, M, L, max_frames, pkt_stride;
+    int occ, cp, zl, L, max_frames;
+    float2* eq;                    // [S][eq_stride][occ] equalised vectors (ofdm_frame_acquisition output)
+    int64_t eq_stride;             // vectors per stream in eq
+    float2* eq_tap;                // optional copy for the parity tests / --log (io->eq_syms), single stream
+    float2* fft_tap;               // optional: shifted spectra [max_vectors][N] (ofdm_receiver-fft_out_c.dat)
+    float2* samp_tap;              // optional: derotated sampler vectors [max_vectors][N] (sampler_c / sigmix)
+    int64_t max_vectors;
+};
+
+struct SinkParams {
+    const float2* eq;
+    int64_t eq_stride;
+    int per_stream;                // 1: tables are per stream (blockIdx.y)
+    const int32_t* n_frames;
+    const int64_t* vbase;
+    const float2* cst;
+    const int16_t* sinkmap;
+    int occ, ncar, nbits, M, max_frames, pkt_stride;
     int grid_L;
     float grid_x0, grid_y0, grid_inv_dx, grid_inv_dy;
     const uint8_t* grid;
@@ -33,8 +59,7 @@ struct DemodParams {
     int32_t* pkt_len;
     int32_t* sess_nvec;
     uint8_t* pkt_bytes;
-    float2* eq_syms;
-    uint8_t* sym_idx;
+    uint8_t* sym_idx;              // optional taps (single stream), indexed by vector
     float2* derot_syms;
     int64_t max_vectors;
 };
@@ -198,14 +223,15 @@ struct Slicer {
         return b;
     }
 };
-
+// ---------------------------------------------------------------------------------------------
+// acq_kernel: sigmix + fft_demod + ofdm_frame_acq (ofdm_receiver.py~:124-129) for all vectors of one frame per CTA.
+// ---------------------------------------------------------------------------------------------
 template <int N, bool TAPS>
 __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E),
-                                  TAPS ? 1 : (FftPlan<N>::E == 8 ? 1024 : 512) / ((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E))) demod_kernel(const DemodParams p_all) {
+                                  TAPS ? 1 : (FftPlan<N>::E == 8 ? 1024 : 512) / ((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N>::E))) acq_kernel(const AcqParams p) {
     // The tables of this CTA's stream (blockIdx.y): CTA-uniform offsets on top of the kernel parameters, held in a
     // view of their own (v) -- a locally modified COPY of the parameter struct is not safe: nvcc kept reading the
     // unshifted y pointer from the parameter space in the instantiations that load samples straight from global memory.
-    const DemodParams& p = p_all;
     struct {
         const float2* y;
         const int64_t* trig_idx;
@@ -217,22 +243,18 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
         const int32_t* n_frames;
         const int32_t* frame_ndata;
         const int64_t* vbase;
-        uint8_t* frame_status;
-        int32_t* pkt_len;
-        int32_t* sess_nvec;
-        uint8_t* pkt_bytes;
+        float2* eq;
     } v;
     {
-        const int64_t sidx = p_all.soff ? (int64_t)blockIdx.y : 0;
-        const int64_t mf = p_all.max_frames;
-        const int64_t a = p_all.soff ? p_all.soff[sidx] : 0;
-        v.y = p_all.y + a;
-        v.trig_idx = p_all.trig_idx + sidx * mf; v.phi0 = p_all.phi0 + sidx * mf; v.step = p_all.step + sidx * mf;
-        v.nco_init = p_all.nco_init + sidx; v.n_trig = p_all.n_trig + sidx; v.first_ok = p_all.first_ok + sidx;
-        v.n_frames = p_all.n_frames + sidx; v.frame_ndata = p_all.frame_ndata + sidx * mf;
-        v.vbase = p_all.vbase + sidx * (mf + 1); v.frame_status = p_all.frame_status + sidx * mf;
-        v.pkt_len = p_all.pkt_len + sidx * mf; v.sess_nvec = p_all.sess_nvec + sidx * mf;
-        v.pkt_bytes = p_all.pkt_bytes + sidx * mf * (int64_t)p_all.pkt_stride;
+        const int64_t sidx = p.soff ? (int64_t)blockIdx.y : 0;
+        const int64_t mf = p.max_frames;
+        const int64_t a = p.soff ? p.soff[sidx] : 0;
+        v.y = p.y + a;
+        v.trig_idx = p.trig_idx + sidx * mf; v.phi0 = p.phi0 + sidx * mf; v.step = p.step + sidx * mf;
+        v.nco_init = p.nco_init + sidx; v.n_trig = p.n_trig + sidx; v.first_ok = p.first_ok + sidx;
+        v.n_frames = p.n_frames + sidx; v.frame_ndata = p.frame_ndata + sidx * mf;
+        v.vbase = p.vbase + sidx * (mf + 1);
+        v.eq = p.eq + sidx * p.eq_stride * p.occ;
     }
     using P = FftPlan<N>;
     constexpr int E = P::E;
@@ -243,35 +265,23 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
     extern __shared__ double smem_d[];
     double* red = smem_d;                                   // [8*NW]
-    // N = 4096: two FFT buffers + H + dfe would be 125 KB, one CTA per SM; with a single buffer (in-place passes, a
-    // barrier between their loads and stores, no prefetch) two CTAs fit
+    // N = 4096: a single FFT buffer (in-place passes with a barrier between their loads and stores, no prefetch), so
+    // that several CTAs fit an SM
     constexpr bool ONEBUF = (N == 4096);
     float2* bufA = (float2*)(red + 8 * NW);
     float2* bufB = ONEBUF ? bufA : bufA + SB;
     float2* H = bufB + SB;                                  // [occ]
-    float2* dfe = H + p.occ;                                // [ncar]
-    float2* s_cst = dfe + p.occ;                            // [M]
-    uint8_t* sym = (uint8_t*)(s_cst + p.M);                 // [ncar]
-    uint8_t* vb = sym + ((p.ncar + 15) & ~15);              // bytes of the current vector
-    uint8_t* s_grid = vb + ((p.ncar * p.nbits / 8 + 16 + 15) & ~15);   // [grid_L^2] cell -> constellation index
-    __shared__ int s_delta, s_hdr_ok, s_len;
-    __shared__ float2 s_cc[2], s_car[2], s_W[E];
-    __shared__ float s_phase, s_freq;
-    __shared__ unsigned s_carry;
+    __shared__ int s_delta;
+    __shared__ float2 s_cc[2], s_W[E];
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int F = *v.n_frames;
     int K = *v.n_trig;
     if (K > p.max_frames) K = p.max_frames;
     const int first_ok = *v.first_ok;
-    const int occ = p.occ, ncar = p.ncar, nbits = p.nbits, zl = p.zl, L = p.L;
-    for (int i = tid; i < p.M; i += BT) s_cst[i] = p.cst[i];
-    for (int i = tid; i < p.grid_L * p.grid_L; i += BT) s_grid[i] = p.grid[i];
-    const Slicer slicer{s_cst, s_grid, p.M, p.grid_L, p.grid_x0, p.grid_y0, p.grid_inv_dx, p.grid_inv_dy};
+    const int occ = p.occ, zl = p.zl, L = p.L;
     float2* S = (P::NP == 2) ? bufB : bufA;                 // shifted spectrum of the current vector
-    const int bits_this = ncar * nbits;
-    const BitDiv bd(nbits);
-    // Three-pass plans leave bufB idle while a vector is sliced: the next vector's samples are copied into it
+    // Three-pass plans leave bufB idle while a vector is equalised: the next vector's samples are copied into it
     // asynchronously meanwhile, so the first FFT pass never waits on HBM.
     constexpr bool PF = (P::NP == 3) && !ONEBUF;
     auto prefetch = [&](int64_t st2) {
@@ -284,21 +294,20 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
     };
 
     for (int f = blockIdx.x; f < F; f += gridDim.x) {
-        int g = f, m = 0, vi = 0, cnt = 1, delta = 0, bit_base = 0;
-        int status = 3, nvec = INT_MAX / 2, len = 0;
-        int last_vi = INT_MAX;                              // data vector that completes the packet, once the header is in
+        const int kg = first_ok + f;
+        const int64_t t = v.trig_idx[kg];
+        const int nd = v.frame_ndata[f];
+        const int64_t vb0 = v.vbase[f];
+        int cnt = 1, delta = 0;
         int kk_w = INT_MIN;                                 // trigger segment the table s_W belongs to
-        if (PF) cp_async_wait_all();                        // a copy left in flight by the previous session
+        if (PF) cp_async_wait_all();                        // a copy left in flight by the previous frame
         __syncthreads();
-        if (PF) prefetch(v.trig_idx[first_ok + f] - N + 1);
-        while (g < F) {
-            const int kg = first_ok + g;
-            const int64_t t = v.trig_idx[kg];
+        if (PF) prefetch(t - N + 1);
+        for (int m = 0; m <= nd; ++m) {
             const int64_t st = t - N + 1 + (int64_t)m * L;
             const bool flag = (m == 0);
-            const int64_t vglob = TAPS ? v.vbase[g] + m : 0;
-            const bool tap = TAPS && (g == f) && vglob < p.max_vectors;
-            const int par = vi & 1;
+            const int64_t vglob = vb0 + m;
+            const int par = m & 1;
             // ---- sigmix + fft_demod ----
             int kk = kg;
             if (flag) {
@@ -325,9 +334,18 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
             }
             DemodLoad<PF> ld{PF ? bufB : v.y, st, t_next, v.trig_idx, v.phi0, v.step, K, kk < 0 ? 0 : kk, phasor_f64(ph_base), s_W};
             if (kk < 0) ld.t_next = (K > 0) ? v.trig_idx[0] : LLONG_MAX;
-            if (PF) {
-                cp_async_wait_all();
-                __syncthreads();
+            if (PF) cp_async_wait_all();
+            if (P::NP == 3) __syncthreads();                // S (= bufA) of the previous vector has been read by everyone
+            if (TAPS && p.samp_tap && vglob < p.max_vectors && tid < T) {
+                // the sampler's output vector (ofdm_receiver-sampler_c.dat; sigmix sits in front of the sampler, so it
+                // is derotated already): the very values the first FFT pass reads, through the same functor
+#pragma unroll
+                for (int q = 0; q < E / R0; ++q)
+#pragma unroll
+                    for (int r = 0; r < R0; ++r) {
+                        const int idx = tid + q * T + r * (N / R0);
+                        p.samp_tap[vglob * N + idx] = ld(idx, q * R0 + r);
+                    }
             }
             if (tid < T) fft_pass<N, R0, 1, -1>(tid, p.tw, ld, SmemOut{bufA});
             __syncthreads();
@@ -339,21 +357,19 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 if (tid < T) fft_pass<N, R2, R0 * R1, -1, SmemIn, ShiftStore<N>, ONEBUF>(tid, p.tw, SmemIn{bufB}, ShiftStore<N>{S});
             }
             __syncthreads();
-            if (vi < last_vi) {                             // fetch the vector that follows
-                int g2 = g, m2 = m + 1;
-                if (m2 > v.frame_ndata[g]) { ++g2; m2 = 0; }
-                if (g2 < F) {
-                    const int64_t st2 = v.trig_idx[first_ok + g2] - N + 1 + (int64_t)m2 * L;
-                    if (PF) {
-                        prefetch(st2);                      // bufB is free: asynchronous copy into it
-                    } else {
-                        // two-pass plans and the single-buffer layout have no landing zone in shared memory: at least pull the vector's lines
-                        // into L2 while this one is sliced (one 128-byte line per thread)
-                        for (int i = tid * 16; i < N; i += BT * 16)
-                            asm volatile("prefetch.global.L2 [%0];" :: "l"(v.y + st2 + i));
-                    }
+            if (m < nd) {                                   // fetch the vector that follows
+                const int64_t st2 = st + L;
+                if (PF) {
+                    prefetch(st2);                          // bufB is free: asynchronous copy into it
+                } else {
+                    // two-pass plans and the single-buffer layout have no landing zone in shared memory: at least pull
+                    // the vector's lines into L2 while this one is equalised (one 128-byte line per thread)
+                    for (int i = tid * 16; i < N; i += BT * 16)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(v.y + st2 + i));
                 }
             }
+            if (TAPS && p.fft_tap && vglob < p.max_vectors)
+                for (int i = tid; i < N; i += BT) p.fft_tap[vglob * N + i] = S[i];
             // ---- ofdm_frame_acquisition: correlate + calculate_equalizer on a flagged vector ----
             if (flag) {
                 double acc[2 * OFDM_MAX_SHIFT];
@@ -370,19 +386,19 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 }
 #pragma unroll
                 for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) {
-                    double v = acc[s];
+                    double q = acc[s];
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                    if (lane == 0) red[w * 8 + s] = v;
+                    for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+                    if (lane == 0) red[w * 8 + s] = q;
                 }
                 __syncthreads();
                 if (tid == 0) {
                     float best = 0.f;
                     int index = 0;
                     for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) {
-                        double v = 0.0;
-                        for (int ww = 0; ww < NW; ++ww) v += red[ww * 8 + s];
-                        const float sf = (float)v;
+                        double q = 0.0;
+                        for (int ww = 0; ww < NW; ++ww) q += red[ww * 8 + s];
+                        const float sf = (float)q;
                         if (sf > best) { best = sf; index = zl - OFDM_MAX_SHIFT + s; }
                     }
                     s_delta = index - zl;
@@ -404,205 +420,278 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 if (tid == 0 && (occ & 1) == 0) H[occ - 1] = H[occ - 2];
                 __syncthreads();
             }
-            // one-tap equaliser with the coarse-offset CP phase compensation: comp(delta, cnt) is in s_cc[par]
-            // (written by the acquisition above, or during the previous vector's serial section)
+            // ---- one-tap equaliser with the coarse-offset CP phase compensation: comp(delta, cnt) is in s_cc[par]
+            // (written by the acquisition above, or while the previous vector was equalised).  No coarse offset:
+            // comp = (1, -0) and H * comp is H itself (up to the sign of an exact zero, which no comparison downstream
+            // can see), so that multiply is skipped
             const float2 cc = s_cc[par];
-            if (TAPS) {
-                if (tap && p.eq_syms)
-                    for (int i = tid; i < occ; i += BT)
-                        p.eq_syms[vglob * occ + i] = cmul_x(cmul_x(H[i], cc), S[i + zl + delta]);
-            }
             int cnt_next = cnt + 1;
             if (cnt_next == OFDM_ACQ_MAX_SYMBOLS) cnt_next = 1;
-            // ---- ofdm_frame_sink ----
-            if (vi == 0) {
-                // enter_have_sync: the flagged vector itself is not demapped
-                for (int c = tid; c < ncar; c += BT) dfe[c] = make_float2(1.f, 0.f);
-                if (tid == 0) {
-                    s_phase = 0.f; s_freq = 0.f; s_carry = 0u; s_hdr_ok = 0; s_len = 0;
-                    s_car[par ^ 1] = make_float2(1.f, 0.f);                       // expj(0)
-                }
-                if (tid == 32) s_cc[par ^ 1] = coarse_comp(delta, p.cp, N, cnt_next);
-                __syncthreads();
-            } else {
-                const float2 car = s_car[par];
-                double er = 0.0, ei = 0.0;
-                // two carriers per pass with every load ahead of the first store: the two slicer chains are
-                // independent, which the compiler cannot see through the shared-memory stores of a one-carrier loop
-                for (int c = tid; c < ncar; c += 2 * BT) {
-                    const int c2 = c + BT;
-                    const bool two = c2 < ncar;
-                    const int cb = two ? c2 : c;
-                    const float2 d0a = dfe[c], d0b = dfe[cb];
-                    const int ia = LDG(p.sinkmap + c), ib = LDG(p.sinkmap + cb);
-                    const float2 Ha = H[ia], Hb = H[ib];
-                    const float2 Sa = S[ia + zl + delta], Sb = S[ib + zl + delta];
-                    // no coarse offset: comp = (1, -0) and H * comp is H itself (up to the sign of an exact zero, which no
-                    // comparison downstream can see), so the multiply is skipped
-                    const float2 Hca = (delta == 0) ? Ha : cmul_x(Ha, cc), Hcb = (delta == 0) ? Hb : cmul_x(Hb, cc);
-                    const float2 eqa = cmul_x(Hca, Sa), eqb = cmul_x(Hcb, Sb);
-                    const float2 ra = cmul_x(cmul_x(eqa, car), d0a), rb = cmul_x(cmul_x(eqb, car), d0b);
-                    int ba, bb;
-                    if (p.grid_L > 0) {
-                        ba = slicer(ra);
-                        bb = slicer(rb);
-                    } else {
-                        // small constellations: both scans fused so the two chains interleave
-                        ba = 0; bb = 0;
-                        float besta, bestb;
-                        {
-                            const float2 c0 = s_cst[0];
-                            besta = norm_x(csub_x(ra, c0));
-                            bestb = norm_x(csub_x(rb, c0));
-                        }
-                        for (int k = 1; k < p.M; ++k) {
-                            const float2 ck = s_cst[k];
-                            const float dda = norm_x(csub_x(ra, ck));
-                            const float ddb = norm_x(csub_x(rb, ck));
-                            if (dda < besta) { besta = dda; ba = k; }
-                            if (ddb < bestb) { bestb = ddb; bb = k; }
-                        }
-                    }
-                    const float2 cla = s_cst[ba], clb = s_cst[bb];
-                    const float2 ea = cmulc_x(ra, cla), eb = cmulc_x(rb, clb);
-                    er += (double)ea.x;
-                    ei += (double)ea.y;
-                    if (norm_x(ra) > 0.001f) {
-                        const float2 dq = cscale_x(csub_x(cdiv_x(cla, ra), d0a), 0.05f);      // eq_gain * (q - dfe)
-                        dfe[c] = make_float2(fadd_rn(d0a.x, dq.x), fadd_rn(d0a.y, dq.y));
-                    }
-                    sym[c] = (uint8_t)ba;
-                    if (TAPS && tap) {
-                        if (p.sym_idx) p.sym_idx[vglob * ncar + c] = (uint8_t)ba;
-                        if (p.derot_syms) p.derot_syms[vglob * ncar + c] = ra;
-                    }
-                    if (two) {
-                        er += (double)eb.x;
-                        ei += (double)eb.y;
-                        if (norm_x(rb) > 0.001f) {
-                            const float2 dq = cscale_x(csub_x(cdiv_x(clb, rb), d0b), 0.05f);
-                            dfe[c2] = make_float2(fadd_rn(d0b.x, dq.x), fadd_rn(d0b.y, dq.y));
-                        }
-                        sym[c2] = (uint8_t)bb;
-                        if (TAPS && tap) {
-                            if (p.sym_idx) p.sym_idx[vglob * ncar + c2] = (uint8_t)bb;
-                            if (p.derot_syms) p.derot_syms[vglob * ncar + c2] = rb;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    er += __shfl_xor_sync(0xffffffffu, er, d);
-                    ei += __shfl_xor_sync(0xffffffffu, ei, d);
-                }
-                if (lane == 0) { red[w * 8] = er; red[w * 8 + 1] = ei; }
-                __syncthreads();
-                const int B0 = bit_base >> 3, B1 = (bit_base + bits_this) >> 3;
-                if (tid == 0) {
-                    // PLL update, and the carrier of the next vector while we are at it
-                    double sr = 0.0, si = 0.0;
-                    for (int ww = 0; ww < NW; ++ww) { sr += red[ww * 8]; si += red[ww * 8 + 1]; }
-                    const float angle = (float)atan2((double)(float)si, (double)(float)sr);
-                    const float freq = fsub_rn(s_freq, fmul_rn(0.015625f, angle));       // freq_gain = 0.25^2/4
-                    float ph = fsub_rn(fadd_rn(s_phase, freq), fmul_rn(0.25f, angle));   // phase_gain = 0.25
-                    if ((double)ph >= 6.283185307179586) ph = (float)((double)ph - 6.283185307179586);
-                    if ((double)ph < 0.0) ph = (float)((double)ph + 6.283185307179586);
-                    s_freq = freq;
-                    s_phase = ph;
-                    s_car[par ^ 1] = expj_f32(ph);
-                }
-                if (tid == 32) s_cc[par ^ 1] = coarse_comp(delta, p.cp, N, cnt_next);
-                // LSB-first byte packing; bits left over from the previous vector sit in s_carry
-                const unsigned carry = s_carry;
-                pack_bytes(sym, vb, B0, B1, bit_base, carry, tid, BT, bd);
-                __syncthreads();
-                if (tid == 0) {
-                    if (vi == 1) {
-                        const unsigned hdr = ((unsigned)vb[0] << 24) | ((unsigned)vb[1] << 16) | ((unsigned)vb[2] << 8) | vb[3];
-                        s_hdr_ok = (((hdr >> 16) ^ (hdr & 0xFFFFu)) == 0u) ? 1 : 0;
-                        s_len = (int)((hdr >> 16) & 0x0FFFu);
-                    }
-                    const int nrb = bit_base + bits_this - 8 * B1;
-                    unsigned nc = 0;
-                    for (int i = 0; i < nrb; ++i) {
-                        const int rel = 8 * B1 + i - bit_base;
-                        const int c = bd.div(rel);
-                        nc |= (((unsigned)sym[c] >> (rel - c * nbits)) & 1u) << i;
-                    }
-                    s_carry = nc;
-                }
-                __syncthreads();
-                const bool hdr_ok = s_hdr_ok != 0;
-                len = s_len;
-                if (vi == 1 && !hdr_ok) { status = 1; nvec = 2; len = 0; break; }
-                if (vi == 1) last_vi = (8 * (4 + len) + bits_this - 1) / bits_this;
-                for (int q = B0 + tid; q < B1; q += BT) {
-                    const int pq = q - 4;
-                    if (pq >= 0 && pq < len && pq < p.pkt_stride) v.pkt_bytes[(size_t)f * p.pkt_stride + pq] = vb[q - B0];
-                }
-                bit_base += bits_this;
-                if (B1 >= 4 + len) { status = 2; nvec = vi + 1; break; }
+            if (tid == BT - 1 && m < nd) s_cc[par ^ 1] = coarse_comp(delta, p.cp, N, cnt_next);
+            float2* dst = v.eq + vglob * occ;
+            for (int i = tid; i < occ; i += BT) {
+                const float2 Hi = H[i];
+                const float2 o = cmul_x(delta == 0 ? Hi : cmul_x(Hi, cc), S[i + zl + delta]);
+                dst[i] = o;
+                if (TAPS && p.eq_tap && vglob < p.max_vectors) p.eq_tap[vglob * occ + i] = o;
             }
             cnt = cnt_next;
-            ++vi;
-            ++m;
-            if (m > v.frame_ndata[g]) { ++g; m = 0; }
-        }
-        if (tid == 0) {
-            v.frame_status[f] = (uint8_t)status;
-            v.pkt_len[f] = status == 2 ? len : 0;
-            v.sess_nvec[f] = nvec;
         }
     }
     if (PF) cp_async_wait_all();
 }
 
+// ---------------------------------------------------------------------------------------------
+// sink_kernel: ofdm_frame_sink (ofdm.py:238-247), one warp per speculative session.
+// Session f starts at frame f's flagged vector (position vbase[f] of the equalised vector stream) as if the sink were
+// in SYNC_SEARCH there, and walks on -- over later frames' vectors too: flags are ignored outside SYNC_SEARCH -- until
+// its header turns out bad (2 vectors), its packet is complete, or the stream ends.  The liveness walk (launch_finish)
+// then decides which sessions the one real sink would have run.
+// ---------------------------------------------------------------------------------------------
+// TPS = threads per session: 32 (a warp; several sessions per CTA) for the usual layouts, 128 (the whole CTA works on
+// one session, block barriers instead of warp barriers) when a vector has thousands of data carriers.
+template <bool TAPS, int TPS>
+__global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
+    extern __shared__ __align__(16) unsigned char sink_smem[];
+    __shared__ double s_red[2][4][2];
+    constexpr bool WARP = (TPS == 32);
+    const int lane = WARP ? (threadIdx.x & 31) : threadIdx.x;          // thread index inside the session
+    const int w = WARP ? (threadIdx.x >> 5) : 0, W = WARP ? (blockDim.x >> 5) : 1;
+    auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
+    const int ncar = p.ncar, nbits = p.nbits, occ = p.occ;
+    // shared: constellation [M], grid table [grid_L^2] (CTA-wide), then per warp: dfe [ncar] float2, sym [ncar], vb
+    float2* s_cst = (float2*)sink_smem;
+    uint8_t* s_grid = (uint8_t*)(s_cst + p.M);
+    const int grid_bytes = (p.grid_L * p.grid_L + 15) & ~15;
+    const int sym_bytes = (ncar + 15) & ~15, vb_bytes = (ncar * nbits / 8 + 16 + 15) & ~15;
+    const size_t per_warp = (size_t)ncar * sizeof(float2) + sym_bytes + vb_bytes;
+    unsigned char* mine = (unsigned char*)(s_grid + grid_bytes) + (size_t)w * per_warp;
+    float2* dfe = (float2*)mine;
+    uint8_t* sym = (uint8_t*)(dfe + ncar);
+    uint8_t* vb = sym + sym_bytes;
+    for (int i = threadIdx.x; i < p.M; i += blockDim.x) s_cst[i] = p.cst[i];
+    for (int i = threadIdx.x; i < p.grid_L * p.grid_L; i += blockDim.x) s_grid[i] = p.grid[i];
+    __syncthreads();
+    const Slicer slicer{s_cst, s_grid, p.M, p.grid_L, p.grid_x0, p.grid_y0, p.grid_inv_dx, p.grid_inv_dy};
+    const int64_t sidx = p.per_stream ? (int64_t)blockIdx.y : 0;
+    const int64_t mf = p.max_frames;
+    const int F = p.n_frames[sidx];
+    const int64_t* vbase = p.vbase + sidx * (mf + 1);
+    const float2* eq = p.eq + sidx * p.eq_stride * occ;
+    uint8_t* frame_status = p.frame_status + sidx * mf;
+    int32_t* pkt_len = p.pkt_len + sidx * mf;
+    int32_t* sess_nvec = p.sess_nvec + sidx * mf;
+    uint8_t* pkt_bytes = p.pkt_bytes + sidx * mf * (int64_t)p.pkt_stride;
+    const int64_t vtot = F > 0 ? vbase[F] : 0;              // vectors in the stream
+    const int bits_this = ncar * nbits;
+    const BitDiv bd(nbits);
+
+    for (int f = blockIdx.x * W + w; f < F; f += gridDim.x * W) {
+        const int64_t v0 = vbase[f];
+        const int64_t v_own_end = vbase[f + 1];             // taps: only the vectors of the session's own frame
+        // enter_have_sync: the flagged vector itself is not demapped
+        for (int c = lane; c < ncar; c += TPS) dfe[c] = make_float2(1.f, 0.f);
+        float phase = 0.f, freq = 0.f;
+        float2 car = make_float2(1.f, 0.f);                 // expj(0)
+        unsigned carry = 0u;
+        int bit_base = 0, len = 0, status = 3, nvec = INT_MAX / 2;
+        sync();
+        for (int vi = 1; v0 + vi < vtot; ++vi) {
+            const int64_t vg = v0 + vi;
+            const float2* e = eq + vg * occ;
+            const bool tap = TAPS && vg < v_own_end && vg < p.max_vectors;
+            double er = 0.0, ei = 0.0;
+            // two carriers per pass with every load ahead of the first store: two independent slicer chains
+            for (int c = lane; c < ncar; c += 2 * TPS) {
+                const int c2 = c + TPS;
+                const bool two = c2 < ncar;
+                const int cb = two ? c2 : c;
+                const float2 d0a = dfe[c], d0b = dfe[cb];
+                const int ia = LDG(p.sinkmap + c), ib = LDG(p.sinkmap + cb);
+                const float2 eqa = LDG(e + ia), eqb = LDG(e + ib);
+                const float2 ra = cmul_x(cmul_x(eqa, car), d0a), rb = cmul_x(cmul_x(eqb, car), d0b);
+                int ba, bb;
+                if (p.grid_L > 0) {
+                    ba = slicer(ra);
+                    bb = slicer(rb);
+                } else {
+                    // small constellations: both scans fused so the two chains interleave
+                    ba = 0; bb = 0;
+                    const float2 c0 = s_cst[0];
+                    float besta = norm_x(csub_x(ra, c0)), bestb = norm_x(csub_x(rb, c0));
+                    for (int k = 1; k < p.M; ++k) {
+                        const float2 ck = s_cst[k];
+                        const float dda = norm_x(csub_x(ra, ck));
+                        const float ddb = norm_x(csub_x(rb, ck));
+                        if (dda < besta) { besta = dda; ba = k; }
+                        if (ddb < bestb) { bestb = ddb; bb = k; }
+                    }
+                }
+                const float2 cla = s_cst[ba], clb = s_cst[bb];
+                const float2 ea = cmulc_x(ra, cla), eb = cmulc_x(rb, clb);
+                er += (double)ea.x;
+                ei += (double)ea.y;
+                if (norm_x(ra) > 0.001f) {
+                    const float2 dq = cscale_x(csub_x(cdiv_x(cla, ra), d0a), 0.05f);      // eq_gain * (q - dfe)
+                    dfe[c] = make_float2(fadd_rn(d0a.x, dq.x), fadd_rn(d0a.y, dq.y));
+                }
+                sym[c] = (uint8_t)ba;
+                if (TAPS && tap) {
+                    if (p.sym_idx) p.sym_idx[vg * ncar + c] = (uint8_t)ba;
+                    if (p.derot_syms) p.derot_syms[vg * ncar + c] = ra;
+                }
+                if (two) {
+                    er += (double)eb.x;
+                    ei += (double)eb.y;
+                    if (norm_x(rb) > 0.001f) {
+                        const float2 dq = cscale_x(csub_x(cdiv_x(clb, rb), d0b), 0.05f);
+                        dfe[c2] = make_float2(fadd_rn(d0b.x, dq.x), fadd_rn(d0b.y, dq.y));
+                    }
+                    sym[c2] = (uint8_t)bb;
+                    if (TAPS && tap) {
+                        if (p.sym_idx) p.sym_idx[vg * ncar + c2] = (uint8_t)bb;
+                        if (p.derot_syms) p.derot_syms[vg * ncar + c2] = rb;
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                er += __shfl_xor_sync(0xffffffffu, er, d);
+                ei += __shfl_xor_sync(0xffffffffu, ei, d);
+            }
+            if (!WARP) {                                    // warp sums -> shared memory (double-buffered by vi) -> everyone
+                if ((threadIdx.x & 31) == 0) { s_red[vi & 1][threadIdx.x >> 5][0] = er; s_red[vi & 1][threadIdx.x >> 5][1] = ei; }
+                __syncthreads();
+                er = 0.0; ei = 0.0;
+#pragma unroll
+                for (int ww = 0; ww < TPS / 32; ++ww) { er += s_red[vi & 1][ww][0]; ei += s_red[vi & 1][ww][1]; }
+            }
+            // PLL update and the carrier of the next vector: every lane holds the same sums and computes the same values
+            {
+                const float angle = (float)atan2((double)(float)ei, (double)(float)er);
+                freq = fsub_rn(freq, fmul_rn(0.015625f, angle));                 // freq_gain = 0.25^2/4
+                float ph = fsub_rn(fadd_rn(phase, freq), fmul_rn(0.25f, angle)); // phase_gain = 0.25
+                if ((double)ph >= 6.283185307179586) ph = (float)((double)ph - 6.283185307179586);
+                if ((double)ph < 0.0) ph = (float)((double)ph + 6.283185307179586);
+                phase = ph;
+                car = expj_f32(ph);
+            }
+            sync();
+            // LSB-first byte packing; bits left over from the previous vector sit in carry
+            const int B0 = bit_base >> 3, B1 = (bit_base + bits_this) >> 3;
+            pack_bytes(sym, vb, B0, B1, bit_base, carry, lane, TPS, bd);
+            sync();
+            if (vi == 1) {
+                const unsigned hdr = ((unsigned)vb[0] << 24) | ((unsigned)vb[1] << 16) | ((unsigned)vb[2] << 8) | vb[3];
+                const bool hdr_ok = ((hdr >> 16) ^ (hdr & 0xFFFFu)) == 0u;
+                len = hdr_ok ? (int)((hdr >> 16) & 0x0FFFu) : 0;
+                if (!hdr_ok) { status = 1; nvec = 2; break; }
+            }
+            {
+                const int nrb = bit_base + bits_this - 8 * B1;
+                unsigned nc = 0;
+                for (int i = 0; i < nrb; ++i) {
+                    const int rel = 8 * B1 + i - bit_base;
+                    const int c = bd.div(rel);
+                    nc |= (((unsigned)sym[c] >> (rel - c * nbits)) & 1u) << i;
+                }
+                carry = nc;
+            }
+            for (int q = B0 + lane; q < B1; q += TPS) {
+                const int pq = q - 4;
+                if (pq >= 0 && pq < len && pq < p.pkt_stride) pkt_bytes[(size_t)f * p.pkt_stride + pq] = vb[q - B0];
+            }
+            sync();                                         // sym / vb are rewritten by the next vector
+            bit_base += bits_this;
+            if (B1 >= 4 + len) { status = 2; nvec = vi + 1; break; }
+        }
+        if (lane == 0) {
+            frame_status[f] = (uint8_t)status;
+            pkt_len[f] = status == 2 ? len : 0;
+            sess_nvec[f] = nvec;
+        }
+        sync();
+    }
+}
+
 template <int N, bool TAPS>
-static int launch_demod_nt(ofdm_handle* h, const DemodParams& p, int max_frames, int S, cudaStream_t st) {
+static int launch_acq_nt(ofdm_handle* h, const AcqParams& p, int max_frames, int S, cudaStream_t st) {
     constexpr int T = N / FftPlan<N>::E;
     constexpr int BT = T < 64 ? 64 : T;
     constexpr int NW = BT / 32;
-    size_t smem = sizeof(double) * 8 * NW + sizeof(float2) * ((N == 4096 ? 1 : 2) * (size_t)fft_smem_elems<N>() + 2 * (size_t)p.occ + p.M) +
-                  ((p.ncar + 15) & ~15) + (size_t)((p.ncar * p.nbits / 8 + 16 + 15) & ~15) + (size_t)p.grid_L * p.grid_L;
-    OFDM_SET_MAX_SMEM((demod_kernel<N, TAPS>), smem, h->device);
+    size_t smem = sizeof(double) * 8 * NW + sizeof(float2) * ((N == 4096 ? 1 : 2) * (size_t)fft_smem_elems<N>() + (size_t)p.occ);
+    OFDM_SET_MAX_SMEM((acq_kernel<N, TAPS>), smem, h->device);
     int grid = (h->sms * 32 + S - 1) / S;                  // resident CTAs are shared by the streams
     if (grid > max_frames) grid = max_frames;
     if (grid < 1) grid = 1;
-    demod_kernel<N, TAPS><<<dim3(grid, S), BT, smem, st>>>(p);
+    acq_kernel<N, TAPS><<<dim3(grid, S), BT, smem, st>>>(p);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
 
 template <int N>
-static int launch_demod_n(ofdm_handle* h, const DemodParams& p, int max_frames, int S, cudaStream_t st) {
-    const bool taps = p.eq_syms || p.sym_idx || p.derot_syms;
-    if (taps && S > 1) { ofdm_set_error("demod: the parity taps (eq_syms / sym_idx / derot_syms) are single-stream only"); return OFDM_E_INVAL; }
-    return taps ? launch_demod_nt<N, true>(h, p, max_frames, S, st) : launch_demod_nt<N, false>(h, p, max_frames, S, st);
+static int launch_acq_n(ofdm_handle* h, const AcqParams& p, int max_frames, int S, bool taps, cudaStream_t st) {
+    return taps ? launch_acq_nt<N, true>(h, p, max_frames, S, st) : launch_acq_nt<N, false>(h, p, max_frames, S, st);
 }
 
 int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
-    DemodParams p;
-    p.y = y; p.soff = ss.off; p.n = ss.n_max; p.trig_idx = io->trig_idx; p.phi0 = ws->phi0; p.step = ws->step; p.nco_init = ws->nco_init; p.n_trig = io->n_trig;
-    p.first_ok = ws->first_ok; p.n_frames = io->n_frames; p.frame_ndata = io->frame_ndata; p.vbase = ws->vbase;
-    p.tw = h->d_tw; p.cst = h->d_const; p.sinkmap = h->d_sinkmap; p.ks = h->d_ks; p.kd = h->d_kd;
-    p.occ = h->occ; p.cp = h->cp; p.zl = h->zl; p.ncar = h->ncar; p.nbits = h->nbits; p.M = h->M; p.L = h->L;
+    const bool taps = io->eq_syms || io->sym_idx || io->derot_syms || io->fft_out || io->sampler_out;
+    if (taps && ss.S > 1) { ofdm_set_error("demod: the parity taps (eq_syms / sym_idx / derot_syms / ...) are single-stream only"); return OFDM_E_INVAL; }
+    AcqParams a;
+    a.y = y; a.soff = ss.off; a.n = ss.n_max; a.trig_idx = io->trig_idx; a.phi0 = ws->phi0; a.step = ws->step; a.nco_init = ws->nco_init;
+    a.n_trig = io->n_trig; a.first_ok = ws->first_ok; a.n_frames = io->n_frames; a.frame_ndata = io->frame_ndata; a.vbase = ws->vbase;
+    a.tw = h->d_tw; a.ks = h->d_ks; a.kd = h->d_kd;
+    a.occ = h->occ; a.cp = h->cp; a.zl = h->zl; a.L = h->L; a.max_frames = io->max_frames;
+    a.eq = ws->eq; a.eq_stride = ws->eq_stride;
+    a.eq_tap = (float2*)io->eq_syms; a.fft_tap = (float2*)io->fft_out; a.samp_tap = (float2*)io->sampler_out;
+    a.max_vectors = io->max_vectors;
+    int rc;
+    switch (h->N) {
+        case 64:   rc = launch_acq_n<64>(h, a, io->max_frames, ss.S, taps, st); break;
+        case 128:  rc = launch_acq_n<128>(h, a, io->max_frames, ss.S, taps, st); break;
+        case 256:  rc = launch_acq_n<256>(h, a, io->max_frames, ss.S, taps, st); break;
+        case 512:  rc = launch_acq_n<512>(h, a, io->max_frames, ss.S, taps, st); break;
+        case 1024: rc = launch_acq_n<1024>(h, a, io->max_frames, ss.S, taps, st); break;
+        case 2048: rc = launch_acq_n<2048>(h, a, io->max_frames, ss.S, taps, st); break;
+        case 4096: rc = launch_acq_n<4096>(h, a, io->max_frames, ss.S, taps, st); break;
+        default:
+            ofdm_set_error("demod: unsupported fft_length %d", h->N);
+            return OFDM_E_INVAL;
+    }
+    if (rc) return rc;
+
+    SinkParams p;
+    p.eq = ws->eq; p.eq_stride = ws->eq_stride; p.per_stream = ss.off ? 1 : 0;
+    p.n_frames = io->n_frames; p.vbase = ws->vbase; p.cst = h->d_const; p.sinkmap = h->d_sinkmap;
+    p.occ = h->occ; p.ncar = h->ncar; p.nbits = h->nbits; p.M = h->M; p.max_frames = io->max_frames; p.pkt_stride = io->pkt_stride;
     p.grid_L = h->grid_L; p.grid_x0 = h->grid_x0; p.grid_y0 = h->grid_y0; p.grid_inv_dx = h->grid_inv_dx;
     p.grid_inv_dy = h->grid_inv_dy; p.grid = h->d_grid;
-    p.max_frames = io->max_frames; p.pkt_stride = io->pkt_stride;
     p.frame_status = io->frame_status; p.pkt_len = io->pkt_len; p.sess_nvec = ws->sess_nvec; p.pkt_bytes = io->pkt_bytes;
-    p.eq_syms = (float2*)io->eq_syms; p.sym_idx = io->sym_idx; p.derot_syms = (float2*)io->derot_syms;
-    p.max_vectors = io->max_vectors;
-    switch (h->N) {
-        case 64:   return launch_demod_n<64>(h, p, io->max_frames, ss.S, st);
-        case 128:  return launch_demod_n<128>(h, p, io->max_frames, ss.S, st);
-        case 256:  return launch_demod_n<256>(h, p, io->max_frames, ss.S, st);
-        case 512:  return launch_demod_n<512>(h, p, io->max_frames, ss.S, st);
-        case 1024: return launch_demod_n<1024>(h, p, io->max_frames, ss.S, st);
-        case 2048: return launch_demod_n<2048>(h, p, io->max_frames, ss.S, st);
-        case 4096: return launch_demod_n<4096>(h, p, io->max_frames, ss.S, st);
-    }
-    ofdm_set_error("demod: unsupported fft_length %d", h->N);
-    return OFDM_E_INVAL;
+    p.sym_idx = io->sym_idx; p.derot_syms = (float2*)io->derot_syms; p.max_vectors = io->max_vectors;
+    // threads per session: a warp (several sessions per CTA, as many as keep the per-session tables -- DFE taps, symbols,
+    // bytes -- within ~48 KB) or, for vectors with more than 1024 data carriers, a whole 128-thread CTA
+    const size_t per_sess = (size_t)h->ncar * sizeof(float2) + ((h->ncar + 15) & ~15) + ((h->ncar * h->nbits / 8 + 16 + 15) & ~15);
+    const size_t fixed = (size_t)h->M * sizeof(float2) + (((size_t)h->grid_L * h->grid_L + 15) & ~(size_t)15);
+    const bool wide = h->ncar > 1024;
+    int W = wide ? 1 : 4;
+    while (W > 1 && fixed + W * per_sess > 48 * 1024) W >>= 1;
+    const size_t smem = fixed + W * per_sess;
+    const bool staps = io->sym_idx || io->derot_syms;
+    int grid = (io->max_frames + W - 1) / W;
+    const int cap = (h->sms * 16 + ss.S - 1) / ss.S;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    const dim3 g(grid, ss.S);
+#define OFDM_SINK_LAUNCH(TAPS_, TPS_)                                                       \
+    do {                                                                                    \
+        OFDM_SET_MAX_SMEM((sink_kernel<TAPS_, TPS_>), smem, h->device);                     \
+        sink_kernel<TAPS_, TPS_><<<g, (TPS_) == 32 ? 32 * W : 128, smem, st>>>(p);          \
+    } while (0)
+    if (wide) { if (staps) OFDM_SINK_LAUNCH(true, 128); else OFDM_SINK_LAUNCH(false, 128); }
+    else      { if (staps) OFDM_SINK_LAUNCH(true, 32); else OFDM_SINK_LAUNCH(false, 32); }
+#undef OFDM_SINK_LAUNCH
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

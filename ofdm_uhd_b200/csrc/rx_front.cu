@@ -41,6 +41,9 @@ int rx_workspace_layout(const ofdm_handle* h, const StreamSet& ss, int32_t max_f
     ws->seg_count = (int32_t*)take(sizeof(int32_t) * (size_t)(ws->n_seg + 1) * S);
     ws->seg_off = (int32_t*)take(sizeof(int32_t) * (size_t)(ws->n_seg + 1) * S);
     ws->seg_trig = (int64_t*)take(sizeof(int64_t) * (size_t)(ws->n_seg * ws->seg_cap) * S);
+    // every frame is a flagged vector plus at most (distance to the next trigger) / L data vectors
+    ws->eq_stride = (h ? n_max / h->L : 0) + max_frames + 2;
+    ws->eq = (float2*)take(sizeof(float2) * (size_t)ws->eq_stride * (size_t)(h ? h->occ : 0) * S);
     ws->mf = (float*)take(sizeof(float) * (size_t)n_total);
     ws->y = (float2*)take(sizeof(float2) * (size_t)n_total);
     *need = off;
