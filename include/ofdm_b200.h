@@ -83,6 +83,15 @@ int ofdm_tx_modulate_batch(ofdm_handle* h, const uint8_t* pkts, const int64_t* p
                            int64_t first_frame, const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms,
                            float* out_iq, void* stream);
 
+/* ofdm_tx_modulate_batch plus the reference's options.log taps (ofdm.py:123-129), fft_length complex values per
+ * OFDM symbol each, any of them NULL: mapper_out = ofdm_mapper_bcv's output vectors (data symbols only; frame f's
+ * data symbol d is row sym_off[f] - f + d), preambles_out = the stream behind ofdm_insert_preamble (every symbol),
+ * ifft_out = the unscaled fft_vcc output (every symbol).  The samples written to out_iq are those of
+ * ofdm_tx_modulate_batch (the reference's fourth tap, ofdm_cp_adder_c.dat, up to the two scale stages). */
+int ofdm_tx_modulate_taps(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames,
+                          int64_t first_frame, const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms,
+                          float* out_iq, float* mapper_out, float* preambles_out, float* ifft_out, void* stream);
+
 /* The same transmit chain for the frames of several independent streams in one launch (the transmit side of
  * ofdm_rx_demodulate_batch; the reference runs one benchmark_ofdm_tx.py flowgraph per stream): frames
  * [stream_frame0[s], stream_frame0[s+1]) belong to stream s, whose first OFDM symbol is written at
@@ -186,6 +195,12 @@ size_t ofdm_rx_workspace_bytes_batch(const ofdm_handle* h, int32_t n_streams, in
                                      int64_t max_stream_samples, int32_t max_frames_per_stream);
 int ofdm_rx_demodulate_batch(ofdm_handle* h, const float* x_iq, const int64_t* stream_off, int32_t n_streams,
                              int64_t total_samples, int64_t max_stream_samples, ofdm_rx_io* io, void* stream);
+/* options.log taps of the receiver that are per-sample streams (ofdm_receiver.py~:150-151), to be called after
+ * ofdm_rx_plan / ofdm_rx_demodulate on the same io: nco_out[n] = e^{j phi[n]} (gr.frequency_modulator_fc driven by the
+ * held sync angle), sigmix_out[n] = y[n] * nco_out[n]; y is the filtered stream (ofdm_rx_workspace_ptr(.., 0)).  Either
+ * output may be NULL.  Single stream. */
+int ofdm_rx_nco_taps(ofdm_handle* h, const float* y_iq, int64_t n, ofdm_rx_io* io, float* nco_out, float* sigmix_out,
+                     void* stream);
 /* The hand-over of the delivered messages to the host (the reference pushes every message the frame sink completes
  * into a gr.msg_queue popped by _queue_watcher_thread, ofdm.py:290-305): after ofdm_rx_finish / ofdm_rx_demodulate
  * [_batch], pack the messages of all n_streams streams (frames with frame_live && frame_status == 2, in stream and

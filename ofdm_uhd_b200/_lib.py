@@ -15,10 +15,10 @@ LIB_PATH = os.path.join(_HERE, "libofdm_b200.so")
 
 EXPORTS = [
     "ofdm_last_error", "ofdm_version", "ofdm_selftest_packed_math", "ofdm_create", "ofdm_destroy", "ofdm_set_tx_amplitude", "ofdm_get_layout",
-    "ofdm_get_chan_taps", "ofdm_packet_len", "ofdm_make_packets", "ofdm_frame_symbols", "ofdm_tx_modulate_batch", "ofdm_tx_modulate_streams",
+    "ofdm_get_chan_taps", "ofdm_packet_len", "ofdm_make_packets", "ofdm_frame_symbols", "ofdm_tx_modulate_batch", "ofdm_tx_modulate_taps", "ofdm_tx_modulate_streams",
     "ofdm_rx_workspace_bytes", "ofdm_rx_chan_filter", "ofdm_rx_sync_metric", "ofdm_rx_peak_detect", "ofdm_rx_sync",
     "ofdm_rx_plan",
-    "ofdm_rx_demod", "ofdm_rx_finish", "ofdm_rx_liveness", "ofdm_rx_sync_fixed", "ofdm_rx_demodulate_fixed", "ofdm_rx_demodulate", "ofdm_rx_workspace_bytes_batch", "ofdm_rx_demodulate_batch", "ofdm_rx_compact", "ofdm_rx_workspace_ptr", "ofdm_channel",
+    "ofdm_rx_demod", "ofdm_rx_finish", "ofdm_rx_liveness", "ofdm_rx_sync_fixed", "ofdm_rx_demodulate_fixed", "ofdm_rx_demodulate", "ofdm_rx_workspace_bytes_batch", "ofdm_rx_demodulate_batch", "ofdm_rx_nco_taps", "ofdm_rx_compact", "ofdm_rx_workspace_ptr", "ofdm_channel",
     "ofdm_sense_create", "ofdm_sense_destroy", "ofdm_sense", "ofdm_sense_fft", "ofdm_sense_decide", "ofdm_sense_hop",
 ]
 
@@ -67,6 +67,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.ofdm_frame_symbols.argtypes = [vp, i32]
     L.ofdm_frame_symbols.restype = i32
     L.ofdm_tx_modulate_batch.argtypes = [vp, vp, vp, i32, i64, vp, i64, i32, vp, vp]
+    L.ofdm_tx_modulate_taps.argtypes = [vp, vp, vp, i32, i64, vp, i64, i32, vp, vp, vp, vp, vp]
+    L.ofdm_rx_nco_taps.argtypes = [vp, vp, i64, C.POINTER(RxIo), vp, vp, vp]
     L.ofdm_tx_modulate_streams.argtypes = [vp, vp, vp, i32, i64, vp, i64, i32, vp, vp, i32, vp, vp]
     L.ofdm_rx_workspace_bytes.argtypes = [vp, i64, i32]
     L.ofdm_rx_workspace_bytes.restype = C.c_size_t

@@ -200,7 +200,7 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
     }
 
     // time-domain preamble: N*ifft(ifftshift(X)), CP, * 1/sqrt(N) (float32 after each stage, A.4)
-    std::vector<float2> pre(N + cp);
+    std::vector<float2> pre(N + cp), pre_ifft(N), pre_freq(N, make_float2(0.f, 0.f));
     {
         std::vector<std::complex<double>> x(N);
         for (int n = 0; n < N; ++n) {
@@ -217,6 +217,8 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
             std::complex<double> v = x[(n + N - cp) % N];
             pre[n] = make_float2((float)v.real() * s1, (float)v.imag() * s1);
         }
+        for (int n = 0; n < N; ++n) pre_ifft[n] = make_float2((float)x[n].real(), (float)x[n].imag());
+        for (int i = 0; i < occ; ++i) pre_freq[h->zl + i] = make_float2(ks[i], 0.f);
     }
 
     std::vector<float2> cst(M);
@@ -284,6 +286,8 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
     rc |= upload(&h->d_tw_os, twiddles(h->NOS));
     rc |= upload(&h->d_Hos, Hos);
     rc |= upload(&h->d_pre_time, pre);
+    rc |= upload(&h->d_pre_freq, pre_freq);
+    rc |= upload(&h->d_pre_ifft, pre_ifft);
     rc |= upload(&h->d_mask, mask);
     rc |= upload(&h->d_crctab, crct);
     if (h->grid_L) rc |= upload(&h->d_grid, grid);
@@ -295,7 +299,7 @@ extern "C" void ofdm_destroy(ofdm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_const); cudaFree(h->d_bin2car); cudaFree(h->d_sinkmap); cudaFree(h->d_ks); cudaFree(h->d_kd);
-    cudaFree(h->d_tw); cudaFree(h->d_tw_os); cudaFree(h->d_Hos); cudaFree(h->d_pre_time); cudaFree(h->d_mask);
+    cudaFree(h->d_tw); cudaFree(h->d_tw_os); cudaFree(h->d_Hos); cudaFree(h->d_pre_time); cudaFree(h->d_pre_freq); cudaFree(h->d_pre_ifft); cudaFree(h->d_mask);
     cudaFree(h->d_crctab); cudaFree(h->d_grid);
     delete h;
 }
@@ -349,6 +353,16 @@ extern "C" int ofdm_tx_modulate_batch(ofdm_handle* h, const uint8_t* pkts, const
     if (uniform_syms <= 0 && !sym_off) { ofdm_set_error("tx: sym_off required for ragged frames"); return OFDM_E_INVAL; }
     return launch_tx(h, pkts, pkt_off, n_frames, first_frame, sym_off, total_syms, uniform_syms, nullptr, nullptr, 0,
                      (float2*)out_iq, (cudaStream_t)stream);
+}
+
+extern "C" int ofdm_tx_modulate_taps(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames,
+                                     int64_t first_frame, const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms,
+                                     float* out_iq, float* mapper_out, float* preambles_out, float* ifft_out, void* stream) {
+    NEED(h);
+    if (n_frames <= 0) return OFDM_OK;
+    if (uniform_syms <= 0 && !sym_off) { ofdm_set_error("tx: sym_off required for ragged frames"); return OFDM_E_INVAL; }
+    return launch_tx(h, pkts, pkt_off, n_frames, first_frame, sym_off, total_syms, uniform_syms, nullptr, nullptr, 0,
+                     (float2*)out_iq, (cudaStream_t)stream, (float2*)mapper_out, (float2*)preambles_out, (float2*)ifft_out);
 }
 
 extern "C" int ofdm_tx_modulate_streams(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames,
@@ -541,6 +555,15 @@ extern "C" int ofdm_rx_demodulate_fixed(ofdm_handle* h, const float* x, int64_t 
     if ((rc = launch_plan(h, ss, io, &ws, st))) return rc;
     if ((rc = launch_demod(h, (const float2*)x, ss, io, &ws, st))) return rc;
     return launch_finish(h, 1, io, &ws, st);
+}
+
+extern "C" int ofdm_rx_nco_taps(ofdm_handle* h, const float* y, int64_t n, ofdm_rx_io* io, float* nco_out, float* sigmix_out,
+                                void* stream) {
+    NEED(h);
+    RxWorkspace ws;
+    int rc = get_ws(h, single_stream(n), io, &ws);
+    if (rc) return rc;
+    return launch_nco_taps(h, (const float2*)y, n, io, &ws, (float2*)nco_out, (float2*)sigmix_out, (cudaStream_t)stream);
 }
 
 extern "C" int ofdm_rx_compact(ofdm_handle* h, const ofdm_rx_io* io, int32_t n_streams, uint8_t* out_bytes,

@@ -47,6 +47,8 @@ struct ofdm_handle {
     float2* d_tw_os;       // [NOS]
     float2* d_Hos;         // [NOS] FFT of the channel taps / NOS
     float2* d_pre_time;    // [N+cp] time-domain preamble incl. CP, scaled by 1/sqrt(N)
+    float2* d_pre_freq;    // [N] the known symbol as the mapper-order (unshifted) vector   (options.log taps)
+    float2* d_pre_ifft;    // [N] its unscaled IFFT
     uint8_t* d_mask;       // [4096] whitening mask
     uint32_t* d_crctab;    // [256]
     float h_taps[OFDM_MAX_TAPS];
@@ -120,7 +122,10 @@ int launch_make_packets(ofdm_handle* h, const uint8_t* payload, const int64_t* p
                         int whitening, uint8_t* pkts, const int64_t* pkt_off, cudaStream_t st);
 int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames, int64_t first_frame,
               const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms, const int64_t* stream_frame0,
-              const int64_t* stream_out_off, int32_t n_streams, float2* out, cudaStream_t st);
+              const int64_t* stream_out_off, int32_t n_streams, float2* out, cudaStream_t st, float2* map_tap = nullptr,
+              float2* pre_tap = nullptr, float2* ifft_tap = nullptr);
+int launch_nco_taps(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, float2* nco_out,
+                    float2* sigmix_out, cudaStream_t st);
 int launch_chan_filter(ofdm_handle* h, const float2* x, const StreamSet& ss, float2* y, cudaStream_t st);
 int launch_sync_metric(ofdm_handle* h, const float2* y, int64_t n, float* mf, int64_t* first_nan, cudaStream_t st);
 int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t n, const int64_t* first_nan,

@@ -695,6 +695,41 @@ int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_i
 }
 
 // ---------------------------------------------------------------------------------------------
+// options.log taps of the receiver (ofdm_receiver.py~:150-151): the NCO output e^{j phi[n]} (frequency_modulator_fc
+// driven by the held angle, A.8) and sigmix = chan_filt * nco, per sample.  Debugging aid, not on the hot path.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nco_tap_kernel(const float2* __restrict__ y, int64_t n, const int32_t* __restrict__ n_trig,
+                                                      int max_frames, const int64_t* __restrict__ trig, const double* __restrict__ phi0,
+                                                      const double* __restrict__ step, const double* __restrict__ nco_init,
+                                                      float2* __restrict__ nco_out, float2* __restrict__ sigmix_out) {
+    int K = *n_trig;
+    if (K > max_frames) K = max_frames;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int lo = 0, hi = K;                              // triggers at indices <= i
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (trig[mid] <= i) lo = mid + 1; else hi = mid;
+        }
+        const int k = lo - 1;
+        const double ph = (k >= 0) ? phi0[k] + step[k] * (double)(i - trig[k] + 1) : *nco_init * (double)(i + 1);
+        const float2 w = phasor_f64(ph);
+        if (nco_out) nco_out[i] = w;
+        if (sigmix_out) sigmix_out[i] = cmul_x(y[i], w);
+    }
+}
+
+int launch_nco_taps(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, float2* nco_out,
+                    float2* sigmix_out, cudaStream_t st) {
+    if (n <= 0 || (!nco_out && !sigmix_out)) return OFDM_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > (int64_t)h->sms * 16) blocks = (int64_t)h->sms * 16;
+    nco_tap_kernel<<<(int)blocks, 256, 0, st>>>(y, n, io->n_trig, io->max_frames, io->trig_idx, ws->phi0, ws->step, ws->nco_init,
+                                               nco_out, sigmix_out);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Frame-sink liveness: the sink only starts on a preamble it sees in SYNC_SEARCH; a session started at
 // frame f swallows sess_nvec[f] vectors of the sampler's stream, flagged ones included (A.11).  The live
 // frames are the orbit of frame 0 under next(f) = first frame whose preamble lies at or after the end of

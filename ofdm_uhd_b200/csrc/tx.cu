@@ -118,12 +118,19 @@ struct TxParams {
     const int64_t* stream_frame0;
     const int64_t* stream_out_off;
     int n_streams;
+    // options.log taps (ofdm.py:123-129): mapper output (data symbols only), the symbol stream behind
+    // ofdm_insert_preamble, and the unscaled IFFT output, fft_length complex values per symbol
+    float2* map_tap;             // [data symbols][N]
+    float2* pre_tap;             // [symbols][N]
+    float2* ifft_tap;            // [symbols][N]
+    const float2* pre_freq;      // [N] the known symbol as the mapper-order vector
+    const float2* pre_ifft;      // [N] its unscaled IFFT
 };
 
 // The carrier map and the bytes of the symbol are staged in shared memory before the first pass: from global memory
 // the map lookup and the packet byte it leads to are two dependent loads per carrier (a quarter of this kernel's
 // stall samples were long-scoreboard waits on them).
-template <int N>
+template <int N, bool TAPS>
 struct TxLoad {
     const TxParams& p;
     const uint8_t* s_bytes;      // packet bytes from byte0 on (this symbol's share)
@@ -134,7 +141,18 @@ struct TxLoad {
     int dsym;                    // data symbol number inside the frame
     const float2* s_cst;
     const int16_t* s_b2c;
+    float2* map_tap;             // this symbol's row of the mapper tap / of the preambles tap (TAPS only)
+    float2* pre_tap;
     __device__ __forceinline__ float2 operator()(int idx, int) const {
+        const float2 o = value(idx);
+        if (TAPS) {
+            const int v = (idx + N / 2) & (N - 1);
+            if (map_tap) map_tap[v] = o;
+            if (pre_tap) pre_tap[v] = o;
+        }
+        return o;
+    }
+    __device__ __forceinline__ float2 value(int idx) const {
         const int v = (idx + N / 2) & (N - 1);          // ifftshift: IFFT input idx holds vector bin v
         const int c = s_b2c[v];
         if (c < 0) return make_float2(0.f, 0.f);
@@ -152,12 +170,14 @@ struct TxLoad {
     }
 };
 
-template <int N>
+template <int N, bool TAPS>
 struct TxStore {
     float2* dst;                 // start of this symbol (its cyclic prefix)
     int cp;
     float s1, amp;
+    float2* ifft_tap;            // this symbol's row of the IFFT tap (TAPS only)
     __device__ __forceinline__ void operator()(int n, float2 v, int) const {
+        if (TAPS && ifft_tap) ifft_tap[n] = v;
         // float32 after each multiply_const, like the two upstream blocks
         const float2 o = cscale_x(cscale_x(v, s1), amp);
         dst[cp + n] = o;
@@ -165,7 +185,7 @@ struct TxStore {
     }
 };
 
-template <int N, int G>
+template <int N, int G, bool TAPS>
 __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ? 1024 : 512) / (G * (N / FftPlan<N>::E))) tx_kernel(const TxParams p) {
     constexpr int T = N / FftPlan<N>::E;
     constexpr int SB = fft_smem_elems<N>();
@@ -228,6 +248,12 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
                 float2 v = LDG(p.pre_time + i);
                 dst[i] = cscale_x(v, p.amp);
             }
+            if (TAPS) {
+                for (int i = tid; i < N; i += T) {
+                    if (p.pre_tap) p.pre_tap[(size_t)s * N + i] = LDG(p.pre_freq + i);
+                    if (p.ifft_tap) p.ifft_tap[(size_t)s * N + i] = LDG(p.pre_ifft + i);
+                }
+            }
         }
         const int64_t o0 = active ? LDG(p.pkt_off + f) : 0;
         const int64_t o1 = active ? LDG(p.pkt_off + f + 1) : 0;
@@ -240,8 +266,11 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
             for (int i = tid; i < nb; i += T) my_bytes[i] = LDG(src + i);
         }
         bar();
-        TxLoad<N> ld{p, my_bytes, byte0, pkt_len * 8, frame_id, seed, m - 1, s_cst, s_b2c};
-        TxStore<N> st{dst, p.cp, p.s1, p.amp};
+        // data symbols before this one in the batch: s minus the preambles of frames 0 .. f
+        TxLoad<N, TAPS> ld{p, my_bytes, byte0, pkt_len * 8, frame_id, seed, m - 1, s_cst, s_b2c,
+                           (TAPS && p.map_tap) ? p.map_tap + ((size_t)s - (size_t)f - 1) * N : nullptr,
+                           (TAPS && p.pre_tap) ? p.pre_tap + (size_t)s * N : nullptr};
+        TxStore<N, TAPS> st{dst, p.cp, p.s1, p.amp, (TAPS && p.ifft_tap) ? p.ifft_tap + (size_t)s * N : nullptr};
         using P = FftPlan<N>;
         constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
         if (data) fft_pass<N, R0, 1, 1>(tid, p.tw, ld, SmemOut{bufA});
@@ -263,20 +292,24 @@ static int launch_tx_n(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
     const int sym_bytes = (p.ncar * p.nbits + 7) / 8 + 2;
     size_t smem = (256 + (size_t)G * 2 * fft_smem_elems<N>()) * sizeof(float2) + (size_t)N * sizeof(int16_t) +
                   (size_t)G * ((sym_bytes + 15) & ~15);
-    OFDM_SET_MAX_SMEM((tx_kernel<N, G>), smem, h->device);
+    const bool taps = p.map_tap || p.pre_tap || p.ifft_tap;
+    if (taps) { OFDM_SET_MAX_SMEM((tx_kernel<N, G, true>), smem, h->device); } else { OFDM_SET_MAX_SMEM((tx_kernel<N, G, false>), smem, h->device); }
     const int sms = h->sms;
     int64_t want = (p.total_syms + G - 1) / G;
     int64_t cap = (int64_t)sms * (64 / G);
     int grid = (int)(want < cap ? want : cap);
-    tx_kernel<N, G><<<grid, G * T, smem, st>>>(p);
+    if (taps) tx_kernel<N, G, true><<<grid, G * T, smem, st>>>(p);
+    else tx_kernel<N, G, false><<<grid, G * T, smem, st>>>(p);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
 
 int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames, int64_t first_frame,
               const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms, const int64_t* stream_frame0,
-              const int64_t* stream_out_off, int32_t n_streams, float2* out, cudaStream_t st) {
+              const int64_t* stream_out_off, int32_t n_streams, float2* out, cudaStream_t st, float2* map_tap,
+              float2* pre_tap, float2* ifft_tap) {
     TxParams p;
+    p.map_tap = map_tap; p.pre_tap = pre_tap; p.ifft_tap = ifft_tap; p.pre_freq = h->d_pre_freq; p.pre_ifft = h->d_pre_ifft;
     p.stream_frame0 = stream_frame0; p.stream_out_off = stream_out_off; p.n_streams = n_streams;
     p.pkts = pkts; p.pkt_off = pkt_off; p.sym_off = sym_off; p.n_frames = n_frames; p.uniform_syms = uniform_syms;
     p.first_frame = first_frame; p.seed = h->pad_seed; p.out = out; p.cst = h->d_const; p.bin2car = h->d_bin2car;

@@ -227,9 +227,11 @@ class OfdmEngine:
                                              self._p(pkts), self._p(d_koff), self._stream()), "make_packets")
         return pkts, pkt_off, d_koff
 
-    def modulate(self, pkts, pkt_off: np.ndarray, d_pkt_off=None, first_frame: int = 0, out=None):
+    def modulate(self, pkts, pkt_off: np.ndarray, d_pkt_off=None, first_frame: int = 0, out=None, taps: Optional[dict] = None):
         """pkts: uint8 cuda tensor of concatenated packets; pkt_off: host int64 [F+1].
-        Returns complex64 cuda tensor with all frames back to back."""
+        Returns complex64 cuda tensor with all frames back to back.  ``taps``: a dict that receives the reference's
+        options.log stage outputs (ofdm.py:123-129) as complex64 cuda tensors: "mapper" [data symbols, N],
+        "preambles" [symbols, N], "ifft" [symbols, N]."""
         torch = self.torch
         pkt_off = np.ascontiguousarray(pkt_off, dtype=np.int64)
         F = len(pkt_off) - 1
@@ -251,6 +253,15 @@ class OfdmEngine:
             out = torch.empty(total * self.L, dtype=torch.complex64, device=self.dev)
         elif out.numel() < total * self.L:
             raise ValueError("modulate: output buffer too small")
+        if taps is not None:
+            taps["mapper"] = torch.zeros((total - F, self.N), dtype=torch.complex64, device=self.dev)
+            taps["preambles"] = torch.zeros((total, self.N), dtype=torch.complex64, device=self.dev)
+            taps["ifft"] = torch.zeros((total, self.N), dtype=torch.complex64, device=self.dev)
+            _lib.check(self.L_.ofdm_tx_modulate_taps(self.h, self._p(pkts), self._p(d_pkt_off), F, int(first_frame),
+                                                     self._p(d_sym_off), total, uniform, self._p(out), self._p(taps["mapper"]),
+                                                     self._p(taps["preambles"]), self._p(taps["ifft"]), self._stream()),
+                       "tx_modulate_taps")
+            return out[:total * self.L]
         _lib.check(self.L_.ofdm_tx_modulate_batch(self.h, self._p(pkts), self._p(d_pkt_off), F, int(first_frame),
                                                   self._p(d_sym_off), total, uniform, self._p(out), self._stream()),
                    "tx_modulate_batch")
@@ -272,7 +283,7 @@ class OfdmEngine:
         torch = self.torch
         if max_frames is None:
             max_frames = max(64, int(n // self.L) + 64)
-        key = (int(n), int(max_frames), bool(taps), int(max_vectors))
+        key = (int(n), int(max_frames), taps, int(max_vectors))
         if self._ws_key == key and not fresh:
             return self._ws
         dev = self.dev
@@ -296,6 +307,9 @@ class OfdmEngine:
             b["eq_syms"] = torch.zeros(max_vectors * self.occ, dtype=torch.complex64, device=dev)
             b["sym_idx"] = torch.zeros(max_vectors * self.ncar, dtype=torch.uint8, device=dev)
             b["derot_syms"] = torch.zeros(max_vectors * self.ncar, dtype=torch.complex64, device=dev)
+            if taps == "all":                      # options.log: the vector taps in front of the frame acquisition too
+                b["fft_out"] = torch.zeros(max_vectors * self.N, dtype=torch.complex64, device=dev)
+                b["sampler_out"] = torch.zeros(max_vectors * self.N, dtype=torch.complex64, device=dev)
         io = _lib.RxIo()
         io.max_frames = int(max_frames)
         io.pkt_stride = self.pkt_stride
@@ -308,6 +322,8 @@ class OfdmEngine:
         io.sym_idx = b["sym_idx"].data_ptr() if taps else None
         io.derot_syms = b["derot_syms"].data_ptr() if taps else None
         io.max_vectors = int(max_vectors) if taps else 0
+        io.fft_out = b["fft_out"].data_ptr() if "fft_out" in b else None
+        io.sampler_out = b["sampler_out"].data_ptr() if "sampler_out" in b else None
         b["io"] = io
         b["n"] = int(n)
         if not fresh:
@@ -409,6 +425,15 @@ class OfdmEngine:
             out.append(RxBatch(nt, nf, 0, *extra, live.copy(), fstat.copy(), plen.copy(), pok.copy(),
                                host["counters"][8 * s:8 * s + 8].copy(), packets, sel, rows))
         return out
+
+    def nco_taps(self, bufs, n: int):
+        """(nco, sigmix) per-sample streams of the last receive call on ``bufs`` (ofdm_receiver.py~:150-151)."""
+        torch = self.torch
+        nco = torch.empty(n, dtype=torch.complex64, device=self.dev)
+        mix = torch.empty(n, dtype=torch.complex64, device=self.dev)
+        _lib.check(self.L_.ofdm_rx_nco_taps(self.h, self._p(self.ws_view(bufs, 0, n)), int(n), C.byref(bufs["io"]), self._p(nco),
+                                            self._p(mix), self._stream()), "rx_nco_taps")
+        return nco, mix
 
     def ws_view(self, bufs, which: int, n: int):
         """Tensor views of the workspace taps (0: filtered stream y, 1: timing metric mf)."""

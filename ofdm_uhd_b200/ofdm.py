@@ -197,10 +197,19 @@ class ofdm_mod:
             np.cumsum([len(p) for p in pkts], out=off[1:])
             host = torch.frombuffer(bytearray(b"".join(pkts)), dtype=torch.uint8)
             dev = host.to(self._engine.dev, non_blocking=False)
-            out = self._engine.modulate(dev, off, first_frame=self._frames_sent)
+            taps = {} if self._log else None
+            out = self._engine.modulate(dev, off, first_frame=self._frames_sent, taps=taps)
             self._frames_sent += len(pkts)
             if self._log:
-                out.cpu().numpy().tofile("ofdm_cp_adder_c.dat")        # same name/format as ofdm.py:130-131
+                # the reference's four file sinks (ofdm.py:123-131), raw interleaved float32 I/Q; truncated by the first
+                # batch, appended to afterwards.  ofdm_cp_adder_c.dat holds what leaves this block (the reference taps it
+                # in front of its 1/sqrt(N) scale stage)
+                mode = "ab" if getattr(self, "_log_started", False) else "wb"
+                self._log_started = True
+                for name, t in (("ofdm_mapper_c.dat", taps["mapper"]), ("ofdm_preambles.dat", taps["preambles"]),
+                                ("ofdm_ifft_c.dat", taps["ifft"]), ("ofdm_cp_adder_c.dat", out)):
+                    with open(name, mode) as fh:
+                        t.cpu().numpy().tofile(fh)
             return out
 
     def flush(self):
@@ -394,32 +403,35 @@ class ofdm_demod:
 
     def _feed_logged(self, samples, max_frames):
         """options.log: dump the stage taps with the reference's file names and raw layout (ofdm.py:253-254,
-        ofdm_receiver.py~:144-152; interleaved float32 I/Q, utils/read_complex_binary.m:39-46).  Files are
-        truncated by the first feed() and appended to afterwards.  sampler_c / fft_out_c / sigmix_c / nco_c are
-        not materialised by the fused kernels and are not written."""
+        ofdm_receiver.py~:144-152; interleaved float32 I/Q, utils/read_complex_binary.m:39-46): chan_filt, fft_out,
+        frame_acq, found_corr, sampler, sigmix, nco and ofdm_frame_sink.  Files are truncated by the first feed() and
+        appended to afterwards."""
         eng = self._engine
         n = int(samples.numel())
         nvec = n // eng.L + 64
-        bufs = eng.rx_alloc(n, max_frames=max_frames, taps=True, max_vectors=nvec)
-        for k in ("eq_syms", "sym_idx", "derot_syms"):
+        bufs = eng.rx_alloc(n, max_frames=max_frames, taps="all", max_vectors=nvec)
+        for k in ("eq_syms", "sym_idx", "derot_syms", "fft_out", "sampler_out"):
             bufs[k].zero_()
         res = eng.collect(eng.demodulate_async(samples, bufs))
+        nco, sigmix = eng.nco_taps(bufs, n)
         mode = "ab" if getattr(self, "_log_started", False) else "wb"
         self._log_started = True
-        with open("ofdm_receiver-chan_filt_c.dat", mode) as f:
-            eng.ws_view(bufs, 0, n).cpu().numpy().tofile(f)
         flags = np.concatenate([np.concatenate([[1], np.zeros(int(j), np.uint8)]) for j in res.frame_ndata]).astype(np.uint8) \
             if res.n_frames else np.zeros(0, np.uint8)
         nv = len(flags)
-        with open("ofdm_receiver-found_corr_b.dat", mode) as f:
-            flags.tofile(f)
-        with open("ofdm_receiver-frame_acq_c.dat", mode) as f:
-            bufs["eq_syms"][:nv * eng.occ].cpu().numpy().tofile(f)
         derot = bufs["derot_syms"][:nv * eng.ncar].cpu().numpy().reshape(nv, eng.ncar)
         wide = np.zeros((nv, eng.occ), dtype=np.complex64)
         wide[:, :eng.ncar] = derot
-        with open("ofdm_frame_sink_c.dat", mode) as f:
-            wide[np.abs(derot).sum(axis=1) > 0].tofile(f)          # only the vectors the sink demapped
+        for name, arr in (("ofdm_receiver-chan_filt_c.dat", eng.ws_view(bufs, 0, n).cpu().numpy()),
+                          ("ofdm_receiver-fft_out_c.dat", bufs["fft_out"][:nv * eng.N].cpu().numpy()),
+                          ("ofdm_receiver-frame_acq_c.dat", bufs["eq_syms"][:nv * eng.occ].cpu().numpy()),
+                          ("ofdm_receiver-found_corr_b.dat", flags),
+                          ("ofdm_receiver-sampler_c.dat", bufs["sampler_out"][:nv * eng.N].cpu().numpy()),
+                          ("ofdm_receiver-sigmix_c.dat", sigmix.cpu().numpy()),
+                          ("ofdm_receiver-nco_c.dat", nco.cpu().numpy()),
+                          ("ofdm_frame_sink_c.dat", wide[np.abs(derot).sum(axis=1) > 0])):   # only the vectors the sink demapped
+            with open(name, mode) as f:
+                arr.tofile(f)
         return res
 
     def wait(self, timeout=None):

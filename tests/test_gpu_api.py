@@ -159,6 +159,36 @@ def test_log_option_dumps_stage_taps(tmp_path, monkeypatch):
     assert eq.shape[0] == len(ref.flags)
     sink = np.fromfile("ofdm_frame_sink_c.dat", dtype=np.complex64).reshape(-1, 200)
     assert sink.shape[0] == len(ref.derot) and np.linalg.norm(sink[:, :198] - np.array(ref.derot)) / np.linalg.norm(np.array(ref.derot)) < 1e-4
+    # the taps between the channel filter and the frame acquisition (ofdm_receiver.py~:145,148-151)
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    plan = o.plan_frames(ref.trig, ref.ang, len(cap), 512, 640)
+    ph = o.nco_phase_at(plan, np.arange(len(cap)), 512)
+    nco_ref = (np.cos(ph) + 1j * np.sin(ph)).astype(np.complex64)
+    nco = np.fromfile("ofdm_receiver-nco_c.dat", dtype=np.complex64)
+    sigmix = np.fromfile("ofdm_receiver-sigmix_c.dat", dtype=np.complex64)
+    assert nco.shape == nco_ref.shape and rel(nco, nco_ref) < 1e-5 and rel(sigmix, ref.y * nco_ref) < 1e-4
+    samp = np.fromfile("ofdm_receiver-sampler_c.dat", dtype=np.complex64).reshape(-1, 512)
+    samp_ref = np.array([o.derotate(ref.y, st + np.arange(512), plan, 512) for st in ref.vec_start])
+    assert samp.shape == samp_ref.shape and rel(samp, samp_ref) < 1e-4
+    fft = np.fromfile("ofdm_receiver-fft_out_c.dat", dtype=np.complex64).reshape(-1, 512)
+    fft_ref = np.array([o._fft_shift(v) for v in samp_ref])
+    assert fft.shape == fft_ref.shape and rel(fft, fft_ref) < 1e-4
+    assert rel(eq, ref.eq) < 1e-4
+    # transmit side (ofdm.py:123-131): mapper output, the stream behind insert_preamble, IFFT output, samples
+    mod = ofdm.ofdm_mod(options(log=True), pad_for_usrp=False, pad_seed=0)
+    for p in pay:
+        mod.send_pkt(p)
+    out = mod.flush().cpu().numpy()
+    pk = [o.make_packet(p, 1, 1, False) for p in pay]
+    X = [o.tx_symbols_freq(q, lay, f, 0) for f, q in enumerate(pk)]
+    pre = np.fromfile("ofdm_preambles.dat", dtype=np.complex64).reshape(-1, 512)
+    assert np.array_equal(pre, np.concatenate(X))
+    mapper = np.fromfile("ofdm_mapper_c.dat", dtype=np.complex64).reshape(-1, 512)
+    assert np.array_equal(mapper, np.concatenate([x_[1:] for x_ in X]))
+    ifft = np.fromfile("ofdm_ifft_c.dat", dtype=np.complex64).reshape(-1, 512)
+    assert rel(ifft, o._ifft_unnorm(np.concatenate(X))) < 1e-5
+    cpa = np.fromfile("ofdm_cp_adder_c.dat", dtype=np.complex64)
+    assert np.array_equal(cpa, out) and rel(out, o.tx_modulate(pk, lay, 1.0, seed=0)) < 1e-5
 
 
 def test_rendezvous_over_the_modem():
