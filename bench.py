@@ -602,6 +602,49 @@ def packet_surface(torch, eng_unused, args, device):
         out["bulk"] = {"seconds": dt, "packets_per_s": F / dt, "Msamples_per_s": (samples / dt / 1e6) if samples else None,
                        "ok": int(sum(batches)),
                        "what": "send_pkts(list) (make_packets_kernel on the device) -> feed -> rx_callback_batch(ok[], bytes, offsets)"}
+    # a continuous source delivered in radio-sized buffers: feed_stream with batching vs one whole-stream feed
+    try:
+        n_frames = 20000
+        body2 = make_payloads(n_frames, 402, 777)
+        eng2 = tx.ofdm_tx._engine
+        plan = eng2.tx_plan(np.arange(n_frames + 1, dtype=np.int64) * 402)
+        xs = eng2.tx_run(plan, torch.from_numpy(body2.reshape(-1)).to(eng2.dev))
+        cap = chan.process(xs)
+        cnt = [0]
+        rx2 = rp_mod.receive_path(lambda ok, p: None, opt, device=device, max_pkt_bytes=416)
+        rx2.set_batch_callback(lambda oks, blob, off: cnt.__setitem__(0, cnt[0] + int(np.count_nonzero(oks))))
+        for timed in (False, True):
+            cnt[0] = 0
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rx2.feed(cap)
+            torch.cuda.synchronize()
+            dt_whole = time.perf_counter() - t0
+        whole_ok = cnt[0]
+        res = {}
+        for buf in (65536, 1 << 20):
+            rx3 = rp_mod.receive_path(lambda ok, p: None, opt, device=device, max_pkt_bytes=416)
+            got3 = [0]
+            rx3.ofdm_rx.stream_batch_samples = 1 << 24
+            rx3.set_batch_callback(lambda oks, blob, off: got3.__setitem__(0, got3[0] + int(np.count_nonzero(oks))))
+            for timed in (False, True):
+                got3[0] = 0
+                rx3.ofdm_rx._carry, rx3.ofdm_rx._carry_abs, rx3.ofdm_rx._last_abs_start = None, 0, None
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for a in range(0, cap.numel(), buf):
+                    rx3.feed_stream(cap[a:a + buf])
+                rx3.flush_stream()
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+            res["%d-sample buffers" % buf] = {"seconds": dt, "Msamples_per_s": cap.numel() / dt / 1e6, "ok": got3[0]}
+        out["feed_stream"] = {"samples": int(cap.numel()), "whole_stream_feed": {"seconds": dt_whole, "Msamples_per_s": cap.numel() / dt_whole / 1e6, "ok": whole_ok},
+                              "batched": res, "stream_batch_samples": 1 << 24,
+                              "what": "ofdm_demod.feed_stream on consecutive buffers of one capture (queued on the device, one receiver pass per "
+                                      "stream_batch_samples new samples + the carried tail) vs one feed() of the whole capture; host-side "
+                                      "packet assembly included"}
+    except Exception as e:
+        out["feed_stream"] = {"error": repr(e)}
     return out
 
 

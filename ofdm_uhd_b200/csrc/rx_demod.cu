@@ -88,8 +88,9 @@ __device__ __noinline__ float2 derot_slow(float2 v, int64_t s, const int64_t* tr
 
 template <bool SMEM>
 struct DemodLoad {
-    const float2* y;               // SMEM: the vector's samples staged in shared memory, else the stream
-    int64_t st, t_next;
+    const float2* y;               // the vector's samples: staged in shared memory (SMEM), else the stream at `st`
+    int64_t st;
+    int lim;                       // points idx < lim lie before the next trigger (32-bit compare per point)
     const int64_t* trig;
     const double* phi0;
     const double* step;
@@ -97,10 +98,9 @@ struct DemodLoad {
     float2 ph0;
     const float2* Wt;
     __device__ __forceinline__ float2 operator()(int idx, int slot) const {
-        const int64_t s = st + idx;
-        const float2 v = SMEM ? y[idx] : LDG(y + s);
-        if (s < t_next) return cmul_x(v, cmul(ph0, Wt[slot]));
-        return derot_slow(v, s, trig, phi0, step, K, kk0);
+        const float2 v = SMEM ? y[idx] : LDG(y + idx);
+        if (idx < lim) return cmul_x(v, cmul(ph0, Wt[slot]));
+        return derot_slow(v, st + idx, trig, phi0, step, K, kk0);
     }
 };
 
@@ -332,8 +332,9 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 kk_w = kk;
                 __syncthreads();
             }
-            DemodLoad<PF> ld{PF ? bufB : v.y, st, t_next, v.trig_idx, v.phi0, v.step, K, kk < 0 ? 0 : kk, phasor_f64(ph_base), s_W};
-            if (kk < 0) ld.t_next = (K > 0) ? v.trig_idx[0] : LLONG_MAX;
+            const int64_t t_lim = (kk < 0) ? ((K > 0) ? v.trig_idx[0] : LLONG_MAX) : t_next;
+            const int lim = (t_lim - st >= (int64_t)N) ? N : (t_lim > st ? (int)(t_lim - st) : 0);
+            DemodLoad<PF> ld{PF ? bufB : v.y + st, st, lim, v.trig_idx, v.phi0, v.step, K, kk < 0 ? 0 : kk, phasor_f64(ph_base), s_W};
             if (PF) cp_async_wait_all();
             if (P::NP == 3) __syncthreads();                // S (= bufA) of the previous vector has been read by everyone
             if (TAPS && p.samp_tap && vglob < p.max_vectors && tid < T) {

@@ -325,6 +325,12 @@ class ofdm_demod:
         self._carry = None
         self._carry_abs = 0
         self._last_abs_start = None
+        # feed_stream batches small buffers: the receiver runs once this many new samples are pending (a receive pass is
+        # ~17 kernel launches and re-reads the carried tail, so per-buffer passes on radio-sized buffers would be
+        # launch-bound); 0 = run on every call
+        self.stream_batch_samples = int(getattr(options, "stream_batch_samples", 0))
+        self._stream_pending = []
+        self._stream_pending_n = 0
 
     def stream_carry_samples(self):
         """Samples of the past that feed_stream() keeps in front of every new buffer: the detector's IIR warm-up
@@ -334,20 +340,55 @@ class ofdm_demod:
         longest = 1 + -(-8 * (4095 + 9) // (eng.ncar * eng.nbits))
         return 24576 + eng.ntaps + (longest + 1) * eng.L
 
-    def feed_stream(self, samples, max_frames=None):
+    def feed_stream(self, samples, max_frames=None, flush=False):
         """feed() for a source delivered in consecutive buffers (a file read in pieces, a radio): the receiver runs
         on [carried tail | new samples] and only frames that start after the last delivered one reach the callback,
         so every frame is delivered once, in order, wherever the buffer boundaries fall.  (The reference's flowgraph
-        is continuous; feed() by itself treats each buffer as a separate stream.)"""
+        is continuous; feed() by itself treats each buffer as a separate stream.)
+
+        With ``stream_batch_samples`` > 0 the buffers are queued (on the device) until that many new samples are
+        pending -- or ``flush`` / flush_stream() -- and then go through the receiver in one pass: the cost of a pass
+        (launches + the carried tail of stream_carry_samples()) is amortised over the batch, so a source that delivers
+        64 k-sample buffers runs at the whole-stream rate; delivery is delayed by at most one batch."""
         import torch
-        if not isinstance(samples, torch.Tensor):
-            samples = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.complex64))
-        if samples.device.type != "cuda":
-            samples = samples.to(self._engine.dev)
-        buf = samples.contiguous() if self._carry is None else torch.cat([self._carry, samples.contiguous()])
+        if samples is not None:
+            if not isinstance(samples, torch.Tensor):
+                samples = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.complex64))
+            if samples.device.type != "cuda":
+                samples = samples.to(self._engine.dev)
+            if samples.numel():
+                self._stream_pending.append(samples.contiguous())
+                self._stream_pending_n += int(samples.numel())
+        if not self._stream_pending or (not flush and self._stream_pending_n < self.stream_batch_samples):
+            return None
+        parts = ([self._carry] if self._carry is not None else []) + self._stream_pending
+        buf = parts[0] if len(parts) == 1 else torch.cat(parts)
+        self._stream_pending, self._stream_pending_n = [], 0
         abs0 = self._carry_abs
-        res = self.feed(buf, max_frames=max_frames, _deliver=False)
         L = self._engine.L
+        if self._batch_callback is not None and self._sync == "pn" and not self._log:
+            # dense hand-over: the messages come back as one byte array + offsets; the ones already delivered by the
+            # previous pass (frames inside the carried tail) are a prefix of the list
+            eng = self._engine
+            bufs = eng.demodulate_async(buf, max_frames=max_frames)
+            r = eng.deliver_end(eng.deliver_begin(bufs))
+            n = r["n_msgs"]
+            fstart = bufs["frame_start"][:int(r["counters"][0][0])].cpu().numpy()
+            starts = abs0 + fstart[r["frame"]] if n else np.zeros(0, np.int64)
+            k0 = 0
+            if self._last_abs_start is not None and n:
+                k0 = int(np.searchsorted(starts, self._last_abs_start + L, side="right"))
+            if n > k0:
+                self._last_abs_start = int(starts[-1])
+                off = r["off"]
+                self._batch_callback(r["ok"][k0:], r["data"][int(off[k0]):int(off[n])], off[k0:] - off[k0])
+            keep = min(self.stream_carry_samples(), buf.numel())
+            self._carry = buf[buf.numel() - keep:].clone()
+            self._carry_abs = abs0 + buf.numel() - keep
+            r["stream_delivered"] = n - k0
+            self.last = r
+            return r
+        res = self.feed(buf, max_frames=max_frames, _deliver=False)
         # a frame still open at the end of the buffer (the sink ran out of vectors) is left to the next call
         delivered = []
         for k, f in enumerate(res.msg_frames):
@@ -363,6 +404,10 @@ class ofdm_demod:
         self._carry_abs = abs0 + buf.numel() - keep
         res.stream_delivered = delivered
         return res
+
+    def flush_stream(self, max_frames=None):
+        """Run the receiver on whatever feed_stream() has queued."""
+        return self.feed_stream(None, max_frames=max_frames, flush=True)
 
     def set_batch_callback(self, fn):
         """Bulk twin of the per-packet callback: with ``fn`` set, every feed() hands ALL the packets it produced to

@@ -25,9 +25,12 @@ class receive_path:
         """Run the receiver on one buffer of complex64 baseband samples."""
         return self.ofdm_rx.feed(samples, max_frames=max_frames)
 
-    def feed_stream(self, samples, max_frames=None):
+    def feed_stream(self, samples, max_frames=None, flush=False):
         """feed() for consecutive buffers of one continuous stream (see ofdm_demod.feed_stream)."""
-        return self.ofdm_rx.feed_stream(samples, max_frames=max_frames)
+        return self.ofdm_rx.feed_stream(samples, max_frames=max_frames, flush=flush)
+
+    def flush_stream(self, max_frames=None):
+        return self.ofdm_rx.flush_stream(max_frames=max_frames)
 
     def set_batch_callback(self, fn):
         """rx_callback_batch(ok[], bytes, offsets): one call per feed() instead of one per packet (ofdm_demod.set_batch_callback)."""

@@ -269,6 +269,26 @@ def test_feed_stream_equals_whole_stream(chunk):
     good_p = [p for ok, p in parts if ok]
     assert good_p == good_w                                  # same good packets, same order, none twice
     assert len(parts) == len(whole)
+    # radio-sized buffers queued into batches: one receiver pass per 300 000 new samples, then a flush for the rest
+    batched = []
+    rx3 = receive_path.receive_path(lambda ok, p: batched.append((ok, p)), opts)
+    rx3.ofdm_rx.stream_batch_samples = 300_000
+    passes = 0
+    for a in range(0, len(xc), 4096):
+        passes += rx3.feed_stream(xc[a:a + 4096]) is not None
+    passes += rx3.flush_stream() is not None
+    rx3.wait(timeout=60)
+    assert 2 <= passes <= len(xc) // 300_000 + 1
+    assert [p for ok, p in batched if ok] == good_w and len(batched) == len(whole)
+    # the same through the dense hand-over (rx_callback_batch)
+    dense = []
+    rx4 = receive_path.receive_path(None, opts)
+    rx4.set_batch_callback(lambda ok, data, off: dense.extend((bool(ok[k]), data[off[k]:off[k + 1] - 4].tobytes()) for k in range(len(ok))))
+    rx4.ofdm_rx.stream_batch_samples = 250_000
+    for a in range(0, len(xc), chunk):
+        rx4.feed_stream(xc[a:a + chunk])
+    rx4.flush_stream()
+    assert dense == whole
 
 
 def test_benchmark_loopback_example_script(tmp_path):
