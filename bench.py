@@ -34,8 +34,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # make_packets, tx, chan_filter, stream_init, metric_chunk, detect_seg, seg_scan, trig_gather, plan_init, plan_local,
-# plan_offset, demod, next, liveness_fast, liveness (general walk, idle), crc
-KERNELS_PER_STEP = 16
+# plan_offset, acq, sink, next, liveness_fast, liveness (general walk, idle), crc
+KERNELS_PER_STEP = 17
 PROFILE = "r02_traffic.json"
 
 
@@ -380,9 +380,12 @@ def run_b200(args):
         "tx_kernel": lambda: L_.ofdm_tx_modulate_batch(eng.h, eng._p(plan.pkts), eng._p(plan.d_pkt_off), F, 0, None,
                                                        plan.total_syms, plan.uniform_syms, eng._p(xs), st),
         "chan_filter_kernel": lambda: L_.ofdm_rx_chan_filter(eng.h, eng._p(xc), n, eng._p(y), st),
-        "metric_chunk_kernel+detect_seg_kernel(+scan,gather)": lambda: L_.ofdm_rx_sync(eng.h, eng._p(y), n, C.byref(io), st),
+        "metric_chunk_kernel": lambda: L_.ofdm_rx_stage(eng.h, eng._p(y), n, C.byref(io), 0, st),
+        "detect_seg_kernel": lambda: L_.ofdm_rx_stage(eng.h, eng._p(y), n, C.byref(io), 1, st),
+        "seg_scan+trig_gather": lambda: L_.ofdm_rx_stage(eng.h, eng._p(y), n, C.byref(io), 2, st),
         "plan_kernel": lambda: L_.ofdm_rx_plan(eng.h, n, C.byref(io), st),
-        "demod_kernel": lambda: L_.ofdm_rx_demod(eng.h, eng._p(y), n, C.byref(io), st),
+        "acq_kernel": lambda: L_.ofdm_rx_stage(eng.h, eng._p(y), n, C.byref(io), 3, st),
+        "sink_kernel": lambda: L_.ofdm_rx_stage(eng.h, eng._p(y), n, C.byref(io), 4, st),
         "liveness+crc": lambda: L_.ofdm_rx_finish(eng.h, C.byref(io), st),
     }
     kern_ms = {}
@@ -507,7 +510,10 @@ def run_b200(args):
         ms_per_step = total_ms / args.steps
         value = samples_all / (ms_per_step * 1e-3) / 1e6
         dom = max(kern_ms, key=kern_ms.get)
-        alg_bytes = 8.0 * n_sig          # every kernel of the chain streams the capture once: 8 B per sample
+        # algorithmic bytes per launch: 8 B per sample -- every stream kernel sweeps the capture (or its
+        # filtered copy) once.  (The channel filter must also WRITE the 8 B/sample stream it exists to produce; that
+        # second half is not counted here.)
+        alg_bytes = 8.0 * n_sig
         dom_gbs = alg_bytes / (kern_ms[dom] * 1e-3) / 1e9
         traffic, traffic_src = ncu_traffic(dom, n_sig)
         step_gbs = 16.0 * n_sig / (ms_per_step * 1e-3) / 1e9

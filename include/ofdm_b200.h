@@ -160,6 +160,12 @@ int ofdm_rx_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, void* stream);
 /* multiply_cc (derotation) + fft_vcc(forward) + ofdm_frame_acquisition + ofdm_frame_sink
  * (ofdm_receiver.py~:124-129, ofdm.py:240-243) */
 int ofdm_rx_demod(ofdm_handle* h, const float* y_iq, int64_t n, ofdm_rx_io* io, void* stream);
+/* One kernel of the two multi-kernel stages above, for stage-level timing and profiling (ofdm_rx_sync and
+ * ofdm_rx_demod run them back to back): stage 0 = the Schmidl-Cox metric kernel of ofdm_sync_pn (y -> workspace mf),
+ * 1 = its peak_detector_fb kernel (mf -> per-segment triggers), 2 = trigger compaction + angle latch,
+ * 3 = acq_kernel (multiply_cc + fft_vcc + ofdm_frame_acquisition, ofdm_receiver.py~:124-129),
+ * 4 = sink_kernel (ofdm_frame_sink, ofdm.py:240-243).  Each needs the outputs of the stages before it. */
+int ofdm_rx_stage(ofdm_handle* h, const float* y_iq, int64_t n, ofdm_rx_io* io, int32_t stage, void* stream);
 /* frame-sink liveness (which preambles the sink accepted), unmake_packet (dewhiten + CRC,
  * ofdm.py:300-305) and the counters */
 int ofdm_rx_finish(ofdm_handle* h, ofdm_rx_io* io, void* stream);

@@ -450,6 +450,25 @@ extern "C" int ofdm_rx_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, void* str
     return launch_plan(h, single_stream(n), io, &ws, (cudaStream_t)stream);
 }
 
+extern "C" int ofdm_rx_stage(ofdm_handle* h, const float* y, int64_t n, ofdm_rx_io* io, int32_t stage, void* stream) {
+    NEED(h);
+    RxWorkspace ws;
+    const StreamSet ss = single_stream(n);
+    int rc = get_ws(h, ss, io, &ws);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (stage) {
+        case 0: rc = launch_sync_stream(h, (const float2*)y, ss, io, &ws, 1, st); break;
+        case 1: rc = launch_sync_stream(h, (const float2*)y, ss, io, &ws, 2, st); break;
+        case 2: return launch_trig_compact(h, (const float2*)y, ss, io, &ws, st);
+        case 3: return launch_demod(h, (const float2*)y, ss, io, &ws, st, 1);
+        case 4: return launch_demod(h, (const float2*)y, ss, io, &ws, st, 2);
+        default: ofdm_set_error("ofdm_rx_stage: stage %d", stage); return OFDM_E_INVAL;
+    }
+    if (rc == 1) { ofdm_set_error("ofdm_rx_stage: this layout has no streaming synchroniser"); return OFDM_E_INVAL; }
+    return rc;
+}
+
 extern "C" int ofdm_rx_demod(ofdm_handle* h, const float* y, int64_t n, ofdm_rx_io* io, void* stream) {
     NEED(h);
     RxWorkspace ws;
@@ -485,7 +504,8 @@ static int rx_sync(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx
                    cudaStream_t st) {
     OFDM_CUDA_CHECK(cudaMemsetAsync(io->status, 0, sizeof(uint32_t) * ss.S, st));
     OFDM_CUDA_CHECK(cudaMemsetAsync(ws->nco_init, 0, sizeof(double) * ss.S, st));     // sample_and_hold starts at 0
-    int rc = launch_sync_stream(h, y, ss, io, ws, force_fused, st);
+    (void)force_fused;
+    int rc = launch_sync_stream(h, y, ss, io, ws, 3, st);
     if (rc == 0) return launch_trig_compact(h, y, ss, io, ws, st);
     if (rc < 0) return rc;
     if (ss.S > 1 || ss.off) {

@@ -131,12 +131,14 @@ int launch_sync_metric(ofdm_handle* h, const float2* y, int64_t n, float* mf, in
 int launch_peak_detect(ofdm_handle* h, const float2* y, const float* mf, int64_t n, const int64_t* first_nan,
                        ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
 int launch_trig_compact(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
-int launch_sync_stream(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, int force,
+int launch_sync_stream(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, int parts,
                        cudaStream_t st);
 int launch_plan(ofdm_handle* h, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
 int launch_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_offset, ofdm_rx_io* io, RxWorkspace* ws,
                       cudaStream_t st);
-int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+// parts: bit 0 acq_kernel (derotation + FFT + frame acquisition), bit 1 sink_kernel (ofdm_frame_sink); 3 = both
+int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st,
+                 int parts = 3);
 int launch_finish(ofdm_handle* h, int S, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
 // per-stream strides: n_frames / overflow 1, vbase max_frames + 1, everything else max_frames
 int launch_liveness(int sms, int S, const int32_t* n_frames, const int64_t* vbase, int64_t vbase_stride, const int32_t* sess_nvec,

@@ -635,7 +635,8 @@ static int launch_acq_n(ofdm_handle* h, const AcqParams& p, int max_frames, int 
     return taps ? launch_acq_nt<N, true>(h, p, max_frames, S, st) : launch_acq_nt<N, false>(h, p, max_frames, S, st);
 }
 
-int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
+int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st,
+                 int parts) {
     const bool taps = io->eq_syms || io->sym_idx || io->derot_syms || io->fft_out || io->sampler_out;
     if (taps && ss.S > 1) { ofdm_set_error("demod: the parity taps (eq_syms / sym_idx / derot_syms / ...) are single-stream only"); return OFDM_E_INVAL; }
     AcqParams a;
@@ -646,8 +647,8 @@ int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_i
     a.eq = ws->eq; a.eq_stride = ws->eq_stride;
     a.eq_tap = (float2*)io->eq_syms; a.fft_tap = (float2*)io->fft_out; a.samp_tap = (float2*)io->sampler_out;
     a.max_vectors = io->max_vectors;
-    int rc;
-    switch (h->N) {
+    int rc = OFDM_OK;
+    if (parts & 1) switch (h->N) {
         case 64:   rc = launch_acq_n<64>(h, a, io->max_frames, ss.S, taps, st); break;
         case 128:  rc = launch_acq_n<128>(h, a, io->max_frames, ss.S, taps, st); break;
         case 256:  rc = launch_acq_n<256>(h, a, io->max_frames, ss.S, taps, st); break;
@@ -660,6 +661,7 @@ int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_i
             return OFDM_E_INVAL;
     }
     if (rc) return rc;
+    if (!(parts & 2)) return OFDM_OK;
 
     SinkParams p;
     p.eq = ws->eq; p.eq_stride = ws->eq_stride; p.per_stream = ss.off ? 1 : 0;

@@ -97,7 +97,15 @@ __global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 512 / (G * (NOS /
     auto prefetch = [&](float2* dst, int64_t blk) {
         if (blk < nblk) {
             const int64_t in0 = blk * p.V - p.hist;
-            if (al16) {
+            if (al16 && in0 >= 0 && in0 + NOS <= s_n) {
+                // interior block (all but the first and the last few of a stream): no bounds to check
+                const float2* src = px + in0;
+#pragma unroll
+                for (int i = 0; i < E / 2; ++i) {
+                    const int idx = 2 * (tid + i * T);
+                    cp_async16(dst + idx, src + idx, 16);
+                }
+            } else if (al16) {
 #pragma unroll
                 for (int i = 0; i < E / 2; ++i) {
                     const int idx = 2 * (tid + i * T);
@@ -131,6 +139,10 @@ __global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 512 / (G * (NOS /
                 if (o < s_n) py[o] = v;
             }
         };
+        // interior block: every output lands inside the stream
+        float2* const yb = py + (blk * p.V - p.hist);
+        auto st_in = [&](int idx, float2 v, int) { if (idx >= p.hist) yb[idx] = v; };
+        const bool inner = active && (blk + 1) * p.V <= s_n;
         cp_async_wait_all();
         __syncthreads();
         if (active) fft_pass<NOS, R0, 1, -1>(tid, p.tw, SmemRawIn{raw}, SmemOut{oth});
@@ -144,7 +156,8 @@ __global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 512 / (G * (NOS /
         if (active) fft_pass<NOS, R1, R2, 1>(tid, p.tw, SmemIn{oth}, SmemOut{raw});
         __syncthreads();
         prefetch(oth, blk + (int64_t)gridDim.x * G);
-        if (active) fft_pass<NOS, R0, R2 * R1, 1>(tid, p.tw, SmemIn{raw}, st);
+        if (inner) fft_pass<NOS, R0, R2 * R1, 1>(tid, p.tw, SmemIn{raw}, st_in);
+        else if (active) fft_pass<NOS, R0, R2 * R1, 1>(tid, p.tw, SmemIn{raw}, st);
         float2* t = raw; raw = oth; oth = t;
     }
     cp_async_wait_all();

@@ -625,9 +625,10 @@ __global__ void stream_init_kernel(int64_t* first_nan, int S) {
 }
 
 template <int K>
-static int launch_split_k(const StreamParams& p, float* mt, int m, int S, cudaStream_t st) {
+static int launch_split_k(const StreamParams& p, float* mt, int m, int S, int parts, cudaStream_t st) {
     constexpr int SZ = 32 * K;
-    if (m == 1) {
+    if (!(parts & 1)) {
+    } else if (m == 1) {
         const int64_t chunks = (p.n + (int64_t)MC_STEPS * SZ - 1) / ((int64_t)MC_STEPS * SZ);
         metric_chunk_kernel<K><<<dim3((unsigned)chunks, S), 32, 0, st>>>(p.y, mt, p.n, p.soff);
     } else {
@@ -637,6 +638,7 @@ static int launch_split_k(const StreamParams& p, float* mt, int m, int S, cudaSt
         metric_wide_kernel<K><<<dim3((unsigned)chunks, S), 32, 0, st>>>(p.y, mt, p.n, p.soff, m, chunk_blocks);
     }
     OFDM_LAUNCH_CHECK();
+    if (!(parts & 2)) return OFDM_OK;
     int ring_steps = 2;
     while (ring_steps < (p.cp + SZ - 1) / SZ + 1) ring_steps *= 2;
     detect_seg_kernel<K><<<dim3((unsigned)p.n_seg, S), 32, sizeof(double) * ring_steps * SZ, st>>>(p, mt, ring_steps);
@@ -645,11 +647,11 @@ static int launch_split_k(const StreamParams& p, float* mt, int m, int S, cudaSt
 }
 
 // returns 1 if the streaming kernels do not apply (the caller then runs the tile-parallel stage kernels, single
-// stream only): N = 64 or cp > N/2.  `force` is kept for the stage-level entry point; every stream length takes the
-// streaming pair now (one warp per >= 65 536-sample detector segment: short streams simply use few warps).
-int launch_sync_stream(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, int force,
+// stream only): N = 64 or cp > N/2.  Every stream length takes the streaming pair (one warp per >= 65 536-sample
+// detector segment: short streams simply use few warps).
+// `parts`: bit 0 the metric kernel, bit 1 the detector kernel (3 = both; the stage-timing entry point runs them apart).
+int launch_sync_stream(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, int parts,
                        cudaStream_t st) {
-    (void)force;
     // a step is 32*K samples: N/2 for N <= 512, else 256 with m = N/512 sub-steps per N/2-wide block
     const int K = h->N >= 512 ? 8 : h->N / 64;
     const int m = h->N >= 512 ? h->N / 512 : 1;
@@ -658,11 +660,13 @@ int launch_sync_stream(ofdm_handle* h, const float2* y, const StreamSet& ss, ofd
     p.y = y; p.soff = ss.off; p.max_frames = io->max_frames; p.n = ss.n_max; p.cp = h->cp; p.tapf = (float)(1.0 / (double)h->cp);
     p.seg_len = ws->seg_len; p.n_seg = ws->n_seg; p.seg_cap = (int)ws->seg_cap;
     p.seg_count = ws->seg_count; p.seg_trig = ws->seg_trig; p.first_nan = ws->first_nan; p.status = io->status;
-    stream_init_kernel<<<(ss.S + 255) / 256, 256, 0, st>>>(p.first_nan, ss.S);
-    OFDM_LAUNCH_CHECK();
+    if (parts & 2) {                                   // the detector owns first_nan
+        stream_init_kernel<<<(ss.S + 255) / 256, 256, 0, st>>>(p.first_nan, ss.S);
+        OFDM_LAUNCH_CHECK();
+    }
     switch (K) {
-        case 2: return launch_split_k<2>(p, ws->mf, 1, ss.S, st);
-        case 4: return launch_split_k<4>(p, ws->mf, 1, ss.S, st);
-        default: return launch_split_k<8>(p, ws->mf, m, ss.S, st);
+        case 2: return launch_split_k<2>(p, ws->mf, 1, ss.S, parts, st);
+        case 4: return launch_split_k<4>(p, ws->mf, 1, ss.S, parts, st);
+        default: return launch_split_k<8>(p, ws->mf, m, ss.S, parts, st);
     }
 }
