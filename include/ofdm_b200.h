@@ -155,6 +155,21 @@ int ofdm_rx_sync(ofdm_handle* h, const float* y_iq, int64_t n, ofdm_rx_io* io, v
  * (index N+cp-1 + k*nsymbols*(N+cp)), every angle = pi*freq_offset, and the NCO already turning at that rate before the
  * first trigger.  Replaces ofdm_rx_sync in the stage sequence; fills io->n_trig / trig_idx / trig_ang. */
 int ofdm_rx_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_offset, ofdm_rx_io* io, void* stream);
+/* The two other synchronisers ofdm_receiver.py~:89-107 names: host_sync = "pnac" (upstream ofdm_sync_pnac(fft_length,
+ * cp_length, ks0time): cross-correlation with the known symbol, then its N/2-delayed auto-correlation against the N-sample
+ * energy, threshold_ff(0,0,0)) or "ml" (upstream ofdm_sync_ml(fft_length, cp_length, snr, ks0time): van de Beek's
+ * cyclic-prefix correlator, peak_detector_fb(0.2, 0.25, 30, 0.0005), timing gated by the known-symbol correlation; the
+ * NCO's held angle changes at EVERY detector peak, nco_sensitivity = -1/N).  The reference hard-codes SYNC = "pn", so
+ * these are functional restatements (plain kernels, not tuned; oracle: sync_pnac / sync_ml in oracle/ofdm_oracle.py).
+ * ofdm_rx_sync_alt replaces ofdm_rx_sync in the stage sequence (timing triggers -> io->n_trig / trig_idx / trig_ang; for
+ * "ml" the NCO events go to the workspace, ofdm_rx_workspace_ptr which = 7 count, 8 indices, 9 angles);
+ * ofdm_rx_demodulate_alt is the whole chain.  scratch: DEVICE memory of ofdm_rx_sync_alt_scratch_bytes(n) bytes.
+ * "ml" needs fft_length <= 2048 (its known-symbol correlator has fft_length taps).  Single stream. */
+size_t ofdm_rx_sync_alt_scratch_bytes(const ofdm_handle* h, int64_t n_samples);
+int ofdm_rx_sync_alt(ofdm_handle* h, const float* y_iq, int64_t n, const char* host_sync, float snr_db, ofdm_rx_io* io,
+                     void* scratch, size_t scratch_bytes, void* stream);
+int ofdm_rx_demodulate_alt(ofdm_handle* h, const float* x_iq, int64_t n, const char* host_sync, float snr_db, ofdm_rx_io* io,
+                           void* scratch, size_t scratch_bytes, void* stream);
 /* gr.frequency_modulator_fc + digital.ofdm_sampler (ofdm_receiver.py~:123-125,133-136) as a frame table */
 int ofdm_rx_plan(ofdm_handle* h, int64_t n, ofdm_rx_io* io, void* stream);
 /* multiply_cc (derotation) + fft_vcc(forward) + ofdm_frame_acquisition + ofdm_frame_sink

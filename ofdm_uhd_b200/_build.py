@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libofdm_b200.so")
-UNITS = ["api", "tx", "sense", "rx_front", "rx_sync_stream", "rx_demod", "selftest"]
+UNITS = ["api", "tx", "sense", "rx_front", "rx_sync_stream", "rx_sync_alt", "rx_demod", "selftest"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 

@@ -18,7 +18,7 @@ EXPORTS = [
     "ofdm_get_chan_taps", "ofdm_packet_len", "ofdm_make_packets", "ofdm_frame_symbols", "ofdm_tx_modulate_batch", "ofdm_tx_modulate_taps", "ofdm_tx_modulate_streams",
     "ofdm_rx_workspace_bytes", "ofdm_rx_chan_filter", "ofdm_rx_sync_metric", "ofdm_rx_peak_detect", "ofdm_rx_sync",
     "ofdm_rx_plan",
-    "ofdm_rx_demod", "ofdm_rx_stage", "ofdm_rx_finish", "ofdm_rx_liveness", "ofdm_rx_sync_fixed", "ofdm_rx_demodulate_fixed", "ofdm_rx_demodulate", "ofdm_rx_workspace_bytes_batch", "ofdm_rx_demodulate_batch", "ofdm_rx_nco_taps", "ofdm_rx_compact", "ofdm_rx_workspace_ptr", "ofdm_channel",
+    "ofdm_rx_demod", "ofdm_rx_stage", "ofdm_rx_finish", "ofdm_rx_liveness", "ofdm_rx_sync_alt_scratch_bytes", "ofdm_rx_sync_alt", "ofdm_rx_demodulate_alt", "ofdm_rx_sync_fixed", "ofdm_rx_demodulate_fixed", "ofdm_rx_demodulate", "ofdm_rx_workspace_bytes_batch", "ofdm_rx_demodulate_batch", "ofdm_rx_nco_taps", "ofdm_rx_compact", "ofdm_rx_workspace_ptr", "ofdm_channel",
     "ofdm_sense_create", "ofdm_sense_destroy", "ofdm_sense", "ofdm_sense_fft", "ofdm_sense_decide", "ofdm_sense_hop",
 ]
 
@@ -81,6 +81,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.ofdm_rx_stage.argtypes = [vp, vp, i64, C.POINTER(RxIo), i32, vp]
     L.ofdm_rx_finish.argtypes = [vp, C.POINTER(RxIo), vp]
     L.ofdm_rx_liveness.argtypes = [vp, vp, vp, i32, vp, vp, C.c_int, vp]
+    L.ofdm_rx_sync_alt_scratch_bytes.argtypes = [vp, i64]
+    L.ofdm_rx_sync_alt_scratch_bytes.restype = C.c_size_t
+    L.ofdm_rx_sync_alt.argtypes = [vp, vp, i64, C.c_char_p, f32, C.POINTER(RxIo), vp, C.c_size_t, vp]
+    L.ofdm_rx_demodulate_alt.argtypes = [vp, vp, i64, C.c_char_p, f32, C.POINTER(RxIo), vp, C.c_size_t, vp]
     L.ofdm_rx_sync_fixed.argtypes = [vp, i64, i32, f32, C.POINTER(RxIo), vp]
     L.ofdm_rx_demodulate_fixed.argtypes = [vp, vp, i64, i32, f32, C.POINTER(RxIo), vp]
     L.ofdm_rx_demodulate.argtypes = [vp, vp, i64, C.POINTER(RxIo), vp]

@@ -300,7 +300,7 @@ extern "C" void ofdm_destroy(ofdm_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_const); cudaFree(h->d_bin2car); cudaFree(h->d_sinkmap); cudaFree(h->d_ks); cudaFree(h->d_kd);
     cudaFree(h->d_tw); cudaFree(h->d_tw_os); cudaFree(h->d_Hos); cudaFree(h->d_pre_time); cudaFree(h->d_pre_freq); cudaFree(h->d_pre_ifft); cudaFree(h->d_mask);
-    cudaFree(h->d_crctab); cudaFree(h->d_grid);
+    cudaFree(h->d_crctab); cudaFree(h->d_grid); cudaFree(h->d_Hks_half); cudaFree(h->d_Hks_full); cudaFree(h->d_tw_os_alt);
     delete h;
 }
 
@@ -417,6 +417,9 @@ extern "C" void* ofdm_rx_workspace_ptr(const ofdm_handle* h, const ofdm_rx_io* i
         case 4: return ws.step;
         case 5: return ws.vbase;
         case 6: return ws.sess_nvec;
+        case 7: return ws.n_nco;
+        case 8: return ws.nco_idx;
+        case 9: return ws.nco_ang;
         default: return nullptr;
     }
 }
@@ -439,6 +442,7 @@ extern "C" int ofdm_rx_peak_detect(ofdm_handle* h, const float* y, const float* 
     int rc = get_ws(h, single_stream(n), io, &ws);
     if (rc) return rc;
     OFDM_CUDA_CHECK(cudaMemsetAsync(ws.nco_init, 0, sizeof(double), (cudaStream_t)stream));
+    if ((rc = launch_nco_mode(h, &ws, 1, -2.0, (cudaStream_t)stream))) return rc;
     return launch_peak_detect(h, (const float2*)y, mf, n, first_nan, io, &ws, (cudaStream_t)stream);
 }
 
@@ -504,6 +508,7 @@ static int rx_sync(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx
                    cudaStream_t st) {
     OFDM_CUDA_CHECK(cudaMemsetAsync(io->status, 0, sizeof(uint32_t) * ss.S, st));
     OFDM_CUDA_CHECK(cudaMemsetAsync(ws->nco_init, 0, sizeof(double) * ss.S, st));     // sample_and_hold starts at 0
+    { int rc0 = launch_nco_mode(h, ws, ss.S, -2.0, st); if (rc0) return rc0; }        // the NCO follows the triggers, -2/N
     (void)force_fused;
     int rc = launch_sync_stream(h, y, ss, io, ws, 3, st);
     if (rc == 0) return launch_trig_compact(h, y, ss, io, ws, st);
@@ -553,12 +558,53 @@ extern "C" int ofdm_rx_demodulate_batch(ofdm_handle* h, const float* x, const in
     return rx_chain(h, (const float2*)x, ss, io, (cudaStream_t)stream);
 }
 
+extern "C" size_t ofdm_rx_sync_alt_scratch_bytes(const ofdm_handle* h, int64_t n) {
+    (void)h;
+    return sync_alt_scratch_bytes(n);
+}
+
+static int alt_mode(const char* sync) {
+    if (sync && !strcmp(sync, "pnac")) return 1;
+    if (sync && !strcmp(sync, "ml")) return 2;
+    ofdm_set_error("sync %s: this entry point serves \"pnac\" and \"ml\" (\"pn\": ofdm_rx_sync, \"fixed\": ofdm_rx_sync_fixed)", sync ? sync : "(null)");
+    return 0;
+}
+
+extern "C" int ofdm_rx_sync_alt(ofdm_handle* h, const float* y, int64_t n, const char* host_sync, float snr_db, ofdm_rx_io* io,
+                                void* scratch, size_t scratch_bytes, void* stream) {
+    NEED(h);
+    const int mode = alt_mode(host_sync);
+    if (!mode) return OFDM_E_INVAL;
+    RxWorkspace ws;
+    int rc = get_ws(h, single_stream(n), io, &ws);
+    if (rc) return rc;
+    return launch_sync_alt(h, (const float2*)y, n, mode, snr_db, io, &ws, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int ofdm_rx_demodulate_alt(ofdm_handle* h, const float* x, int64_t n, const char* host_sync, float snr_db, ofdm_rx_io* io,
+                                      void* scratch, size_t scratch_bytes, void* stream) {
+    NEED(h);
+    const int mode = alt_mode(host_sync);
+    if (!mode) return OFDM_E_INVAL;
+    RxWorkspace ws;
+    const StreamSet ss = single_stream(n);
+    int rc = get_ws(h, ss, io, &ws);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = launch_chan_filter(h, (const float2*)x, ss, ws.y, st))) return rc;
+    if ((rc = launch_sync_alt(h, ws.y, n, mode, snr_db, io, &ws, scratch, scratch_bytes, st))) return rc;
+    if ((rc = launch_plan(h, ss, io, &ws, st))) return rc;
+    if ((rc = launch_demod(h, ws.y, ss, io, &ws, st))) return rc;
+    return launch_finish(h, 1, io, &ws, st);
+}
+
 extern "C" int ofdm_rx_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_offset, ofdm_rx_io* io,
                                   void* stream) {
     NEED(h);
     RxWorkspace ws;
     int rc = get_ws(h, single_stream(n), io, &ws);
     if (rc) return rc;
+    if ((rc = launch_nco_mode(h, &ws, 1, -2.0, (cudaStream_t)stream))) return rc;
     return launch_sync_fixed(h, n, nsymbols, freq_offset, io, &ws, (cudaStream_t)stream);
 }
 
@@ -571,6 +617,7 @@ extern "C" int ofdm_rx_demodulate_fixed(ofdm_handle* h, const float* x, int64_t 
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     // chan_filt = gr.multiply_const_cc(1.0): the capture itself is what the sampler reads
+    if ((rc = launch_nco_mode(h, &ws, 1, -2.0, st))) return rc;
     if ((rc = launch_sync_fixed(h, n, nsymbols, freq_offset, io, &ws, st))) return rc;
     if ((rc = launch_plan(h, ss, io, &ws, st))) return rc;
     if ((rc = launch_demod(h, (const float2*)x, ss, io, &ws, st))) return rc;

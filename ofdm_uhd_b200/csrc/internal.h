@@ -47,6 +47,11 @@ struct ofdm_handle {
     float2* d_tw_os;       // [NOS]
     float2* d_Hos;         // [NOS] FFT of the channel taps / NOS
     float2* d_pre_time;    // [N+cp] time-domain preamble incl. CP, scaled by 1/sqrt(N)
+    // known-symbol correlators of the "pnac" / "ml" synchronisers (created on first use, rx_sync_alt.cu)
+    float2* d_Hks_half;    // [nos_ks_half] response of conj(ks0time[:N/2]) reversed
+    float2* d_Hks_full;    // [nos_ks_full] response of conj(ks0time) reversed
+    int nos_ks_half, nos_ks_full;
+    float2* d_tw_os_alt;   // twiddles of the overlap-save size the channel filter does not use (2048 <-> 4096)
     float2* d_pre_freq;    // [N] the known symbol as the mapper-order (unshifted) vector   (options.log taps)
     float2* d_pre_ifft;    // [N] its unscaled IFFT
     uint8_t* d_mask;       // [4096] whitening mask
@@ -109,6 +114,10 @@ struct RxWorkspace {
     int32_t* next_frame;   // per stream [max_frames] scratch of the liveness walk
     int32_t* exit_frame;   // per stream [max_frames] scratch of the liveness walk
     int32_t* seg_off;      // per stream [n_seg + 1] exclusive scan of seg_count
+    int64_t* nco_idx;      // per stream [max_frames] NCO events of ofdm_sync_ml (every detector peak)
+    float* nco_ang;        // per stream [max_frames]
+    int32_t* n_nco;        // per stream [1]; -1: the NCO follows the trigger list (pn, pnac, fixed)
+    double* nco_sens;      // per stream [1] NCO sensitivity, set by the synchroniser stage
     float2* eq;            // per stream [eq_stride * occ] equalised vectors (acq_kernel -> sink_kernel)
     int64_t eq_stride;     // vectors per stream: n_max / L + max_frames + 2 bounds what the sampler can emit
     int64_t n_seg, seg_len, seg_cap;      // n_seg: detector segments of the LONGEST stream (table stride)
@@ -124,6 +133,10 @@ int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32
               const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms, const int64_t* stream_frame0,
               const int64_t* stream_out_off, int32_t n_streams, float2* out, cudaStream_t st, float2* map_tap = nullptr,
               float2* pre_tap = nullptr, float2* ifft_tap = nullptr);
+int launch_xcorr(ofdm_handle* h, const float2* x, int64_t n, const float2* H, int nos, int ntaps, float2* out, cudaStream_t st);
+size_t sync_alt_scratch_bytes(int64_t n);
+int launch_sync_alt(ofdm_handle* h, const float2* y, int64_t n, int mode, float snr_db, ofdm_rx_io* io, RxWorkspace* ws,
+                    void* scratch, size_t scratch_bytes, cudaStream_t st);
 int launch_nco_taps(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, RxWorkspace* ws, float2* nco_out,
                     float2* sigmix_out, cudaStream_t st);
 int launch_chan_filter(ofdm_handle* h, const float2* x, const StreamSet& ss, float2* y, cudaStream_t st);
@@ -134,6 +147,7 @@ int launch_trig_compact(ofdm_handle* h, const float2* y, const StreamSet& ss, of
 int launch_sync_stream(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, int parts,
                        cudaStream_t st);
 int launch_plan(ofdm_handle* h, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st);
+int launch_nco_mode(ofdm_handle* h, RxWorkspace* ws, int S, double sens_times_n, cudaStream_t st);
 int launch_sync_fixed(ofdm_handle* h, int64_t n, int32_t nsymbols, float freq_offset, ofdm_rx_io* io, RxWorkspace* ws,
                       cudaStream_t st);
 // parts: bit 0 acq_kernel (derotation + FFT + frame acquisition), bit 1 sink_kernel (ofdm_frame_sink); 3 = both

@@ -31,6 +31,8 @@ struct AcqParams {
     const int32_t* n_frames;
     const int32_t* frame_ndata;
     const int64_t* vbase;
+    const int32_t* n_nco;          // the NCO's own event list (ofdm_sync_ml); *n_nco < 0: it follows the triggers
+    const int64_t* nco_idx;
     const float2* tw;
     const float* ks;
     const float* kd;
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
         const int32_t* n_frames;
         const int32_t* frame_ndata;
         const int64_t* vbase;
+        const int64_t* nidx;       // sample index of every NCO event (the trigger list unless ofdm_sync_ml supplied its own)
         float2* eq;
     } v;
     {
@@ -255,6 +258,7 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
         v.n_frames = p.n_frames + sidx; v.frame_ndata = p.frame_ndata + sidx * mf;
         v.vbase = p.vbase + sidx * (mf + 1);
         v.eq = p.eq + sidx * p.eq_stride * p.occ;
+        v.nidx = (p.n_nco[sidx] >= 0) ? p.nco_idx + sidx * mf : v.trig_idx;
     }
     using P = FftPlan<N>;
     constexpr int E = P::E;
@@ -276,8 +280,10 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int F = *v.n_frames;
-    int K = *v.n_trig;
+    int K = *v.n_trig;                                      // NCO events: the triggers, or ofdm_sync_ml's own list
     if (K > p.max_frames) K = p.max_frames;
+    const bool own_nco = v.nidx != v.trig_idx;
+    if (own_nco) { K = p.n_nco[p.soff ? blockIdx.y : 0]; if (K > p.max_frames) K = p.max_frames; }
     const int first_ok = *v.first_ok;
     const int occ = p.occ, zl = p.zl, L = p.L;
     float2* S = (P::NP == 2) ? bufB : bufA;                 // shifted spectrum of the current vector
@@ -310,15 +316,22 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
             const int par = m & 1;
             // ---- sigmix + fft_demod ----
             int kk = kg;
-            if (flag) {
+            if (own_nco) {                                  // last NCO event at or before the vector's first sample
+                int lo = 0, hi = K;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (v.nidx[mid] <= st) lo = mid + 1; else hi = mid;
+                }
+                kk = lo - 1;
+            } else if (flag) {
                 kk = kg - 1;
-                while (kk >= 0 && v.trig_idx[kk] > st) --kk;
+                while (kk >= 0 && v.nidx[kk] > st) --kk;
             }
-            const int64_t t_next = (kk + 1 < K) ? v.trig_idx[kk + 1] : LLONG_MAX;
+            const int64_t t_next = (kk + 1 < K) ? v.nidx[kk + 1] : LLONG_MAX;
             double stp, ph_base;
             if (kk >= 0) {
                 stp = v.step[kk];
-                ph_base = v.phi0[kk] + stp * (double)(st + tid - v.trig_idx[kk] + 1);
+                ph_base = v.phi0[kk] + stp * (double)(st + tid - v.nidx[kk] + 1);
             } else {                                        // before the first trigger (0 behind ofdm_sync_pn)
                 stp = *v.nco_init;
                 ph_base = stp * (double)(st + tid + 1);
@@ -332,9 +345,9 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
                 kk_w = kk;
                 __syncthreads();
             }
-            const int64_t t_lim = (kk < 0) ? ((K > 0) ? v.trig_idx[0] : LLONG_MAX) : t_next;
+            const int64_t t_lim = (kk < 0) ? ((K > 0) ? v.nidx[0] : LLONG_MAX) : t_next;
             const int lim = (t_lim - st >= (int64_t)N) ? N : (t_lim > st ? (int)(t_lim - st) : 0);
-            DemodLoad<PF> ld{PF ? bufB : v.y + st, st, lim, v.trig_idx, v.phi0, v.step, K, kk < 0 ? 0 : kk, phasor_f64(ph_base), s_W};
+            DemodLoad<PF> ld{PF ? bufB : v.y + st, st, lim, v.nidx, v.phi0, v.step, K, kk < 0 ? 0 : kk, phasor_f64(ph_base), s_W};
             if (PF) cp_async_wait_all();
             if (P::NP == 3) __syncthreads();                // S (= bufA) of the previous vector has been read by everyone
             if (TAPS && p.samp_tap && vglob < p.max_vectors && tid < T) {
@@ -642,6 +655,7 @@ int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_i
     AcqParams a;
     a.y = y; a.soff = ss.off; a.n = ss.n_max; a.trig_idx = io->trig_idx; a.phi0 = ws->phi0; a.step = ws->step; a.nco_init = ws->nco_init;
     a.n_trig = io->n_trig; a.first_ok = ws->first_ok; a.n_frames = io->n_frames; a.frame_ndata = io->frame_ndata; a.vbase = ws->vbase;
+    a.n_nco = ws->n_nco; a.nco_idx = ws->nco_idx;
     a.tw = h->d_tw; a.ks = h->d_ks; a.kd = h->d_kd;
     a.occ = h->occ; a.cp = h->cp; a.zl = h->zl; a.L = h->L; a.max_frames = io->max_frames;
     a.eq = ws->eq; a.eq_stride = ws->eq_stride;
@@ -702,10 +716,14 @@ int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_i
 // driven by the held angle, A.8) and sigmix = chan_filt * nco, per sample.  Debugging aid, not on the hot path.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nco_tap_kernel(const float2* __restrict__ y, int64_t n, const int32_t* __restrict__ n_trig,
-                                                      int max_frames, const int64_t* __restrict__ trig, const double* __restrict__ phi0,
-                                                      const double* __restrict__ step, const double* __restrict__ nco_init,
-                                                      float2* __restrict__ nco_out, float2* __restrict__ sigmix_out) {
-    int K = *n_trig;
+                                                      const int32_t* __restrict__ n_nco, int max_frames,
+                                                      const int64_t* __restrict__ trig_in, const int64_t* __restrict__ nco_idx,
+                                                      const double* __restrict__ phi0, const double* __restrict__ step,
+                                                      const double* __restrict__ nco_init, float2* __restrict__ nco_out,
+                                                      float2* __restrict__ sigmix_out) {
+    const bool own = *n_nco >= 0;                      // ofdm_sync_ml: the NCO has its own event list
+    const int64_t* trig = own ? nco_idx : trig_in;
+    int K = own ? *n_nco : *n_trig;
     if (K > max_frames) K = max_frames;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int lo = 0, hi = K;                              // triggers at indices <= i
@@ -726,8 +744,8 @@ int launch_nco_taps(ofdm_handle* h, const float2* y, int64_t n, ofdm_rx_io* io, 
     if (n <= 0 || (!nco_out && !sigmix_out)) return OFDM_OK;
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)h->sms * 16) blocks = (int64_t)h->sms * 16;
-    nco_tap_kernel<<<(int)blocks, 256, 0, st>>>(y, n, io->n_trig, io->max_frames, io->trig_idx, ws->phi0, ws->step, ws->nco_init,
-                                               nco_out, sigmix_out);
+    nco_tap_kernel<<<(int)blocks, 256, 0, st>>>(y, n, io->n_trig, ws->n_nco, io->max_frames, io->trig_idx, ws->nco_idx, ws->phi0,
+                                               ws->step, ws->nco_init, nco_out, sigmix_out);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }

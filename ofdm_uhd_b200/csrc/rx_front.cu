@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include "fft.cuh"
 #include <limits.h>
+#include <vector>
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -29,6 +30,8 @@ int rx_workspace_layout(const ofdm_handle* h, const StreamSet& ss, int32_t max_f
     ws->first_ok = (int32_t*)take(sizeof(int32_t) * S);
     ws->live_overflow = (int32_t*)take(sizeof(int32_t) * S);
     ws->nco_init = (double*)take(sizeof(double) * S);
+    ws->n_nco = (int32_t*)take(sizeof(int32_t) * S);
+    ws->nco_sens = (double*)take(sizeof(double) * S);
     ws->plan_hdr = (int32_t*)take(4 * sizeof(int32_t) * S);
     ws->plan_blk_d = (double*)take(sizeof(double) * 1024 * S);
     ws->plan_blk_i = (int64_t*)take(sizeof(int64_t) * 1024 * S);
@@ -41,6 +44,8 @@ int rx_workspace_layout(const ofdm_handle* h, const StreamSet& ss, int32_t max_f
     ws->seg_count = (int32_t*)take(sizeof(int32_t) * (size_t)(ws->n_seg + 1) * S);
     ws->seg_off = (int32_t*)take(sizeof(int32_t) * (size_t)(ws->n_seg + 1) * S);
     ws->seg_trig = (int64_t*)take(sizeof(int64_t) * (size_t)(ws->n_seg * ws->seg_cap) * S);
+    ws->nco_idx = (int64_t*)take(sizeof(int64_t) * max_frames * S);
+    ws->nco_ang = (float*)take(sizeof(float) * max_frames * S);
     // every frame is a flagged vector plus at most (distance to the next trigger) / L data vectors
     ws->eq_stride = (h ? n_max / h->L : 0) + max_frames + 2;
     ws->eq = (float2*)take(sizeof(float2) * (size_t)ws->eq_stride * (size_t)(h ? h->occ : 0) * S);
@@ -188,6 +193,28 @@ int launch_chan_filter(ofdm_handle* h, const float2* x, const StreamSet& ss, flo
     if (h->NOS == 2048) return launch_filter_n<2048, 1>(h, p, nblk_max, ss.S, st);   // one block per CTA: 4 independent CTAs per SM
     if (h->NOS == 4096) return launch_filter_n<4096, 1>(h, p, nblk_max, ss.S, st);
     ofdm_set_error("chan_filter: unsupported overlap-save size %d", h->NOS);
+    return OFDM_E_INVAL;
+}
+
+// gr.fir_filter_ccc with `ntaps` complex taps whose overlap-save response is H (rx_sync_alt.cu): the same kernel
+int launch_xcorr(ofdm_handle* h, const float2* x, int64_t n, const float2* H, int nos, int ntaps, float2* out, cudaStream_t st) {
+    if (n <= 0) return OFDM_OK;
+    const float2* tw = h->d_tw_os;
+    if (nos != h->NOS) {
+        if (!h->d_tw_os_alt) {
+            std::vector<float2> t((size_t)fft_twiddle_elems(nos), make_float2(0.f, 0.f));
+            fft_fill_twiddles_n(nos, t.data());
+            OFDM_CUDA_CHECK(cudaMalloc((void**)&h->d_tw_os_alt, sizeof(float2) * t.size()));
+            OFDM_CUDA_CHECK(cudaMemcpy(h->d_tw_os_alt, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
+        }
+        tw = h->d_tw_os_alt;
+    }
+    FiltParams p;
+    p.x = x; p.y = out; p.soff = nullptr; p.n = n; p.hist = ntaps - 1; p.V = nos - p.hist; p.tw = tw; p.H = H;
+    const int64_t nblk = (n + p.V - 1) / p.V;
+    if (nos == 2048) return launch_filter_n<2048, 1>(h, p, nblk, 1, st);
+    if (nos == 4096) return launch_filter_n<4096, 1>(h, p, nblk, 1, st);
+    ofdm_set_error("xcorr: unsupported overlap-save size %d", nos);
     return OFDM_E_INVAL;
 }
 
@@ -693,6 +720,12 @@ struct PlanParams {
     int32_t* hdr;          // [4] scratch: K, first_ok, frames before the first call that cannot run
     double* blk_d;         // [nblk] CTA totals of the phase increments
     long long* blk_i;      // [nblk] CTA totals of the vector counts
+    // the NCO's own event list (ofdm_sync_ml: the held angle changes at every detector peak, only some of which are timing
+    // triggers); *n_nco < 0: the NCO follows the trigger list.  sens = the NCO sensitivity (-2/N; ofdm_sync_ml: -1/N)
+    const int32_t* n_nco;
+    const int64_t* nco_idx;
+    const float* nco_ang;
+    const double* sens;    // [1] written by the synchroniser stage
 };
 
 __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -710,6 +743,7 @@ __device__ __forceinline__ PlanParams plan_stream_view(const PlanParams& q, int 
     p.frame_start = q.frame_start + s * mf; p.frame_ndata = q.frame_ndata + s * mf; p.vbase = q.vbase + s * (mf + 1);
     p.counters = q.counters + s * 8; p.nco_init = q.nco_init + s; p.hdr = q.hdr + s * 4; p.blk_d = q.blk_d + s * 1024;
     p.blk_i = q.blk_i + s * 1024;
+    p.n_nco = q.n_nco + s; p.nco_idx = q.nco_idx + s * mf; p.nco_ang = q.nco_ang + s * mf; p.sens = q.sens + s;
     return p;
 }
 
@@ -753,7 +787,7 @@ __global__ void __launch_bounds__(1024) plan_local_kernel(const PlanParams p_all
     const PlanParams p = plan_stream_view(p_all, blockIdx.y);
     __shared__ double s_wd[33];
     __shared__ long long s_wi[33];
-    __shared__ int s_K, s_first_ok;
+    __shared__ int s_K, s_first_ok, s_Kn;
     const int tid = threadIdx.x;
     const int64_t N = p.N, L = p.L, n = p.n;
     if (tid == 0) {
@@ -774,21 +808,28 @@ __global__ void __launch_bounds__(1024) plan_local_kernel(const PlanParams p_all
             const int mid = (lo + hi) >> 1;
             if (p.trig_idx[mid] < N) lo = mid + 1; else hi = mid;
         }
-        s_K = K; s_first_ok = lo;
-        if (blockIdx.x == 0) { p.hdr[0] = K; p.hdr[1] = lo; }
+        int Kn = *p.n_nco;
+        if (Kn < 0) Kn = K; else if (Kn > p.max_frames) Kn = p.max_frames;
+        s_K = K; s_first_ok = lo; s_Kn = Kn;
+        if (blockIdx.x == 0) { p.hdr[0] = K; p.hdr[1] = lo; p.hdr[3] = Kn; }
     }
     __syncthreads();
-    const int K = s_K, first_ok = s_first_ok;
+    const int K = s_K, first_ok = s_first_ok, Kn = s_Kn;
+    const bool own = *p.n_nco >= 0;                        // the NCO has its own event list
+    const int64_t* nidx = own ? p.nco_idx : p.trig_idx;
+    const float* nang = own ? p.nco_ang : p.trig_ang;
     const int k = blockIdx.x * 1024 + tid;
     double d = 0.0;
     long long v = 0;
+    if (k < Kn) {
+        // (1) NCO: step_k = sens * ang_k ; phi0_k = sum_{j<k} step_j * (t_{j+1} - t_j) over the NCO's events
+        const double stp = *p.sens * (double)nang[k];
+        p.step[k] = stp;
+        if (k + 1 < Kn) d = stp * (double)(nidx[k + 1] - nidx[k]);
+    }
     if (k < K) {
         const int64_t t = p.trig_idx[k];
         const int64_t tn = (k + 1 < K) ? p.trig_idx[k + 1] : 0;
-        // (1) NCO: step_k = -2/N * ang_k ; phi0_k = sum_{j<k} step_j * (t_{j+1} - t_j)
-        const double stp = (-2.0 / (double)N) * (double)p.trig_ang[k];
-        p.step[k] = stp;
-        if (k + 1 < K) d = stp * (double)(tn - t);
         if (k >= first_ok) {
             // (3) can the call that finds trigger k run?  (a call at read pointer pos needs pos+L+N < n)
             bool ok;
@@ -827,10 +868,8 @@ __global__ void __launch_bounds__(1024) plan_local_kernel(const PlanParams p_all
     long long tot_i;
     const double ex_d = plan_block_scan<double>(d, s_wd, tot_d);
     const long long ex_i = plan_block_scan<long long>(v, s_wi, tot_i);
-    if (k < K) {
-        p.phi0[k] = ex_d;
-        if (k >= first_ok) p.vbase[k - first_ok] = ex_i;
-    }
+    if (k < Kn) p.phi0[k] = ex_d;
+    if (k < K && k >= first_ok) p.vbase[k - first_ok] = ex_i;
     if (tid == 0) { p.blk_d[blockIdx.x] = tot_d; p.blk_i[blockIdx.x] = tot_i; }
 }
 
@@ -842,7 +881,8 @@ __global__ void __launch_bounds__(1024) plan_offset_kernel(const PlanParams p_al
     __shared__ double s_off_d;
     __shared__ long long s_off_i;
     const int tid = threadIdx.x;
-    const int K = p.hdr[0], first_ok = p.hdr[1];
+    const int K = p.hdr[0], first_ok = p.hdr[1], Kn = p.hdr[3];
+    const int64_t* nidx = (*p.n_nco >= 0) ? p.nco_idx : p.trig_idx;
     int F = K - first_ok;
     if (p.hdr[2] < F) F = p.hdr[2];
     if (F < 0) F = 0;
@@ -852,13 +892,13 @@ __global__ void __launch_bounds__(1024) plan_offset_kernel(const PlanParams p_al
     const long long ex_i = plan_block_scan<long long>(tid < nblk ? p.blk_i[tid] : 0, s_wi, tot_i);
     if (tid == blockIdx.x) {
         // phase accumulated over samples 0 .. t0-1 (non-zero only behind ofdm_sync_fixed)
-        s_off_d = ex_d + (K > 0 ? *p.nco_init * (double)p.trig_idx[0] : 0.0);
+        s_off_d = ex_d + (Kn > 0 ? *p.nco_init * (double)nidx[0] : 0.0);
         s_off_i = ex_i;
     }
     __syncthreads();
     const int k = blockIdx.x * 1024 + tid;
+    if (k < Kn) p.phi0[k] = s_off_d + p.phi0[k];
     if (k < K) {
-        p.phi0[k] = s_off_d + p.phi0[k];
         const int f = k - first_ok;
         if (f >= 0 && f <= F) {
             const long long vb = s_off_i + p.vbase[f];
@@ -879,11 +919,25 @@ __global__ void __launch_bounds__(1024) plan_offset_kernel(const PlanParams p_al
 
 __global__ void plan_init_kernel(int32_t* hdr, int S) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < S) { hdr[4 * s] = 0; hdr[4 * s + 1] = 0; hdr[4 * s + 2] = INT_MAX; }
+    if (s < S) { hdr[4 * s] = 0; hdr[4 * s + 1] = 0; hdr[4 * s + 2] = INT_MAX; hdr[4 * s + 3] = 0; }
+}
+
+__global__ void nco_mode_kernel(int32_t* n_nco, double* sens, int S, int32_t n_value, double sens_value) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) { n_nco[s] = n_value; sens[s] = sens_value; }
+}
+
+// what the synchroniser stage leaves for the NCO: its sensitivity (x fft_length: -2 behind ofdm_sync_pn / pnac / fixed, -1
+// behind ofdm_sync_ml, ofdm_receiver.py~:91,97,103,115) and whether it brings its own event list (n_nco >= 0 is written later)
+int launch_nco_mode(ofdm_handle* h, RxWorkspace* ws, int S, double sens_times_n, cudaStream_t st) {
+    nco_mode_kernel<<<(S + 255) / 256, 256, 0, st>>>(ws->n_nco, ws->nco_sens, S, -1, sens_times_n / (double)h->N);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
 }
 
 int launch_plan(ofdm_handle* h, const StreamSet& ss, ofdm_rx_io* io, RxWorkspace* ws, cudaStream_t st) {
     PlanParams p;
+    p.n_nco = ws->n_nco; p.nco_idx = ws->nco_idx; p.nco_ang = ws->nco_ang; p.sens = ws->nco_sens;
     p.n = ss.n_max; p.soff = ss.off; p.N = h->N; p.L = h->L; p.max_frames = io->max_frames; p.n_trig = io->n_trig; p.first_nan = ws->first_nan;
     p.trig_idx = io->trig_idx;
     p.trig_ang = io->trig_ang; p.phi0 = ws->phi0; p.step = ws->step; p.first_ok = ws->first_ok; p.n_frames = io->n_frames;

@@ -330,10 +330,12 @@ class OfdmEngine:
             self._ws, self._ws_key = b, key
         return b
 
-    def demodulate_async(self, x, bufs=None, sync: str = "pn", nsymbols: int = 18, freq_offset: float = 0.0, **kw):
+    def demodulate_async(self, x, bufs=None, sync: str = "pn", nsymbols: int = 18, freq_offset: float = 0.0,
+                         snr_db: float = 30.0, **kw):
         """Run the whole receive chain on the current stream; returns the buffer dict (no sync).
-        ``sync="fixed"`` is the reference's test mode (ofdm_receiver.py~:108-119): no channel filter, a trigger
-        every ``nsymbols`` symbols, constant frequency offset ``freq_offset`` (subcarrier spacings)."""
+        ``sync`` selects the synchroniser like the SYNC constant of ofdm_receiver.py~:89-119: "pn" (the live one),
+        "pnac", "ml" (``snr_db`` = options.snr feeds its rho), or "fixed" -- the reference's test mode: no channel filter,
+        a trigger every ``nsymbols`` symbols, constant frequency offset ``freq_offset`` (subcarrier spacings)."""
         n = int(x.numel())
         if bufs is None:
             bufs = self.rx_alloc(n, **kw)
@@ -343,9 +345,30 @@ class OfdmEngine:
         elif sync == "fixed":
             _lib.check(self.L_.ofdm_rx_demodulate_fixed(self.h, self._p(x), n, int(nsymbols), float(freq_offset),
                                                         C.byref(bufs["io"]), self._stream()), "rx_demodulate_fixed")
+        elif sync in ("pnac", "ml"):
+            need = int(self.L_.ofdm_rx_sync_alt_scratch_bytes(self.h, n))
+            sc = bufs.get("_alt_scratch")
+            if sc is None or sc.numel() < need:
+                sc = bufs["_alt_scratch"] = self.torch.empty(need, dtype=self.torch.uint8, device=self.dev)
+            _lib.check(self.L_.ofdm_rx_demodulate_alt(self.h, self._p(x), n, sync.encode("ascii"), float(snr_db),
+                                                      C.byref(bufs["io"]), self._p(sc), sc.numel(), self._stream()),
+                       "rx_demodulate_alt")
         else:
-            raise ValueError("sync %r: only 'pn' and 'fixed' exist (ml / pnac are not wired in the reference)" % (sync,))
+            raise ValueError("sync %r: the reference names 'pn', 'ml', 'pnac' and 'fixed'" % (sync,))
         return bufs
+
+    def nco_events(self, bufs, n: int):
+        """(indices, angles) of the NCO's own event list after a sync="ml" call (every detector peak)."""
+        torch = self.torch
+        base = bufs["workspace"].data_ptr()
+        ptr = lambda which: int(self.L_.ofdm_rx_workspace_ptr(self.h, C.byref(bufs["io"]), int(n), which)) - base
+        torch.cuda.current_stream(self.dev).synchronize()
+        k = int(bufs["workspace"][ptr(7):ptr(7) + 4].view(torch.int32).item())
+        if k < 0:
+            return None
+        idx = bufs["workspace"][ptr(8):ptr(8) + 8 * k].view(torch.int64).cpu().numpy()
+        ang = bufs["workspace"][ptr(9):ptr(9) + 4 * k].view(torch.float32).cpu().numpy()
+        return idx, ang
 
     # ---- many independent streams in one call (ofdm_rx_demodulate_batch) ----
     def rx_alloc_batch(self, stream_off, max_frames: int):

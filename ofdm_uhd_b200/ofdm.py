@@ -313,8 +313,8 @@ class ofdm_demod:
         self._sync = getattr(options, "sync", "pn")
         self._sync_nsymbols = int(getattr(options, "sync_nsymbols", 18))
         self._sync_freq_offset = float(getattr(options, "sync_freq_offset", 0.0))
-        if self._sync not in ("pn", "fixed"):
-            raise ValueError("sync %r: only 'pn' and 'fixed' exist (ml / pnac are not wired in the reference)" % (self._sync,))
+        if self._sync not in ("pn", "ml", "pnac", "fixed"):
+            raise ValueError("sync %r: ofdm_receiver.py names 'pn', 'ml', 'pnac' and 'fixed'" % (self._sync,))
         if options.verbose:
             self._print_verbage()
         self._watcher = _queue_watcher_thread(self._rcvd_pktq, callback)
@@ -436,6 +436,9 @@ class ofdm_demod:
             return r
         if self._sync == "fixed":
             res = self._engine.demodulate_fixed(samples, self._sync_nsymbols, self._sync_freq_offset, max_frames=max_frames)
+        elif self._sync in ("ml", "pnac"):
+            res = self._engine.collect(self._engine.demodulate_async(samples, sync=self._sync, snr_db=float(self._snr),
+                                                                     max_frames=max_frames))
         elif self._log:
             res = self._feed_logged(samples, max_frames)
         else:

@@ -633,6 +633,141 @@ def peak_detect(mf: np.ndarray) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# The two other synchronisers named by the reference (ofdm_receiver.py~:89-107): "pnac" and "ml".  The reference
+# hard-codes SYNC = "pn" (:89), so these branches are never taken there; their hier-blocks (gr-digital 3.6
+# ofdm_sync_pnac.py / ofdm_sync_ml.py) are restated from memory like the rest of Appendix A -- PARITY UNPINNED.
+# Precision policy as everywhere: streams float32, FIR / moving sums accumulated in float64 and rounded once.
+# --------------------------------------------------------------------------
+
+def known_symbol_time(lay: "Layout") -> np.ndarray:
+    """ks0time of ofdm_receiver.py~:80-87: ifft(ifftshift(padded known symbol)) (numpy's 1/N-normalised inverse),
+    complex64 like the taps gr.fir_filter_ccc holds."""
+    N, occ, zl = lay.fft_length, lay.occupied_tones, lay.zl
+    ks0 = np.zeros(N, dtype=np.complex128)
+    ks0[zl:zl + occ] = lay.ks
+    return np.fft.ifft(np.fft.ifftshift(ks0)).astype(C64)
+
+
+def _fir_c(x: np.ndarray, taps: np.ndarray) -> np.ndarray:
+    """gr.fir_filter_ccc: y[n] = sum_k taps[k] x[n-k], zero history, float64 accumulation."""
+    from scipy.signal import oaconvolve
+    if len(x) == 0:
+        return np.zeros(0, dtype=C64)
+    return oaconvolve(x.astype(np.complex128), taps.astype(np.complex128))[:len(x)].astype(C64)
+
+
+def _window_sum64(v: np.ndarray, w: int, tap: float = 1.0) -> np.ndarray:
+    """fir_filter with w equal taps: sum_{k<w} tap * v[n-k], products and sum in float64 (difference of prefix sums),
+    rounded to float32 / complex64."""
+    c = np.cumsum(v.astype(np.complex128 if np.iscomplexobj(v) else np.float64) * np.float64(tap))
+    out = c.copy()
+    out[w:] -= c[:-w]
+    return out.astype(C64 if np.iscomplexobj(v) else F32)
+
+
+def _delay(x: np.ndarray, d: int) -> np.ndarray:
+    out = np.zeros_like(x)
+    if len(x) > d:
+        out[d:] = x[:len(x) - d]
+    return out
+
+
+def _threshold_ff(v: np.ndarray, lo: float, hi: float) -> np.ndarray:
+    """gr.threshold_ff(lo, hi, 0): 1 above hi, 0 below lo, else the previous output."""
+    up, down = v > F32(hi), v < F32(lo)
+    out = np.zeros(len(v), dtype=np.uint8)
+    last = 0
+    for i in np.flatnonzero(~(up | down)).tolist() if (~(up | down)).any() else []:
+        pass
+    state = np.where(up, 1, np.where(down, 0, -1)).astype(np.int8)
+    # forward-fill the undecided samples
+    idx = np.where(state >= 0, np.arange(len(v)), -1)
+    np.maximum.accumulate(idx, out=idx)
+    out = np.where(idx >= 0, state[np.maximum(idx, 0)], 0).astype(np.uint8)
+    return out
+
+
+def peak_detector_fb_sequential(v: np.ndarray, rise: float, fall: float, alpha: float) -> np.ndarray:
+    """gr.peak_detector_fb(rise, fall, look_ahead (unused), alpha), whole-stream semantics (A.7), any rise / fall.
+    Returns the trigger indices.  Pure Python: small inputs only."""
+    a1 = float(np.float64(F32(alpha)))
+    a2 = 1.0 - a1
+    rise_f, fall_f = F32(rise), F32(fall)
+    avg, state, peak, ind = 0.0, 0, -math.inf, 0
+    trig = []
+    i, n = 0, len(v)
+    while i < n:
+        x = v[i]
+        if state == 0:
+            if x > F32(avg) * rise_f:
+                state = 1
+            else:
+                avg = a1 * float(x) + a2 * avg
+                i += 1
+        else:
+            if x > peak:
+                peak, ind = x, i
+                avg = a1 * float(x) + a2 * avg
+                i += 1
+            elif x > F32(avg) * fall_f:
+                avg = a1 * float(x) + a2 * avg
+                i += 1
+            else:
+                trig.append(ind)
+                state, peak = 0, -math.inf
+    return np.array(trig, dtype=np.int64)
+
+
+def sync_pnac(y: np.ndarray, lay: "Layout"):
+    """upstream ofdm_sync_pnac(fft_length, cp_length, ks0time) (ofdm_receiver.py~:101-107): cross-correlate with the
+    conjugated, reversed first half of the known symbol, delay-correlate the result over N/2, compare |corr|^2 with the
+    N-sample energy of the cross-correlation; timing = threshold_ff(0, 0, 0) of the difference, angle = arg(corr) held at
+    the timing samples.  Returns (trigger indices, float32 angles); every sample above the threshold is a trigger."""
+    N = lay.fft_length
+    kst = known_symbol_time(lay)
+    taps = np.conj(kst[:N // 2])[::-1].astype(C64)
+    cc = _fir_c(y, taps)
+    d = _delay(cc, N // 2)
+    cr, ci = _cmul(cc.real.astype(F32), cc.imag.astype(F32), d.real.astype(F32), (-d.imag).astype(F32))
+    c2 = (cr * cr + ci * ci).astype(F32)
+    mag = (cc.real.astype(F32) ** 2 + cc.imag.astype(F32) ** 2).astype(F32)
+    power = _window_sum64(mag, N)
+    cmp_ = (c2 - power).astype(F32)
+    peaks = _threshold_ff(cmp_, 0.0, 0.0)
+    trig = np.flatnonzero(peaks).astype(np.int64)
+    ang = np.arctan2(ci[trig].astype(np.float64), cr[trig].astype(np.float64)).astype(F32)
+    return trig, ang
+
+
+def sync_ml(y: np.ndarray, lay: "Layout", snr_db: float):
+    """upstream ofdm_sync_ml(fft_length, cp_length, snr, ks0time) (ofdm_receiver.py~:91-96; van de Beek et al.):
+    theta = |sum_cp y[n] conj(y[n-N])| - rho/2 * sum_cp (|y[n]|^2 + |y[n-N]|^2) -> peak_detector_fb(0.2, 0.25, 30, 0.0005);
+    the angle of the cp correlation is held at EVERY such peak (the NCO input, sensitivity -1/N); the timing output
+    keeps only the peaks where |y (*) known symbol|^2 / energy exceeds 0.1.
+    Returns (event indices, float32 angles, uint8 timing flags)."""
+    N, cp = lay.fft_length, lay.cp_length
+    snr = 10.0 ** (snr_db / 10.0)
+    rho = snr / (snr + 1.0)
+    yd = _delay(y, N)
+    e = ((y.real.astype(F32) ** 2 + y.imag.astype(F32) ** 2).astype(F32)
+         + (yd.real.astype(F32) ** 2 + yd.imag.astype(F32) ** 2).astype(F32)).astype(F32)
+    energy = _window_sum64(e, cp, float(F32(rho / 2.0)))
+    mr, mi = _cmul(yd.real.astype(F32), (-yd.imag).astype(F32), y.real.astype(F32), y.imag.astype(F32))
+    ms2 = _window_sum64((mr + 1j * mi).astype(C64), cp)
+    c2mag = np.sqrt((ms2.real.astype(F32) ** 2 + ms2.imag.astype(F32) ** 2).astype(F32)).astype(F32)
+    diff = (c2mag - energy).astype(F32)
+    ev = peak_detector_fb_sequential(diff, 0.2, 0.25, 0.0005)
+    ang = np.arctan2(ms2.imag[ev].astype(np.float64), ms2.real[ev].astype(np.float64)).astype(F32)
+    kst = known_symbol_time(lay)
+    kc = _fir_c(y, np.conj(kst)[::-1].astype(C64))
+    corrmag = (kc.real.astype(F32) ** 2 + kc.imag.astype(F32) ** 2).astype(F32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        div = (corrmag[ev] / energy[ev]).astype(F32)
+    timing = (div > F32(0.1)).astype(np.uint8)      # threshold_ff(0.1, 0.1, 0) on a stream that is 0 between the peaks
+    return ev, ang, timing
+
+
+# --------------------------------------------------------------------------
 # A.8 / A.9  NCO phase and sampler plan
 # --------------------------------------------------------------------------
 
@@ -646,6 +781,7 @@ class Plan:
     frame_trig: np.ndarray    # index into trig of each frame the sampler emits
     n_data: np.ndarray        # data vectors emitted after each frame's preamble vector
     init_step: float = 0.0    # NCO phase step per sample before the first trigger (0 for sync_pn: held angle starts at 0)
+    sensitivity: float = -2.0  # NCO sensitivity * N
 
 
 def sampler_sim(trig: np.ndarray, n: int, N: int, L: int, timeout_max: int = 1000):
@@ -683,21 +819,28 @@ def sampler_sim(trig: np.ndarray, n: int, N: int, L: int, timeout_max: int = 100
 
 
 def plan_frames(trig: np.ndarray, ang: np.ndarray, n: int, N: int, L: int, timeout: int = 1000,
-                init_ang: float = 0.0) -> Plan:
+                init_ang: float = 0.0, timing: Optional[np.ndarray] = None, sensitivity: float = -2.0) -> Plan:
     """``init_ang``: the frequency-offset input of the NCO before the first trigger -- 0 behind ofdm_sync_pn
-    (sample_and_hold starts at 0), pi*freq_offset behind ofdm_sync_fixed (a constant stream)."""
+    (sample_and_hold starts at 0), pi*freq_offset behind ofdm_sync_fixed (a constant stream).
+    ``timing``: behind ofdm_sync_ml the NCO's held angle changes at every event of (trig, ang) but only the flagged
+    events are timing triggers for the sampler; ``sensitivity``/N is the NCO's (-2/N, ofdm_sync_ml: -1/N)."""
     trig = np.asarray(trig, dtype=np.int64)
     ang = np.asarray(ang, dtype=F32)
     T = len(trig)
-    step = (-2.0 / N) * ang.astype(np.float64)
-    init_step = (-2.0 / N) * float(F32(init_ang))
+    step = (sensitivity / N) * ang.astype(np.float64)
+    init_step = (sensitivity / N) * float(F32(init_ang))
     phi0 = np.zeros(T, dtype=np.float64)
     if T:
         phi0[0] = init_step * float(trig[0])          # samples 0 .. t0-1 each advanced the phase by init_step
     for k in range(1, T):
         phi0[k] = phi0[k - 1] + step[k - 1] * float(trig[k] - trig[k - 1])
-    vs, vf, ft, nd = sampler_sim(trig, n, N, L, timeout)
-    return Plan(trig, ang, phi0, vs, vf, ft, nd, init_step)
+    if timing is None:
+        vs, vf, ft, nd = sampler_sim(trig, n, N, L, timeout)
+    else:
+        sel = np.flatnonzero(np.asarray(timing) != 0)
+        vs, vf, ft, nd = sampler_sim(trig[sel], n, N, L, timeout)
+        ft = sel[ft] if len(ft) else ft                  # frame_trig indexes the full event list
+    return Plan(trig, ang, phi0, vs, vf, ft, nd, init_step, sensitivity)
 
 
 def nco_phase_at(plan: Plan, idx: np.ndarray, N: int) -> np.ndarray:
@@ -707,7 +850,7 @@ def nco_phase_at(plan: Plan, idx: np.ndarray, N: int) -> np.ndarray:
     if len(plan.trig) == 0:
         return before
     k = np.searchsorted(plan.trig, idx, side="right") - 1
-    step = (-2.0 / N) * plan.ang.astype(np.float64)
+    step = (plan.sensitivity / N) * plan.ang.astype(np.float64)
     kk = np.maximum(k, 0)
     ph = plan.phi0[kk] + step[kk] * (idx - plan.trig[kk] + 1).astype(np.float64)
     return np.where(k >= 0, ph, before)
@@ -967,7 +1110,7 @@ def sync_fixed(n: int, N: int, cp: int, nsymbols: int, freq_offset: float):
 
 
 def rx_demodulate(x: np.ndarray, lay: Layout, keep: bool = False, sync: str = "pn", nsymbols: int = 18,
-                  freq_offset: float = 0.0) -> RxResult:
+                  freq_offset: float = 0.0, snr_db: float = 30.0) -> RxResult:
     """chan_filt -> sync_pn -> NCO -> sampler -> FFT -> frame_acq -> frame_sink -> unmake_packet
     (ofdm_receiver.py~:131-142, ofdm.py:245-247,300-305), whole-stream semantics.  ``sync="fixed"`` is the
     reference's test mode (ofdm_receiver.py~:108-119): no channel filter, triggers and frequency offset given."""
@@ -986,8 +1129,19 @@ def rx_demodulate(x: np.ndarray, lay: Layout, keep: bool = False, sync: str = "p
         trig = peak_detect(mf)
         ang = np.arctan2(Pi[trig].astype(np.float64), Pr[trig].astype(np.float64)).astype(F32)
         plan = plan_frames(trig, ang, n, N, L)
+    elif sync == "pnac":
+        y = chan_filter(x, chan_filter_taps(lay))
+        mf = np.zeros(0, dtype=F32)
+        trig, ang = sync_pnac(y, lay)
+        plan = plan_frames(trig, ang, n, N, L)
+    elif sync == "ml":
+        y = chan_filter(x, chan_filter_taps(lay))
+        mf = np.zeros(0, dtype=F32)
+        ev, ang, timing = sync_ml(y, lay, snr_db)
+        plan = plan_frames(ev, ang, n, N, L, timing=timing, sensitivity=-1.0)
+        trig = ev
     else:
-        raise ValueError("sync %r: only 'pn' and 'fixed' are restated (ml / pnac are not wired in the reference)" % sync)
+        raise ValueError("sync %r: the reference names 'pn', 'ml', 'pnac' and 'fixed'" % sync)
     acq = FrameAcquisition(lay)
     sink = FrameSink(lay)
     eqs, flags, vstart = [], [], []

@@ -50,3 +50,22 @@ def test_no_cpu_fallback_without_cuda():
         ofdm.ofdm_mod(opt)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ofdm.ofdm_demod(opt)
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof / offsetof of ofdm_cfg and ofdm_rx_io as a C compiler lays them out == the ctypes mirrors in _lib.py
+    (a binding with a field missing hands the library a short struct)."""
+    import ctypes as C
+    import subprocess
+    from ofdm_uhd_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ofdm_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(ofdm_cfg), offsetof(ofdm_cfg, host_carrier_map), '
+                   'sizeof(ofdm_rx_io), offsetof(ofdm_rx_io, counters), offsetof(ofdm_rx_io, max_vectors), '
+                   'offsetof(ofdm_rx_io, sampler_out)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(_lib.OfdmCfg), _lib.OfdmCfg.host_carrier_map.offset, C.sizeof(_lib.RxIo), _lib.RxIo.counters.offset,
+            _lib.RxIo.max_vectors.offset, _lib.RxIo.sampler_out.offset]
+    assert got == want

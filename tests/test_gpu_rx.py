@@ -629,3 +629,45 @@ def test_sampler_emits_1001_data_vectors():
     assert np.array_equal(got.frame_ndata, plan.n_data) and got.frame_ndata[0] == 1001
     assert np.array_equal(got.frame_start, trig[plan.frame_trig] - N + 1)
     eng.close()
+
+
+@pytest.mark.parametrize("sync,gain,N,occ,cp,mod", [("pnac", 8.0, 512, 200, 128, "qpsk"), ("pnac", 10.0, 512, 200, 128, "bpsk"),
+                                                     ("ml", 1.0, 512, 200, 128, "qpsk"), ("ml", 1.0, 1024, 400, 256, "qam16"),
+                                                     ("pnac", 8.0, 256, 104, 64, "qpsk")])
+def test_alternative_synchronisers_equal_oracle(sync, gain, N, occ, cp, mod):
+    """SYNC == "pnac" / "ml" of ofdm_receiver.py~:89-107 (never taken in the reference: SYNC is hard-coded to "pn"):
+    triggers, angles, the NCO's own event list (ml) and the delivered packets are the oracle's.  pnac compares a fourth
+    power with a second power of the input, so (as upstream's own docstring says) it only works at a suitable signal
+    level: the capture is scaled by `gain`."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    lay = o.Layout(N, occ, cp, mod)
+    rng = np.random.default_rng(17)
+    pay = payloads(rng, 8)
+    _, xc = loopback_capture(lay, pay, 30, 0.05, seed=31)
+    xc = (xc * np.float32(gain)).astype(np.complex64)
+    ref = o.rx_demodulate(xc, lay, keep=True, sync=sync, snr_db=30.0)
+    eng = OfdmEngine(N, occ, cp, mod)
+    bufs = eng.rx_alloc(len(xc), max_frames=max(64, 4 * len(ref.trig) + 64))
+    got = eng.collect(eng.demodulate_async(torch.from_numpy(xc).cuda(), bufs, sync=sync, snr_db=30.0))
+    if sync == "ml":
+        ev_idx, ev_ang = eng.nco_events(bufs, len(xc))
+        assert np.array_equal(ev_idx, ref.trig) and np.allclose(ev_ang, ref.ang, atol=2e-4)      # one event per OFDM symbol
+        assert len(ev_idx) > 5 * len(got.trig_idx) > 0
+        assert np.array_equal(got.frame_start, ref.frame_start) and np.array_equal(got.frame_ndata, ref.n_data)
+    else:
+        # indices exact; the angles come from the float32 FFT correlator here and a float64 FIR in the oracle
+        assert np.array_equal(got.trig_idx, ref.trig) and np.allclose(got.trig_ang, ref.ang, atol=2e-4)
+        assert np.array_equal(got.frame_start, ref.frame_start) and np.array_equal(got.frame_ndata, ref.n_data)
+    assert got.packets == ref.packets
+    assert sum(1 for ok, _ in got.packets if ok) >= (6 if sync == "ml" or gain == 8.0 else 1)
+    # the same through the reference-shaped class (options.sync)
+    from types import SimpleNamespace
+    from ofdm_uhd_b200 import ofdm
+    seen = []
+    d = ofdm.ofdm_demod(SimpleNamespace(modulation=mod, fft_length=N, occupied_tones=occ, cp_length=cp, snr=30.0, verbose=False,
+                                        log=False, sync=sync), callback=lambda ok, p: seen.append((ok, p)))
+    d.feed(xc)
+    d.wait(30)
+    assert seen == ref.packets
+    eng.close()
