@@ -653,7 +653,7 @@ def test_alternative_synchronisers_equal_oracle(sync, gain, N, occ, cp, mod):
     if sync == "ml":
         ev_idx, ev_ang = eng.nco_events(bufs, len(xc))
         assert np.array_equal(ev_idx, ref.trig) and np.allclose(ev_ang, ref.ang, atol=2e-4)      # one event per OFDM symbol
-        assert len(ev_idx) > 5 * len(got.trig_idx) > 0
+        assert len(ev_idx) >= 3 * len(got.trig_idx) > 0       # one NCO event per symbol, one timing trigger per frame
         assert np.array_equal(got.frame_start, ref.frame_start) and np.array_equal(got.frame_ndata, ref.n_data)
     else:
         # indices exact; the angles come from the float32 FFT correlator here and a float64 FIR in the oracle
