@@ -29,9 +29,12 @@ y = eng.ws_view(bufs, 0, n)
 stages = {
     "tx": lambda: eng.tx_run(plan, body, out=xs),
     "filter": lambda: eng.L_.ofdm_rx_chan_filter(eng.h, eng._p(xc), n, eng._p(y), st),
-    "sync": lambda: eng.L_.ofdm_rx_sync(eng.h, eng._p(y), n, C.byref(io), st),
+    "metric": lambda: eng.L_.ofdm_rx_stage(eng.h, eng._p(y), n, C.byref(io), 0, st),
+    "detect": lambda: eng.L_.ofdm_rx_stage(eng.h, eng._p(y), n, C.byref(io), 1, st),
+    "gather": lambda: eng.L_.ofdm_rx_stage(eng.h, eng._p(y), n, C.byref(io), 2, st),
     "plan": lambda: eng.L_.ofdm_rx_plan(eng.h, n, C.byref(io), st),
-    "demod": lambda: eng.L_.ofdm_rx_demod(eng.h, eng._p(y), n, C.byref(io), st),
+    "acq": lambda: eng.L_.ofdm_rx_stage(eng.h, eng._p(y), n, C.byref(io), 3, st),
+    "sink": lambda: eng.L_.ofdm_rx_stage(eng.h, eng._p(y), n, C.byref(io), 4, st),
     "finish": lambda: eng.L_.ofdm_rx_finish(eng.h, C.byref(io), st),
 }
 eng.demodulate_async(xc, bufs)
