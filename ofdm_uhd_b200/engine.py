@@ -286,6 +286,11 @@ class OfdmEngine:
         key = (int(n), int(max_frames), taps, int(max_vectors))
         if self._ws_key == key and not fresh:
             return self._ws
+        # a cached set that is large enough serves a shorter stream as well (the workspace is carved by the n of the
+        # call): consecutive feed_stream passes of slightly different lengths must not re-allocate gigabytes
+        if (not fresh and self._ws_key is not None and not taps and self._ws_key[2] == taps and self._ws_key[0] >= n
+                and self._ws_key[1] == int(max_frames) and self._ws_key[0] <= 2 * int(n) + (1 << 20)):
+            return self._ws
         dev = self.dev
         need = int(self.L_.ofdm_rx_workspace_bytes(self.h, int(n), int(max_frames)))
         b = {}

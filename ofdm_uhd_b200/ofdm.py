@@ -370,7 +370,11 @@ class ofdm_demod:
             # dense hand-over: the messages come back as one byte array + offsets; the ones already delivered by the
             # previous pass (frames inside the carried tail) are a prefix of the list
             eng = self._engine
-            bufs = eng.demodulate_async(buf, max_frames=max_frames)
+            # one buffer set sized for the largest pass seen (batch + tail), reused by every later pass
+            cap = max(int(buf.numel()), getattr(self, "_stream_cap", 0))
+            self._stream_cap = cap
+            mf = max_frames if max_frames is not None else max(64, cap // L + 64)
+            bufs = eng.demodulate_async(buf, eng.rx_alloc(cap, max_frames=mf))
             r = eng.deliver_end(eng.deliver_begin(bufs))
             n = r["n_msgs"]
             fstart = bufs["frame_start"][:int(r["counters"][0][0])].cpu().numpy()
