@@ -101,3 +101,28 @@ def test_tx_full_size_properties(torch_cuda):
     want = 0.25 ** 2 * 198 * (10 / 9) / 512                       # amp^2 * ncar * E|c|^2 / N
     assert abs(p / want - 1) < 0.02
     eng.close()
+
+
+@pytest.mark.parametrize("pad", [False, True])
+def test_payload_limit_matches_host_make_packet(torch_cuda, pad):
+    """The whitened body payload || crc32 || 0x55 [|| padding] must fit the 4096-byte PN table: the longest payload the
+    reference's make_packet frames is 4091 bytes (4087 with pad_for_usrp); one byte more raises on the host
+    (ofdm_packet_utils.py:117-135: the numpy XOR against the table) and must raise here too, not wrap the table.
+    At the limit the device framing is byte-identical to the host's."""
+    from ofdm_uhd_b200 import ofdm_packet_utils
+    from ofdm_uhd_b200.engine import OfdmEngine
+    from gpu_helpers import tx_gpu
+    limit = 4087 if pad else 4091
+    rng = np.random.default_rng(9)
+    eng = OfdmEngine(512, 200, 128, "qpsk")
+    ok = bytes(rng.integers(0, 256, limit, dtype=np.uint8))
+    _, plan = tx_gpu(eng, [ok], pad_for_usrp=pad)
+    assert plan.pkts.cpu().numpy().tobytes() == ofdm_packet_utils.make_packet(ok, 1, 1, pad)
+    too_long = ok + b"\x00" * (1 if not pad else 5)              # the padded length moves in steps of 16
+    with pytest.raises(ValueError):
+        ofdm_packet_utils.make_packet(too_long, 1, 1, pad)
+    with pytest.raises(ValueError):
+        eng.tx_plan(np.array([0, len(too_long)], dtype=np.int64), pad_for_usrp=pad)
+    with pytest.raises(ValueError):
+        eng.make_packets(None, np.array([0, len(too_long)], dtype=np.int64), pad_for_usrp=pad)
+    eng.close()

@@ -158,3 +158,22 @@ def test_usrp_path_shims_options_and_missing_frequency():
         utx.usrp_transmit_path(opts2)
     with pytest.raises(SystemExit):
         urx.usrp_receive_path(lambda ok, p: None, opts2)
+
+
+def test_watcher_thread_survives_a_failing_callback():
+    """An exception in the user's rx callback must not end the watcher: later packets are still delivered and wait()
+    returns."""
+    from ofdm_uhd_b200 import ofdm
+    seen = []
+
+    def cb(ok, payload):
+        if payload == b"boom":
+            raise RuntimeError("user callback failed")
+        seen.append(payload)
+
+    q = ofdm.msg_queue()
+    w = ofdm._queue_watcher_thread(q, cb)
+    for p in (b"a", b"boom", b"b"):
+        q.insert_tail(ofdm._rx_message(True, p))
+    w.drain(timeout=10)
+    assert seen == [b"a", b"b"] and w.errors == 1 and w.is_alive()
