@@ -202,6 +202,95 @@ struct MetricCtx {
                 if (b0 + i < n) mt[b0 + i] = q[i];
         }
     }
+
+    // ---- N/2 = MW * 256: MW warps of one CTA share a van Herk block, warp w owning its w-th quarter ---------------
+    // A window is still [tail of the previous block] + [head of this one]; inside a warp the sums are the ones of step(),
+    // and what the other warps contribute is a warp-uniform offset: head += totals of the earlier warps of THIS block,
+    // tail += totals of the later warps of the PREVIOUS block.  s_tot[slot][array][warp] holds the per-warp totals of
+    // a block; slots rotate over three blocks, so one __syncthreads per step orders writers and readers.
+    template <int MW>
+    __device__ __forceinline__ void prime_multi(const StepHist<K>& prev, StepHist<K>& cur, double (*s_tot)[3][MW], const int slot,
+                                                const int w) const {
+        products(prev, cur);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double run = 0.0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) run += (double)cur.x[a][i];
+            double bi = run;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
+            cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
+            if (lane == 0) s_tot[slot][a][w] = bi;           // lane 0's inclusive backward scan = the warp's total
+        }
+    }
+    template <int MW>
+    __device__ __forceinline__ void step_multi(StepHist<K>& prev, StepHist<K>& cur, const int64_t i0, const bool more,
+                                               double (*s_tot)[3][MW], const int slot, const int pslot, const int w) {
+        products(prev, cur);
+        if (more) load(prev.y, i0 + (int64_t)MW * SZ);           // the next block's samples of this warp into the dead buffer
+        float PR[3][K];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            // one array at a time (its 32 doubles of prefixes / tails are the register budget), a block barrier per array
+            double pre[K], tail[K];
+            double run;
+            if constexpr (K == 8) {
+                double xd[8], pd[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { xd[i] = (double)cur.x[a][i]; pd[i] = (double)prev.x[a][i]; }
+                prefix8_tree(xd, pre);
+                run = pre[7];
+                suffix8_tree(pd, prev.bwd[a], tail);
+            } else {
+                run = 0.0;
+#pragma unroll
+                for (int i = 0; i < K; ++i) { run += (double)cur.x[a][i]; pre[i] = run; }
+                double sfx = prev.bwd[a];
+                tail[K - 1] = sfx;
+#pragma unroll
+                for (int i = K - 2; i >= 0; --i) { sfx += (double)prev.x[a][i + 1]; tail[i] = sfx; }
+            }
+            double fi = run, bi = run;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                fi = fma(shfl_up_d(fi, 1 << k), mu[k], fi);
+                bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
+            }
+            const double fwd = shfl_up_d(fi, 1) * mu[0];
+            cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
+            if (lane == 0) s_tot[slot][a][w] = bi;
+            __syncthreads();
+            double head = 0.0, tl = 0.0;
+#pragma unroll
+            for (int j = 0; j < MW; ++j) {
+                if (j < w) head += s_tot[slot][a][j];
+                if (j > w) tl += s_tot[pslot][a][j];
+            }
+#pragma unroll
+            for (int i = 0; i < K; ++i) PR[a][i] = (float)((tail[i] + tl) + ((pre[i] + fwd) + head));
+        }
+        float q[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const float num = fadd_rn(fmul_rn(PR[0][i], PR[0][i]), fmul_rn(PR[1][i], PR[1][i]));
+            const float den = fmul_rn(PR[2][i], PR[2][i]);
+            q[i] = fdiv_rn(num, den);
+        }
+        const int64_t b0 = i0 + (int64_t)lane * K;
+        if (i0 + SZ <= n && st_ok) {
+            if constexpr (K == 8) {
+                stg256(mt + b0, q);
+            } else {
+#pragma unroll
+                for (int i = 0; i < K; i += 4) *(float4*)(mt + b0 + i) = make_float4(q[i], q[i + 1], q[i + 2], q[i + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+                if (b0 + i < n) mt[b0 + i] = q[i];
+        }
+    }
 };
 
 template <int K>
@@ -245,6 +334,64 @@ __global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __re
         if (i0 >= i_end) break;
         c.step(B, A, i0, i0 + SZ < i_end);
         i0 += SZ;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// N/2 = MW * 256 (N = 1024, 2048, 4096): one CTA of MW warps walks MC_STEPS van Herk blocks of N/2 samples (+1 priming
+// block); warp w owns the w-th 256-sample quarter of every block, with its history in registers exactly like the
+// one-warp kernel -- the stream is read once.  (Round 1 ran these layouts on metric_wide_kernel below: one warp per
+// 256-sample sub-step, previous-block products recomputed from y[n-W] and y[n-2W], three stream reads per sample.)
+// ---------------------------------------------------------------------------------------------
+template <int K, int MW>
+__global__ void __launch_bounds__(32 * MW, (10 / MW) > 0 ? (10 / MW) : 1) metric_multi_kernel(const float2* __restrict__ y, float* __restrict__ mt,
+                                                                                             const int64_t n_single,
+                                                                                             const int64_t* __restrict__ soff) {
+    constexpr int SZ = 32 * K;
+    constexpr int64_t W = (int64_t)MW * SZ;
+    __shared__ double s_tot[3][3][MW];
+    int64_t s_a, n;
+    stream_span(soff, blockIdx.y, n_single, s_a, n);
+    y += s_a;
+    mt += s_a;
+    MetricCtx<K> c;
+    c.y = y; c.mt = mt; c.n = n; c.lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    c.vec_ok = (((uintptr_t)y) & 31) == 0;
+    c.st_ok = (((uintptr_t)mt) & 31) == 0 && (K % 4) == 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        c.mu[k] = (c.lane >= (1 << k)) ? 1.0 : 0.0;
+        c.md[k] = (c.lane + (1 << k) < 32) ? 1.0 : 0.0;
+    }
+    const int64_t b_begin = (int64_t)blockIdx.x * MC_STEPS * W;          // first sample of the chunk
+    if (b_begin >= n) return;
+    const int64_t b_end = (b_begin + (int64_t)MC_STEPS * W < n) ? b_begin + (int64_t)MC_STEPS * W : n;
+    const int64_t off = (int64_t)w * SZ;                                  // this warp's quarter
+    StepHist<K> A, B;
+    if (b_begin == 0) {                              // zero history in front of the stream
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            A.y[i] = make_float2(0.f, 0.f);
+            A.x[0][i] = A.x[1][i] = A.x[2][i] = 0.f;
+        }
+        A.bwd[0] = A.bwd[1] = A.bwd[2] = 0.0;
+        if (c.lane == 0) { s_tot[2][0][w] = 0.0; s_tot[2][1][w] = 0.0; s_tot[2][2][w] = 0.0; }
+    } else {                                         // the block in front of the chunk, from the two blocks before it
+        c.load(B.y, b_begin - 2 * W + off);
+        c.load(A.y, b_begin - W + off);
+        c.template prime_multi<MW>(B, A, s_tot, 2, w);
+    }
+    c.load(B.y, b_begin + off);
+    int slot = 0, pslot = 2;
+    for (int64_t i0 = b_begin; i0 < b_end;) {
+        c.template step_multi<MW>(A, B, i0 + off, i0 + W < b_end, s_tot, slot, pslot, w);
+        i0 += W;
+        pslot = slot; slot = (slot == 2) ? 0 : slot + 1;
+        if (i0 >= b_end) break;
+        c.template step_multi<MW>(B, A, i0 + off, i0 + W < b_end, s_tot, slot, pslot, w);
+        i0 += W;
+        pslot = slot; slot = (slot == 2) ? 0 : slot + 1;
     }
 }
 
@@ -631,11 +778,18 @@ static int launch_split_k(const StreamParams& p, float* mt, int m, int S, int pa
     } else if (m == 1) {
         const int64_t chunks = (p.n + (int64_t)MC_STEPS * SZ - 1) / ((int64_t)MC_STEPS * SZ);
         metric_chunk_kernel<K><<<dim3((unsigned)chunks, S), 32, 0, st>>>(p.y, mt, p.n, p.soff);
-    } else {
-        const int chunk_blocks = (2 * MC_STEPS + m - 1) / m;             // ~64 sub-steps per warp: priming costs ~m light ones
+    } else if constexpr (K == 8) {
         const int64_t W = (int64_t)m * SZ;
-        const int64_t chunks = (p.n + W * chunk_blocks - 1) / (W * chunk_blocks);
-        metric_wide_kernel<K><<<dim3((unsigned)chunks, S), 32, 0, st>>>(p.y, mt, p.n, p.soff, m, chunk_blocks);
+        const int64_t chunks = (p.n + W * MC_STEPS - 1) / (W * MC_STEPS);
+        const dim3 g((unsigned)chunks, S);
+        if (m == 2) metric_multi_kernel<8, 2><<<g, 64, 0, st>>>(p.y, mt, p.n, p.soff);
+        else if (m == 4) metric_multi_kernel<8, 4><<<g, 128, 0, st>>>(p.y, mt, p.n, p.soff);
+        else if (m == 8) metric_multi_kernel<8, 8><<<g, 256, 0, st>>>(p.y, mt, p.n, p.soff);
+        else {
+            const int chunk_blocks = (2 * MC_STEPS + m - 1) / m;
+            const int64_t chunks_w = (p.n + W * chunk_blocks - 1) / (W * chunk_blocks);
+            metric_wide_kernel<K><<<dim3((unsigned)chunks_w, S), 32, 0, st>>>(p.y, mt, p.n, p.soff, m, chunk_blocks);
+        }
     }
     OFDM_LAUNCH_CHECK();
     if (!(parts & 2)) return OFDM_OK;
