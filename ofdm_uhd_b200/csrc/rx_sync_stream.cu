@@ -1,9 +1,9 @@
 // K_RX2: the whole of upstream ofdm_sync_pn (Schmidl-Cox metric + peak_detector_fb) as two streaming kernels.
 // Reference wiring: ofdm_receiver.py~:97-101; math: SURVEY.md A.6-A.7; same arithmetic (operation order,
 // float64 accumulation, float32 rounding points) as sync_metric_kernel + peak_detect_kernel in rx_front.cu,
-// which remain the stage-level entry points (ofdm_rx_sync_metric / ofdm_rx_peak_detect) and serve N >= 1024.
+// which remain the stage-level entry points (ofdm_rx_sync_metric / ofdm_rx_peak_detect) and serve N = 64 / cp > N/2.
 //
-// Both kernels run one warp per CTA (segment index and loop bounds are then CTA-uniform, so the compiler can
+// Both kernels run one warp per CTA (the metric kernel of N >= 1024: N/512 warps, see metric_multi_kernel) (segment index and loop bounds are then CTA-uniform, so the compiler can
 // prove every shuffle convergent) and walk a contiguous piece of the stream, 32*K samples per step with K
 // consecutive samples per lane, where 32*K = N/2: a step is exactly one van Herk block, so
 //   * y[n - N/2] is the same lane's sample of the previous step (kept in registers, never re-read),
@@ -18,6 +18,7 @@
 // hand-over is noise next to the instruction-issue / XU-pipe limit both halves sit on (a fused single kernel
 // measured 5.3 ms on the 640 M-sample bench capture, the pair 3.4 ms).
 //   metric_chunk_kernel  one warp per chunk of MC_STEPS blocks (+1 priming block): y -> M = |P|^2 / R^2
+//   metric_multi_kernel  the same for N/2 = MW * 256: MW warps per CTA share every block
 //   detect_seg_kernel    one warp per detector segment: M -> cp-average - 1 -> peak_detector_fb -> triggers;
 //                        a segment starts OFDM_PEAK_WARM samples early and runs past its end until an open run
 //                        closes; a run belongs to the segment it starts in.
@@ -340,8 +341,8 @@ __global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __re
 // ---------------------------------------------------------------------------------------------
 // N/2 = MW * 256 (N = 1024, 2048, 4096): one CTA of MW warps walks MC_STEPS van Herk blocks of N/2 samples (+1 priming
 // block); warp w owns the w-th 256-sample quarter of every block, with its history in registers exactly like the
-// one-warp kernel -- the stream is read once.  (Round 1 ran these layouts on metric_wide_kernel below: one warp per
-// 256-sample sub-step, previous-block products recomputed from y[n-W] and y[n-2W], three stream reads per sample.)
+// one-warp kernel -- the stream is read once.  (Round 1 ran these layouts with one warp per 256-sample sub-step and the
+// previous block's products recomputed from y[n-W] and y[n-2W]: three stream reads per sample.)
 // ---------------------------------------------------------------------------------------------
 template <int K, int MW>
 __global__ void __launch_bounds__(32 * MW, (10 / MW) > 0 ? (10 / MW) : 1) metric_multi_kernel(const float2* __restrict__ y, float* __restrict__ mt,
@@ -392,155 +393,6 @@ __global__ void __launch_bounds__(32 * MW, (10 / MW) > 0 ? (10 / MW) : 1) metric
         c.template step_multi<MW>(B, A, i0 + off, i0 + W < b_end, s_tot, slot, pslot, w);
         i0 += W;
         pslot = slot; slot = (slot == 2) ? 0 : slot + 1;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// The same metric for N/2 = m * 256 (N = 1024, 2048, 4096): a window still is [tail of the previous W-block] +
-// [head of this one], but a step (256 samples, 8 per lane) is only one of the m sub-steps of a block, so
-//   head(o) = C_j + in-step prefix,   C_j = sum of this block's sub-steps before j      (warp-uniform, float64)
-//   tail(o) = in-step suffix of the PREVIOUS block's sub-step j + D_j,  D_j = sum of that block's sub-steps after j
-// with the previous block's products recomputed from y[n-W] and y[n-2W] (three stream reads per sample instead of
-// one -- HBM has the room -- rather than W-wide per-lane history).  A warp walks MW_BLOCKS blocks after collecting
-// the m sub-step totals of the block in front of its chunk.
-// ---------------------------------------------------------------------------------------------
-constexpr int MW_MAX_SUB = 8;
-
-template <int K>
-__global__ void __launch_bounds__(32, 12) metric_wide_kernel(const float2* __restrict__ y, float* __restrict__ mt,
-                                                             const int64_t n_single, const int64_t* __restrict__ soff,
-                                                             const int m, const int chunk_blocks) {
-    constexpr int SZ = 32 * K;
-    __shared__ double s_T[3][MW_MAX_SUB];            // sub-step totals of the block being walked
-    __shared__ double s_D[3][MW_MAX_SUB];            // previous block: sum of the sub-steps after j
-    int64_t s_a, n;
-    stream_span(soff, blockIdx.y, n_single, s_a, n);
-    y += s_a;
-    mt += s_a;
-    MetricCtx<K> c;
-    c.y = y; c.mt = mt; c.n = n; c.lane = threadIdx.x;
-    c.vec_ok = (((uintptr_t)y) & 31) == 0;
-    c.st_ok = (((uintptr_t)mt) & 31) == 0 && (K % 4) == 0;
-    const int lane = c.lane;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        c.mu[k] = (lane >= (1 << k)) ? 1.0 : 0.0;
-        c.md[k] = (lane + (1 << k) < 32) ? 1.0 : 0.0;
-    }
-    const int64_t W = (int64_t)m * SZ;
-    const int64_t blk0 = (int64_t)blockIdx.x * chunk_blocks;
-    if (blk0 * W >= n) return;
-    // totals of the block in front of the chunk (zero history in front of the stream)
-    if (blk0 == 0) {
-        if (lane < 3 * MW_MAX_SUB) (&s_D[0][0])[lane] = 0.0;
-    } else {
-        for (int j = 0; j < m; ++j) {
-            const int64_t i0 = (blk0 - 1) * W + (int64_t)j * SZ;
-            float2 ya[K], yb[K];
-            c.load(ya, i0);
-            c.load(yb, i0 - W);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                double run = 0.0;
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    const float2 cc = cmulc_x(ya[i], yb[i]);
-                    const float xv = (a == 0) ? cc.x : (a == 1) ? cc.y : norm_x(ya[i]);
-                    run += (double)xv;
-                }
-                double fi = run;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) fi = fma(shfl_up_d(fi, 1 << k), c.mu[k], fi);
-                if (lane == 31) s_T[a][j] = fi;
-            }
-        }
-        __syncwarp();
-        if (lane < 3) {
-            double d = 0.0;
-            for (int j = m - 1; j >= 0; --j) { s_D[lane][j] = d; d += s_T[lane][j]; }
-        }
-    }
-    __syncwarp();
-    for (int64_t blk = blk0; blk < blk0 + chunk_blocks && blk * W < n; ++blk) {
-        double C[3] = {0.0, 0.0, 0.0};
-        for (int j = 0; j < m; ++j) {
-            const int64_t i0 = blk * W + (int64_t)j * SZ;
-            if (i0 >= n) break;
-            float2 yc[K], yp[K], ypp[K];
-            c.load(yc, i0);
-            c.load(yp, i0 - W);
-            c.load(ypp, i0 - 2 * W);
-            float PR[3][K];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                double pre[K], xq[K], xc[K];
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    const float2 cc = cmulc_x(yc[i], yp[i]);
-                    const float2 cq = cmulc_x(yp[i], ypp[i]);
-                    xc[i] = (double)((a == 0) ? cc.x : (a == 1) ? cc.y : norm_x(yc[i]));
-                    xq[i] = (double)((a == 0) ? cq.x : (a == 1) ? cq.y : norm_x(yp[i]));
-                }
-                double run, runp;
-                if constexpr (K == 8) {
-                    prefix8_tree(xc, pre);
-                    run = pre[7];
-                    runp = ((xq[0] + xq[1]) + (xq[2] + xq[3])) + ((xq[4] + xq[5]) + (xq[6] + xq[7]));
-                } else {
-                    run = 0.0; runp = 0.0;
-#pragma unroll
-                    for (int i = 0; i < K; ++i) { run += xc[i]; pre[i] = run; runp += xq[i]; }
-                }
-                double fi = run, bi = runp;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    fi = fma(shfl_up_d(fi, 1 << k), c.mu[k], fi);
-                    bi = fma(shfl_down_d(bi, 1 << k), c.md[k], bi);
-                }
-                const double tot = __shfl_sync(0xffffffffu, fi, 31);
-                const double head0 = fma(shfl_up_d(fi, 1), c.mu[0], C[a]);           // earlier lanes + earlier sub-steps
-                double sfx = fma(shfl_down_d(bi, 1), c.md[0], s_D[a][j]);           // later lanes + later sub-steps
-                double tail[K];
-                if constexpr (K == 8) {
-                    suffix8_tree(xq, sfx, tail);
-                } else {
-                    tail[K - 1] = sfx;
-#pragma unroll
-                    for (int i = K - 2; i >= 0; --i) { sfx += xq[i + 1]; tail[i] = sfx; }
-                }
-#pragma unroll
-                for (int i = 0; i < K; ++i) PR[a][i] = (float)(tail[i] + (pre[i] + head0));
-                C[a] += tot;
-                if (lane == 0) s_T[a][j] = tot;
-            }
-            float q[K];
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-                const float num = fadd_rn(fmul_rn(PR[0][i], PR[0][i]), fmul_rn(PR[1][i], PR[1][i]));
-                const float den = fmul_rn(PR[2][i], PR[2][i]);
-                q[i] = fdiv_rn(num, den);
-            }
-            const int64_t b0 = i0 + (int64_t)lane * K;
-            if (i0 + SZ <= n && c.st_ok) {
-                if constexpr (K == 8) {
-                    stg256(mt + b0, q);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < K; i += 4) *(float4*)(mt + b0 + i) = make_float4(q[i], q[i + 1], q[i + 2], q[i + 3]);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < K; ++i)
-                    if (b0 + i < n) mt[b0 + i] = q[i];
-            }
-        }
-        // this block's totals become the next block's "sub-steps after j" sums
-        __syncwarp();
-        if (lane < 3) {
-            double d = 0.0;
-            for (int j = m - 1; j >= 0; --j) { const double t = s_T[lane][j]; s_D[lane][j] = d; d += t; }
-        }
-        __syncwarp();
     }
 }
 
@@ -785,11 +637,7 @@ static int launch_split_k(const StreamParams& p, float* mt, int m, int S, int pa
         if (m == 2) metric_multi_kernel<8, 2><<<g, 64, 0, st>>>(p.y, mt, p.n, p.soff);
         else if (m == 4) metric_multi_kernel<8, 4><<<g, 128, 0, st>>>(p.y, mt, p.n, p.soff);
         else if (m == 8) metric_multi_kernel<8, 8><<<g, 256, 0, st>>>(p.y, mt, p.n, p.soff);
-        else {
-            const int chunk_blocks = (2 * MC_STEPS + m - 1) / m;
-            const int64_t chunks_w = (p.n + W * chunk_blocks - 1) / (W * chunk_blocks);
-            metric_wide_kernel<K><<<dim3((unsigned)chunks_w, S), 32, 0, st>>>(p.y, mt, p.n, p.soff, m, chunk_blocks);
-        }
+        else { ofdm_set_error("sync: no metric kernel for N/2 = %d x 256", m); return OFDM_E_INVAL; }
     }
     OFDM_LAUNCH_CHECK();
     if (!(parts & 2)) return OFDM_OK;
@@ -809,7 +657,7 @@ int launch_sync_stream(ofdm_handle* h, const float2* y, const StreamSet& ss, ofd
     // a step is 32*K samples: N/2 for N <= 512, else 256 with m = N/512 sub-steps per N/2-wide block
     const int K = h->N >= 512 ? 8 : h->N / 64;
     const int m = h->N >= 512 ? h->N / 512 : 1;
-    if (!(K == 2 || K == 4 || K == 8) || m > MW_MAX_SUB || h->cp > h->N / 2 || ws->n_seg == 0 || !ws->mf) return 1;
+    if (!(K == 2 || K == 4 || K == 8) || m > 8 || h->cp > h->N / 2 || ws->n_seg == 0 || !ws->mf) return 1;
     StreamParams p;
     p.y = y; p.soff = ss.off; p.max_frames = io->max_frames; p.n = ss.n_max; p.cp = h->cp; p.tapf = (float)(1.0 / (double)h->cp);
     p.seg_len = ws->seg_len; p.n_seg = ws->n_seg; p.seg_cap = (int)ws->seg_cap;

@@ -89,7 +89,6 @@ def best_band(avg_inorder, lo=200, span=17):
     size = len(avg_inorder)
     if size - 217 <= lo:
         return -1
-    c = np.concatenate([[0.0], np.cumsum(np.asarray(avg_inorder, dtype=np.float64))])
     power_temp, index = 50.0, -1
     for i in range(lo, size - 217):
         power = 0.0

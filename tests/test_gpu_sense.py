@@ -70,9 +70,10 @@ def test_wideband_capture_bands_detected():
 
 @pytest.mark.parametrize("N", [512, 1024, 2048])
 def test_hop_decision_on_device(N):
-    """ofdm_sense_hop (secondary_tx.py:268-295) against the host transcription in sensing.py: busy count of the
-    32-bin window with Python slice semantics (also for windows that run off either end) and the quietest
-    17-bin band, exact (same left-to-right double sums, first strict minimum)."""
+    """ofdm_sense_hop (secondary_tx.py:268-295) against the ORACLE's best_band (oracle/ofdm_oracle.py) and the reference's
+    own slice arithmetic: busy count of the 32-bin window with Python slice semantics (also for windows that run off
+    either end) and the quietest 17-bin band, exact (same left-to-right double sums, first strict minimum).  The host
+    transcription in sensing.py is held to the same oracle."""
     import math
     from types import SimpleNamespace
     import torch
@@ -89,12 +90,12 @@ def test_hop_decision_on_device(N):
             busy, index, wlen = tb.engine.hop(d_avg, d_free, ri)
             win = list(free)[ri - 16:ri + 16]
             assert wlen == len(win) and busy == sum(1 for v in win if v == 0)
-            assert index == sensing.best_band(avg)
+            assert index == o.best_band(avg) == sensing.best_band(avg)
         freq = 905 * 10 ** 6
         ri = int(math.ceil((freq - 8925 * 10 ** 5) * N / tb.samp_rate))
         busy, newf = sensing.hop_decision(tb, d_avg, d_free, freq, 905e6)
         assert busy == sensing.busy_count(list(free), freq, tb.samp_rate, N)
-        idx = sensing.best_band(avg)
+        idx = o.best_band(avg)
         if busy >= 9 and idx >= 0:
             assert newf == int(1e5 * math.ceil(sensing.sensed_frequency(905e6, tb.samp_rate, N, idx) / 1e5))
             assert abs(newf - (905e6 + (idx - N / 2 + 1) * tb.samp_rate / N)) <= 1e5
