@@ -447,11 +447,21 @@ def run_b200(args):
     torch.cuda.synchronize()
     exp_bytes = F * (psize + 4)
 
+    compute_done = [None]              # event after the kernels of the step launched last (on the other lane)
+
     def e2e_launch(ln):
         with torch.cuda.stream(ln.stream):
             ln.d_pay.copy_(h_pay, non_blocking=True)
+            # classic double buffering: this step's kernels start when the previous step's kernels are done, so the two
+            # lanes never interleave their kernels (they would then finish together and leave the GPU idle during both
+            # lanes' copies); the copies of one lane overlap the kernels of the other
+            if compute_done[0] is not None:
+                ln.stream.wait_event(compute_done[0])
             eng.tx_run(ln.plan, ln.d_pay, out=ln.xs)
             eng.demodulate_async(ln.xc, ln.bufs)
+            ev = torch.cuda.Event()
+            ev.record(ln.stream)
+            compute_done[0] = ev
             ln.ticket = eng.deliver_begin(ln.bufs, expect_msgs=F, expect_bytes=exp_bytes)
 
     trace = [] if os.environ.get("OFDM_E2E_TRACE") else None
