@@ -664,7 +664,7 @@ def packet_surface(torch, eng_unused, args, device):
             rx3.set_batch_callback(lambda oks, blob, off: got3.__setitem__(0, got3[0] + int(np.count_nonzero(oks))))
             for timed in (False, True):
                 got3[0] = 0
-                rx3.ofdm_rx._carry, rx3.ofdm_rx._carry_abs, rx3.ofdm_rx._last_abs_start = None, 0, None
+                rx3.ofdm_rx.reset_stream()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 for a in range(0, cap.numel(), buf):

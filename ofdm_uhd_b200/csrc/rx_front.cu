@@ -16,7 +16,9 @@ int rx_workspace_layout(const ofdm_handle* h, const StreamSet& ss, int32_t max_f
     const int sms = (h && h->sms > 0) ? h->sms : 148;
     // one full wave of the detector kernel (24 one-warp CTAs per SM) over all streams together
     int64_t seg_len = (n_total + (int64_t)sms * 24 - 1) / ((int64_t)sms * 24);
-    if (seg_len < 65536) seg_len = 65536;
+    // (a segment re-runs OFDM_PEAK_WARM samples of warm-up: 16 384 keeps a short capture -- a feed_stream pass, one
+    // stream of a batch -- on a few thousand warps at 2.5x the detector work, instead of a few hundred at 1.4x)
+    if (seg_len < 16384) seg_len = 16384;
     seg_len = (seg_len + 31) / 32 * 32;
     ws->seg_len = seg_len;
     ws->n_seg = n_max > 0 ? (n_max + seg_len - 1) / seg_len : 0;

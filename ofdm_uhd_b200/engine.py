@@ -604,12 +604,15 @@ class OfdmEngine:
 
 
     # ---- dense hand-over of the delivered messages (ofdm_rx_compact) ----
-    def deliver_begin(self, bufs, expect_msgs: Optional[int] = None, expect_bytes: Optional[int] = None):
+    def deliver_begin(self, bufs, expect_msgs: Optional[int] = None, expect_bytes: Optional[int] = None,
+                      frame_starts: bool = False):
         """Queue, on the current stream, the device-side packing of every delivered message of one receive call
         (single stream or batch) into a dense byte array and the device->host copies of the result; returns a ticket
         for :meth:`deliver_end`.  The copies are sized by what the caller expects to come back (``expect_msgs``
         messages, ``expect_bytes`` payload+crc bytes -- e.g. what it transmitted), not by max_frames * pkt_stride;
-        messages beyond that are reported by ``overflow`` in the result and can be fetched with :meth:`collect`."""
+        messages beyond that are reported by ``overflow`` in the result (``deliver_end(complete=True)`` fetches them
+        with a second, exactly sized copy).  ``frame_starts``: also bring back the first sample of every message's
+        frame (single stream only), for callers that place messages on a continuous stream."""
         torch = self.torch
         S = int(bufs.get("S", 1))
         mf = int(bufs["io"].max_frames)
@@ -631,9 +634,14 @@ class OfdmEngine:
         nb = d["bytes"].numel() if expect_bytes is None else min(int(expect_bytes), d["bytes"].numel())
         host = {}
         nbytes = 0
-        for key, src, cnt in (("totals", d["totals"], 3), ("counters", bufs["counters"], 8 * S), ("status", bufs["status"], S),
-                              ("ok", d["ok"], (nm + 31) // 32), ("off", d["off"], nm + 1), ("frame", d["frame"], nm),
-                              ("bytes", d["bytes"], nb)):
+        items = [("totals", d["totals"], 3), ("counters", bufs["counters"], 8 * S), ("status", bufs["status"], S),
+                 ("ok", d["ok"], (nm + 31) // 32), ("off", d["off"], nm + 1), ("frame", d["frame"], nm),
+                 ("bytes", d["bytes"], nb)]
+        if frame_starts and S == 1 and nm:
+            # frame_start[frame[k]] gathered on the device (entries past the message count are clamped, never read)
+            idx = d["frame"][:nm].to(torch.int64).clamp_(0, mf - 1)
+            items.append(("frame_start", bufs["frame_start"][idx], nm))
+        for key, src, cnt in items:
             t = self._pinned(bufs, "dense_" + key, src, cnt)
             if cnt:
                 t[:cnt].copy_(src[:cnt], non_blocking=True)
@@ -641,9 +649,10 @@ class OfdmEngine:
             nbytes += cnt * t.element_size()
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
-        return {"event": ev, "host": host, "nm": nm, "nb": nb, "d2h_bytes": nbytes, "S": S}
+        return {"event": ev, "host": host, "nm": nm, "nb": nb, "d2h_bytes": nbytes, "S": S, "bufs": bufs,
+                "frame_starts": frame_starts}
 
-    def deliver_end(self, ticket):
+    def deliver_end(self, ticket, complete: bool = False):
         """Wait for :meth:`deliver_begin`; returns a dict: n_msgs, ok (bool [n]), off (int64 [n+1]), frame (int32 [n]),
         data (uint8, dense payload||crc bytes), counters ([S, 8]), overflow (messages or bytes beyond the expected
         sizes), d2h_bytes.  Arrays are views of pinned staging buffers reused by the next call on the buffer set."""
@@ -656,11 +665,23 @@ class OfdmEngine:
         off = h["off"].numpy()[:n + 1]
         while n > 0 and off[n] > ticket["nb"]:           # messages whose bytes were not copied
             n -= 1
+        if complete and n < n_all:
+            # more came back than the caller expected: one more copy, sized exactly (the device arrays are intact)
+            t2 = self.deliver_begin(ticket["bufs"], expect_msgs=n_all, expect_bytes=b_all, frame_starts=ticket["frame_starts"])
+            r = self.deliver_end(t2)
+            r["d2h_bytes"] += ticket["d2h_bytes"]
+            r["refetched"] = True
+            return r
         okw = h["ok"].numpy().view(np.uint32)
         ok = ((okw[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool) if n else np.zeros(0, bool)
-        return {"n_msgs": n, "n_msgs_device": n_all, "ok": ok, "off": off[:n + 1], "frame": h["frame"].numpy()[:n],
-                "data": h["bytes"].numpy(), "counters": h["counters"].numpy().reshape(ticket["S"], 8).copy(),
-                "overflow": n_all - n, "d2h_bytes": ticket["d2h_bytes"], "bytes_device": b_all}
+        out = {"n_msgs": n, "n_msgs_device": n_all, "ok": ok, "off": off[:n + 1], "frame": h["frame"].numpy()[:n],
+               "data": h["bytes"].numpy(), "counters": h["counters"].numpy().reshape(ticket["S"], 8).copy(),
+               "overflow": n_all - n, "d2h_bytes": ticket["d2h_bytes"], "bytes_device": b_all}
+        if "frame_start" in h:
+            out["frame_start"] = h["frame_start"].numpy()[:n]
+        elif ticket.get("frame_starts"):
+            out["frame_start"] = np.zeros(0, np.int64)
+        return out
 
     def deliver(self, bufs, **kw):
         """(ok, payload) of every delivered message, in stream / arrival order, through the dense hand-over."""

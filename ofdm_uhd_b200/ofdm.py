@@ -324,6 +324,10 @@ class ofdm_demod:
         # absolute start of the last frame handed to the callback
         self._carry = None
         self._carry_abs = 0
+        self._stream_job = None                       # dense pass queued on the device, not yet handed to the callback
+        self._stream_sets = ({}, {})                  # its two alternating buffer sets
+        self._stream_passes = 0
+        self._dense_rate = None                       # (messages, payload bytes) per sample seen so far: sizes the D2H
         self._last_abs_start = None
         # feed_stream batches small buffers: the receiver runs once this many new samples are pending (a receive pass is
         # ~17 kernel launches and re-reads the carried tail, so per-buffer passes on radio-sized buffers would be
@@ -349,49 +353,59 @@ class ofdm_demod:
         With ``stream_batch_samples`` > 0 the buffers are queued (on the device) until that many new samples are
         pending -- or ``flush`` / flush_stream() -- and then go through the receiver in one pass: the cost of a pass
         (launches + the carried tail of stream_carry_samples()) is amortised over the batch, so a source that delivers
-        64 k-sample buffers runs at the whole-stream rate; delivery is delayed by at most one batch."""
-        import torch
+        64 k-sample buffers runs at the whole-stream rate; delivery is delayed by at most one batch.  With a batch
+        callback set (set_batch_callback) a pass is handed over while the NEXT one runs on the device -- one more batch
+        of delay, no host wait; flush_stream() delivers everything outstanding."""
+        torch = self._engine.torch
         if samples is not None:
-            if not isinstance(samples, torch.Tensor):
+            # (this prologue is all a call costs until a batch is full: keep it to a few attribute reads)
+            if type(samples) is not torch.Tensor:
                 samples = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.complex64))
-            if samples.device.type != "cuda":
+            if not samples.is_cuda:
                 samples = samples.to(self._engine.dev)
-            if samples.numel():
-                self._stream_pending.append(samples.contiguous())
-                self._stream_pending_n += int(samples.numel())
-        if not self._stream_pending or (not flush and self._stream_pending_n < self.stream_batch_samples):
+            n_new = samples.numel()
+            if n_new:
+                self._stream_pending.append(samples if samples.is_contiguous() else samples.contiguous())
+                n_new += self._stream_pending_n
+                self._stream_pending_n = n_new
+                if not flush and n_new < self.stream_batch_samples:
+                    return None
+        if not flush and self._stream_pending_n < self.stream_batch_samples:
             return None
+        dense = self._batch_callback is not None and self._sync == "pn" and not self._log
+        if not self._stream_pending:
+            return self._stream_finish(True) if dense else None
         parts = ([self._carry] if self._carry is not None else []) + self._stream_pending
         buf = parts[0] if len(parts) == 1 else torch.cat(parts)
         self._stream_pending, self._stream_pending_n = [], 0
         abs0 = self._carry_abs
         L = self._engine.L
-        if self._batch_callback is not None and self._sync == "pn" and not self._log:
-            # dense hand-over: the messages come back as one byte array + offsets; the ones already delivered by the
-            # previous pass (frames inside the carried tail) are a prefix of the list
+        if dense:
+            # dense hand-over, one pass behind: this pass is queued on the device (receiver, packing, device->host
+            # copies sized by what earlier passes brought back) and the PREVIOUS pass, long finished, is handed to the
+            # callback, so the host never waits for the GPU while the source keeps delivering buffers.  The two passes
+            # alternate between two buffer sets, each sized for the largest pass seen and reused.
             eng = self._engine
-            # one buffer set sized for the largest pass seen (batch + tail), reused by every later pass
-            cap = max(int(buf.numel()), getattr(self, "_stream_cap", 0))
-            self._stream_cap = cap
+            n = int(buf.numel())
+            job = {"k": self._stream_passes, "abs0": abs0, "buf": buf, "n": n}
+            self._stream_passes += 1
+            slot = self._stream_sets[job["k"] & 1]
+            cap = max(n, slot.get("cap", 0))
             mf = max_frames if max_frames is not None else max(64, cap // L + 64)
-            bufs = eng.demodulate_async(buf, eng.rx_alloc(cap, max_frames=mf))
-            r = eng.deliver_end(eng.deliver_begin(bufs))
-            n = r["n_msgs"]
-            fstart = bufs["frame_start"][:int(r["counters"][0][0])].cpu().numpy()
-            starts = abs0 + fstart[r["frame"]] if n else np.zeros(0, np.int64)
-            k0 = 0
-            if self._last_abs_start is not None and n:
-                k0 = int(np.searchsorted(starts, self._last_abs_start + L, side="right"))
-            if n > k0:
-                self._last_abs_start = int(starts[-1])
-                off = r["off"]
-                self._batch_callback(r["ok"][k0:], r["data"][int(off[k0]):int(off[n])], off[k0:] - off[k0])
-            keep = min(self.stream_carry_samples(), buf.numel())
-            self._carry = buf[buf.numel() - keep:].clone()
-            self._carry_abs = abs0 + buf.numel() - keep
-            r["stream_delivered"] = n - k0
-            self.last = r
-            return r
+            if slot.get("bufs") is None or slot["cap"] < cap or slot["mf"] != mf:
+                slot.update(bufs=eng.rx_alloc(cap, max_frames=mf, fresh=True), cap=cap, mf=mf)
+            bufs = eng.demodulate_async(buf, slot["bufs"])
+            em, eb = self._dense_expect(n)
+            job["bufs"] = bufs
+            job["ticket"] = eng.deliver_begin(bufs, expect_msgs=em, expect_bytes=eb, frame_starts=True)
+            keep = min(self.stream_carry_samples(), n)
+            self._carry = buf[n - keep:].clone()
+            self._carry_abs = abs0 + n - keep
+            r = self._stream_finish(False)                       # the pass before this one
+            self._stream_job = job
+            if flush:
+                r = self._stream_finish(True)
+            return r if r is not None else {"stream_delivered": 0, "n_msgs": 0, "pending_pass": job["k"]}
         res = self.feed(buf, max_frames=max_frames, _deliver=False)
         # a frame still open at the end of the buffer (the sink ran out of vectors) is left to the next call
         delivered = []
@@ -408,6 +422,49 @@ class ofdm_demod:
         self._carry_abs = abs0 + buf.numel() - keep
         res.stream_delivered = delivered
         return res
+
+    def _dense_expect(self, n):
+        """Sizes of the dense hand-over's device->host copies for a pass over n samples: what earlier passes brought
+        back per sample, + 25 % (None, None = everything, before anything is known).  A pass that exceeds them costs
+        one more, exactly sized copy (deliver_end(complete=True)), never a lost message."""
+        if self._dense_rate is None:
+            return None, None
+        return (int(1.25 * self._dense_rate[0] * n) + 64,
+                int(1.25 * self._dense_rate[1] * n) + 64 * self._engine.pkt_stride)
+
+    def _dense_learn(self, r, n):
+        m = r["n_msgs"]
+        if m and n > 0:
+            old = self._dense_rate or (0.0, 0.0)
+            self._dense_rate = (max(old[0], m / n), max(old[1], float(r["off"][m]) / n))
+
+    def _stream_finish(self, _unused=None):
+        """Hand the queued dense pass (if any) to the batch callback: its messages come back as one byte array +
+        offsets; the ones already delivered by the pass before (frames inside the carried tail) are a prefix."""
+        job, self._stream_job = self._stream_job, None
+        if job is None:
+            return None
+        eng = self._engine
+        r = eng.deliver_end(job["ticket"], complete=True)
+        n = r["n_msgs"]
+        L = eng.L
+        self._dense_learn(r, job["n"])
+        starts = job["abs0"] + r["frame_start"] if n else np.zeros(0, np.int64)
+        k0 = 0
+        if self._last_abs_start is not None and n:
+            k0 = int(np.searchsorted(starts, self._last_abs_start + L, side="right"))
+        if n > k0:
+            self._last_abs_start = int(starts[-1])
+            off = r["off"]
+            self._batch_callback(r["ok"][k0:], r["data"][int(off[k0]):int(off[n])], off[k0:] - off[k0])
+        r["stream_delivered"] = n - k0
+        self.last = r
+        return r
+
+    def reset_stream(self):
+        """Forget the continuous stream seen so far (a new capture starts): anything still queued is dropped."""
+        self._carry, self._carry_abs, self._last_abs_start = None, 0, None
+        self._stream_pending, self._stream_pending_n, self._stream_job = [], 0, None
 
     def flush_stream(self, max_frames=None):
         """Run the receiver on whatever feed_stream() has queued."""
@@ -433,8 +490,10 @@ class ofdm_demod:
         samples = samples.contiguous()
         if self._batch_callback is not None and _deliver and self._sync == "pn" and not self._log:
             bufs = self._engine.demodulate_async(samples, max_frames=max_frames)
-            r = self._engine.deliver_end(self._engine.deliver_begin(bufs))
+            em, eb = self._dense_expect(int(samples.numel()))
+            r = self._engine.deliver_end(self._engine.deliver_begin(bufs, expect_msgs=em, expect_bytes=eb), complete=True)
             n = r["n_msgs"]
+            self._dense_learn(r, int(samples.numel()))
             self._batch_callback(r["ok"], r["data"][:int(r["off"][n])] if n else r["data"][:0], r["off"])
             self.last = r
             return r

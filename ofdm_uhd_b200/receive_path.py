@@ -20,6 +20,8 @@ class receive_path:
                                        max_pkt_bytes=max_pkt_bytes)
         if self._verbose:
             self._print_verbage()
+        # a radio-sized buffer is a microsecond of receiver time: the per-buffer call goes straight to the demodulator
+        self.feed_stream = self.ofdm_rx.feed_stream
 
     def feed(self, samples, max_frames=None):
         """Run the receiver on one buffer of complex64 baseband samples."""
@@ -27,7 +29,7 @@ class receive_path:
 
     def feed_stream(self, samples, max_frames=None, flush=False):
         """feed() for consecutive buffers of one continuous stream (see ofdm_demod.feed_stream)."""
-        return self.ofdm_rx.feed_stream(samples, max_frames=max_frames, flush=flush)
+        return self.ofdm_rx.feed_stream(samples, max_frames, flush)
 
     def flush_stream(self, max_frames=None):
         return self.ofdm_rx.flush_stream(max_frames=max_frames)
