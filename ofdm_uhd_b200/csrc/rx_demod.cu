@@ -516,8 +516,43 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
             const bool tap = TAPS && vg < v_own_end && vg < p.max_vectors;
             double er = 0.0, ei = 0.0;
             // two carriers per pass with every load ahead of the first store: two independent slicer chains
-            for (int c = lane; c < ncar; c += 2 * TPS) {
-                const int c2 = c + TPS;
+            for (int cbase = 0; cbase < ncar; cbase += 2 * TPS) {
+                const int c = cbase + lane;
+                if (cbase + TPS >= ncar) {
+                    // last pass of a vector whose carriers do not fill a pair of rows (session-uniform branch): one
+                    // chain, instead of a second one computed and thrown away (198 carriers = 3 pairs + 6)
+                    if (c < ncar) {
+                        const float2 d0a = dfe[c];
+                        const float2 eqa = LDG(e + LDG(p.sinkmap + c));
+                        const float2 ra = cmul_x(cmul_x(eqa, car), d0a);
+                        int ba;
+                        if (p.grid_L > 0) {
+                            ba = slicer(ra);
+                        } else {
+                            ba = 0;
+                            float besta = norm_x(csub_x(ra, s_cst[0]));
+                            for (int k = 1; k < p.M; ++k) {
+                                const float dda = norm_x(csub_x(ra, s_cst[k]));
+                                if (dda < besta) { besta = dda; ba = k; }
+                            }
+                        }
+                        const float2 cla = s_cst[ba];
+                        const float2 ea = cmulc_x(ra, cla);
+                        er += (double)ea.x;
+                        ei += (double)ea.y;
+                        if (norm_x(ra) > 0.001f) {
+                            const float2 dq = cscale_x(csub_x(cdiv_x(cla, ra), d0a), 0.05f);
+                            dfe[c] = make_float2(fadd_rn(d0a.x, dq.x), fadd_rn(d0a.y, dq.y));
+                        }
+                        sym[c] = (uint8_t)ba;
+                        if (TAPS && tap) {
+                            if (p.sym_idx) p.sym_idx[vg * ncar + c] = (uint8_t)ba;
+                            if (p.derot_syms) p.derot_syms[vg * ncar + c] = ra;
+                        }
+                    }
+                    break;
+                }
+                const int c2 = c + TPS;                     // c < cbase + TPS < ncar
                 const bool two = c2 < ncar;
                 const int cb = two ? c2 : c;
                 const float2 d0a = dfe[c], d0b = dfe[cb];
