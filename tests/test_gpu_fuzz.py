@@ -1,0 +1,83 @@
+"""Randomised parity: layouts, constellations, ragged payload sizes, bursts separated by noise-only gaps, carrier offsets
+and noise levels drawn from a seeded generator; the receiver's packet list must equal the C port of the oracle's
+(oracle/ofdm_oracle_c.c == ofdm_oracle.py by tests/test_c_port.py) on every draw.  Same comparison rule as
+tests/test_gpu_scale.py: frames whose trigger the two channel filters' 1e-7 difference moved by a sample are counted,
+not compared; everything else -- message count, CRC verdicts, bytes of CRC-good packets, latched angles -- is exact."""
+import numpy as np
+import pytest
+
+from oracle import c_port
+from oracle import ofdm_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+LAYOUTS = [(64, 48, 16), (128, 80, 32), (256, 200, 64), (512, 200, 128), (512, 400, 64), (1024, 400, 256), (1024, 800, 128),
+           (2048, 1200, 256), (4096, 3200, 512)]
+MODS = {"bpsk": 12.0, "qpsk": 15.0, "8psk": 21.0, "qam16": 22.0, "qam64": 29.0, "qam256": 36.0}    # lowest SNR drawn (dB)
+
+
+def _draw(rng):
+    N, occ, cp = LAYOUTS[int(rng.integers(len(LAYOUTS)))]
+    mod = list(MODS)[int(rng.integers(len(MODS)))]
+    bursts = int(rng.integers(1, 4))
+    frames = [int(rng.integers(1, 14)) for _ in range(bursts)]
+    hi = 1500 if N >= 512 else 300
+    sizes = [rng.integers(1, hi, size=f) for f in frames]
+    if rng.random() < 0.3:
+        sizes[0][0] = 4091 if N >= 1024 else sizes[0][0]         # the longest payload a header can announce
+    snr = MODS[mod] + float(rng.uniform(0.0, 12.0))
+    cfo = float(rng.uniform(-0.45, 0.45))
+    gaps = [int(rng.integers(2, 9)) for _ in range(bursts + 1)]     # noise-only symbols around / between the bursts
+    pad = bool(rng.random() < 0.25) and max(int(z.max()) for z in sizes) < 4000     # padding lowers the payload limit
+    return N, occ, cp, mod, sizes, snr, cfo, gaps, pad
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_random_capture_equals_oracle(seed):
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    rng = np.random.default_rng(7000 + seed)
+    N, occ, cp, mod, sizes, snr, cfo, gaps, pad = _draw(rng)
+    eng = OfdmEngine(N, occ, cp, mod, 0.25, pad_seed=seed)
+    L = eng.L
+    parts, sent = [torch.zeros(gaps[0] * L, dtype=torch.complex64, device="cuda")], []
+    first = 0
+    for b, sz in enumerate(sizes):
+        off = np.concatenate([[0], np.cumsum(sz)]).astype(np.int64)
+        body = rng.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+        plan = eng.tx_plan(off, pad_for_usrp=pad)
+        parts.append(eng.tx_run(plan, torch.from_numpy(body).cuda(), first_frame=first).clone())
+        # the transmit side of the same draw: samples of the burst against the oracle's modulator
+        want = c_port.tx(c_port.make_cfg(N, occ, cp, mod, 0.25, seed),
+                         [o.make_packet(bytes(body[off[k]:off[k + 1]]), 1, 1, pad) for k in range(len(sz))], first_frame=first)
+        got = parts[-1].cpu().numpy()
+        assert got.shape == want.shape
+        assert np.linalg.norm(got - want) <= 1e-4 * np.linalg.norm(want) and np.abs(got - want).max() < 1e-5
+        parts.append(torch.zeros(gaps[b + 1] * L, dtype=torch.complex64, device="cuda"))
+        sent += [bytes(body[off[k]:off[k + 1]]) for k in range(len(sz))]
+        first += len(sz)
+    x = torch.cat(parts)
+    sig = torch.cat(parts[1::2])
+    p_sig = float((sig.abs() ** 2).mean().item())
+    sigma = (p_sig / (10 ** (snr / 10.0)) / 2.0) ** 0.5
+    xc = eng.channel(x, cfo=cfo, sigma=sigma, seed=100 + seed)
+    F = len(sent)
+    r = eng.demodulate(xc, max_frames=F + 64)
+    rpk, rtrig, rang, _ = c_port.rx(c_port.make_cfg(N, occ, cp, mod), xc.cpu().numpy(), max_pkts=F + 64)
+    eng.close()
+    what = "seed %d: %d/%d/%d %s, %d frames in %d bursts, %.1f dB, cfo %.2f" % (seed, N, occ, cp, mod, F, len(sizes), snr, cfo)
+    assert len(r.trig_idx) == len(rtrig), what
+    assert len(r.packets) == len(rpk), what
+    moved = set(np.flatnonzero(r.trig_idx != rtrig).tolist())
+    assert len(moved) <= max(1, len(rtrig) // 8) and (np.abs(r.trig_idx - rtrig) <= max(1, cp // 64)).all(), what
+    first_ok = int(np.searchsorted(r.trig_idx, N))
+    keep = [i for i, f in enumerate(r.msg_frames) if (first_ok + int(f)) not in moved]
+    assert [r.packets[i][0] for i in keep] == [rpk[i][0] for i in keep], what
+    assert all(r.packets[i][1] == rpk[i][1] for i in keep if r.packets[i][0]), what
+    unmoved = np.setdiff1d(np.arange(len(rtrig)), sorted(moved))
+    assert np.abs(r.trig_ang - rang)[unmoved].max(initial=0) < 2e-3, what
+    # what comes back good is what was sent, in order
+    good = [p for ok, p in r.packets if ok]
+    it = iter(sent)
+    assert all(any(p == q for q in it) for p in good), what
+    print(what, "->", len(r.packets), "messages,", len(good), "good,", len(moved), "moved triggers")
