@@ -462,16 +462,21 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
 // its header turns out bad (2 vectors), its packet is complete, or the stream ends.  The liveness walk (launch_finish)
 // then decides which sessions the one real sink would have run.
 // ---------------------------------------------------------------------------------------------
-// TPS = threads per session: 32 (a warp; several sessions per CTA) for the usual layouts, 128 (the whole CTA works on
-// one session, block barriers instead of warp barriers) when a vector has thousands of data carriers.
+// TPS = threads per session: 16 / 32 lanes of a warp (32 / TPS sessions per warp, several warps per CTA) for the
+// usual layouts -- the per-vector serial section (float64 atan2 + sincos of the PLL, header check, leftover bits) is
+// issued once per warp, so sub-warp sessions share it -- or 128 (the whole CTA works on one session, block barriers
+// instead of warp barriers) when a vector has thousands of data carriers.
 template <bool TAPS, int TPS>
 __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
     extern __shared__ __align__(16) unsigned char sink_smem[];
     __shared__ double s_red[2][4][2];
-    constexpr bool WARP = (TPS == 32);
-    const int lane = WARP ? (threadIdx.x & 31) : threadIdx.x;          // thread index inside the session
-    const int w = WARP ? (threadIdx.x >> 5) : 0, W = WARP ? (blockDim.x >> 5) : 1;
-    auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
+    constexpr bool WARP = (TPS <= 32);                                 // a session lives inside one warp
+    const int lane = WARP ? (threadIdx.x & (TPS - 1)) : threadIdx.x;   // thread index inside the session
+    const int w = WARP ? (threadIdx.x / TPS) : 0, W = WARP ? (blockDim.x / TPS) : 1;
+    // the lanes of this session inside its warp: barriers and shuffles name exactly them, so the sessions of a warp may
+    // part ways (one header bad, one packet longer) without waiting for each other
+    const unsigned gmask = TPS >= 32 ? 0xffffffffu : (((1u << (TPS & 31)) - 1u) << ((threadIdx.x & 31) & ~(TPS - 1)));
+    auto sync = [&] { if (WARP) __syncwarp(gmask); else __syncthreads(); };
     const int ncar = p.ncar, nbits = p.nbits, occ = p.occ;
     // shared: constellation [M], grid table [grid_L^2] (CTA-wide), then per warp: dfe [ncar] float2, sym [ncar], vb
     float2* s_cst = (float2*)sink_smem;
@@ -604,9 +609,9 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
                 }
             }
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                er += __shfl_xor_sync(0xffffffffu, er, d);
-                ei += __shfl_xor_sync(0xffffffffu, ei, d);
+            for (int d = (TPS < 32 ? TPS / 2 : 16); d > 0; d >>= 1) {
+                er += __shfl_xor_sync(gmask, er, d);
+                ei += __shfl_xor_sync(gmask, ei, d);
             }
             if (!WARP) {                                    // warp sums -> shared memory (double-buffered by vi) -> everyone
                 if ((threadIdx.x & 31) == 0) { s_red[vi & 1][threadIdx.x >> 5][0] = er; s_red[vi & 1][threadIdx.x >> 5][1] = ei; }
@@ -725,7 +730,11 @@ int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_i
     const size_t per_sess = (size_t)h->ncar * sizeof(float2) + ((h->ncar + 15) & ~15) + ((h->ncar * h->nbits / 8 + 16 + 15) & ~15);
     const size_t fixed = (size_t)h->M * sizeof(float2) + (((size_t)h->grid_L * h->grid_L + 15) & ~(size_t)15);
     const bool wide = h->ncar > 1024;
-    int W = wide ? 1 : 4;
+    // half-warp sessions while a session's tables are small (measured, sink kernel alone: 512/200 QPSK 1.50 -> 1.26 ms,
+    // QAM16 1.17 -> 1.05; at 398 carriers two sessions' tables per warp cost more occupancy than the shared serial
+    // section saves: 0.55 -> 0.60)
+    const int tps = wide ? 128 : (h->ncar <= 256 ? 16 : 32);
+    int W = wide ? 1 : 128 / tps;
     while (W > 1 && fixed + W * per_sess > 48 * 1024) W >>= 1;
     const size_t smem = fixed + W * per_sess;
     const bool staps = io->sym_idx || io->derot_syms;
@@ -737,10 +746,11 @@ int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_i
 #define OFDM_SINK_LAUNCH(TAPS_, TPS_)                                                       \
     do {                                                                                    \
         OFDM_SET_MAX_SMEM((sink_kernel<TAPS_, TPS_>), smem, h->device);                     \
-        sink_kernel<TAPS_, TPS_><<<g, (TPS_) == 32 ? 32 * W : 128, smem, st>>>(p);          \
+        sink_kernel<TAPS_, TPS_><<<g, (TPS_) <= 32 ? (TPS_) * W : 128, smem, st>>>(p);      \
     } while (0)
     if (wide) { if (staps) OFDM_SINK_LAUNCH(true, 128); else OFDM_SINK_LAUNCH(false, 128); }
-    else      { if (staps) OFDM_SINK_LAUNCH(true, 32); else OFDM_SINK_LAUNCH(false, 32); }
+    else if (tps == 16) { if (staps) OFDM_SINK_LAUNCH(true, 16); else OFDM_SINK_LAUNCH(false, 16); }
+    else { if (staps) OFDM_SINK_LAUNCH(true, 32); else OFDM_SINK_LAUNCH(false, 32); }
 #undef OFDM_SINK_LAUNCH
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
