@@ -188,7 +188,9 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
     double bw = ((double)occ / (double)N) / 2.0, tb = bw * 0.08;
     h->ntaps = firdes_lowpass(bw + tb, tb, h->h_taps, OFDM_MAX_TAPS);
     if (h->ntaps < 0) { ofdm_set_error("ofdm_create: channel filter needs more than %d taps", OFDM_MAX_TAPS); delete h; return nullptr; }
-    h->NOS = 2048;
+    // overlap-save size: 1024 (the warp-per-block kernel, 2 radix-32 passes) while at least 3/4 of a block is output
+    h->NOS = 1024;
+    if (const char* e = getenv("OFDM_FILTER_NOS")) { if (atoi(e) == 2048 || atoi(e) == 4096) h->NOS = atoi(e); }
     while (h->NOS < 4 * h->ntaps) h->NOS *= 2;
     if (h->NOS > 4096) { ofdm_set_error("ofdm_create: channel filter too long"); delete h; return nullptr; }
     std::vector<float2> Hos(h->NOS);
@@ -283,7 +285,14 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
     rc |= upload(&h->d_ks, ks);
     rc |= upload(&h->d_kd, kd);
     rc |= upload(&h->d_tw, twiddles(N));
-    rc |= upload(&h->d_tw_os, twiddles(h->NOS));
+    if (h->NOS == 1024) {
+        std::vector<float2> tw((size_t)fft_twiddle_elems(1024), make_float2(0.f, 0.f));
+        fft_fill_twiddles<1024, FftPlanW1024>(tw.data());
+        rc |= upload(&h->d_tw_os, tw);
+        std::fill(tw.begin(), tw.end(), make_float2(0.f, 0.f));
+        fft_fill_twiddles<1024, FftPlanW1024, true>(tw.data());
+        rc |= upload(&h->d_tw_os_full, tw);
+    } else rc |= upload(&h->d_tw_os, twiddles(h->NOS));
     rc |= upload(&h->d_Hos, Hos);
     rc |= upload(&h->d_pre_time, pre);
     rc |= upload(&h->d_pre_freq, pre_freq);
@@ -300,7 +309,7 @@ extern "C" void ofdm_destroy(ofdm_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_const); cudaFree(h->d_bin2car); cudaFree(h->d_sinkmap); cudaFree(h->d_ks); cudaFree(h->d_kd);
     cudaFree(h->d_tw); cudaFree(h->d_tw_os); cudaFree(h->d_Hos); cudaFree(h->d_pre_time); cudaFree(h->d_pre_freq); cudaFree(h->d_pre_ifft); cudaFree(h->d_mask);
-    cudaFree(h->d_crctab); cudaFree(h->d_grid); cudaFree(h->d_Hks_half); cudaFree(h->d_Hks_full); cudaFree(h->d_tw_os_alt);
+    cudaFree(h->d_crctab); cudaFree(h->d_grid); cudaFree(h->d_Hks_half); cudaFree(h->d_Hks_full); cudaFree(h->d_tw_os_alt); cudaFree(h->d_tw_os_full);
     delete h;
 }
 

@@ -24,6 +24,10 @@ template <> struct FftPlan<512>  { static constexpr int E = 8,  NP = 3; static c
 template <> struct FftPlan<1024> { static constexpr int E = 16, NP = 3; static constexpr int R[4] = {4, 16, 16, 1}; };
 template <> struct FftPlan<2048> { static constexpr int E = 16, NP = 3; static constexpr int R[4] = {8, 16, 16, 1}; };
 template <> struct FftPlan<4096> { static constexpr int E = 16, NP = 3; static constexpr int R[4] = {16, 16, 16, 1}; };
+// Warp-wide plans: 32 points per thread, radix-32 register butterflies, ONE shared-memory exchange per transform and
+// at most 32 threads per transform (a warp: __syncwarp() instead of block barriers).  1024 = 32 x 32.
+struct FftPlanW1024 { static constexpr int E = 32, NP = 2; static constexpr int R[4] = {32, 32, 1, 1}; };
+#define FFT_PAD32(i) ((i) + ((i) >> 5))
 
 // ---- twiddle table, one section per pass, laid out for the threads that read it -------------------------------
 // A pass of radix R after NS = 2^s points of earlier radices needs, per thread and butterfly, the log2(R) power-of-two
@@ -35,12 +39,21 @@ template <> struct FftPlan<4096> { static constexpr int E = 16, NP = 3; static c
 HD constexpr int fft_ilog2(int v) { return v <= 1 ? 0 : 1 + fft_ilog2(v >> 1); }
 HD constexpr int fft_twiddle_elems(int N) { return 12 * (N / 2); }
 
-template <int N> inline void fft_fill_twiddles(float2* t) {           // t: fft_twiddle_elems(N) entries, zero-initialised
-    using P = FftPlan<N>;
+// FULLTW: every twiddle w^r, r = 1 .. R-1, is stored ([r-1][thread]; single-butterfly plans only) and none is derived
+template <int N, class P = FftPlan<N>, bool FULLTW = false> inline void fft_fill_twiddles(float2* t) {   // t: fft_twiddle_elems(N) entries, zero-initialised
     constexpr int E = P::E, T = N / E;
     auto fill = [&](int R, int NS) {
         if (NS <= 1 || R <= 1) return;
         const int s = fft_ilog2(NS), LG = fft_ilog2(R);
+        if (FULLTW) {
+            for (int r = 1; r < R; ++r)
+                for (int tid = 0; tid < T; ++tid) {
+                    const long idx = (long)r * (tid & (NS - 1)) * (N / (NS * R));
+                    const double a = 2.0 * 3.14159265358979323846 * (double)idx / (double)N;
+                    t[(size_t)s * (N / 2) + (size_t)(r - 1) * T + tid] = make_float2((float)cos(a), (float)(-sin(a)));
+                }
+            return;
+        }
         for (int q = 0; q < E / R; ++q)
             for (int li = 0; li < LG; ++li)
                 for (int tid = 0; tid < T; ++tid) {
@@ -76,7 +89,15 @@ template <int R, int K, int S> HD float2 tw_const(float2 o) {
     constexpr float C8 = 0.70710678118654752440f;
     constexpr float C16a = 0.92387953251128675613f;   // cos(pi/8)
     constexpr float C16b = 0.38268343236508977173f;   // sin(pi/8)
-    constexpr int Q = (16 / R) * K;                   // position on the 16-point circle
+    constexpr int Q32 = (32 / R) * K;                 // position on the 32-point circle
+    if (Q32 & 1) {
+        constexpr float C32[8] = {0.98078528040323044913f, 0.83146961230254523708f, 0.55557023301960222474f, 0.19509032201612826785f,
+                                  -0.19509032201612826785f, -0.55557023301960222474f, -0.83146961230254523708f, -0.98078528040323044913f};
+        constexpr float S32[8] = {0.19509032201612826785f, 0.55557023301960222474f, 0.83146961230254523708f, 0.98078528040323044913f,
+                                  0.98078528040323044913f, 0.83146961230254523708f, 0.55557023301960222474f, 0.19509032201612826785f};
+        return cmul_const(o, C32[(Q32 >> 1) & 7], S * S32[(Q32 >> 1) & 7]);
+    }
+    constexpr int Q = Q32 / 2;                        // position on the 16-point circle
     if (Q == 0) return o;
     if (Q == 4) return S < 0 ? make_float2(o.y, -o.x) : make_float2(-o.y, o.x);
     if (Q == 2) return cmul_const(o, C8, S * C8);
@@ -109,6 +130,7 @@ template <int S, int K> struct DftCombine<4, S, K> {
 };
 template <int S> struct DftCombine<8, S, 4> { HDM static void run(float2*, const float2*, const float2*) {} };
 template <int S> struct DftCombine<16, S, 8> { HDM static void run(float2*, const float2*, const float2*) {} };
+template <int S> struct DftCombine<32, S, 16> { HDM static void run(float2*, const float2*, const float2*) {} };
 
 // in-register DFT of size R (decimation in time, natural order in and out)
 template <int R, int S> struct DftReg {
@@ -128,10 +150,11 @@ template <int R, int S> struct DftReg {
 // first-pass inputs / last-pass outputs in a register array (slot <-> index tid + q*T + r*N/R).
 // BAR: __syncthreads() between the loads and the stores of the pass, for passes that read and write the SAME buffer
 // (allowed only when a thread's E points form one butterfly, E == R, so that every load precedes every store).
-template <int N, int R, int NS, int S, class In, class Out, bool BAR = false>
+template <int N, int R, int NS, int S, class In, class Out, bool BAR = false, class P = FftPlan<N>, bool FULLTW = false>
 HD void fft_pass(int tid, const float2* __restrict__ tw, In in, Out out) {
-    static_assert(!BAR || FftPlan<N>::E == R, "in-place pass needs one butterfly per thread");
-    constexpr int E = FftPlan<N>::E;
+    static_assert(!BAR || P::E == R, "in-place pass needs one butterfly per thread");
+    static_assert(!FULLTW || P::E == R, "full twiddle rows need one butterfly per thread");
+    constexpr int E = P::E;
     constexpr int T = N / E;
 #pragma unroll
     for (int q = 0; q < E / R; ++q) {
@@ -149,19 +172,28 @@ HD void fft_pass(int tid, const float2* __restrict__ tw, In in, Out out) {
             float2 w[R];
             constexpr int LG = fft_ilog2(R);
             const float2* twp = tw + fft_ilog2(NS) * (N / 2) + q * LG * T + tid;    // this pass, this butterfly, this thread
+            if (FULLTW) {
 #pragma unroll
-            for (int li = 0; li < LG; ++li) {
-                w[1 << li] = LDG(twp + li * T);
-                if (S > 0) w[1 << li].y = -w[1 << li].y;
-            }
+                for (int r = 1; r < R; ++r) {
+                    float2 wr = LDG(twp + (r - 1) * T);
+                    if (S > 0) wr.y = -wr.y;
+                    v[r] = cmul(v[r], wr);
+                }
+            } else {
 #pragma unroll
-            for (int r = 3; r < R; ++r)
-                if (r & (r - 1)) {                                   // not a power of two
-                    const int hi = (r >= 8) ? 8 : ((r >= 4) ? 4 : 2);
-                    w[r] = cmul(w[hi], w[r - hi]);
+                for (int li = 0; li < LG; ++li) {
+                    w[1 << li] = LDG(twp + li * T);
+                    if (S > 0) w[1 << li].y = -w[1 << li].y;
                 }
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
+                for (int r = 3; r < R; ++r)
+                    if (r & (r - 1)) {                                   // not a power of two
+                        const int hi = (r >= 16) ? 16 : ((r >= 8) ? 8 : ((r >= 4) ? 4 : 2));
+                        w[r] = cmul(w[hi], w[r - hi]);
+                    }
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
+            }
         }
         DftReg<R, S>::run(v);
         const int j0 = (j - k) * R + k;

@@ -45,6 +45,7 @@ struct ofdm_handle {
     float* d_kd;           // [occ] |ks[i]-ks[i+2]|^2 on even i
     float2* d_tw;          // [N]   exp(-2*pi*j*i/N)
     float2* d_tw_os;       // [NOS]
+    float2* d_tw_os_full;  // NOS == 1024: every twiddle of the second radix-32 pass stored (fft.cuh FULLTW)
     float2* d_Hos;         // [NOS] FFT of the channel taps / NOS
     float2* d_pre_time;    // [N+cp] time-domain preamble incl. CP, scaled by 1/sqrt(N)
     // known-symbol correlators of the "pnac" / "ml" synchronisers (created on first use, rx_sync_alt.cu)

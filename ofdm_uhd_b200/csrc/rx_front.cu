@@ -170,6 +170,70 @@ __global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 512 / (G * (NOS /
     cp_async_wait_all();
 }
 
+// Warp-per-block overlap-save at NOS = 1024 = 32 x 32: one warp owns a block, 32 points per lane.  The first forward
+// pass takes its points straight from global memory (stride-1 across the lanes), the last inverse pass stores y the
+// same way; two radix-32 passes each way leave ONE shared-memory exchange per transform (2 per block of V outputs
+// against 5 per block in the 3-pass kernel above) and no block barrier at all.
+struct SmemIn32 {
+    const float2* p;
+    HDM float2 operator()(int i, int) const { return p[FFT_PAD32(i)]; }
+};
+struct SmemOut32 {
+    float2* p;
+    HDM void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; }
+};
+template <int WPC, int MINB, bool FT>
+__global__ void __launch_bounds__(32 * WPC, MINB) chan_filter_warp_kernel(const FiltParams p) {
+    constexpr int NOS = 1024;
+    using P = FftPlanW1024;
+    constexpr int SB = FFT_PAD32(NOS) + 2;
+    __shared__ __align__(16) float2 smem[WPC * SB];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float2* buf = smem + w * SB;
+    int64_t s_a, s_n;
+    stream_span(p.soff, blockIdx.y, p.n, s_a, s_n);
+    const float2* __restrict__ px = p.x + s_a;
+    float2* __restrict__ py = p.y + s_a;
+    const int64_t nblk = (s_n + p.V - 1) / p.V;
+    for (int64_t blk = (int64_t)blockIdx.x * WPC + w; blk < nblk; blk += (int64_t)gridDim.x * WPC) {
+        const int64_t in0 = blk * p.V - p.hist;
+        const bool inner = in0 >= 0 && in0 + NOS <= s_n;
+        float2 regs[32];
+        auto mulH = [&](int idx, float2 v, int slot) { regs[slot] = cmul(v, LDG(p.H + idx)); };
+        auto fromRegs = [&](int, int slot) -> float2 { return regs[slot]; };
+        const float2* src = px + in0;
+        auto ld_in = [&](int idx, int) -> float2 { return src[idx]; };
+        auto ld = [&](int idx, int) -> float2 {
+            const int64_t gi = in0 + idx;
+            return (gi >= 0 && gi < s_n) ? px[gi] : make_float2(0.f, 0.f);
+        };
+        float2* const yb = py + in0;
+        auto st_in = [&](int idx, float2 v, int) { if (idx >= p.hist) yb[idx] = v; };
+        auto st = [&](int idx, float2 v, int) { if (idx >= p.hist && in0 + idx < s_n) yb[idx] = v; };
+        if (inner) fft_pass<NOS, 32, 1, -1, decltype(ld_in), SmemOut32, false, P>(lane, p.tw, ld_in, SmemOut32{buf});
+        else fft_pass<NOS, 32, 1, -1, decltype(ld), SmemOut32, false, P>(lane, p.tw, ld, SmemOut32{buf});
+        __syncwarp();
+        fft_pass<NOS, 32, 32, -1, SmemIn32, decltype(mulH), false, P, FT>(lane, p.tw, SmemIn32{buf}, mulH);
+        __syncwarp();
+        fft_pass<NOS, 32, 1, 1, decltype(fromRegs), SmemOut32, false, P>(lane, p.tw, fromRegs, SmemOut32{buf});
+        __syncwarp();
+        if (inner) fft_pass<NOS, 32, 32, 1, SmemIn32, decltype(st_in), false, P, FT>(lane, p.tw, SmemIn32{buf}, st_in);
+        else fft_pass<NOS, 32, 32, 1, SmemIn32, decltype(st), false, P, FT>(lane, p.tw, SmemIn32{buf}, st);
+        __syncwarp();
+    }
+}
+
+template <int WPC, int MINB, bool FT>
+static int launch_filter_warp(ofdm_handle* h, const FiltParams& p, int64_t nblk_max, int S, cudaStream_t st) {
+    int64_t want = (nblk_max + WPC - 1) / WPC;
+    int64_t cap = ((int64_t)h->sms * MINB * 4 + S - 1) / S;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    chan_filter_warp_kernel<WPC, MINB, FT><<<dim3(grid, S), 32 * WPC, 0, st>>>(p);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
 template <int NOS, int G>
 static int launch_filter_n(ofdm_handle* h, const FiltParams& p, int64_t nblk_max, int S, cudaStream_t st) {
     constexpr int T = NOS / FftPlan<NOS>::E;
@@ -192,6 +256,18 @@ int launch_chan_filter(ofdm_handle* h, const float2* x, const StreamSet& ss, flo
     p.x = x; p.y = y; p.soff = ss.off; p.n = ss.n_max; p.hist = h->ntaps - 1; p.V = h->NOS - p.hist;
     p.tw = h->d_tw_os; p.H = h->d_Hos;
     const int64_t nblk_max = (ss.n_max + p.V - 1) / p.V;
+    if (h->NOS == 1024) {                                                             // one block per warp
+        static int mode = getenv("OFDM_FILTER_MODE") ? atoi(getenv("OFDM_FILTER_MODE")) : 2;
+        p.tw = (mode & 1) ? h->d_tw_os_full : h->d_tw_os;
+        switch (mode) {
+            case 0: return launch_filter_warp<4, 4, false>(h, p, nblk_max, ss.S, st);
+            case 1: return launch_filter_warp<4, 4, true>(h, p, nblk_max, ss.S, st);
+            case 2: return launch_filter_warp<1, 16, false>(h, p, nblk_max, ss.S, st);
+            case 3: return launch_filter_warp<1, 16, true>(h, p, nblk_max, ss.S, st);
+            case 4: return launch_filter_warp<2, 8, false>(h, p, nblk_max, ss.S, st);
+            case 5: return launch_filter_warp<2, 8, true>(h, p, nblk_max, ss.S, st);
+        }
+    }
     if (h->NOS == 2048) return launch_filter_n<2048, 1>(h, p, nblk_max, ss.S, st);   // one block per CTA: 4 independent CTAs per SM
     if (h->NOS == 4096) return launch_filter_n<4096, 1>(h, p, nblk_max, ss.S, st);
     ofdm_set_error("chan_filter: unsupported overlap-save size %d", h->NOS);
