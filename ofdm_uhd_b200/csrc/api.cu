@@ -173,6 +173,14 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
                 sinkmap.push_back((int16_t)(4 * i + j));
             }
     h->ncar = ord;
+    {   // the longest run of 32nd-of-the-band rows of the IFFT input without a carrier, around row 16 (the band edges)
+        bool used[32] = {false};
+        if (N >= 32) for (int v = 0; v < N; ++v) if (bin2car[v] >= 0) used[(((v + N / 2) % N) * 32) / N] = true;
+        h->tx_row_lo = 16; h->tx_row_hi = 16;
+        while (h->tx_row_lo > 0 && !used[h->tx_row_lo - 1]) --h->tx_row_lo;
+        while (h->tx_row_hi < 32 && !used[h->tx_row_hi]) ++h->tx_row_hi;
+        if (used[16] && h->tx_row_hi == 16) h->tx_row_lo = 16;
+    }
     if (h->ncar * nbits < 32) { ofdm_set_error("ofdm_create: fewer than 32 bits per OFDM symbol"); delete h; return nullptr; }
     if (h->zl < OFDM_MAX_SHIFT || h->zl + occ + OFDM_MAX_SHIFT + 2 > N) {
         ofdm_set_error("ofdm_create: layout leaves no room for the +/-%d bin coarse search", OFDM_MAX_SHIFT); delete h; return nullptr;
@@ -285,13 +293,15 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
     rc |= upload(&h->d_ks, ks);
     rc |= upload(&h->d_kd, kd);
     rc |= upload(&h->d_tw, twiddles(N));
+    if (N == 512 || N == 1024) {
+        std::vector<float2> tw((size_t)fft_twiddle_elems(N), make_float2(0.f, 0.f));
+        if (N == 512) fft_fill_twiddles<512, FftPlanW512>(tw.data()); else fft_fill_twiddles<1024, FftPlanW1024>(tw.data());
+        rc |= upload(&h->d_tw_w, tw);
+    }
     if (h->NOS == 1024) {
         std::vector<float2> tw((size_t)fft_twiddle_elems(1024), make_float2(0.f, 0.f));
         fft_fill_twiddles<1024, FftPlanW1024>(tw.data());
         rc |= upload(&h->d_tw_os, tw);
-        std::fill(tw.begin(), tw.end(), make_float2(0.f, 0.f));
-        fft_fill_twiddles<1024, FftPlanW1024, true>(tw.data());
-        rc |= upload(&h->d_tw_os_full, tw);
     } else rc |= upload(&h->d_tw_os, twiddles(h->NOS));
     rc |= upload(&h->d_Hos, Hos);
     rc |= upload(&h->d_pre_time, pre);
@@ -308,8 +318,8 @@ extern "C" void ofdm_destroy(ofdm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_const); cudaFree(h->d_bin2car); cudaFree(h->d_sinkmap); cudaFree(h->d_ks); cudaFree(h->d_kd);
-    cudaFree(h->d_tw); cudaFree(h->d_tw_os); cudaFree(h->d_Hos); cudaFree(h->d_pre_time); cudaFree(h->d_pre_freq); cudaFree(h->d_pre_ifft); cudaFree(h->d_mask);
-    cudaFree(h->d_crctab); cudaFree(h->d_grid); cudaFree(h->d_Hks_half); cudaFree(h->d_Hks_full); cudaFree(h->d_tw_os_alt); cudaFree(h->d_tw_os_full);
+    cudaFree(h->d_tw); cudaFree(h->d_tw_w); cudaFree(h->d_tw_os); cudaFree(h->d_Hos); cudaFree(h->d_pre_time); cudaFree(h->d_pre_freq); cudaFree(h->d_pre_ifft); cudaFree(h->d_mask);
+    cudaFree(h->d_crctab); cudaFree(h->d_grid); cudaFree(h->d_Hks_half); cudaFree(h->d_Hks_full); cudaFree(h->d_tw_os_alt[0]); cudaFree(h->d_tw_os_alt[1]);
     delete h;
 }
 

@@ -26,7 +26,12 @@ template <> struct FftPlan<2048> { static constexpr int E = 16, NP = 3; static c
 template <> struct FftPlan<4096> { static constexpr int E = 16, NP = 3; static constexpr int R[4] = {16, 16, 16, 1}; };
 // Warp-wide plans: 32 points per thread, radix-32 register butterflies, ONE shared-memory exchange per transform and
 // at most 32 threads per transform (a warp: __syncwarp() instead of block barriers).  1024 = 32 x 32.
+// 512 = 32 x 16 (16 threads per transform, two transforms per warp; the radix-16 pass runs two butterflies per thread).
 struct FftPlanW1024 { static constexpr int E = 32, NP = 2; static constexpr int R[4] = {32, 32, 1, 1}; };
+struct FftPlanW512 { static constexpr int E = 32, NP = 2; static constexpr int R[4] = {32, 16, 1, 1}; };
+template <int N> struct FftPlanW;
+template <> struct FftPlanW<512> { using type = FftPlanW512; };
+template <> struct FftPlanW<1024> { using type = FftPlanW1024; };
 #define FFT_PAD32(i) ((i) + ((i) >> 5))
 
 // ---- twiddle table, one section per pass, laid out for the threads that read it -------------------------------
@@ -39,21 +44,11 @@ struct FftPlanW1024 { static constexpr int E = 32, NP = 2; static constexpr int 
 HD constexpr int fft_ilog2(int v) { return v <= 1 ? 0 : 1 + fft_ilog2(v >> 1); }
 HD constexpr int fft_twiddle_elems(int N) { return 12 * (N / 2); }
 
-// FULLTW: every twiddle w^r, r = 1 .. R-1, is stored ([r-1][thread]; single-butterfly plans only) and none is derived
-template <int N, class P = FftPlan<N>, bool FULLTW = false> inline void fft_fill_twiddles(float2* t) {   // t: fft_twiddle_elems(N) entries, zero-initialised
+template <int N, class P = FftPlan<N>> inline void fft_fill_twiddles(float2* t) {   // t: fft_twiddle_elems(N) entries, zero-initialised
     constexpr int E = P::E, T = N / E;
     auto fill = [&](int R, int NS) {
         if (NS <= 1 || R <= 1) return;
         const int s = fft_ilog2(NS), LG = fft_ilog2(R);
-        if (FULLTW) {
-            for (int r = 1; r < R; ++r)
-                for (int tid = 0; tid < T; ++tid) {
-                    const long idx = (long)r * (tid & (NS - 1)) * (N / (NS * R));
-                    const double a = 2.0 * 3.14159265358979323846 * (double)idx / (double)N;
-                    t[(size_t)s * (N / 2) + (size_t)(r - 1) * T + tid] = make_float2((float)cos(a), (float)(-sin(a)));
-                }
-            return;
-        }
         for (int q = 0; q < E / R; ++q)
             for (int li = 0; li < LG; ++li)
                 for (int tid = 0; tid < T; ++tid) {
@@ -150,10 +145,9 @@ template <int R, int S> struct DftReg {
 // first-pass inputs / last-pass outputs in a register array (slot <-> index tid + q*T + r*N/R).
 // BAR: __syncthreads() between the loads and the stores of the pass, for passes that read and write the SAME buffer
 // (allowed only when a thread's E points form one butterfly, E == R, so that every load precedes every store).
-template <int N, int R, int NS, int S, class In, class Out, bool BAR = false, class P = FftPlan<N>, bool FULLTW = false>
+template <int N, int R, int NS, int S, class In, class Out, bool BAR = false, class P = FftPlan<N>>
 HD void fft_pass(int tid, const float2* __restrict__ tw, In in, Out out) {
     static_assert(!BAR || P::E == R, "in-place pass needs one butterfly per thread");
-    static_assert(!FULLTW || P::E == R, "full twiddle rows need one butterfly per thread");
     constexpr int E = P::E;
     constexpr int T = N / E;
 #pragma unroll
@@ -172,28 +166,19 @@ HD void fft_pass(int tid, const float2* __restrict__ tw, In in, Out out) {
             float2 w[R];
             constexpr int LG = fft_ilog2(R);
             const float2* twp = tw + fft_ilog2(NS) * (N / 2) + q * LG * T + tid;    // this pass, this butterfly, this thread
-            if (FULLTW) {
 #pragma unroll
-                for (int r = 1; r < R; ++r) {
-                    float2 wr = LDG(twp + (r - 1) * T);
-                    if (S > 0) wr.y = -wr.y;
-                    v[r] = cmul(v[r], wr);
-                }
-            } else {
-#pragma unroll
-                for (int li = 0; li < LG; ++li) {
-                    w[1 << li] = LDG(twp + li * T);
-                    if (S > 0) w[1 << li].y = -w[1 << li].y;
-                }
-#pragma unroll
-                for (int r = 3; r < R; ++r)
-                    if (r & (r - 1)) {                                   // not a power of two
-                        const int hi = (r >= 16) ? 16 : ((r >= 8) ? 8 : ((r >= 4) ? 4 : 2));
-                        w[r] = cmul(w[hi], w[r - hi]);
-                    }
-#pragma unroll
-                for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
+            for (int li = 0; li < LG; ++li) {
+                w[1 << li] = LDG(twp + li * T);
+                if (S > 0) w[1 << li].y = -w[1 << li].y;
             }
+#pragma unroll
+            for (int r = 3; r < R; ++r)
+                if (r & (r - 1)) {                                   // not a power of two
+                    const int hi = (r >= 16) ? 16 : ((r >= 8) ? 8 : ((r >= 4) ? 4 : 2));
+                    w[r] = cmul(w[hi], w[r - hi]);
+                }
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
         }
         DftReg<R, S>::run(v);
         const int j0 = (j - k) * R + k;

@@ -37,6 +37,7 @@ struct ofdm_handle {
     int N, occ, cp, L, zl, M, nbits, ncar, ntaps, NOS, pkt_stride;
     float amp;
     uint64_t pad_seed;
+    int tx_row_lo, tx_row_hi;   // IFFT input rows (of N/32 bins, ifftshift applied) [lo, hi) carry no data carrier
     // device tables
     float2* d_const;       // [M]
     int16_t* d_bin2car;    // [N]  FFT-vector index -> data-carrier ordinal, -1 if unused (A.3 mapper map)
@@ -44,15 +45,15 @@ struct ofdm_handle {
     float* d_ks;           // [occ] known symbol with odd bins zeroed
     float* d_kd;           // [occ] |ks[i]-ks[i+2]|^2 on even i
     float2* d_tw;          // [N]   exp(-2*pi*j*i/N)
+    float2* d_tw_w;        // N == 512 / 1024: twiddles of the warp plan (fft.cuh FftPlanW), else null
     float2* d_tw_os;       // [NOS]
-    float2* d_tw_os_full;  // NOS == 1024: every twiddle of the second radix-32 pass stored (fft.cuh FULLTW)
     float2* d_Hos;         // [NOS] FFT of the channel taps / NOS
     float2* d_pre_time;    // [N+cp] time-domain preamble incl. CP, scaled by 1/sqrt(N)
     // known-symbol correlators of the "pnac" / "ml" synchronisers (created on first use, rx_sync_alt.cu)
     float2* d_Hks_half;    // [nos_ks_half] response of conj(ks0time[:N/2]) reversed
     float2* d_Hks_full;    // [nos_ks_full] response of conj(ks0time) reversed
     int nos_ks_half, nos_ks_full;
-    float2* d_tw_os_alt;   // twiddles of the overlap-save size the channel filter does not use (2048 <-> 4096)
+    float2* d_tw_os_alt[2];// twiddles of the 2048 / 4096-point overlap-save sizes the channel filter itself does not use
     float2* d_pre_freq;    // [N] the known symbol as the mapper-order (unshifted) vector   (options.log taps)
     float2* d_pre_ifft;    // [N] its unscaled IFFT
     uint8_t* d_mask;       // [4096] whitening mask

@@ -182,21 +182,21 @@ struct SmemOut32 {
     float2* p;
     HDM void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; }
 };
-template <int WPC, int MINB, bool FT>
-__global__ void __launch_bounds__(32 * WPC, MINB) chan_filter_warp_kernel(const FiltParams p) {
-    constexpr int NOS = 1024;
+// HR: rows of 32 outputs discarded in front of a block (32 * HR >= ntaps - 1, a compile-time row predicate in the last
+// pass); with 128-byte aligned streams every global row a warp loads or stores is two full lines.
+template <int HR>
+__global__ void __launch_bounds__(32, 16) chan_filter_warp_kernel(const FiltParams p) {
+    constexpr int NOS = 1024, HIST = 32 * HR, V = NOS - HIST;
     using P = FftPlanW1024;
-    constexpr int SB = FFT_PAD32(NOS) + 2;
-    __shared__ __align__(16) float2 smem[WPC * SB];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float2* buf = smem + w * SB;
+    __shared__ __align__(16) float2 buf[FFT_PAD32(NOS) + 2];
+    const int lane = threadIdx.x;
     int64_t s_a, s_n;
     stream_span(p.soff, blockIdx.y, p.n, s_a, s_n);
     const float2* __restrict__ px = p.x + s_a;
     float2* __restrict__ py = p.y + s_a;
-    const int64_t nblk = (s_n + p.V - 1) / p.V;
-    for (int64_t blk = (int64_t)blockIdx.x * WPC + w; blk < nblk; blk += (int64_t)gridDim.x * WPC) {
-        const int64_t in0 = blk * p.V - p.hist;
+    const int64_t nblk = (s_n + V - 1) / V;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int64_t in0 = blk * V - HIST;
         const bool inner = in0 >= 0 && in0 + NOS <= s_n;
         float2 regs[32];
         auto mulH = [&](int idx, float2 v, int slot) { regs[slot] = cmul(v, LDG(p.H + idx)); };
@@ -208,28 +208,28 @@ __global__ void __launch_bounds__(32 * WPC, MINB) chan_filter_warp_kernel(const 
             return (gi >= 0 && gi < s_n) ? px[gi] : make_float2(0.f, 0.f);
         };
         float2* const yb = py + in0;
-        auto st_in = [&](int idx, float2 v, int) { if (idx >= p.hist) yb[idx] = v; };
-        auto st = [&](int idx, float2 v, int) { if (idx >= p.hist && in0 + idx < s_n) yb[idx] = v; };
+        auto st_in = [&](int idx, float2 v, int slot) { if (slot >= HR) yb[idx] = v; };
+        auto st = [&](int idx, float2 v, int slot) { if (slot >= HR && in0 + idx < s_n) yb[idx] = v; };
         if (inner) fft_pass<NOS, 32, 1, -1, decltype(ld_in), SmemOut32, false, P>(lane, p.tw, ld_in, SmemOut32{buf});
         else fft_pass<NOS, 32, 1, -1, decltype(ld), SmemOut32, false, P>(lane, p.tw, ld, SmemOut32{buf});
         __syncwarp();
-        fft_pass<NOS, 32, 32, -1, SmemIn32, decltype(mulH), false, P, FT>(lane, p.tw, SmemIn32{buf}, mulH);
+        fft_pass<NOS, 32, 32, -1, SmemIn32, decltype(mulH), false, P>(lane, p.tw, SmemIn32{buf}, mulH);
         __syncwarp();
         fft_pass<NOS, 32, 1, 1, decltype(fromRegs), SmemOut32, false, P>(lane, p.tw, fromRegs, SmemOut32{buf});
         __syncwarp();
-        if (inner) fft_pass<NOS, 32, 32, 1, SmemIn32, decltype(st_in), false, P, FT>(lane, p.tw, SmemIn32{buf}, st_in);
-        else fft_pass<NOS, 32, 32, 1, SmemIn32, decltype(st), false, P, FT>(lane, p.tw, SmemIn32{buf}, st);
+        if (inner) fft_pass<NOS, 32, 32, 1, SmemIn32, decltype(st_in), false, P>(lane, p.tw, SmemIn32{buf}, st_in);
+        else fft_pass<NOS, 32, 32, 1, SmemIn32, decltype(st), false, P>(lane, p.tw, SmemIn32{buf}, st);
         __syncwarp();
     }
 }
 
-template <int WPC, int MINB, bool FT>
-static int launch_filter_warp(ofdm_handle* h, const FiltParams& p, int64_t nblk_max, int S, cudaStream_t st) {
-    int64_t want = (nblk_max + WPC - 1) / WPC;
-    int64_t cap = ((int64_t)h->sms * MINB * 4 + S - 1) / S;
+template <int HR>
+static int launch_filter_warp(ofdm_handle* h, const FiltParams& p, int64_t n_max, int S, cudaStream_t st) {
+    const int64_t want = (n_max + (1024 - 32 * HR) - 1) / (1024 - 32 * HR);
+    const int64_t cap = ((int64_t)h->sms * 64 + S - 1) / S;      // 16 one-warp CTAs per SM, four waves
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    chan_filter_warp_kernel<WPC, MINB, FT><<<dim3(grid, S), 32 * WPC, 0, st>>>(p);
+    chan_filter_warp_kernel<HR><<<dim3(grid, S), 32, 0, st>>>(p);
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
@@ -257,16 +257,9 @@ int launch_chan_filter(ofdm_handle* h, const float2* x, const StreamSet& ss, flo
     p.tw = h->d_tw_os; p.H = h->d_Hos;
     const int64_t nblk_max = (ss.n_max + p.V - 1) / p.V;
     if (h->NOS == 1024) {                                                             // one block per warp
-        static int mode = getenv("OFDM_FILTER_MODE") ? atoi(getenv("OFDM_FILTER_MODE")) : 2;
-        p.tw = (mode & 1) ? h->d_tw_os_full : h->d_tw_os;
-        switch (mode) {
-            case 0: return launch_filter_warp<4, 4, false>(h, p, nblk_max, ss.S, st);
-            case 1: return launch_filter_warp<4, 4, true>(h, p, nblk_max, ss.S, st);
-            case 2: return launch_filter_warp<1, 16, false>(h, p, nblk_max, ss.S, st);
-            case 3: return launch_filter_warp<1, 16, true>(h, p, nblk_max, ss.S, st);
-            case 4: return launch_filter_warp<2, 8, false>(h, p, nblk_max, ss.S, st);
-            case 5: return launch_filter_warp<2, 8, true>(h, p, nblk_max, ss.S, st);
-        }
+        if (p.hist <= 96) return launch_filter_warp<3>(h, p, ss.n_max, ss.S, st);
+        if (p.hist <= 160) return launch_filter_warp<5>(h, p, ss.n_max, ss.S, st);
+        return launch_filter_warp<8>(h, p, ss.n_max, ss.S, st);
     }
     if (h->NOS == 2048) return launch_filter_n<2048, 1>(h, p, nblk_max, ss.S, st);   // one block per CTA: 4 independent CTAs per SM
     if (h->NOS == 4096) return launch_filter_n<4096, 1>(h, p, nblk_max, ss.S, st);
@@ -277,15 +270,15 @@ int launch_chan_filter(ofdm_handle* h, const float2* x, const StreamSet& ss, flo
 // gr.fir_filter_ccc with `ntaps` complex taps whose overlap-save response is H (rx_sync_alt.cu): the same kernel
 int launch_xcorr(ofdm_handle* h, const float2* x, int64_t n, const float2* H, int nos, int ntaps, float2* out, cudaStream_t st) {
     if (n <= 0) return OFDM_OK;
-    const float2* tw = h->d_tw_os;
-    if (nos != h->NOS) {
-        if (!h->d_tw_os_alt) {
-            std::vector<float2> t((size_t)fft_twiddle_elems(nos), make_float2(0.f, 0.f));
-            fft_fill_twiddles_n(nos, t.data());
-            OFDM_CUDA_CHECK(cudaMalloc((void**)&h->d_tw_os_alt, sizeof(float2) * t.size()));
-            OFDM_CUDA_CHECK(cudaMemcpy(h->d_tw_os_alt, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
-        }
-        tw = h->d_tw_os_alt;
+    if (nos != 2048 && nos != 4096) { ofdm_set_error("xcorr: unsupported overlap-save size %d", nos); return OFDM_E_INVAL; }
+    float2*& slot = h->d_tw_os_alt[nos == 4096];               // twiddles of the 3-pass kernel at this size, made on first use
+    const float2* tw = (nos == h->NOS) ? h->d_tw_os : slot;
+    if (!tw) {
+        std::vector<float2> t((size_t)fft_twiddle_elems(nos), make_float2(0.f, 0.f));
+        fft_fill_twiddles_n(nos, t.data());
+        OFDM_CUDA_CHECK(cudaMalloc((void**)&slot, sizeof(float2) * t.size()));
+        OFDM_CUDA_CHECK(cudaMemcpy(slot, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
+        tw = slot;
     }
     FiltParams p;
     p.x = x; p.y = out; p.soff = nullptr; p.n = n; p.hist = ntaps - 1; p.V = nos - p.hist; p.tw = tw; p.H = H;

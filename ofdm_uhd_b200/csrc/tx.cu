@@ -1,6 +1,7 @@
 // Transmit side: packet framing, the fused mapper + preamble + IFFT + cyclic-prefix kernel,
 // and the synthetic channel used by the loopback drivers.
 #include "internal.h"
+#include <stdlib.h>
 #include "fft.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -304,6 +305,176 @@ static int launch_tx_n(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
     return OFDM_OK;
 }
 
+// Warp-plan transmit kernel (N = 512 / 1024): a transform lives on T = N/32 <= 32 lanes of one warp (two symbols per
+// warp at 512), radix-32 first pass, ONE shared-memory exchange, __syncwarp() only.  One warp per CTA.
+struct SmemIn32 {
+    const float2* p;
+    HDM float2 operator()(int i, int) const { return p[FFT_PAD32(i)]; }
+};
+struct SmemOut32 {
+    float2* p;
+    HDM void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; }
+};
+// Mapper of the warp kernel.  Tables are per FFT INPUT index (the ifftshift is folded in): s_bo[idx] = bit offset of the
+// carrier inside a symbol's bit field, -1 for an unused bin; the symbol's bytes are staged as overlapping 16-bit words
+// (s_w[b] = byte b | byte b+1 << 8), so a carrier's bits are one load and one shift.  First-pass rows [RLO, RHI) hold no
+// carrier at all (rows 7 .. 24 of 32 when occupied_tones / fft_length <= 0.41): compile-time zeros, no mapper work and no
+// branch.  PAD: the symbol reaches behind the end of the packet (last symbol of a frame) and fills up with pad symbols.
+static __device__ __noinline__ uint32_t tx_pad_value(uint64_t seed, int64_t frame_id, int dsym, int bit_off, int nbits, int M) {
+    return pad_index(seed, (uint64_t)frame_id, (uint32_t)dsym, (uint32_t)(bit_off / nbits), (uint32_t)M);
+}
+template <int N, int RLO, int RHI, bool PAD>
+struct TxLoadW {
+    const int16_t* s_bo;
+    const uint16_t* s_w;
+    const float2* s_cst;
+    unsigned vmask;
+    int bitbase, rel0, pkt_bits, nbits, dsym, M;
+    int64_t frame_id;
+    uint64_t seed;
+    __device__ __forceinline__ float2 operator()(int idx, int slot) const {
+        if (slot >= RLO && slot < RHI) return make_float2(0.f, 0.f);
+        const int bo = s_bo[idx];
+        const int b = bo < 0 ? 0 : bo;
+        const int rel = rel0 + b;
+        uint32_t val = ((uint32_t)s_w[rel >> 3] >> (rel & 7)) & vmask;
+        if (PAD && bo >= 0 && bitbase + b + nbits > pkt_bits) val = tx_pad_value(seed, frame_id, dsym, b, nbits, M);
+        const float2 pt = s_cst[val];
+        return bo < 0 ? make_float2(0.f, 0.f) : pt;
+    }
+};
+
+template <int N, bool TAPS, int RLO, int RHI>
+__global__ void __launch_bounds__(32, 16) tx_warp_kernel(const TxParams p) {
+    using P = typename FftPlanW<N>::type;
+    constexpr int T = N / P::E, G = 32 / T;
+    constexpr int SB = FFT_PAD32(N) + 2;
+    extern __shared__ float2 smem[];
+    float2* s_cst = smem;                                  // [M]
+    float2* bufs = smem + ((p.M + 15) & ~15);              // G * SB
+    int16_t* s_b2c = (int16_t*)(bufs + (size_t)G * SB);    // [N]
+    const int sym_bytes = (p.ncar * p.nbits + 7) / 8 + 2;
+    const int sb_stride = (sym_bytes + 15) & ~15;
+    uint8_t* s_sym = (uint8_t*)(s_b2c + N);                // [G][sb_stride] (TAPS) / uint16 [G][sb_stride] (word staging)
+    const int g = threadIdx.x / T;
+    const int tid = threadIdx.x - g * T;
+    for (int i = threadIdx.x; i < p.M; i += 32) s_cst[i] = p.cst[i];
+    if (TAPS) {
+        for (int i = threadIdx.x; i < N; i += 32) s_b2c[i] = p.bin2car[i];
+    } else {
+        for (int i = threadIdx.x; i < N; i += 32) {
+            const int c = p.bin2car[(i + N / 2) & (N - 1)];
+            s_b2c[i] = (int16_t)(c < 0 ? -1 : c * p.nbits);
+        }
+    }
+    __syncwarp();
+    float2* buf = bufs + (size_t)g * SB;
+    uint8_t* my_bytes = s_sym + (size_t)g * sb_stride * (TAPS ? 1 : 2);
+    const int L = N + p.cp;
+    const unsigned total = (unsigned)p.total_syms;
+    for (unsigned base = blockIdx.x * G; base < total; base += gridDim.x * G) {
+        const unsigned s = base + g;
+        const bool active = s < total;
+        int f = 0, m = 0;
+        if (active) {
+            if (p.uniform_syms > 0) {
+                f = (int)(s / (unsigned)p.uniform_syms);
+                m = (int)(s - (unsigned)f * (unsigned)p.uniform_syms);
+            } else {
+                int lo = 0, hi = p.n_frames;
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (LDG(p.sym_off + mid) <= (int64_t)s) lo = mid; else hi = mid;
+                }
+                f = lo;
+                m = (int)(s - LDG(p.sym_off + f));
+            }
+        }
+        float2* dst = p.out + (size_t)s * L;
+        int64_t frame_id = p.first_frame + f;
+        uint64_t seed = p.seed;
+        if (p.n_streams > 0 && active) {
+            int lo = 0, hi = p.n_streams;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (LDG(p.stream_frame0 + mid) <= (int64_t)f) lo = mid; else hi = mid;
+            }
+            const int64_t f0 = LDG(p.stream_frame0 + lo);
+            const int64_t sym0 = p.uniform_syms > 0 ? f0 * p.uniform_syms : LDG(p.sym_off + f0);
+            dst = p.out + LDG(p.stream_out_off + lo) + ((int64_t)s - sym0) * L;
+            frame_id = p.first_frame + ((int64_t)f - f0);
+            seed += (uint64_t)lo;
+        }
+        const bool data = active && m > 0;
+        if (active && m == 0) {
+            for (int i = tid; i < L; i += T) dst[i] = cscale_x(LDG(p.pre_time + i), p.amp);
+            if (TAPS) {
+                for (int i = tid; i < N; i += T) {
+                    if (p.pre_tap) p.pre_tap[(size_t)s * N + i] = LDG(p.pre_freq + i);
+                    if (p.ifft_tap) p.ifft_tap[(size_t)s * N + i] = LDG(p.pre_ifft + i);
+                }
+            }
+        }
+        const int64_t o0 = active ? LDG(p.pkt_off + f) : 0;
+        const int64_t o1 = active ? LDG(p.pkt_off + f + 1) : 0;
+        const int pkt_len = (int)(o1 - o0);
+        const int byte0 = data ? ((m - 1) * p.ncar * p.nbits) >> 3 : 0;
+        if (data) {
+            int nb = pkt_len - byte0;
+            if (nb > sym_bytes) nb = sym_bytes;
+            const uint8_t* src = p.pkts + o0 + byte0;
+            if (TAPS) {
+                for (int i = tid; i < nb; i += T) my_bytes[i] = LDG(src + i);
+            } else {
+                const int left = pkt_len - byte0;
+                for (int i = tid; i < nb; i += T)
+                    ((uint16_t*)my_bytes)[i] = (uint16_t)(LDG(src + i) | ((i + 1 < left ? (uint32_t)LDG(src + i + 1) : 0u) << 8));
+            }
+        }
+        __syncwarp();
+        TxLoad<N, TAPS> ld{p, my_bytes, byte0, pkt_len * 8, frame_id, seed, m - 1, s_cst, s_b2c,
+                           (TAPS && p.map_tap) ? p.map_tap + ((size_t)s - (size_t)f - 1) * N : nullptr,
+                           (TAPS && p.pre_tap) ? p.pre_tap + (size_t)s * N : nullptr};
+        TxStore<N, TAPS> st{dst, p.cp, p.s1, p.amp, (TAPS && p.ifft_tap) ? p.ifft_tap + (size_t)s * N : nullptr};
+        if constexpr (TAPS) {
+            if (data) fft_pass<N, P::R[0], 1, 1, decltype(ld), SmemOut32, false, P>(tid, p.tw, ld, SmemOut32{buf});
+        } else {
+            const int bitbase = (m - 1) * p.ncar * p.nbits;
+            const unsigned vmask = (1u << p.nbits) - 1u;
+            if (data && bitbase + p.ncar * p.nbits <= pkt_len * 8) {
+                TxLoadW<N, RLO, RHI, false> ldw{s_b2c, (const uint16_t*)my_bytes, s_cst, vmask, bitbase, bitbase - 8 * byte0,
+                                                pkt_len * 8, p.nbits, m - 1, p.M, frame_id, seed};
+                fft_pass<N, P::R[0], 1, 1, decltype(ldw), SmemOut32, false, P>(tid, p.tw, ldw, SmemOut32{buf});
+            } else if (data) {
+                TxLoadW<N, RLO, RHI, true> ldw{s_b2c, (const uint16_t*)my_bytes, s_cst, vmask, bitbase, bitbase - 8 * byte0,
+                                               pkt_len * 8, p.nbits, m - 1, p.M, frame_id, seed};
+                fft_pass<N, P::R[0], 1, 1, decltype(ldw), SmemOut32, false, P>(tid, p.tw, ldw, SmemOut32{buf});
+            }
+        }
+        __syncwarp();
+        if (data) fft_pass<N, P::R[1], P::R[0], 1, SmemIn32, decltype(st), false, P>(tid, p.tw, SmemIn32{buf}, st);
+        __syncwarp();
+    }
+}
+
+template <int N, int RLO, int RHI>
+static int launch_tx_warp(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
+    using P = typename FftPlanW<N>::type;
+    constexpr int G = 32 / (N / P::E);
+    const int sym_bytes = (p.ncar * p.nbits + 7) / 8 + 2;
+    size_t smem = (((size_t)p.M + 15) / 16 * 16 + (size_t)G * (FFT_PAD32(N) + 2)) * sizeof(float2) + (size_t)N * sizeof(int16_t) +
+                  (size_t)G * ((sym_bytes + 15) & ~15) * 2;
+    const bool taps = p.map_tap || p.pre_tap || p.ifft_tap;
+    if (taps) { OFDM_SET_MAX_SMEM((tx_warp_kernel<N, true, 16, 16>), smem, h->device); } else { OFDM_SET_MAX_SMEM((tx_warp_kernel<N, false, RLO, RHI>), smem, h->device); }
+    int64_t want = (p.total_syms + G - 1) / G;
+    int64_t cap = (int64_t)h->sms * 64;
+    int grid = (int)(want < cap ? want : cap);
+    if (taps) tx_warp_kernel<N, true, 16, 16><<<grid, 32, smem, st>>>(p);
+    else tx_warp_kernel<N, false, RLO, RHI><<<grid, 32, smem, st>>>(p);
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
 int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32_t n_frames, int64_t first_frame,
               const int64_t* sym_off, int64_t total_syms, int32_t uniform_syms, const int64_t* stream_frame0,
               const int64_t* stream_out_off, int32_t n_streams, float2* out, cudaStream_t st, float2* map_tap,
@@ -317,6 +488,15 @@ int launch_tx(ofdm_handle* h, const uint8_t* pkts, const int64_t* pkt_off, int32
     p.s1 = (float)(1.0 / sqrt((double)h->N)); p.amp = h->amp;
     p.total_syms = uniform_syms > 0 ? (int64_t)n_frames * uniform_syms : total_syms;
     if (p.total_syms >= (1ll << 31)) { ofdm_set_error("tx: more than 2^31 OFDM symbols in one batch"); return OFDM_E_INVAL; }
+    static const bool old_plan = getenv("OFDM_TX_OLD") != nullptr;
+    if (!old_plan && h->d_tw_w) {
+        p.tw = h->d_tw_w;
+        // first-pass rows without a carrier: [7, 25) of 32 for every layout with occupied_tones / fft_length <= 0.41
+        const bool narrow = h->tx_row_lo <= 7 && h->tx_row_hi >= 25;
+        if (h->N == 512) return narrow ? launch_tx_warp<512, 7, 25>(h, p, st) : launch_tx_warp<512, 16, 16>(h, p, st);
+        if (h->N == 1024) return narrow ? launch_tx_warp<1024, 7, 25>(h, p, st) : launch_tx_warp<1024, 16, 16>(h, p, st);
+        p.tw = h->d_tw;
+    }
     switch (h->N) {
         case 64:   return launch_tx_n<64, 8>(h, p, st);
         case 128:  return launch_tx_n<128, 8>(h, p, st);
