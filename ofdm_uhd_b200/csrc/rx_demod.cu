@@ -668,6 +668,279 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// acq_warp_kernel (N = 512 / 1024, no taps): the same stage on the warp plan of fft.cuh.  A frame lives on the
+// T = N / 32 lanes of a GROUP (half a warp at 512: two frames per warp, walked in lock step), one warp per CTA:
+// samples go from global memory straight into the radix-32 first pass (32 independent loads per lane; the next
+// vector's lines are pulled into L2 meanwhile), ONE shared-memory exchange, and for data vectors the second pass
+// hands its bins to the one-tap equaliser in registers -- they are stored to the workspace without touching shared
+// memory again.  Only the flagged vector of a frame parks its spectrum (the occupied bins +- the coarse search
+// range) in shared memory for the correlation and the LS estimate.  No block barrier anywhere.
+// ---------------------------------------------------------------------------------------------
+struct SmemIn32 {
+    const float2* p;
+    HDM float2 operator()(int i, int) const { return p[FFT_PAD32(i)]; }
+};
+struct SmemOut32 {
+    float2* p;
+    HDM void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; }
+};
+// NARROW: the layout's occupied band +- the coarse search range lies inside the second-pass rows [0, RLO) and
+// [RHI, R) (rows of 32 bins; 4 / 12 of 16 at N = 512, 7 / 25 of 32 at N = 1024: occupied_tones / fft_length <= 0.41):
+// the rows in between are neither equalised nor stored -- at compile time, so the data-vector path has no branch.
+template <int N, bool NARROW>
+__global__ void __launch_bounds__(32, 14) acq_warp_kernel(const AcqParams p) {
+    struct {
+        const float2* y;
+        const int64_t* trig_idx;
+        const double* phi0;
+        const double* step;
+        const double* nco_init;
+        const int32_t* n_trig;
+        const int32_t* first_ok;
+        const int32_t* n_frames;
+        const int32_t* frame_ndata;
+        const int64_t* vbase;
+        const int64_t* nidx;
+        float2* eq;
+    } v;
+    {
+        const int64_t sidx = p.soff ? (int64_t)blockIdx.y : 0;
+        const int64_t mf = p.max_frames;
+        const int64_t a = p.soff ? p.soff[sidx] : 0;
+        v.y = p.y + a;
+        v.trig_idx = p.trig_idx + sidx * mf; v.phi0 = p.phi0 + sidx * mf; v.step = p.step + sidx * mf;
+        v.nco_init = p.nco_init + sidx; v.n_trig = p.n_trig + sidx; v.first_ok = p.first_ok + sidx;
+        v.n_frames = p.n_frames + sidx; v.frame_ndata = p.frame_ndata + sidx * mf;
+        v.vbase = p.vbase + sidx * (mf + 1);
+        v.eq = p.eq + sidx * p.eq_stride * p.occ;
+        v.nidx = (p.n_nco[sidx] >= 0) ? p.nco_idx + sidx * mf : v.trig_idx;
+    }
+    using P = typename FftPlanW<N>::type;
+    constexpr int T = N / 32, G = 32 / T;
+    constexpr int SB = FFT_PAD32(N) + 2;
+    constexpr int R1 = P::R[1];
+    constexpr int RLO = NARROW ? (N == 512 ? 4 : 7) : R1, RHI = NARROW ? (N == 512 ? 12 : 25) : R1;
+    const int occ = p.occ, zl = p.zl, L = p.L;
+    const int SW = (occ + 2 * OFDM_MAX_SHIFT + 2 + 1) & ~1;  // parked spectrum: bins [zl - MAX_SHIFT, zl + occ + MAX_SHIFT + 2)
+    const int HW = (occ + 1) & ~1;
+    extern __shared__ float2 smem_w[];
+    const int g = threadIdx.x / T, tid = threadIdx.x - g * T;
+    float2* buf = smem_w + (size_t)g * (SB + SW + HW + 32);
+    float2* S = buf + SB;
+    float2* H = S + SW;
+    float2* Wt = H + HW;                                    // [32] e^{j step T r}: NCO turn between the rows of the first pass
+    const unsigned gmask = (T >= 32) ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (g * T));
+    const int F = *v.n_frames;
+    int K = *v.n_trig;
+    if (K > p.max_frames) K = p.max_frames;
+    const bool own_nco = v.nidx != v.trig_idx;
+    if (own_nco) { K = p.n_nco[p.soff ? blockIdx.y : 0]; if (K > p.max_frames) K = p.max_frames; }
+    const int first_ok = *v.first_ok;
+    const double nco_init = *v.nco_init;
+    const int64_t first_evt = (K > 0) ? v.nidx[0] : LLONG_MAX;
+
+    for (int fb = blockIdx.x * G; fb < F; fb += gridDim.x * G) {
+        const int f = fb + g;
+        const bool have = f < F;
+        const int kg = first_ok + (have ? f : fb);
+        const int64_t t = v.trig_idx[kg];
+        const int nd = have ? v.frame_ndata[f] : -1;
+        const int64_t vb0 = have ? v.vbase[f] : 0;
+        int nd_max = nd;
+        if (G > 1) nd_max = max(nd_max, __shfl_xor_sync(0xffffffffu, nd_max, 16));
+        int cnt = 1, delta = 0;
+        // NCO segment of the current vector (event kk): its step, phase and position, and where the next event cuts it
+        int kk = INT_MIN, kk_w = INT_MIN;
+        double stp = 0.0, seg_phi = 0.0;
+        int64_t seg_at = 0, t_lim = LLONG_MAX;
+        auto segment = [&](int k2) {
+            kk = k2;
+            if (kk >= 0) { stp = v.step[kk]; seg_phi = v.phi0[kk]; seg_at = v.nidx[kk] - 1; t_lim = (kk + 1 < K) ? v.nidx[kk + 1] : LLONG_MAX; }
+            else { stp = nco_init; seg_phi = 0.0; seg_at = -1; t_lim = first_evt; }
+        };
+        for (int m = 0; m <= nd_max; ++m) {
+            const bool act = m <= nd;
+            const int64_t st = t - N + 1 + (int64_t)m * L;
+            const int64_t vglob = vb0 + m;
+            // ---- sigmix: NCO phase of this lane's first sample, per-row turn table ----
+            if (own_nco) {
+                int lo = 0, hi = K;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (v.nidx[mid] <= st) lo = mid + 1; else hi = mid;
+                }
+                if (lo - 1 != kk) segment(lo - 1);
+            } else if (m == 0) {
+                int k2 = kg - 1;
+                while (k2 >= 0 && v.nidx[k2] > st) --k2;
+                segment(k2);
+            } else if (m == 1) {
+                segment(kg);
+            }
+            const double ph_base = seg_phi + stp * (double)(st + tid - seg_at);
+            const bool retab = act && kk != kk_w;
+            if (__any_sync(0xffffffffu, retab)) {
+                if (retab) {
+                    for (int r = tid; r < 32; r += T) Wt[r] = phasor_f64(stp * (double)(r * T));
+                    kk_w = kk;
+                }
+                __syncwarp();
+            }
+            const int lim = (t_lim - st >= (int64_t)N) ? N : (t_lim > st ? (int)(t_lim - st) : 0);
+            if (act && m < nd) {                            // the vector that follows: one 128-byte line per lane and step
+                const float2* nx = v.y + st + L;
+                for (int i = tid * 16; i < N; i += T * 16) asm volatile("prefetch.global.L2 [%0];" :: "l"(nx + i));
+            }
+            // Samples at or behind the next NCO event take the exact per-sample phase (derot_slow).  In a flagged
+            // vector that is the last sample (the trigger itself), i.e. the last row of the first pass: it is
+            // settled first, then all 32 samples of the lane are requested before any is used.  An event deeper
+            // inside a vector (a second trigger within a symbol) takes the plain per-point path.
+            const int kk0 = kk < 0 ? 0 : kk;
+            const bool deep = act && lim < N - T;
+            float2 v31 = make_float2(0.f, 0.f);
+            bool have31 = false;
+            if (act && !deep && tid + 31 * T >= lim) {
+                v31 = derot_slow(LDG(v.y + st + tid + 31 * T), st + tid + 31 * T, v.nidx, v.phi0, v.step, K, kk0);
+                have31 = true;
+            }
+            if (__any_sync(0xffffffffu, deep)) {
+                if (act) {
+                    DemodLoad<false> ld{v.y + st, st, lim, v.nidx, v.phi0, v.step, K, kk0, phasor_f64(ph_base), Wt};
+                    fft_pass<N, P::R[0], 1, -1, decltype(ld), SmemOut32, false, P>(tid, p.tw, ld, SmemOut32{buf});
+                }
+            } else if (act) {
+                float2 raw[32];
+                const float2* src = v.y + st + tid;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) raw[r] = LDG(src + r * T);
+                const float2 ph0 = phasor_f64(ph_base);
+                auto ld = [&](int, int slot) -> float2 {
+                    const float2 d = cmul_x(raw[slot], cmul(ph0, Wt[slot]));
+                    return (slot == 31 && have31) ? v31 : d;
+                };
+                fft_pass<N, P::R[0], 1, -1, decltype(ld), SmemOut32, false, P>(tid, p.tw, ld, SmemOut32{buf});
+            }
+            __syncwarp();
+            // A frame whose coarse search found nothing (delta = -zl, see below) keeps the parked path for its data vectors
+            if (m == 0 || __any_sync(0xffffffffu, act && delta == -zl)) {
+                // ---- flagged vector: park the spectrum, correlate, estimate, equalise (ofdm_frame_acquisition) ----
+                // (no shift with a positive correlation -- an all-zero or NaN spectrum -- leaves the upstream search at
+                // index 0, i.e. delta = -zl: the spectrum is parked once more around those bins)
+                int s_lo = zl + (m == 0 ? 0 : delta) - OFDM_MAX_SHIFT;
+                for (int rep = 0; rep < 2; ++rep) {
+                    auto park = [&](int idx, float2 val, int) {
+                        const int sp = ((idx + N / 2) & (N - 1)) - s_lo;
+                        if (sp >= 0 && sp < SW) S[sp] = val;
+                    };
+                    if (act) fft_pass<N, R1, P::R[0], -1, SmemIn32, decltype(park), false, P>(tid, p.tw, SmemIn32{buf}, park);
+                    __syncwarp();
+                    if (rep || m != 0) break;
+                    bool none = false;
+                    if (act) {
+                        double acc[2 * OFDM_MAX_SHIFT];
+#pragma unroll
+                        for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) acc[s] = 0.0;
+                        for (int j = 2 * tid; j < occ - 2; j += 2 * T) {
+                            const float kdj = LDG(p.kd + j);
+#pragma unroll
+                            for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) {
+                                const float2 a = S[s + j], b = S[s + j + 2];
+                                acc[s] += (double)kdj * (double)norm_x(csub_x(a, b));
+                            }
+                        }
+                        float best = 0.f;
+                        int index = -zl;
+#pragma unroll
+                        for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) {
+                            double q = acc[s];
+#pragma unroll
+                            for (int d = T / 2; d > 0; d >>= 1) q += __shfl_xor_sync(gmask, q, d);
+                            const float sf = (float)q;
+                            if (sf > best) { best = sf; index = s - OFDM_MAX_SHIFT; }
+                        }
+                        delta = index;
+                        cnt = 1;
+                        none = index == -zl;
+                    }
+                    if (!__any_sync(0xffffffffu, none)) break;
+                    if (none) s_lo = -OFDM_MAX_SHIFT;
+                }
+                const int sb = zl + delta - s_lo;           // parked position of equalised bin 0
+                if (m == 0) {
+                    if (act) {
+                        const float2 c1 = coarse_comp(delta, p.cp, N, 1);
+                        for (int i = 2 * tid; i < occ; i += 2 * T) {
+                            const float2 b = cmul_x(c1, S[i + sb]);
+                            H[i] = cdiv_x(make_float2(LDG(p.ks + i), 0.f), b);
+                        }
+                    }
+                    __syncwarp();
+                    if (act) {
+                        for (int i = 2 * tid + 1; i + 1 < occ; i += 2 * T) {
+                            const float2 a = H[i + 1], b = H[i - 1];
+                            H[i] = cscale_x(cadd_x(a, b), 0.5f);
+                        }
+                        if (tid == 0 && (occ & 1) == 0) H[occ - 1] = H[occ - 2];
+                    }
+                    __syncwarp();
+                }
+                if (act) {
+                    const float2 cc = coarse_comp(delta, p.cp, N, cnt);
+                    float2* dst = v.eq + vglob * occ;
+                    for (int i = tid; i < occ; i += T) {
+                        const float2 Hi = H[i];
+                        dst[i] = cmul_x(delta == 0 ? Hi : cmul_x(Hi, cc), S[i + sb]);
+                    }
+                }
+            } else {
+                // ---- data vector: one-tap equaliser applied to the second pass's registers.  comp(0, cnt) = (1, -0):
+                // H * comp is then H itself up to the sign of an exact zero, which nothing downstream can see ----
+                const float2 cc = coarse_comp(delta, p.cp, N, cnt);
+                float2* dst = v.eq + vglob * occ;
+                const int lo = zl + delta;
+                auto equalise = [&](int idx, float2 val, int slot) {
+                    const int row = slot & (R1 - 1);        // radix-R1 output row: bins [32 row, 32 row + 32)
+                    if (row >= RLO && row < RHI) return;
+                    const int i = ((idx + N / 2) & (N - 1)) - lo;
+                    const bool ok = (unsigned)i < (unsigned)occ;
+                    const float2 Hi = H[ok ? i : 0];
+                    const float2 o = cmul_x(cmul_x(Hi, cc), val);
+                    if (ok) dst[i] = o;
+                };
+                if (act) fft_pass<N, R1, P::R[0], -1, SmemIn32, decltype(equalise), false, P>(tid, p.tw, SmemIn32{buf}, equalise);
+            }
+            __syncwarp();
+            ++cnt;
+            if (cnt == OFDM_ACQ_MAX_SYMBOLS) cnt = 1;
+        }
+    }
+}
+
+template <int N>
+static int launch_acq_warp(ofdm_handle* h, const AcqParams& p, int max_frames, int S, cudaStream_t st) {
+    constexpr int G = 32 / (N / 32);
+    const int SW = (p.occ + 2 * OFDM_MAX_SHIFT + 2 + 1) & ~1, HW = (p.occ + 1) & ~1;
+    const size_t smem = sizeof(float2) * (size_t)G * (FFT_PAD32(N) + 2 + SW + HW + 32);
+    int grid = (h->sms * 56 + S - 1) / S;                  // 14 one-warp CTAs per SM, four waves
+    const int want = (max_frames + G - 1) / G;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    // bins an equalised vector can come from: [zl - MAX_SHIFT, zl + occ + MAX_SHIFT) of the shifted spectrum
+    const int hi_idx = p.zl + p.occ + OFDM_MAX_SHIFT - N / 2, lo_idx = p.zl - OFDM_MAX_SHIFT + N / 2;
+    const int rlo = N == 512 ? 4 : 7, rhi = N == 512 ? 12 : 25;
+    const bool narrow = hi_idx >= 0 && lo_idx < N && (hi_idx + 31) / 32 <= rlo && lo_idx / 32 >= rhi;
+    if (narrow) {
+        OFDM_SET_MAX_SMEM((acq_warp_kernel<N, true>), smem, h->device);
+        acq_warp_kernel<N, true><<<dim3(grid, S), 32, smem, st>>>(p);
+    } else {
+        OFDM_SET_MAX_SMEM((acq_warp_kernel<N, false>), smem, h->device);
+        acq_warp_kernel<N, false><<<dim3(grid, S), 32, smem, st>>>(p);
+    }
+    OFDM_LAUNCH_CHECK();
+    return OFDM_OK;
+}
+
 template <int N, bool TAPS>
 static int launch_acq_nt(ofdm_handle* h, const AcqParams& p, int max_frames, int S, cudaStream_t st) {
     constexpr int T = N / FftPlan<N>::E;
@@ -702,6 +975,11 @@ int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_i
     a.eq_tap = (float2*)io->eq_syms; a.fft_tap = (float2*)io->fft_out; a.samp_tap = (float2*)io->sampler_out;
     a.max_vectors = io->max_vectors;
     int rc = OFDM_OK;
+    static const bool old_acq = getenv("OFDM_ACQ_OLD") != nullptr;
+    if ((parts & 1) && !taps && !old_acq && h->d_tw_w && (h->N == 512 || h->N == 1024)) {
+        a.tw = h->d_tw_w;
+        rc = h->N == 512 ? launch_acq_warp<512>(h, a, io->max_frames, ss.S, st) : launch_acq_warp<1024>(h, a, io->max_frames, ss.S, st);
+    } else
     if (parts & 1) switch (h->N) {
         case 64:   rc = launch_acq_n<64>(h, a, io->max_frames, ss.S, taps, st); break;
         case 128:  rc = launch_acq_n<128>(h, a, io->max_frames, ss.S, taps, st); break;
