@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 # make_packets, tx, chan_filter, stream_init, metric_chunk, detect_seg, seg_scan, trig_gather, plan_init, plan_local,
 # plan_offset, acq, sink, next, liveness_fast, liveness (general walk, idle), crc
 KERNELS_PER_STEP = 17
-PROFILE = "r02_traffic.json"
+PROFILE = "r02b_traffic.json"
 
 
 def peaks():
@@ -48,7 +48,7 @@ def peaks():
 
 
 def _profile():
-    for name in (PROFILE, "r01_traffic.json"):
+    for name in (PROFILE, "r02_traffic.json", "r01_traffic.json"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             with open(p) as f:
@@ -63,7 +63,7 @@ def ncu_traffic(kernel_label, n_samples):
         return None, None
     tot = 0.0
     for k, v in prof["kernels"].items():
-        if k in kernel_label:
+        if k.replace("_warp", "") in kernel_label:      # tx_warp_kernel etc.: the warp-plan kernels behind the same stage labels
             tot += v["traffic_bytes"] * (n_samples / 640e6)
     return (tot or None), name
 
