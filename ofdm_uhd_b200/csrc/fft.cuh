@@ -79,29 +79,34 @@ inline bool fft_fill_twiddles_n(int N, float2* t) {
 template <int N> HD constexpr int fft_threads() { return N / FftPlan<N>::E; }
 template <int N> HD constexpr int fft_smem_elems() { return FFT_PAD(N) + 1; }   // float2 elements per buffer
 
-// multiply by e^{S*j*2*pi*k/R} for the compile-time cases used inside the register butterflies
-template <int R, int K, int S> HD float2 tw_const(float2 o) {
-    constexpr float C8 = 0.70710678118654752440f;
-    constexpr float C16a = 0.92387953251128675613f;   // cos(pi/8)
-    constexpr float C16b = 0.38268343236508977173f;   // sin(pi/8)
-    constexpr int Q32 = (32 / R) * K;                 // position on the 32-point circle
-    if (Q32 & 1) {
-        constexpr float C32[8] = {0.98078528040323044913f, 0.83146961230254523708f, 0.55557023301960222474f, 0.19509032201612826785f,
-                                  -0.19509032201612826785f, -0.55557023301960222474f, -0.83146961230254523708f, -0.98078528040323044913f};
-        constexpr float S32[8] = {0.19509032201612826785f, 0.55557023301960222474f, 0.83146961230254523708f, 0.98078528040323044913f,
-                                  0.98078528040323044913f, 0.83146961230254523708f, 0.55557023301960222474f, 0.19509032201612826785f};
-        return cmul_const(o, C32[(Q32 >> 1) & 7], S * S32[(Q32 >> 1) & 7]);
+// One butterfly of the register DFTs: (lo, hi) = e +- w o with the compile-time twiddle w = e^{S*j*2*pi*K/R}, written as
+// w = g (1 + j t) (|cos| >= |sin|) or w = g (u + j): the scaled product is one packed FMA and the two outputs are one
+// packed FMA each (common.cuh).  w = 1 and w = +-j stay plain adds.
+HD constexpr double fft_cos32(int q) {                 // cos(2 pi q / 32), q in [0, 16]
+    constexpr double C[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                             0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                             0.19509032201612826785, 0.0};
+    return q <= 8 ? C[q] : -C[16 - q];
+}
+template <int R, int K, int S> HD void tw_butterfly(float2 e, float2 o, float2& lo, float2& hi) {
+    constexpr int Q = (32 / R) * K;                   // position on the 32-point circle, 0 <= Q < 16
+    if constexpr (Q == 0) {
+        lo = cadd(e, o); hi = csub(e, o);
+    } else if constexpr (Q == 8) {
+        const float2 t = S < 0 ? make_float2(o.y, -o.x) : make_float2(-o.y, o.x);
+        lo = cadd(e, t); hi = csub(e, t);
+    } else {
+        constexpr double c = fft_cos32(Q), s = (double)S * fft_cos32(Q <= 8 ? 8 - Q : Q - 8);      // w = c + j s
+        if constexpr (Q <= 4 || Q >= 12) {            // |cos| >= |sin|
+            constexpr float g = (float)c, t = (float)(s / c);
+            const float2 p = cmul_1jt(o, t);
+            lo = caxpy(e, g, p); hi = caxpy(e, -g, p);
+        } else {
+            constexpr float g = (float)s, u = (float)(c / s);
+            const float2 p = cmul_uj(o, u);
+            lo = caxpy(e, g, p); hi = caxpy(e, -g, p);
+        }
     }
-    constexpr int Q = Q32 / 2;                        // position on the 16-point circle
-    if (Q == 0) return o;
-    if (Q == 4) return S < 0 ? make_float2(o.y, -o.x) : make_float2(-o.y, o.x);
-    if (Q == 2) return cmul_const(o, C8, S * C8);
-    if (Q == 6) return cmul_const(o, -C8, S * C8);
-    float c = (Q == 1 || Q == 7) ? C16a : C16b;
-    float s = (Q == 1 || Q == 7) ? C16b : C16a;
-    if (Q == 5 || Q == 7) c = -c;
-    // (x + jy)(c + jSs)
-    return cmul_const(o, c, S * s);
 }
 
 template <int R, int S> struct DftReg;
@@ -110,19 +115,11 @@ template <int S> struct DftReg<2, S> {
 };
 template <int R, int S, int K> struct DftCombine {
     HDM static void run(float2* v, const float2* e, const float2* o) {
-        float2 t = tw_const<R, K, S>(o[K]);
-        v[K] = cadd(e[K], t);
-        v[K + R / 2] = csub(e[K], t);
+        tw_butterfly<R, K, S>(e[K], o[K], v[K], v[K + R / 2]);
         DftCombine<R, S, K + 1>::run(v, e, o);
     }
 };
-template <int S, int K> struct DftCombine<4, S, K> {
-    HDM static void run(float2* v, const float2* e, const float2* o) {
-        float2 t0 = tw_const<4, 0, S>(o[0]), t1 = tw_const<4, 1, S>(o[1]);
-        v[0] = cadd(e[0], t0); v[2] = csub(e[0], t0);
-        v[1] = cadd(e[1], t1); v[3] = csub(e[1], t1);
-    }
-};
+template <int S> struct DftCombine<4, S, 2> { HDM static void run(float2*, const float2*, const float2*) {} };
 template <int S> struct DftCombine<8, S, 4> { HDM static void run(float2*, const float2*, const float2*) {} };
 template <int S> struct DftCombine<16, S, 8> { HDM static void run(float2*, const float2*, const float2*) {} };
 template <int S> struct DftCombine<32, S, 16> { HDM static void run(float2*, const float2*, const float2*) {} };

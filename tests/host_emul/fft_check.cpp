@@ -35,10 +35,36 @@ template <int N, int S> double check() {
     return sqrt(num / den);
 }
 
+// warp plans (FftPlanW: 32 points per thread, radix-32 first pass, padding i + i/32)
+struct In32 { const float2* p; float2 operator()(int i, int) const { return p[FFT_PAD32(i)]; } };
+struct Out32 { float2* p; void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; } };
+template <int N, int S> double check_w() {
+    using P = typename FftPlanW<N>::type;
+    constexpr int T = N / P::E;
+    std::vector<float2> tw(fft_twiddle_elems(N), make_float2(0.f, 0.f)), x(N), out(N), A(FFT_PAD32(N) + 2);
+    fft_fill_twiddles<N, P>(tw.data());
+    for (int i = 0; i < N; ++i) x[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+    auto ld = [&](int i, int) { return x[i]; };
+    auto st = [&](int i, float2 v, int) { out[i] = v; };
+    for (int t = 0; t < T; ++t) fft_pass<N, P::R[0], 1, S, decltype(ld), Out32, false, P>(t, tw.data(), ld, Out32{A.data()});
+    for (int t = 0; t < T; ++t) fft_pass<N, P::R[1], P::R[0], S, In32, decltype(st), false, P>(t, tw.data(), In32{A.data()}, st);
+    double num = 0, den = 0;
+    for (int k = 0; k < N; ++k) {
+        std::complex<double> acc = 0;
+        for (int n = 0; n < N; ++n)
+            acc += std::complex<double>(x[n].x, x[n].y) * std::polar(1.0, S * 2 * M_PI * (double)((long)k * n % N) / N);
+        num += std::norm(acc - std::complex<double>(out[k].x, out[k].y));
+        den += std::norm(acc);
+    }
+    return sqrt(num / den);
+}
+
 int main() {
     double worst = 0;
 #define RUN(N) { double a = check<N, -1>(), b = check<N, 1>(); printf("N=%d fwd %.3g inv %.3g\n", N, a, b); worst = fmax(worst, fmax(a, b)); }
     RUN(64) RUN(128) RUN(256) RUN(512) RUN(1024) RUN(2048) RUN(4096)
+#define RUNW(N) { double a = check_w<N, -1>(), b = check_w<N, 1>(); printf("warp plan N=%d fwd %.3g inv %.3g\n", N, a, b); worst = fmax(worst, fmax(a, b)); }
+    RUNW(512) RUNW(1024)
     printf("worst %.3g\n", worst);
     return worst < 2e-6 ? 0 : 1;
 }

@@ -177,3 +177,18 @@ def test_watcher_thread_survives_a_failing_callback():
         q.insert_tail(ofdm._rx_message(True, p))
     w.drain(timeout=10)
     assert seen == [b"a", b"b"] and w.errors == 1 and w.is_alive()
+
+
+def test_fft_core_host_emulation(tmp_path):
+    """csrc/fft.cuh compiled as plain C++ (OFDM_HOST_EMUL): every plan -- the three-pass Stockham plans and the
+    radix-32 warp plans -- against a float64 DFT, forward and inverse (replaces gr.fft_vcc, ofdm.py:112,
+    ofdm_receiver.py~:126)."""
+    import os, shutil, subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = os.path.join(os.path.dirname(__file__), "host_emul", "fft_check.cpp")
+    exe = str(tmp_path / "fft_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", src, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "warp plan N=1024" in r.stdout
