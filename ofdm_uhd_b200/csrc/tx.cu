@@ -186,6 +186,35 @@ struct TxStore {
     }
 };
 
+// Branch-free mapper (every kernel below without taps).  Tables are per FFT INPUT index (the ifftshift is folded in): s_bo[idx] = bit offset of the
+// carrier inside a symbol's bit field, -1 for an unused bin; the symbol's bytes are staged as overlapping 16-bit words
+// (s_w[b] = byte b | byte b+1 << 8), so a carrier's bits are one load and one shift.  First-pass rows [RLO, RHI) hold no
+// carrier at all (rows 7 .. 24 of 32 when occupied_tones / fft_length <= 0.41): compile-time zeros, no mapper work and no
+// branch.  PAD: the symbol reaches behind the end of the packet (last symbol of a frame) and fills up with pad symbols.
+static __device__ __noinline__ uint32_t tx_pad_value(uint64_t seed, int64_t frame_id, int dsym, int bit_off, int nbits, int M) {
+    return pad_index(seed, (uint64_t)frame_id, (uint32_t)dsym, (uint32_t)(bit_off / nbits), (uint32_t)M);
+}
+template <int N, int RLO, int RHI, bool PAD>
+struct TxLoadW {
+    const int16_t* s_bo;
+    const uint16_t* s_w;
+    const float2* s_cst;
+    unsigned vmask;
+    int bitbase, rel0, pkt_bits, nbits, dsym, M;
+    int64_t frame_id;
+    uint64_t seed;
+    __device__ __forceinline__ float2 operator()(int idx, int slot) const {
+        if (slot >= RLO && slot < RHI) return make_float2(0.f, 0.f);
+        const int bo = s_bo[idx];
+        const int b = bo < 0 ? 0 : bo;
+        const int rel = rel0 + b;
+        uint32_t val = ((uint32_t)s_w[rel >> 3] >> (rel & 7)) & vmask;
+        if (PAD && bo >= 0 && bitbase + b + nbits > pkt_bits) val = tx_pad_value(seed, frame_id, dsym, b, nbits, M);
+        const float2 pt = s_cst[val];
+        return bo < 0 ? make_float2(0.f, 0.f) : pt;
+    }
+};
+
 template <int N, int G, bool TAPS>
 __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ? 1024 : 512) / (G * (N / FftPlan<N>::E))) tx_kernel(const TxParams p) {
     constexpr int T = N / FftPlan<N>::E;
@@ -200,11 +229,18 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
     const int g = threadIdx.x / T;
     const int tid = threadIdx.x - g * T;
     for (int i = threadIdx.x; i < p.M; i += blockDim.x) s_cst[i] = p.cst[i];
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s_b2c[i] = p.bin2car[i];
+    if (TAPS) {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) s_b2c[i] = p.bin2car[i];
+    } else {                                               // per IFFT input index: bit offset of the carrier, -1 if unused
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const int c = p.bin2car[(i + N / 2) & (N - 1)];
+            s_b2c[i] = (int16_t)(c < 0 ? -1 : c * p.nbits);
+        }
+    }
     __syncthreads();
     float2* bufA = bufs + (size_t)g * 2 * SB;
     float2* bufB = bufA + SB;
-    uint8_t* my_bytes = s_sym + (size_t)g * sb_stride;
+    uint8_t* my_bytes = s_sym + (size_t)g * sb_stride * (TAPS ? 1 : 2);     // bytes (TAPS) / overlapping 16-bit words
     const int L = N + p.cp;
     auto bar = [] { __syncthreads(); };
     const unsigned total = (unsigned)p.total_syms;               // launcher guarantees < 2^31
@@ -264,7 +300,13 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
             int nb = pkt_len - byte0;
             if (nb > sym_bytes) nb = sym_bytes;
             const uint8_t* src = p.pkts + o0 + byte0;
-            for (int i = tid; i < nb; i += T) my_bytes[i] = LDG(src + i);
+            if (TAPS) {
+                for (int i = tid; i < nb; i += T) my_bytes[i] = LDG(src + i);
+            } else {
+                const int left = pkt_len - byte0;
+                for (int i = tid; i < nb; i += T)
+                    ((uint16_t*)my_bytes)[i] = (uint16_t)(LDG(src + i) | ((i + 1 < left ? (uint32_t)LDG(src + i + 1) : 0u) << 8));
+            }
         }
         bar();
         // data symbols before this one in the batch: s minus the preambles of frames 0 .. f
@@ -274,7 +316,21 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
         TxStore<N, TAPS> st{dst, p.cp, p.s1, p.amp, (TAPS && p.ifft_tap) ? p.ifft_tap + (size_t)s * N : nullptr};
         using P = FftPlan<N>;
         constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
-        if (data) fft_pass<N, R0, 1, 1>(tid, p.tw, ld, SmemOut{bufA});
+        if constexpr (TAPS) {
+            if (data) fft_pass<N, R0, 1, 1>(tid, p.tw, ld, SmemOut{bufA});
+        } else {
+            const int bitbase = (m - 1) * p.ncar * p.nbits;
+            const unsigned vmask = (1u << p.nbits) - 1u;
+            if (data && bitbase + p.ncar * p.nbits <= pkt_len * 8) {
+                TxLoadW<N, 0, 0, false> ldw{s_b2c, (const uint16_t*)my_bytes, s_cst, vmask, bitbase, bitbase - 8 * byte0,
+                                            pkt_len * 8, p.nbits, m - 1, p.M, frame_id, seed};
+                fft_pass<N, R0, 1, 1>(tid, p.tw, ldw, SmemOut{bufA});
+            } else if (data) {
+                TxLoadW<N, 0, 0, true> ldw{s_b2c, (const uint16_t*)my_bytes, s_cst, vmask, bitbase, bitbase - 8 * byte0,
+                                           pkt_len * 8, p.nbits, m - 1, p.M, frame_id, seed};
+                fft_pass<N, R0, 1, 1>(tid, p.tw, ldw, SmemOut{bufA});
+            }
+        }
         bar();
         if constexpr (P::NP == 2) {
             if (data) fft_pass<N, R1, R0, 1>(tid, p.tw, SmemIn{bufA}, st);
@@ -292,7 +348,7 @@ static int launch_tx_n(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
     constexpr int T = N / FftPlan<N>::E;
     const int sym_bytes = (p.ncar * p.nbits + 7) / 8 + 2;
     size_t smem = (256 + (size_t)G * 2 * fft_smem_elems<N>()) * sizeof(float2) + (size_t)N * sizeof(int16_t) +
-                  (size_t)G * ((sym_bytes + 15) & ~15);
+                  (size_t)G * ((sym_bytes + 15) & ~15) * 2;
     const bool taps = p.map_tap || p.pre_tap || p.ifft_tap;
     if (taps) { OFDM_SET_MAX_SMEM((tx_kernel<N, G, true>), smem, h->device); } else { OFDM_SET_MAX_SMEM((tx_kernel<N, G, false>), smem, h->device); }
     const int sms = h->sms;
@@ -315,35 +371,6 @@ struct SmemOut32 {
     float2* p;
     HDM void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; }
 };
-// Mapper of the warp kernel.  Tables are per FFT INPUT index (the ifftshift is folded in): s_bo[idx] = bit offset of the
-// carrier inside a symbol's bit field, -1 for an unused bin; the symbol's bytes are staged as overlapping 16-bit words
-// (s_w[b] = byte b | byte b+1 << 8), so a carrier's bits are one load and one shift.  First-pass rows [RLO, RHI) hold no
-// carrier at all (rows 7 .. 24 of 32 when occupied_tones / fft_length <= 0.41): compile-time zeros, no mapper work and no
-// branch.  PAD: the symbol reaches behind the end of the packet (last symbol of a frame) and fills up with pad symbols.
-static __device__ __noinline__ uint32_t tx_pad_value(uint64_t seed, int64_t frame_id, int dsym, int bit_off, int nbits, int M) {
-    return pad_index(seed, (uint64_t)frame_id, (uint32_t)dsym, (uint32_t)(bit_off / nbits), (uint32_t)M);
-}
-template <int N, int RLO, int RHI, bool PAD>
-struct TxLoadW {
-    const int16_t* s_bo;
-    const uint16_t* s_w;
-    const float2* s_cst;
-    unsigned vmask;
-    int bitbase, rel0, pkt_bits, nbits, dsym, M;
-    int64_t frame_id;
-    uint64_t seed;
-    __device__ __forceinline__ float2 operator()(int idx, int slot) const {
-        if (slot >= RLO && slot < RHI) return make_float2(0.f, 0.f);
-        const int bo = s_bo[idx];
-        const int b = bo < 0 ? 0 : bo;
-        const int rel = rel0 + b;
-        uint32_t val = ((uint32_t)s_w[rel >> 3] >> (rel & 7)) & vmask;
-        if (PAD && bo >= 0 && bitbase + b + nbits > pkt_bits) val = tx_pad_value(seed, frame_id, dsym, b, nbits, M);
-        const float2 pt = s_cst[val];
-        return bo < 0 ? make_float2(0.f, 0.f) : pt;
-    }
-};
-
 template <int N, bool TAPS, int RLO, int RHI>
 __global__ void __launch_bounds__(32, 16) tx_warp_kernel(const TxParams p) {
     using P = typename FftPlanW<N>::type;
