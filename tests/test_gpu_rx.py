@@ -671,3 +671,30 @@ def test_alternative_synchronisers_equal_oracle(sync, gain, N, occ, cp, mod):
     d.wait(30)
     assert seen == ref.packets
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,occ,cp,mod,nsym", [(512, 200, 128, "qpsk", 10), (1024, 400, 256, "qam16", 4), (512, 400, 64, "qpsk", 6)])
+def test_acquisition_on_silent_frames(N, occ, cp, mod, nsym):
+    """ofdm_frame_acquisition on a flagged vector with an all-zero spectrum: no shift of the coarse search has a positive
+    correlation, the upstream search index stays 0 (delta = -zero_left), the estimate is 0/0 -- and the block goes on
+    equalising the following data vectors with it (digital_swig.py:4316-4330 as restated in oracle.FrameAcquisition).
+    Fixed synchroniser, two frames of a back-to-back capture zeroed: the packet list must equal the oracle's (the
+    warp-plan acquisition kernel re-parks the spectrum around bin 0 for such a frame)."""
+    import torch
+    from ofdm_uhd_b200.engine import OfdmEngine
+    lay = o.Layout(N, occ, cp, mod)
+    rng = np.random.default_rng(N + nsym)
+    pay = payloads(rng, 10)
+    x = o.tx_modulate([o.make_packet(p, 1, 1, False) for p in pay], lay, 0.25, seed=2)
+    L = N + cp
+    assert len(x) == 10 * nsym * L
+    xc = o.channel(np.concatenate([x, np.zeros(3 * L, np.complex64)]), 30.0, 0.1, N, seed=8,
+                   sig_power=float(np.mean(np.abs(x) ** 2)))
+    for f in (3, 7):
+        xc[f * nsym * L:(f + 1) * nsym * L] = 0
+    ref = o.rx_demodulate(xc, lay, sync="fixed", nsymbols=nsym, freq_offset=0.1)
+    assert sum(1 for ok, _ in ref.packets if ok) == 8
+    eng = OfdmEngine(N, occ, cp, mod)
+    got = eng.demodulate_fixed(torch.from_numpy(xc).cuda(), nsym, 0.1)
+    assert got.packets == ref.packets
