@@ -275,8 +275,14 @@ extern "C" ofdm_handle* ofdm_create(const ofdm_cfg* cfg) {
     whitening_mask(mask.data());
     // CRC table, then x^(8*128*j) mod P (j < 32) and x^(8*r) mod P (r < 128): the shift factors with which the
     // warp-per-packet CRC kernel combines the partial CRCs of 128-byte slices
-    std::vector<uint32_t> crct(256 + 32 + 128);
+    std::vector<uint32_t> crct(OFDM_CRC_SLICE + 3 * 256);
     crc_table(crct.data());
+    // slicing tables: T_k[i] = state after byte i and k zero bytes (four bytes per step in the framing / CRC kernels)
+    for (int k = 1; k < 4; ++k)
+        for (int i = 0; i < 256; ++i) {
+            const uint32_t v = crct[(k == 1 ? 0 : OFDM_CRC_SLICE + (k - 2) * 256) + i];
+            crct[OFDM_CRC_SLICE + (k - 1) * 256 + i] = crct[v >> 24] ^ (v << 8);
+        }
     {
         uint32_t s = 1u;                                            // the polynomial 1 = x^0
         for (int r = 0; r <= 128 * 31; ++r) {

@@ -11,6 +11,7 @@
 #define OFDM_ACQ_MAX_SYMBOLS 1000       // upstream MAX_NUM_SYMBOLS
 #define OFDM_MAX_SHIFT 4                // digital_swig.py:4320 (max_fft_shift_len)
 #define OFDM_PEAK_WARM 24576            // samples of IIR warm-up before a detector segment
+#define OFDM_CRC_SLICE (256 + 32 + 128)   // offset of the slicing tables T1, T2, T3 in d_crctab
 #define OFDM_SEG_CAP_SHIFT 6            // detector segment slot list: seg_len >> 6 triggers
 
 // One receive call serves S independent streams laid back to back in one sample buffer (S = 1: the classic
@@ -57,7 +58,7 @@ struct ofdm_handle {
     float2* d_pre_freq;    // [N] the known symbol as the mapper-order (unshifted) vector   (options.log taps)
     float2* d_pre_ifft;    // [N] its unscaled IFFT
     uint8_t* d_mask;       // [4096] whitening mask
-    uint32_t* d_crctab;    // [256]
+    uint32_t* d_crctab;    // [256] byte table, [32] + [128] shift factors (crc_warp_kernel), then 3 x [256] slicing tables T1..T3
     float h_taps[OFDM_MAX_TAPS];
     // square-grid constellations (qam64 / qam256): levels per axis (0 = brute-force slicer only), cell -> index table
     int grid_L;

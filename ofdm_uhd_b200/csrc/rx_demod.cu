@@ -1241,11 +1241,28 @@ __global__ void __launch_bounds__(1024) liveness_kernel(const int32_t* __restric
 // word copies, rows padded by one word against bank conflicts) and each lane works on its own row there.
 constexpr int CRC_SMEM_MAX = 160 * 1024;  // staging is used while 32 padded rows fit (any stride up to 4096 + 16 does)
 
+// b: the packet's row (4-byte aligned when WORDS); s_crc: [T0 | T1 | T2 | T3].  WORDS: dewhitening and CRC run a
+// 32-bit word at a time over the part of the CRC body made of whole words (four independent table lookups per step
+// instead of a dependent chain of four), the rest -- at most 3 body bytes and the 4 CRC bytes -- byte by byte.
+template <bool WORDS>
 __device__ __forceinline__ uint8_t dewhiten_crc_row(uint8_t* b, int len, int stride, const uint8_t* __restrict__ mask,
                                                     const uint32_t* s_crc) {
     const int nst = len < stride ? len : stride;
     uint32_t crc = 0xFFFFFFFFu, tail = 0;
-    for (int i = 0; i < nst; ++i) {
+    int i = 0;
+    if (WORDS) {
+        const int body = len - 4 < nst ? len - 4 : nst;
+        const int nw = body > 0 ? body >> 2 : 0;
+        uint32_t* w = (uint32_t*)b;
+        const uint32_t* m4 = (const uint32_t*)mask;
+        for (int k = 0; k < nw; ++k) {
+            const uint32_t v = w[k] ^ LDG(m4 + (k & 1023));
+            w[k] = v;
+            crc = crc32_step4(crc, __byte_perm(v, 0, 0x0123), s_crc);
+        }
+        i = 4 * nw;
+    }
+    for (; i < nst; ++i) {
         const uint8_t v = (uint8_t)(b[i] ^ mask[i & 4095]);
         b[i] = v;
         if (i < len - 4) crc = s_crc[(v ^ (crc >> 24)) & 0xFF] ^ (crc << 8);
@@ -1264,10 +1281,11 @@ __global__ void __launch_bounds__(32) crc_kernel(const int32_t* __restrict__ n_f
         n_frames += s; live += s * max_frames; status += s * max_frames; pkt_len += s * max_frames;
         pkt_bytes += s * max_frames * (int64_t)stride; pkt_ok += s * max_frames; counters += s * 8;
     }
-    __shared__ uint32_t s_crc[256];
+    __shared__ uint32_t s_crc[1024];                              // T0 .. T3
     extern __shared__ uint32_t s_rows[];                          // [32][stride/4 + 1] when staged, else empty
     const int lane = threadIdx.x;
     for (int i = lane; i < 256; i += 32) s_crc[i] = crctab[i];
+    for (int i = lane; i < 768; i += 32) s_crc[256 + i] = crctab[OFDM_CRC_SLICE + i];
     __syncwarp();
     const int F = *n_frames;
     const int wpr = stride >> 2, spr = wpr + 1;                   // words per row in global / shared memory
@@ -1289,7 +1307,7 @@ __global__ void __launch_bounds__(32) crc_kernel(const int32_t* __restrict__ n_f
                     s_rows[i + r] = g[i];                         // row r starts at r*spr = r*wpr + r
                 }
                 __syncwarp();
-                if (mine) { len = pkt_len[f]; ok = dewhiten_crc_row((uint8_t*)(s_rows + lane * spr), len, stride, mask, s_crc); }
+                if (mine) { len = pkt_len[f]; ok = dewhiten_crc_row<true>((uint8_t*)(s_rows + lane * spr), len, stride, mask, s_crc); }
                 __syncwarp();
 #pragma unroll 4
                 for (int i = lane; i < nw; i += 32) {
@@ -1299,7 +1317,7 @@ __global__ void __launch_bounds__(32) crc_kernel(const int32_t* __restrict__ n_f
                 __syncwarp();
             } else if (mine) {
                 len = pkt_len[f];
-                ok = dewhiten_crc_row(pkt_bytes + (size_t)f * stride, len, stride, mask, s_crc);
+                ok = dewhiten_crc_row<false>(pkt_bytes + (size_t)f * stride, len, stride, mask, s_crc);
             }
         }
         if (f < F) pkt_ok[f] = ok;

@@ -14,7 +14,16 @@ __device__ __forceinline__ void frame_one_packet(const uint8_t* src, int plen, u
     dst[0] = (uint8_t)(v >> 8); dst[1] = (uint8_t)v; dst[2] = (uint8_t)(v >> 8); dst[3] = (uint8_t)v;
     uint32_t crc = 0xFFFFFFFFu;
     int o = 0;                                                      // offset into the whitened body
-    for (int i = 0; i < plen; ++i, ++o) {
+    // four bytes per step: one mask word, four independent CRC table lookups (s_crc = [T0 | T1 | T2 | T3])
+    const uint32_t* m4 = (const uint32_t*)mask;
+    for (; o + 4 <= plen; o += 4) {
+        const uint32_t b0 = src[o], b1 = src[o + 1], b2 = src[o + 2], b3 = src[o + 3];
+        crc = crc32_step4(crc, (b0 << 24) | (b1 << 16) | (b2 << 8) | b3, s_crc);
+        const uint32_t m = whitening ? LDG(m4 + (o >> 2)) : 0u;
+        dst[4 + o] = (uint8_t)(b0 ^ m); dst[5 + o] = (uint8_t)(b1 ^ (m >> 8));
+        dst[6 + o] = (uint8_t)(b2 ^ (m >> 16)); dst[7 + o] = (uint8_t)(b3 ^ (m >> 24));
+    }
+    for (int i = o; i < plen; ++i, ++o) {
         const uint8_t b = src[i];
         crc = s_crc[(b ^ (crc >> 24)) & 0xFF] ^ (crc << 8);
         dst[4 + o] = whitening ? (uint8_t)(b ^ mask[o]) : b;
@@ -55,11 +64,12 @@ __global__ void __launch_bounds__(32) make_packets_kernel(const uint8_t* __restr
                                                            const int64_t* __restrict__ pkt_off,
                                                            const uint8_t* __restrict__ mask,
                                                            const uint32_t* __restrict__ crctab) {
-    __shared__ uint32_t s_crc[256];
+    __shared__ uint32_t s_crc[1024];                                // T0 .. T3
     __shared__ __align__(16) uint8_t s_in[MP_IN];
     __shared__ __align__(16) uint8_t s_out[MP_OUT];
     const int lane = threadIdx.x;
     for (int i = lane; i < 256; i += 32) s_crc[i] = crctab[i];
+    for (int i = lane; i < 768; i += 32) s_crc[256 + i] = crctab[OFDM_CRC_SLICE + i];
     __syncwarp();
     const int f0 = blockIdx.x * 32;
     if (f0 >= n_pkts) return;

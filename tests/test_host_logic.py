@@ -192,3 +192,16 @@ def test_fft_core_host_emulation(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "warp plan N=1024" in r.stdout
+
+
+def test_crc_slicing_host_emulation(tmp_path):
+    """crc32_step4 (csrc/common.cuh, four bytes per step over the slicing tables of ofdm_create) equals the
+    byte-at-a-time CRC-32 of digital.crc32 (digital_swig.py:3151-3168) on random buffers."""
+    import os, shutil, subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = os.path.join(os.path.dirname(__file__), "host_emul", "crc_check.cpp")
+    exe = str(tmp_path / "crc_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", src, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
