@@ -142,17 +142,29 @@ template <int R, int S> struct DftReg {
 // first-pass inputs / last-pass outputs in a register array (slot <-> index tid + q*T + r*N/R).
 // BAR: __syncthreads() between the loads and the stores of the pass, for passes that read and write the SAME buffer
 // (allowed only when a thread's E points form one butterfly, E == R, so that every load precedes every store).
-template <int N, int R, int NS, int S, class In, class Out, bool BAR = false, class P = FftPlan<N>>
+// WPRE (warp plans: the transform's threads sit in one warp): ALL E points of the thread are read first, then a
+// __syncwarp(), then the butterflies and their stores -- the outputs may overwrite the buffer the inputs came from.
+template <int N, int R, int NS, int S, class In, class Out, bool BAR = false, class P = FftPlan<N>, bool WPRE = false>
 HD void fft_pass(int tid, const float2* __restrict__ tw, In in, Out out) {
     static_assert(!BAR || P::E == R, "in-place pass needs one butterfly per thread");
     constexpr int E = P::E;
     constexpr int T = N / E;
+    float2 pre[WPRE ? E : 1];
+    if (WPRE) {
+#pragma unroll
+        for (int q = 0; q < E / R; ++q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) pre[WPRE ? q * R + r : 0] = in(tid + q * T + r * (N / R), q * R + r);
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+    }
 #pragma unroll
     for (int q = 0; q < E / R; ++q) {
         const int j = tid + q * T;
         float2 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = in(j + r * (N / R), q * R + r);
+        for (int r = 0; r < R; ++r) v[r] = WPRE ? pre[WPRE ? q * R + r : 0] : in(j + r * (N / R), q * R + r);
 #if defined(__CUDA_ARCH__)
         if (BAR) __syncthreads();
 #endif

@@ -689,7 +689,7 @@ struct SmemOut32 {
 // [RHI, R) (rows of 32 bins; 4 / 12 of 16 at N = 512, 7 / 25 of 32 at N = 1024: occupied_tones / fft_length <= 0.41):
 // the rows in between are neither equalised nor stored -- at compile time, so the data-vector path has no branch.
 template <int N, bool NARROW>
-__global__ void __launch_bounds__(32, 14) acq_warp_kernel(const AcqParams p) {
+__global__ void __launch_bounds__(32, 16) acq_warp_kernel(const AcqParams p) {
     struct {
         const float2* y;
         const int64_t* trig_idx;
@@ -722,13 +722,12 @@ __global__ void __launch_bounds__(32, 14) acq_warp_kernel(const AcqParams p) {
     constexpr int R1 = P::R[1];
     constexpr int RLO = NARROW ? (N == 512 ? 4 : 7) : R1, RHI = NARROW ? (N == 512 ? 12 : 25) : R1;
     const int occ = p.occ, zl = p.zl, L = p.L;
-    const int SW = (occ + 2 * OFDM_MAX_SHIFT + 2 + 1) & ~1;  // parked spectrum: bins [zl - MAX_SHIFT, zl + occ + MAX_SHIFT + 2)
     const int HW = (occ + 1) & ~1;
     extern __shared__ float2 smem_w[];
     const int g = threadIdx.x / T, tid = threadIdx.x - g * T;
-    float2* buf = smem_w + (size_t)g * (SB + SW + HW + 32);
-    float2* S = buf + SB;
-    float2* H = S + SW;
+    float2* buf = smem_w + (size_t)g * (SB + HW + 32);
+    float2* S = buf;                                        // the parked spectrum overwrites the exchange buffer (WPRE pass)
+    float2* H = buf + SB;
     float2* Wt = H + HW;                                    // [32] e^{j step T r}: NCO turn between the rows of the first pass
     const unsigned gmask = (T >= 32) ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (g * T));
     const int F = *v.n_frames;
@@ -824,20 +823,17 @@ __global__ void __launch_bounds__(32, 14) acq_warp_kernel(const AcqParams p) {
             __syncwarp();
             // A frame whose coarse search found nothing (delta = -zl, see below) keeps the parked path for its data vectors
             if (m == 0 || __any_sync(0xffffffffu, act && delta == -zl)) {
-                // ---- flagged vector: park the spectrum, correlate, estimate, equalise (ofdm_frame_acquisition) ----
-                // (no shift with a positive correlation -- an all-zero or NaN spectrum -- leaves the upstream search at
-                // index 0, i.e. delta = -zl: the spectrum is parked once more around those bins)
-                int s_lo = zl + (m == 0 ? 0 : delta) - OFDM_MAX_SHIFT;
-                for (int rep = 0; rep < 2; ++rep) {
-                    auto park = [&](int idx, float2 val, int) {
-                        const int sp = ((idx + N / 2) & (N - 1)) - s_lo;
-                        if (sp >= 0 && sp < SW) S[sp] = val;
-                    };
-                    if (act) fft_pass<N, R1, P::R[0], -1, SmemIn32, decltype(park), false, P>(tid, p.tw, SmemIn32{buf}, park);
+                // ---- flagged vector: park the (shifted) spectrum, correlate, estimate, equalise (ofdm_frame_acquisition).
+                // The parked spectrum overwrites the exchange buffer: the pass reads all its inputs first (WPRE).
+                // No shift with a positive correlation -- an all-zero or NaN spectrum -- leaves the upstream search at
+                // index 0, i.e. delta = -zl ----
+                {
+                    // (run by every lane -- the pass has a warp barrier inside; a group without a vector stores nothing)
+                    auto park = [&](int idx, float2 val, int) { if (act) S[(idx + N / 2) & (N - 1)] = val; };
+                    fft_pass<N, R1, P::R[0], -1, SmemIn32, decltype(park), false, P, true>(tid, p.tw, SmemIn32{buf}, park);
                     __syncwarp();
-                    if (rep || m != 0) break;
-                    bool none = false;
-                    if (act) {
+                    if (m == 0 && act) {
+                        const float2* Sc = S + (zl - OFDM_MAX_SHIFT);
                         double acc[2 * OFDM_MAX_SHIFT];
 #pragma unroll
                         for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) acc[s] = 0.0;
@@ -845,7 +841,7 @@ __global__ void __launch_bounds__(32, 14) acq_warp_kernel(const AcqParams p) {
                             const float kdj = LDG(p.kd + j);
 #pragma unroll
                             for (int s = 0; s < 2 * OFDM_MAX_SHIFT; ++s) {
-                                const float2 a = S[s + j], b = S[s + j + 2];
+                                const float2 a = Sc[s + j], b = Sc[s + j + 2];
                                 acc[s] += (double)kdj * (double)norm_x(csub_x(a, b));
                             }
                         }
@@ -861,12 +857,9 @@ __global__ void __launch_bounds__(32, 14) acq_warp_kernel(const AcqParams p) {
                         }
                         delta = index;
                         cnt = 1;
-                        none = index == -zl;
                     }
-                    if (!__any_sync(0xffffffffu, none)) break;
-                    if (none) s_lo = -OFDM_MAX_SHIFT;
                 }
-                const int sb = zl + delta - s_lo;           // parked position of equalised bin 0
+                const int sb = zl + delta;                  // parked position of equalised bin 0
                 if (m == 0) {
                     if (act) {
                         const float2 c1 = coarse_comp(delta, p.cp, N, 1);
@@ -920,9 +913,9 @@ __global__ void __launch_bounds__(32, 14) acq_warp_kernel(const AcqParams p) {
 template <int N>
 static int launch_acq_warp(ofdm_handle* h, const AcqParams& p, int max_frames, int S, cudaStream_t st) {
     constexpr int G = 32 / (N / 32);
-    const int SW = (p.occ + 2 * OFDM_MAX_SHIFT + 2 + 1) & ~1, HW = (p.occ + 1) & ~1;
-    const size_t smem = sizeof(float2) * (size_t)G * (FFT_PAD32(N) + 2 + SW + HW + 32);
-    int grid = (h->sms * 56 + S - 1) / S;                  // 14 one-warp CTAs per SM, four waves
+    const int HW = (p.occ + 1) & ~1;
+    const size_t smem = sizeof(float2) * (size_t)G * (FFT_PAD32(N) + 2 + HW + 32);
+    int grid = (h->sms * 64 + S - 1) / S;                  // 16 one-warp CTAs per SM, four waves
     const int want = (max_frames + G - 1) / G;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
