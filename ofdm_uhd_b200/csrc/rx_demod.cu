@@ -658,6 +658,16 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
             sync();                                         // sym / vb are rewritten by the next vector
             bit_base += bits_this;
             if (B1 >= 4 + len) { status = 2; nvec = vi + 1; break; }
+            // A header that announces more than a slot holds (max_pkt_bytes; a bogus length, e.g. of a header read
+            // through a constellation turned by 90 degrees: both copies turn alike and still agree) cannot be delivered
+            // intact: once every byte the slot keeps is written, nothing the remaining vectors decode is observable --
+            // only WHERE the session ends, and that follows from the announced length alone.  (One such 83-vector
+            // session walked to its end by 16 lanes was a 0.2 ms tail behind the whole kernel.)
+            if (!TAPS && len > p.pkt_stride && B1 >= 4 + p.pkt_stride) {
+                const int vi_end = (8 * (4 + len) + bits_this - 1) / bits_this;
+                if (v0 + vi_end < vtot) { status = 2; nvec = vi_end + 1; }
+                break;
+            }
         }
         if (lane == 0) {
             frame_status[f] = (uint8_t)status;

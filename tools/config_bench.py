@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput of mod + demod on the other BASELINE layouts (not bench lines; a health check of the N >= 1024 paths).
 
-usage: config_bench.py N occ cp mod frames [payload_bytes [snr_db]]"""
+usage: config_bench.py N occ cp mod frames [payload_bytes [snr_db [cfo]]]"""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -21,7 +21,8 @@ x = torch.zeros(n, dtype=torch.complex64, device="cuda")
 xs = x[lead:lead + plan.n_samples]
 eng.tx_run(plan, body, out=xs)
 p = float((xs[:1 << 20].abs() ** 2).mean())
-xc = eng.channel(x, cfo=0.27, sigma=(p / 10 ** (snr_db / 10) / 2) ** 0.5, seed=3)
+cfo = float(sys.argv[8]) if len(sys.argv) > 8 else 0.27
+xc = eng.channel(x, cfo=cfo, sigma=(p / 10 ** (snr_db / 10) / 2) ** 0.5, seed=3)
 bufs = eng.rx_alloc(n, max_frames=F + 1024)
 st = eng._stream()
 io = bufs["io"]
