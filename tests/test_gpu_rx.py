@@ -19,7 +19,10 @@ CASES = [(512, 200, 128, "bpsk", 8, 40, 0.0), (512, 200, 128, "qpsk", 24, 20, 0.
          (512, 200, 128, "8psk", 12, 30, 0.2), (512, 200, 128, "qam64", 10, 32, 0.1), (1024, 400, 256, "qam64", 12, 30, 1.3),
          (1024, 800, 256, "qam64", 10, 30, -2.2), (4096, 3200, 512, "qam256", 6, 38, 0.3), (256, 104, 64, "qpsk", 12, 30, 0.1),
          (2048, 800, 512, "qam16", 6, 30, 0.2), (128, 56, 32, "qpsk", 20, 30, 0.05),
-         (512, 200, 100, "qpsk", 10, 30, 0.15)]          # cp not a multiple of the 8 samples a lane owns
+         (512, 200, 100, "qpsk", 10, 30, 0.15),          # cp not a multiple of the 8 samples a lane owns
+         # narrow bands make long channel filters: 241 taps (the 1024-point warp filter with 8 dropped rows) and
+         # 321 taps (beyond it: the three-pass 2048-point filter)
+         (512, 128, 64, "qpsk", 10, 30, 0.1), (512, 96, 64, "qpsk", 10, 30, -0.1)]
 
 
 def stage_run(eng, xc, r, lay):
