@@ -201,10 +201,18 @@ struct TxStore {
 // (s_w[b] = byte b | byte b+1 << 8), so a carrier's bits are one load and one shift.  First-pass rows [RLO, RHI) hold no
 // carrier at all (rows 7 .. 24 of 32 when occupied_tones / fft_length <= 0.41): compile-time zeros, no mapper work and no
 // branch.  PAD: the symbol reaches behind the end of the packet (last symbol of a frame) and fills up with pad symbols.
-static __device__ __noinline__ uint32_t tx_pad_value(uint64_t seed, int64_t frame_id, int dsym, int bit_off, int nbits, int M) {
-    return pad_index(seed, (uint64_t)frame_id, (uint32_t)dsym, (uint32_t)(bit_off / nbits), (uint32_t)M);
+// pad symbol of the carrier at bit offset b of a symbol's bit field; carrier ordinal = b / nbits, nbits in {1, 2, 3, 4, 6,
+// 8}: a shift, then an exact multiply-shift division by 3
+__device__ __forceinline__ uint32_t tx_pad_value(uint64_t base, int b, int nbits, int M) {
+    const int sh = __ffs(nbits) - 1;
+    const unsigned pre = (unsigned)b >> sh;
+    const unsigned c = ((nbits >> sh) == 3) ? (pre * 43691u) >> 17 : pre;
+    return pad_index_from(base, c, (uint32_t)M);
 }
-template <int N, int RLO, int RHI, bool PAD>
+static __device__ __noinline__ uint32_t tx_pad_value_call(uint64_t base, int b, int nbits, int M) { return tx_pad_value(base, b, nbits, M); }
+// PADINL: the pad hash inline (the three-pass kernels: 16 points per thread) or behind a call (the warp kernels: 32
+// points per thread, where 32 inlined copies cost the instruction cache more than the calls: 512-point tx +3 %)
+template <int N, int RLO, int RHI, bool PAD, bool PADINL = false>
 struct TxLoadW {
     const int16_t* s_bo;
     const uint16_t* s_w;
@@ -219,7 +227,10 @@ struct TxLoadW {
         const int b = bo < 0 ? 0 : bo;
         const int rel = rel0 + b;
         uint32_t val = ((uint32_t)s_w[rel >> 3] >> (rel & 7)) & vmask;
-        if (PAD && bo >= 0 && bitbase + b + nbits > pkt_bits) val = tx_pad_value(seed, frame_id, dsym, b, nbits, M);
+        if (PAD && bo >= 0 && bitbase + b + nbits > pkt_bits) {
+            const uint64_t base = pad_base(seed, (uint64_t)frame_id, (uint32_t)dsym);
+            val = PADINL ? tx_pad_value(base, b, nbits, M) : tx_pad_value_call(base, b, nbits, M);
+        }
         const float2 pt = s_cst[val];
         return bo < 0 ? make_float2(0.f, 0.f) : pt;
     }
@@ -336,7 +347,7 @@ __global__ void __launch_bounds__(G * (N / FftPlan<N>::E), (FftPlan<N>::E == 8 ?
                                             pkt_len * 8, p.nbits, m - 1, p.M, frame_id, seed};
                 fft_pass<N, R0, 1, 1>(tid, p.tw, ldw, SmemOut{bufA});
             } else if (data) {
-                TxLoadW<N, 0, 0, true> ldw{s_b2c, (const uint16_t*)my_bytes, s_cst, vmask, bitbase, bitbase - 8 * byte0,
+                TxLoadW<N, 0, 0, true, true> ldw{s_b2c, (const uint16_t*)my_bytes, s_cst, vmask, bitbase, bitbase - 8 * byte0,
                                            pkt_len * 8, p.nbits, m - 1, p.M, frame_id, seed};
                 fft_pass<N, R0, 1, 1>(tid, p.tw, ldw, SmemOut{bufA});
             }
