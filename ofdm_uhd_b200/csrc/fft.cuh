@@ -204,4 +204,12 @@ struct SmemOut {
     float2* p;
     HDM void operator()(int i, float2 v, int) const { p[FFT_PAD(i)] = v; }
 };
-
+// exchange buffer of the warp plans (padding i + i/32: conflict-free 8-byte accesses in both directions)
+struct SmemIn32 {
+    const float2* p;
+    HDM float2 operator()(int i, int) const { return p[FFT_PAD32(i)]; }
+};
+struct SmemOut32 {
+    float2* p;
+    HDM void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; }
+};

@@ -687,14 +687,6 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
 // memory again.  Only the flagged vector of a frame parks its spectrum (the occupied bins +- the coarse search
 // range) in shared memory for the correlation and the LS estimate.  No block barrier anywhere.
 // ---------------------------------------------------------------------------------------------
-struct SmemIn32 {
-    const float2* p;
-    HDM float2 operator()(int i, int) const { return p[FFT_PAD32(i)]; }
-};
-struct SmemOut32 {
-    float2* p;
-    HDM void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; }
-};
 // NARROW: the layout's occupied band +- the coarse search range lies inside the second-pass rows [0, RLO) and
 // [RHI, R) (rows of 32 bins; 4 / 12 of 16 at N = 512, 7 / 25 of 32 at N = 1024: occupied_tones / fft_length <= 0.41):
 // the rows in between are neither equalised nor stored -- at compile time, so the data-vector path has no branch.

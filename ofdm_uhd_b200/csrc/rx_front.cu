@@ -174,14 +174,6 @@ __global__ void __launch_bounds__(G * (NOS / FftPlan<NOS>::E), 512 / (G * (NOS /
 // pass takes its points straight from global memory (stride-1 across the lanes), the last inverse pass stores y the
 // same way; two radix-32 passes each way leave ONE shared-memory exchange per transform (2 per block of V outputs
 // against 5 per block in the 3-pass kernel above) and no block barrier at all.
-struct SmemIn32 {
-    const float2* p;
-    HDM float2 operator()(int i, int) const { return p[FFT_PAD32(i)]; }
-};
-struct SmemOut32 {
-    float2* p;
-    HDM void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; }
-};
 // HR: rows of 32 outputs discarded in front of a block (32 * HR >= ntaps - 1, a compile-time row predicate in the last
 // pass); with 128-byte aligned streams every global row a warp loads or stores is two full lines.
 template <int HR>

@@ -384,14 +384,6 @@ static int launch_tx_n(ofdm_handle* h, const TxParams& p, cudaStream_t st) {
 
 // Warp-plan transmit kernel (N = 512 / 1024): a transform lives on T = N/32 <= 32 lanes of one warp (two symbols per
 // warp at 512), radix-32 first pass, ONE shared-memory exchange, __syncwarp() only.  One warp per CTA.
-struct SmemIn32 {
-    const float2* p;
-    HDM float2 operator()(int i, int) const { return p[FFT_PAD32(i)]; }
-};
-struct SmemOut32 {
-    float2* p;
-    HDM void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; }
-};
 template <int N, bool TAPS, int RLO, int RHI>
 __global__ void __launch_bounds__(32, 16) tx_warp_kernel(const TxParams p) {
     using P = typename FftPlanW<N>::type;

@@ -36,8 +36,8 @@ template <int N, int S> double check() {
 }
 
 // warp plans (FftPlanW: 32 points per thread, radix-32 first pass, padding i + i/32)
-struct In32 { const float2* p; float2 operator()(int i, int) const { return p[FFT_PAD32(i)]; } };
-struct Out32 { float2* p; void operator()(int i, float2 v, int) const { p[FFT_PAD32(i)] = v; } };
+
+
 template <int N, int S> double check_w() {
     using P = typename FftPlanW<N>::type;
     constexpr int T = N / P::E;
@@ -46,8 +46,8 @@ template <int N, int S> double check_w() {
     for (int i = 0; i < N; ++i) x[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
     auto ld = [&](int i, int) { return x[i]; };
     auto st = [&](int i, float2 v, int) { out[i] = v; };
-    for (int t = 0; t < T; ++t) fft_pass<N, P::R[0], 1, S, decltype(ld), Out32, false, P>(t, tw.data(), ld, Out32{A.data()});
-    for (int t = 0; t < T; ++t) fft_pass<N, P::R[1], P::R[0], S, In32, decltype(st), false, P>(t, tw.data(), In32{A.data()}, st);
+    for (int t = 0; t < T; ++t) fft_pass<N, P::R[0], 1, S, decltype(ld), SmemOut32, false, P>(t, tw.data(), ld, SmemOut32{A.data()});
+    for (int t = 0; t < T; ++t) fft_pass<N, P::R[1], P::R[0], S, SmemIn32, decltype(st), false, P>(t, tw.data(), SmemIn32{A.data()}, st);
     double num = 0, den = 0;
     for (int k = 0; k < N; ++k) {
         std::complex<double> acc = 0;
