@@ -327,6 +327,7 @@ class ofdm_demod:
         self._stream_job = None                       # dense pass queued on the device, not yet handed to the callback
         self._stream_sets = ({}, {})                  # its two alternating buffer sets
         self._stream_passes = 0
+        self._pass_streams = None                     # two CUDA streams the dense passes alternate on
         self._dense_rate = None                       # (messages, payload bytes) per sample seen so far: sizes the D2H
         self._last_abs_start = None
         # feed_stream batches small buffers: the receiver runs once this many new samples are pending (a receive pass is
@@ -376,36 +377,12 @@ class ofdm_demod:
         if not self._stream_pending:
             return self._stream_finish(True) if dense else None
         parts = ([self._carry] if self._carry is not None else []) + self._stream_pending
-        buf = parts[0] if len(parts) == 1 else torch.cat(parts)
-        self._stream_pending, self._stream_pending_n = [], 0
         abs0 = self._carry_abs
         L = self._engine.L
         if dense:
-            # dense hand-over, one pass behind: this pass is queued on the device (receiver, packing, device->host
-            # copies sized by what earlier passes brought back) and the PREVIOUS pass, long finished, is handed to the
-            # callback, so the host never waits for the GPU while the source keeps delivering buffers.  The two passes
-            # alternate between two buffer sets, each sized for the largest pass seen and reused.
-            eng = self._engine
-            n = int(buf.numel())
-            job = {"k": self._stream_passes, "abs0": abs0, "buf": buf, "n": n}
-            self._stream_passes += 1
-            slot = self._stream_sets[job["k"] & 1]
-            cap = max(n, slot.get("cap", 0))
-            mf = max_frames if max_frames is not None else max(64, cap // L + 64)
-            if slot.get("bufs") is None or slot["cap"] < cap or slot["mf"] != mf:
-                slot.update(bufs=eng.rx_alloc(cap, max_frames=mf, fresh=True), cap=cap, mf=mf)
-            bufs = eng.demodulate_async(buf, slot["bufs"])
-            em, eb = self._dense_expect(n)
-            job["bufs"] = bufs
-            job["ticket"] = eng.deliver_begin(bufs, expect_msgs=em, expect_bytes=eb, frame_starts=True)
-            keep = min(self.stream_carry_samples(), n)
-            self._carry = buf[n - keep:].clone()
-            self._carry_abs = abs0 + n - keep
-            r = self._stream_finish(False)                       # the pass before this one
-            self._stream_job = job
-            if flush:
-                r = self._stream_finish(True)
-            return r if r is not None else {"stream_delivered": 0, "n_msgs": 0, "pending_pass": job["k"]}
+            return self._stream_pass_dense(parts, abs0, max_frames, flush)
+        buf = parts[0] if len(parts) == 1 else torch.cat(parts)
+        self._stream_pending, self._stream_pending_n = [], 0
         res = self.feed(buf, max_frames=max_frames, _deliver=False)
         # a frame still open at the end of the buffer (the sink ran out of vectors) is left to the next call
         delivered = []
@@ -422,6 +399,49 @@ class ofdm_demod:
         self._carry_abs = abs0 + buf.numel() - keep
         res.stream_delivered = delivered
         return res
+
+    def _stream_pass_dense(self, parts, abs0, max_frames, flush):
+        """One pass of feed_stream with the dense hand-over, one pass behind: this pass is queued on the device
+        (receiver, packing, device->host copies sized by what earlier passes brought back) and the PREVIOUS pass, long
+        finished, is handed to the callback, so the host never waits for the GPU while the source keeps delivering
+        buffers.  Consecutive passes alternate between two buffer sets AND two CUDA streams: a pass depends on its
+        predecessor only through the carried sample tail (copied out on the caller's stream before the receiver
+        starts), so the launch-bound end of pass k (trigger compaction, plan, liveness, CRC, packing, copies) runs
+        under the stream kernels of pass k + 1."""
+        eng = self._engine
+        torch = eng.torch
+        k = self._stream_passes
+        self._stream_passes += 1
+        if self._pass_streams is None:
+            self._pass_streams = (torch.cuda.Stream(device=eng.dev), torch.cuda.Stream(device=eng.dev))
+        ps = self._pass_streams[k & 1]
+        # [carried tail | queued buffers] and the next tail are put together on the CALLER's stream (where the buffers
+        # were produced, and where the next pass will look for the tail); the pass stream picks the batch up from there
+        buf = parts[0] if len(parts) == 1 else torch.cat(parts)
+        self._stream_pending, self._stream_pending_n = [], 0
+        n = int(buf.numel())
+        keep = min(self.stream_carry_samples(), n)
+        self._carry = buf[n - keep:].clone()
+        self._carry_abs = abs0 + n - keep
+        ps.wait_stream(torch.cuda.current_stream(eng.dev))
+        buf.record_stream(ps)
+        with torch.cuda.stream(ps):
+            job = {"k": k, "abs0": abs0, "buf": buf, "n": n}
+            slot = self._stream_sets[k & 1]
+            cap = max(n, slot.get("cap", 0))
+            L = eng.L
+            mf = max_frames if max_frames is not None else max(64, cap // L + 64)
+            if slot.get("bufs") is None or slot["cap"] < cap or slot["mf"] != mf:
+                slot.update(bufs=eng.rx_alloc(cap, max_frames=mf, fresh=True), cap=cap, mf=mf)
+            bufs = eng.demodulate_async(buf, slot["bufs"])
+            em, eb = self._dense_expect(n)
+            job["bufs"] = bufs
+            job["ticket"] = eng.deliver_begin(bufs, expect_msgs=em, expect_bytes=eb, frame_starts=True)
+        r = self._stream_finish(False)                           # the pass before this one
+        self._stream_job = job
+        if flush:
+            r = self._stream_finish(True)
+        return r if r is not None else {"stream_delivered": 0, "n_msgs": 0, "pending_pass": job["k"]}
 
     def _dense_expect(self, n):
         """Sizes of the dense hand-over's device->host copies for a pass over n samples: what earlier passes brought
