@@ -662,13 +662,14 @@ def packet_surface(torch, eng_unused, args, device):
             got3 = [0]
             rx3.ofdm_rx.stream_batch_samples = 1 << 25
             rx3.set_batch_callback(lambda oks, blob, off: got3.__setitem__(0, got3[0] + int(np.count_nonzero(oks))))
+            chunks = [cap[a:a + buf] for a in range(0, cap.numel(), buf)]     # the source's buffers, ready made
             for timed in (False, True):
                 got3[0] = 0
                 rx3.ofdm_rx.reset_stream()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                for a in range(0, cap.numel(), buf):
-                    rx3.feed_stream(cap[a:a + buf])
+                for c in chunks:
+                    rx3.feed_stream(c)
                 rx3.flush_stream()
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
@@ -676,8 +677,9 @@ def packet_surface(torch, eng_unused, args, device):
         out["feed_stream"] = {"samples": int(cap.numel()), "whole_stream_feed": {"seconds": dt_whole, "Msamples_per_s": cap.numel() / dt_whole / 1e6, "ok": whole_ok},
                               "batched": res, "stream_batch_samples": 1 << 25,
                               "what": "ofdm_demod.feed_stream on consecutive buffers of one capture (queued on the device, one receiver pass per "
-                                      "stream_batch_samples new samples + the carried tail) vs one feed() of the whole capture; host-side "
-                                      "packet assembly included"}
+                                      "stream_batch_samples new samples + the carried tail, passes alternating between two CUDA streams) vs one "
+                                      "feed() of the whole capture; the buffers are handed over ready made (device tensors), host-side packet "
+                                      "assembly included"}
     except Exception as e:
         out["feed_stream"] = {"error": repr(e)}
     return out

@@ -35,9 +35,12 @@ rx3.ofdm_rx.stream_batch_samples = batch
 rx3.set_batch_callback(lambda oks, blob, off: got.__setitem__(0, got[0] + int(np.count_nonzero(oks))))
 
 
+chunks = [cap[a:a + buf] for a in range(0, cap.numel(), buf)]      # the source's buffers, ready made
+
+
 def run():
-    for a in range(0, cap.numel(), buf):
-        rx3.feed_stream(cap[a:a + buf])
+    for c in chunks:
+        rx3.feed_stream(c)
     rx3.flush_stream()
     torch.cuda.synchronize()
 
