@@ -485,6 +485,7 @@ class ofdm_demod:
         """Forget the continuous stream seen so far (a new capture starts): anything still queued is dropped."""
         self._carry, self._carry_abs, self._last_abs_start = None, 0, None
         self._stream_pending, self._stream_pending_n, self._stream_job = [], 0, None
+        self._stream_passes = 0                       # the next capture starts on the first buffer set again
 
     def flush_stream(self, max_frames=None):
         """Run the receiver on whatever feed_stream() has queued."""
