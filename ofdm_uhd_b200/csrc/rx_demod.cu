@@ -816,8 +816,9 @@ __global__ void __launch_bounds__(32, 16) acq_warp_kernel(const AcqParams p) {
 #pragma unroll
                 for (int r = 0; r < 32; ++r) raw[r] = LDG(src + r * T);
                 const float2 ph0 = phasor_f64(ph_base);
+                // (plain packed multiply: what follows is a float32 FFT, the last-bit rounding order of its inputs is moot)
                 auto ld = [&](int, int slot) -> float2 {
-                    const float2 d = cmul_x(raw[slot], cmul(ph0, Wt[slot]));
+                    const float2 d = cmul(raw[slot], cmul(ph0, Wt[slot]));
                     return (slot == 31 && have31) ? v31 : d;
                 };
                 fft_pass<N, P::R[0], 1, -1, decltype(ld), SmemOut32, false, P>(tid, p.tw, ld, SmemOut32{buf});
