@@ -9,7 +9,8 @@
 
 // The receive back end is two kernels:
 //   acq_kernel<N>   multiply_cc (NCO derotation) + fft_vcc (forward, shifted) + ofdm_frame_acquisition for every vector
-//                   the sampler emits, one CTA per frame: the equalised occ-wide vectors land in the workspace (they are
+//   / acq_warp_kernel<N>  the sampler emits, one CTA per frame (acq_warp_kernel, N = 512 / 1024 without taps: half a warp
+//                   / a warp per frame on the warp plans): the equalised occ-wide vectors land in the workspace (they are
 //                   a function of the vector stream alone: the acquisition block re-estimates at EVERY flagged vector,
 //                   whatever state the sink is in);
 //   sink_kernel     ofdm_frame_sink, one WARP per speculative session (one per frame): walks the equalised vectors from
@@ -684,8 +685,9 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
 // samples go from global memory straight into the radix-32 first pass (32 independent loads per lane; the next
 // vector's lines are pulled into L2 meanwhile), ONE shared-memory exchange, and for data vectors the second pass
 // hands its bins to the one-tap equaliser in registers -- they are stored to the workspace without touching shared
-// memory again.  Only the flagged vector of a frame parks its spectrum (the occupied bins +- the coarse search
-// range) in shared memory for the correlation and the LS estimate.  No block barrier anywhere.
+// memory again.  Only the flagged vector of a frame parks its (shifted) spectrum in shared memory for the correlation
+// and the LS estimate -- in the exchange buffer itself (fft_pass WPRE), so a warp needs 12.2 KB and 16 warps fit an SM.
+// No block barrier anywhere.
 // ---------------------------------------------------------------------------------------------
 // NARROW: the layout's occupied band +- the coarse search range lies inside the second-pass rows [0, RLO) and
 // [RHI, R) (rows of 32 bins; 4 / 12 of 16 at N = 512, 7 / 25 of 32 at N = 1024: occupied_tones / fft_length <= 0.41):
