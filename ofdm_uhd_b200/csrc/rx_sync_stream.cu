@@ -89,7 +89,8 @@ struct StepHist {
     double bwd[3];                                   // sum of the products of the later lanes
 };
 
-constexpr int MC_STEPS = 32;
+constexpr int MC_STEPS = 32;       // blocks per chunk (+1 priming block) of a short capture; long ones take MC_STEPS_LONG
+constexpr int MC_STEPS_LONG = 64;
 
 template <int K>
 struct MetricCtx {
@@ -296,7 +297,7 @@ struct MetricCtx {
 
 template <int K>
 __global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __restrict__ y, float* __restrict__ mt, const int64_t n_single,
-                                                               const int64_t* __restrict__ soff) {
+                                                               const int64_t* __restrict__ soff, const int mc_steps) {
     constexpr int SZ = 32 * K;
     static_assert(K % 4 == 0 || K == 2, "K");
     int64_t s_a, n;
@@ -312,9 +313,9 @@ __global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __re
         c.mu[k] = (c.lane >= (1 << k)) ? 1.0 : 0.0;
         c.md[k] = (c.lane + (1 << k) < 32) ? 1.0 : 0.0;
     }
-    const int64_t i_begin = (int64_t)blockIdx.x * MC_STEPS * SZ;
+    const int64_t i_begin = (int64_t)blockIdx.x * mc_steps * SZ;
     if (i_begin >= n) return;
-    const int64_t i_end = (i_begin + (int64_t)MC_STEPS * SZ < n) ? i_begin + (int64_t)MC_STEPS * SZ : n;
+    const int64_t i_end = (i_begin + (int64_t)mc_steps * SZ < n) ? i_begin + (int64_t)mc_steps * SZ : n;
     StepHist<K> A, B;
     if (i_begin == 0) {                              // zero history in front of the stream
 #pragma unroll
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __re
 template <int K, int MW>
 __global__ void __launch_bounds__(32 * MW, (10 / MW) > 0 ? (10 / MW) : 1) metric_multi_kernel(const float2* __restrict__ y, float* __restrict__ mt,
                                                                                              const int64_t n_single,
-                                                                                             const int64_t* __restrict__ soff) {
+                                                                                             const int64_t* __restrict__ soff, const int mc_steps) {
     constexpr int SZ = 32 * K;
     constexpr int64_t W = (int64_t)MW * SZ;
     __shared__ double s_tot[3][3][MW];
@@ -365,9 +366,9 @@ __global__ void __launch_bounds__(32 * MW, (10 / MW) > 0 ? (10 / MW) : 1) metric
         c.mu[k] = (c.lane >= (1 << k)) ? 1.0 : 0.0;
         c.md[k] = (c.lane + (1 << k) < 32) ? 1.0 : 0.0;
     }
-    const int64_t b_begin = (int64_t)blockIdx.x * MC_STEPS * W;          // first sample of the chunk
+    const int64_t b_begin = (int64_t)blockIdx.x * mc_steps * W;          // first sample of the chunk
     if (b_begin >= n) return;
-    const int64_t b_end = (b_begin + (int64_t)MC_STEPS * W < n) ? b_begin + (int64_t)MC_STEPS * W : n;
+    const int64_t b_end = (b_begin + (int64_t)mc_steps * W < n) ? b_begin + (int64_t)mc_steps * W : n;
     const int64_t off = (int64_t)w * SZ;                                  // this warp's quarter
     StepHist<K> A, B;
     if (b_begin == 0) {                              // zero history in front of the stream
@@ -624,20 +625,24 @@ __global__ void stream_init_kernel(int64_t* first_nan, int S) {
 }
 
 template <int K>
-static int launch_split_k(const StreamParams& p, float* mt, int m, int S, int parts, cudaStream_t st) {
+static int launch_split_k(const StreamParams& p, float* mt, int m, int S, int parts, int sms, cudaStream_t st) {
     constexpr int SZ = 32 * K;
     if (!(parts & 1)) {
-    } else if (m == 1) {
-        const int64_t chunks = (p.n + (int64_t)MC_STEPS * SZ - 1) / ((int64_t)MC_STEPS * SZ);
-        metric_chunk_kernel<K><<<dim3((unsigned)chunks, S), 32, 0, st>>>(p.y, mt, p.n, p.soff);
-    } else if constexpr (K == 8) {
+    } else {
+        // chunk length: a chunk re-runs one priming block, so long captures take 64-block chunks (1.5 % extra work instead
+        // of 3 %) as long as that still leaves eight waves of chunks; short ones keep 32 blocks and fill the GPU sooner
         const int64_t W = (int64_t)m * SZ;
-        const int64_t chunks = (p.n + W * MC_STEPS - 1) / (W * MC_STEPS);
+        int steps = MC_STEPS_LONG;
+        if ((p.n + W * steps - 1) / (W * steps) * S < (int64_t)sms * 12 * 8) steps = MC_STEPS;
+        const int64_t chunks = (p.n + W * steps - 1) / (W * steps);
         const dim3 g((unsigned)chunks, S);
-        if (m == 2) metric_multi_kernel<8, 2><<<g, 64, 0, st>>>(p.y, mt, p.n, p.soff);
-        else if (m == 4) metric_multi_kernel<8, 4><<<g, 128, 0, st>>>(p.y, mt, p.n, p.soff);
-        else if (m == 8) metric_multi_kernel<8, 8><<<g, 256, 0, st>>>(p.y, mt, p.n, p.soff);
-        else { ofdm_set_error("sync: no metric kernel for N/2 = %d x 256", m); return OFDM_E_INVAL; }
+        if (m == 1) metric_chunk_kernel<K><<<g, 32, 0, st>>>(p.y, mt, p.n, p.soff, steps);
+        else if constexpr (K == 8) {
+            if (m == 2) metric_multi_kernel<8, 2><<<g, 64, 0, st>>>(p.y, mt, p.n, p.soff, steps);
+            else if (m == 4) metric_multi_kernel<8, 4><<<g, 128, 0, st>>>(p.y, mt, p.n, p.soff, steps);
+            else if (m == 8) metric_multi_kernel<8, 8><<<g, 256, 0, st>>>(p.y, mt, p.n, p.soff, steps);
+            else { ofdm_set_error("sync: no metric kernel for N/2 = %d x 256", m); return OFDM_E_INVAL; }
+        }
     }
     OFDM_LAUNCH_CHECK();
     if (!(parts & 2)) return OFDM_OK;
@@ -667,8 +672,8 @@ int launch_sync_stream(ofdm_handle* h, const float2* y, const StreamSet& ss, ofd
         OFDM_LAUNCH_CHECK();
     }
     switch (K) {
-        case 2: return launch_split_k<2>(p, ws->mf, 1, ss.S, parts, st);
-        case 4: return launch_split_k<4>(p, ws->mf, 1, ss.S, parts, st);
-        default: return launch_split_k<8>(p, ws->mf, m, ss.S, parts, st);
+        case 2: return launch_split_k<2>(p, ws->mf, 1, ss.S, parts, h->sms, st);
+        case 4: return launch_split_k<4>(p, ws->mf, 1, ss.S, parts, h->sms, st);
+        default: return launch_split_k<8>(p, ws->mf, m, ss.S, parts, h->sms, st);
     }
 }
