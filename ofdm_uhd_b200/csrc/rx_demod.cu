@@ -903,7 +903,7 @@ __global__ void __launch_bounds__(32, 16) acq_warp_kernel(const AcqParams p) {
                     const int i = ((idx + N / 2) & (N - 1)) - lo;
                     const bool ok = (unsigned)i < (unsigned)occ;
                     const float2 Hi = H[ok ? i : 0];
-                    const float2 o = cmul_x(cmul_x(Hi, cc), val);
+                    const float2 o = cmul(cmul(Hi, cc), val);   // (val is a float32 FFT output: last-bit rounding order is moot)
                     if (ok) dst[i] = o;
                 };
                 if (act) fft_pass<N, R1, P::R[0], -1, SmemIn32, decltype(equalise), false, P>(tid, p.tw, SmemIn32{buf}, equalise);
