@@ -467,7 +467,9 @@ __global__ void __launch_bounds__((N / FftPlan<N>::E) < 64 ? 64 : (N / FftPlan<N
 // usual layouts -- the per-vector serial section (float64 atan2 + sincos of the PLL, header check, leftover bits) is
 // issued once per warp, so sub-warp sessions share it -- or 128 (the whole CTA works on one session, block barriers
 // instead of warp barriers) when a vector has thousands of data carriers.
-template <bool TAPS, int TPS>
+// MC: the constellation size when it is 2 or 4 and known at compile time (the brute-force slicer's scan unrolls: no loop
+// counter, compare and branch per point), 0 = p.M at run time.
+template <bool TAPS, int TPS, int MC = 0>
 __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
     extern __shared__ __align__(16) unsigned char sink_smem[];
     __shared__ double s_red[2][4][2];
@@ -537,7 +539,8 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
                         } else {
                             ba = 0;
                             float besta = norm_x(csub_x(ra, s_cst[0]));
-                            for (int k = 1; k < p.M; ++k) {
+#pragma unroll
+                            for (int k = 1; k < (MC ? MC : p.M); ++k) {
                                 const float dda = norm_x(csub_x(ra, s_cst[k]));
                                 if (dda < besta) { besta = dda; ba = k; }
                             }
@@ -574,7 +577,8 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
                     ba = 0; bb = 0;
                     const float2 c0 = s_cst[0];
                     float besta = norm_x(csub_x(ra, c0)), bestb = norm_x(csub_x(rb, c0));
-                    for (int k = 1; k < p.M; ++k) {
+#pragma unroll
+                    for (int k = 1; k < (MC ? MC : p.M); ++k) {
                         const float2 ck = s_cst[k];
                         const float dda = norm_x(csub_x(ra, ck));
                         const float ddb = norm_x(csub_x(rb, ck));
@@ -1019,15 +1023,19 @@ int launch_demod(ofdm_handle* h, const float2* y, const StreamSet& ss, ofdm_rx_i
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     const dim3 g(grid, ss.S);
-#define OFDM_SINK_LAUNCH(TAPS_, TPS_)                                                       \
+#define OFDM_SINK_LAUNCH_M(TAPS_, TPS_, MC_)                                                \
     do {                                                                                    \
-        OFDM_SET_MAX_SMEM((sink_kernel<TAPS_, TPS_>), smem, h->device);                     \
-        sink_kernel<TAPS_, TPS_><<<g, (TPS_) <= 32 ? (TPS_) * W : 128, smem, st>>>(p);      \
+        OFDM_SET_MAX_SMEM((sink_kernel<TAPS_, TPS_, MC_>), smem, h->device);                \
+        sink_kernel<TAPS_, TPS_, MC_><<<g, (TPS_) <= 32 ? (TPS_) * W : 128, smem, st>>>(p); \
     } while (0)
+#define OFDM_SINK_LAUNCH(TAPS_, TPS_) OFDM_SINK_LAUNCH_M(TAPS_, TPS_, 0)
     if (wide) { if (staps) OFDM_SINK_LAUNCH(true, 128); else OFDM_SINK_LAUNCH(false, 128); }
+    else if (tps == 16 && !staps && h->M == 4) OFDM_SINK_LAUNCH_M(false, 16, 4);          // qpsk, the bench layout
+    else if (tps == 16 && !staps && h->M == 2) OFDM_SINK_LAUNCH_M(false, 16, 2);
     else if (tps == 16) { if (staps) OFDM_SINK_LAUNCH(true, 16); else OFDM_SINK_LAUNCH(false, 16); }
     else { if (staps) OFDM_SINK_LAUNCH(true, 32); else OFDM_SINK_LAUNCH(false, 32); }
 #undef OFDM_SINK_LAUNCH
+#undef OFDM_SINK_LAUNCH_M
     OFDM_LAUNCH_CHECK();
     return OFDM_OK;
 }
