@@ -143,18 +143,22 @@ struct BitDiv {
     }
 };
 
+// NB: bits per symbol when known at compile time (1 or 2: the per-byte loop unrolls), 0 = bd.nbits at run time
+template <int NB = 0>
 __device__ __forceinline__ void pack_bytes(const uint8_t* sym, uint8_t* vb, int B0, int B1, int bit_base, unsigned carry,
                                            int tid, int nthreads, const BitDiv bd) {
-    if (!bd.by3) {
+    if (NB > 0 || !bd.by3) {
         // nbits divides 8 (bpsk, qpsk, qam16, qam256): a symbol never straddles a byte, and bit_base is a multiple of
         // nbits, so a byte is 8/nbits whole symbols (or the previous vector's leftover bits in their place)
-        const int nb = bd.nbits;
+        const int nb = NB > 0 ? NB : bd.nbits;
+        const int lsh = NB > 0 ? NB - 1 : bd.sh;                   // log2(nb)
         const unsigned smask = (1u << nb) - 1u;
         for (int q = B0 + tid; q < B1; q += nthreads) {
             unsigned byte = 0;
             int rel = 8 * q - bit_base;
+#pragma unroll
             for (int sh = 0; sh < 8; sh += nb, rel += nb) {
-                const unsigned v = (rel < 0) ? ((carry >> sh) & smask) : (unsigned)sym[rel >> bd.sh];
+                const unsigned v = (rel < 0) ? ((carry >> sh) & smask) : (unsigned)sym[rel >> lsh];
                 byte |= v << sh;
             }
             vb[q - B0] = (uint8_t)byte;
@@ -638,7 +642,7 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
             sync();
             // LSB-first byte packing; bits left over from the previous vector sit in carry
             const int B0 = bit_base >> 3, B1 = (bit_base + bits_this) >> 3;
-            pack_bytes(sym, vb, B0, B1, bit_base, carry, lane, TPS, bd);
+            pack_bytes<(MC == 4 ? 2 : (MC == 2 ? 1 : 0))>(sym, vb, B0, B1, bit_base, carry, lane, TPS, bd);
             sync();
             if (vi == 1) {
                 const unsigned hdr = ((unsigned)vb[0] << 24) | ((unsigned)vb[1] << 16) | ((unsigned)vb[2] << 8) | vb[3];
