@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
                         const float2 eqa = LDG(e + LDG(p.sinkmap + c));
                         const float2 ra = cmul_x(cmul_x(eqa, car), d0a);
                         int ba;
-                        if (p.grid_L > 0) {
+                        if (MC == 0 && p.grid_L > 0) {
                             ba = slicer(ra);
                         } else {
                             ba = 0;
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(128) sink_kernel(const SinkParams p) {
                 const float2 eqa = LDG(e + ia), eqb = LDG(e + ib);
                 const float2 ra = cmul_x(cmul_x(eqa, car), d0a), rb = cmul_x(cmul_x(eqb, car), d0b);
                 int ba, bb;
-                if (p.grid_L > 0) {
+                if (MC == 0 && p.grid_L > 0) {
                     ba = slicer(ra);
                     bb = slicer(rb);
                 } else {
