@@ -8,7 +8,8 @@
 // consecutive samples per lane, where 32*K = N/2: a step is exactly one van Herk block, so
 //   * y[n - N/2] is the same lane's sample of the previous step (kept in registers, never re-read),
 //   * a window sum = [same lane's later elements + later lanes of the previous step] + [earlier lanes + own
-//     elements of this step]: two warp scans per sum, no shared memory, no subtraction,
+//     elements of this step]: both exclusive lane scans of a sum from one recursive-doubling pass (bfly_scan: five
+//     exchanges), no shared memory, no subtraction,
 //   * the cp-wide average of the metric is a float64 prefix difference through a per-warp ring in shared memory,
 //   * the detector (IIR average scan, threshold ballot, run / arg-max state machine) consumes the K metric values
 //     straight from registers.
@@ -25,6 +26,8 @@
 #include "internal.h"
 #include "common.cuh"
 #include <limits.h>
+#include <stdlib.h>
+#include <string.h>
 
 struct StreamParams {
     const float2* y;
@@ -41,8 +44,9 @@ struct StreamParams {
     uint32_t* status;
 };
 
-// Warp scans of doubles.  A conditional add after a shuffle compiles to DADD + two FSEL; multiplying the shuffled
-// value by a per-lane 1.0 / 0.0 mask inside one DFMA is exact (x*1 = x, x*0 = 0 for finite x) and a single instruction.
+// Warp scans of doubles.  The Kogge-Stone pair (OFDM_METRIC_SCAN=ks, what the round measured before bfly_scan; the
+// detector's scans too): a conditional add after a shuffle compiles to DADD + two FSEL; multiplying the shuffled value by
+// a per-lane 1.0 / 0.0 mask inside one DFMA is exact (x*1 = x, x*0 = 0 for finite x) and a single instruction.
 __device__ __forceinline__ double shfl_up_d(double x, int d) {
     return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(x), d),
                             __shfl_up_sync(0xffffffffu, __double2loint(x), d));
@@ -50,6 +54,31 @@ __device__ __forceinline__ double shfl_up_d(double x, int d) {
 __device__ __forceinline__ double shfl_down_d(double x, int d) {
     return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(x), d),
                             __shfl_down_sync(0xffffffffu, __double2loint(x), d));
+}
+__device__ __forceinline__ double shfl_xor_d(double x, int d) {
+    return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(x), d),
+                            __shfl_xor_sync(0xffffffffu, __double2loint(x), d));
+}
+// Both exclusive lane scans of one double per lane by recursive doubling: after level k every lane holds the total of
+// its 2^(k+1)-lane group, and the partner group's total (ONE exchange) belongs to the lanes in front of this lane if the
+// lane sits in the upper half of the group, to the lanes behind it otherwise.  Five exchanges serve both directions and
+// leave them exclusive -- the Kogge-Stone pair takes ten and two more to shift.  The routing is an integer AND on the two
+// halves of the exchanged double (x + 0.0 is exact, and a NaN / Inf behind a lane never reaches the sum of the lanes in
+// front of it, which a multiply by a 0.0 mask would let through); the ANDs run on the ALU pipe, which these kernels leave
+// idle.  Additions only (an all-zero group sums to exactly 0); `tot` is the same bit pattern on every lane (IEEE
+// addition commutes).
+__device__ __forceinline__ void bfly_scan(const double run, const int lane, double& fwd, double& bwd, double& tot) {
+    double s = run, f = 0.0, b = 0.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int hi = __shfl_xor_sync(0xffffffffu, __double2hiint(s), 1 << k);
+        const int lo = __shfl_xor_sync(0xffffffffu, __double2loint(s), 1 << k);
+        const int up = -((lane >> k) & 1);                 // all ones: the partner group is in front of this lane
+        f += __hiloint2double(hi & up, lo & up);
+        b += __hiloint2double(hi & ~up, lo & ~up);
+        s += __hiloint2double(hi, lo);
+    }
+    fwd = f; bwd = b; tot = s;
 }
 
 // 256-bit global accesses (sm_100): a lane owns K consecutive samples, i.e. lanes sit 8K bytes apart, and the L1 data
@@ -92,7 +121,7 @@ struct StepHist {
 constexpr int MC_STEPS = 32;       // blocks per chunk (+1 priming block) of a short capture; long ones take MC_STEPS_LONG
 constexpr int MC_STEPS_LONG = 64;
 
-template <int K>
+template <int K, bool BF = false>          // BF: bfly_scan instead of the Kogge-Stone scan pair
 struct MetricCtx {
     static constexpr int SZ = 32 * K;
     const float2* y;
@@ -142,10 +171,15 @@ struct MetricCtx {
             double run = 0.0;
 #pragma unroll
             for (int i = 0; i < K; ++i) run += (double)cur.x[a][i];
-            double bi = run;
+            if constexpr (BF) {
+                double fwd, tot;
+                bfly_scan(run, lane, fwd, cur.bwd[a], tot);
+            } else {
+                double bi = run;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
-            cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
+                for (int k = 0; k < 5; ++k) bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
+                cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
+            }
         }
     }
     __device__ __forceinline__ void step(StepHist<K>& prev, StepHist<K>& cur, const int64_t i0, const bool more) {
@@ -172,14 +206,20 @@ struct MetricCtx {
 #pragma unroll
                 for (int i = K - 2; i >= 0; --i) { sfx += (double)prev.x[a][i + 1]; tail[i] = sfx; }
             }
-            double fi = run, bi = run;                           // inclusive scans: earlier lanes, later lanes
+            double fwd;
+            if constexpr (BF) {
+                double tot;
+                bfly_scan(run, lane, fwd, cur.bwd[a], tot);
+            } else {
+                double fi = run, bi = run;                       // inclusive scans: earlier lanes, later lanes
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                fi = fma(shfl_up_d(fi, 1 << k), mu[k], fi);
-                bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
+                for (int k = 0; k < 5; ++k) {
+                    fi = fma(shfl_up_d(fi, 1 << k), mu[k], fi);
+                    bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
+                }
+                fwd = shfl_up_d(fi, 1) * mu[0];
+                cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
             }
-            const double fwd = shfl_up_d(fi, 1) * mu[0];
-            cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
 #pragma unroll
             for (int i = 0; i < K; ++i) PR[a][i] = (float)(tail[i] + (pre[i] + fwd));
         }
@@ -219,10 +259,16 @@ struct MetricCtx {
             double run = 0.0;
 #pragma unroll
             for (int i = 0; i < K; ++i) run += (double)cur.x[a][i];
-            double bi = run;
+            double bi;                                       // the warp's total
+            if constexpr (BF) {
+                double fwd;
+                bfly_scan(run, lane, fwd, cur.bwd[a], bi);
+            } else {
+                bi = run;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
-            cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
+                for (int k = 0; k < 5; ++k) bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
+                cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
+            }
             if (lane == 0) s_tot[slot][a][w] = bi;           // lane 0's inclusive backward scan = the warp's total
         }
     }
@@ -253,14 +299,20 @@ struct MetricCtx {
 #pragma unroll
                 for (int i = K - 2; i >= 0; --i) { sfx += (double)prev.x[a][i + 1]; tail[i] = sfx; }
             }
-            double fi = run, bi = run;
+            double fwd, bi;
+            if constexpr (BF) {
+                bfly_scan(run, lane, fwd, cur.bwd[a], bi);
+            } else {
+                double fi = run;
+                bi = run;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                fi = fma(shfl_up_d(fi, 1 << k), mu[k], fi);
-                bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
+                for (int k = 0; k < 5; ++k) {
+                    fi = fma(shfl_up_d(fi, 1 << k), mu[k], fi);
+                    bi = fma(shfl_down_d(bi, 1 << k), md[k], bi);
+                }
+                fwd = shfl_up_d(fi, 1) * mu[0];
+                cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
             }
-            const double fwd = shfl_up_d(fi, 1) * mu[0];
-            cur.bwd[a] = shfl_down_d(bi, 1) * md[0];
             if (lane == 0) s_tot[slot][a][w] = bi;
             __syncthreads();
             double head = 0.0, tl = 0.0;
@@ -295,7 +347,7 @@ struct MetricCtx {
     }
 };
 
-template <int K>
+template <int K, bool BF>
 __global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __restrict__ y, float* __restrict__ mt, const int64_t n_single,
                                                                const int64_t* __restrict__ soff, const int mc_steps) {
     constexpr int SZ = 32 * K;
@@ -304,7 +356,7 @@ __global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __re
     stream_span(soff, blockIdx.y, n_single, s_a, n);        // zero history in front of every stream
     y += s_a;
     mt += s_a;
-    MetricCtx<K> c;
+    MetricCtx<K, BF> c;
     c.y = y; c.mt = mt; c.n = n; c.lane = threadIdx.x;
     c.vec_ok = (((uintptr_t)y) & 31) == 0;
     c.st_ok = (((uintptr_t)mt) & 31) == 0 && (K % 4) == 0;
@@ -345,7 +397,7 @@ __global__ void __launch_bounds__(32, 12) metric_chunk_kernel(const float2* __re
 // one-warp kernel -- the stream is read once.  (Round 1 ran these layouts with one warp per 256-sample sub-step and the
 // previous block's products recomputed from y[n-W] and y[n-2W]: three stream reads per sample.)
 // ---------------------------------------------------------------------------------------------
-template <int K, int MW>
+template <int K, int MW, bool BF>
 __global__ void __launch_bounds__(32 * MW, (10 / MW) > 0 ? (10 / MW) : 1) metric_multi_kernel(const float2* __restrict__ y, float* __restrict__ mt,
                                                                                              const int64_t n_single,
                                                                                              const int64_t* __restrict__ soff, const int mc_steps) {
@@ -356,7 +408,7 @@ __global__ void __launch_bounds__(32 * MW, (10 / MW) > 0 ? (10 / MW) : 1) metric
     stream_span(soff, blockIdx.y, n_single, s_a, n);
     y += s_a;
     mt += s_a;
-    MetricCtx<K> c;
+    MetricCtx<K, BF> c;
     c.y = y; c.mt = mt; c.n = n; c.lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
     c.vec_ok = (((uintptr_t)y) & 31) == 0;
@@ -624,6 +676,16 @@ __global__ void stream_init_kernel(int64_t* first_nan, int S) {
     if (s < S) first_nan[s] = LLONG_MAX;
 }
 
+template <int K, bool BF>
+static void launch_metric(const dim3 g, const int m, const StreamParams& p, float* mt, const int steps, cudaStream_t st) {
+    if (m == 1) metric_chunk_kernel<K, BF><<<g, 32, 0, st>>>(p.y, mt, p.n, p.soff, steps);
+    else if constexpr (K == 8) {
+        if (m == 2) metric_multi_kernel<8, 2, BF><<<g, 64, 0, st>>>(p.y, mt, p.n, p.soff, steps);
+        else if (m == 4) metric_multi_kernel<8, 4, BF><<<g, 128, 0, st>>>(p.y, mt, p.n, p.soff, steps);
+        else metric_multi_kernel<8, 8, BF><<<g, 256, 0, st>>>(p.y, mt, p.n, p.soff, steps);
+    }
+}
+
 template <int K>
 static int launch_split_k(const StreamParams& p, float* mt, int m, int S, int parts, int sms, cudaStream_t st) {
     constexpr int SZ = 32 * K;
@@ -636,13 +698,14 @@ static int launch_split_k(const StreamParams& p, float* mt, int m, int S, int pa
         if ((p.n + W * steps - 1) / (W * steps) * S < (int64_t)sms * 12 * 8) steps = MC_STEPS;
         const int64_t chunks = (p.n + W * steps - 1) / (W * steps);
         const dim3 g((unsigned)chunks, S);
-        if (m == 1) metric_chunk_kernel<K><<<g, 32, 0, st>>>(p.y, mt, p.n, p.soff, steps);
-        else if constexpr (K == 8) {
-            if (m == 2) metric_multi_kernel<8, 2><<<g, 64, 0, st>>>(p.y, mt, p.n, p.soff, steps);
-            else if (m == 4) metric_multi_kernel<8, 4><<<g, 128, 0, st>>>(p.y, mt, p.n, p.soff, steps);
-            else if (m == 8) metric_multi_kernel<8, 8><<<g, 256, 0, st>>>(p.y, mt, p.n, p.soff, steps);
-            else { ofdm_set_error("sync: no metric kernel for N/2 = %d x 256", m); return OFDM_E_INVAL; }
+        // A/B switch for measurements (read once): OFDM_METRIC_SCAN=ks selects the Kogge-Stone scan pair
+        static const bool ks = [] { const char* e = getenv("OFDM_METRIC_SCAN"); return e && !strcmp(e, "ks"); }();
+        if ((m != 1 && K != 8) || !(m == 1 || m == 2 || m == 4 || m == 8)) {
+            ofdm_set_error("sync: no metric kernel for N/2 = %d x %d", m, SZ);
+            return OFDM_E_INVAL;
         }
+        if (ks) launch_metric<K, false>(g, m, p, mt, steps, st);
+        else launch_metric<K, true>(g, m, p, mt, steps, st);
     }
     OFDM_LAUNCH_CHECK();
     if (!(parts & 2)) return OFDM_OK;
