@@ -223,13 +223,13 @@ struct MetricCtx {
 #pragma unroll
             for (int i = 0; i < K; ++i) PR[a][i] = (float)(tail[i] + (pre[i] + fwd));
         }
-        float q[K];
+        float q[K], num[K], den[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            const float num = fadd_rn(fmul_rn(PR[0][i], PR[0][i]), fmul_rn(PR[1][i], PR[1][i]));
-            const float den = fmul_rn(PR[2][i], PR[2][i]);
-            q[i] = fdiv_rn(num, den);
+            num[i] = fadd_rn(fmul_rn(PR[0][i], PR[0][i]), fmul_rn(PR[1][i], PR[1][i]));
+            den[i] = fmul_rn(PR[2][i], PR[2][i]);
         }
+        fdiv_block<K>(num, den, q);                              // all lanes of the warp are here (CTA-uniform loops)
         const int64_t b0 = i0 + (int64_t)lane * K;
         if (i0 + SZ <= n && st_ok) {
             if constexpr (K == 8) {
@@ -324,13 +324,13 @@ struct MetricCtx {
 #pragma unroll
             for (int i = 0; i < K; ++i) PR[a][i] = (float)((tail[i] + tl) + ((pre[i] + fwd) + head));
         }
-        float q[K];
+        float q[K], num[K], den[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            const float num = fadd_rn(fmul_rn(PR[0][i], PR[0][i]), fmul_rn(PR[1][i], PR[1][i]));
-            const float den = fmul_rn(PR[2][i], PR[2][i]);
-            q[i] = fdiv_rn(num, den);
+            num[i] = fadd_rn(fmul_rn(PR[0][i], PR[0][i]), fmul_rn(PR[1][i], PR[1][i]));
+            den[i] = fmul_rn(PR[2][i], PR[2][i]);
         }
+        fdiv_block<K>(num, den, q);                              // all lanes of the warp are here (CTA-uniform loops)
         const int64_t b0 = i0 + (int64_t)lane * K;
         if (i0 + SZ <= n && st_ok) {
             if constexpr (K == 8) {

@@ -32,7 +32,7 @@ __device__ __forceinline__ bool st_same2(float2 a, float2 b) { return st_same(a.
 
 __global__ void __launch_bounds__(256) selftest_kernel(int64_t n, uint64_t seed, unsigned long long* bad) {
     unsigned long long local = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i - (threadIdx.x & 31) < n; i += (int64_t)gridDim.x * blockDim.x) {   // whole warps (fdiv_block votes)
         const uint64_t h0 = st_mix(seed ^ (uint64_t)i), h1 = st_mix(h0), h2 = st_mix(h1), h3 = st_mix(h2);
         const float2 a = make_float2(st_float(h0), st_float(h1)), b = make_float2(st_float(h2), st_float(h3));
         const float s = st_float(st_mix(h3));
@@ -67,6 +67,22 @@ __global__ void __launch_bounds__(256) selftest_kernel(int64_t n, uint64_t seed,
         m |= st_same(norm_x(e), r_dist) ? 0u : 128u;
         m |= st_same2(g_dfe, r_dfe) ? 0u : 256u;
         m |= st_same2(cscale_x(cadd_x(a, b), 0.5f), r_mid) ? 0u : 512u;
+        // fdiv_block: in-range operands take the branch-free chains, anything else the compiler's division -- whole warps
+        // at a time, so every eighth warp draws all its operands from the in-range window
+        {
+            const bool tame = ((threadIdx.x >> 5) & 7) == 0;
+            float nn[4] = {fabsf(a.x), fabsf(a.y), fabsf(b.x), fabsf(s)}, dd[4] = {fabsf(b.y), fabsf(s), fabsf(a.y), fabsf(a.x)}, qq[4];
+            if (tame) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    nn[j] = __uint_as_float(((100u + ((uint32_t)(h1 >> (8 * j)) & 63u)) << 23) | (__float_as_uint(nn[j]) & 0x7FFFFFu));
+                    dd[j] = __uint_as_float(((100u + ((uint32_t)(h2 >> (8 * j)) & 63u)) << 23) | (__float_as_uint(dd[j]) & 0x7FFFFFu));
+                }
+            }
+            fdiv_block<4>(nn, dd, qq);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m |= st_same(qq[j], __fdiv_rn(nn[j], dd[j])) ? 0u : 1024u;
+        }
         if (m) { ++local; atomicOr(bad + 1, (unsigned long long)m); }
     }
     if (local) atomicAdd(bad, local);
