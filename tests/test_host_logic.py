@@ -205,3 +205,18 @@ def test_crc_slicing_host_emulation(tmp_path):
     subprocess.run(["g++", "-O2", "-std=c++17", src, "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_metric_math_host_emulation(tmp_path):
+    """The two arithmetic arguments of the metric kernels (ofdm_sync_pn's window sums and |P|^2 / R^2, ofdm_receiver.py~:97-101),
+    restated lane by lane on the CPU: the division sequence of fdiv_inrange (common.cuh) is the correctly rounded quotient for
+    in-window operands whatever reciprocal within 2 ulp it starts from, and bfly_scan (rx_sync_stream.cu) yields the exact
+    exclusive sums of the lanes in front / behind with NaN confinement."""
+    import os, shutil, subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = os.path.join(os.path.dirname(__file__), "host_emul", "metric_math_check.cpp")
+    exe = str(tmp_path / "metric_math_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", src, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "division sequence ok" in r.stdout and "bfly_scan ok" in r.stdout, r.stdout + r.stderr
