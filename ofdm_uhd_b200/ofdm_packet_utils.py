@@ -6,6 +6,7 @@ time); batches go through the CUDA kernels behind ``ofdm_make_packets`` / ``ofdm
 produce byte-identical results (tests/test_gpu_tx.py)."""
 import math
 import struct
+import zlib
 
 import numpy
 
@@ -70,13 +71,25 @@ for _i in range(256):
     _CRC_TABLE.append(_c)
 
 
-def crc32(data):
-    """gnuradio digital.crc32 (reference digital_swig.py:3151-3168): register initialised to all ones,
-    MSB-first polynomial 0x04C11DB7, transmitted value is the one's complement."""
+def _crc32_table(data):
+    """The byte-at-a-time table form (what digital.crc32 does); crc32() below must equal it (tests/test_tables.py)."""
     reg = 0xFFFFFFFF
     for b in _as_bytes(data):
         reg = (_CRC_TABLE[(b ^ (reg >> 24)) & 0xFF] ^ (reg << 8)) & 0xFFFFFFFF
     return reg ^ 0xFFFFFFFF
+
+
+_REV8 = bytes(int("{:08b}".format(_i)[::-1], 2) for _i in range(256))
+
+
+def crc32(data):
+    """gnuradio digital.crc32 (reference digital_swig.py:3151-3168): register initialised to all ones,
+    MSB-first polynomial 0x04C11DB7, transmitted value is the one's complement.  That is zlib's CRC-32 with the bit
+    order mirrored (same polynomial, same all-ones init / final xor): mirror every input byte, take zlib.crc32 (C speed
+    instead of a Python loop per byte: the per-packet send_pkt / rx_callback surface spends its time here), mirror the
+    32-bit result."""
+    z = zlib.crc32(_as_bytes(data).translate(_REV8)) & 0xFFFFFFFF
+    return int.from_bytes(z.to_bytes(4, "little").translate(_REV8), "big")
 
 
 def gen_and_append_crc32(s):

@@ -60,6 +60,16 @@ def test_crc32_known_answer():
     assert o.crc32_gr(b"") == 0 and pu.crc32(b"") == 0
 
 
+def test_crc32_mirrored_zlib_equals_table_form():
+    """pu.crc32 computes digital.crc32 (digital_swig.py:3151-3168) as zlib's CRC-32 on bit-mirrored bytes; it must equal the
+    byte-at-a-time table form and the oracle on ragged random buffers (0 .. 4095 bytes)."""
+    rng = np.random.default_rng(5)
+    for n in list(range(0, 40)) + [255, 256, 257, 402, 1500, 4091, 4095]:
+        for _ in range(8):
+            b = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+            assert pu.crc32(b) == pu._crc32_table(b) == o.crc32_gr(b), n
+
+
 def test_docstring_examples():
     assert pu.conv_packed_binary_string_to_1_0_string(b"\xAF") == "10101111"       # ofdm_packet_utils.py:29
     assert pu.conv_1_0_string_to_packed_binary_string("10101111") == (b"\xAF", False)  # :42
